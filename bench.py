@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json metric on BASELINE.json configs[1] (chr21-scale sweep).
+
+A "step" is one pass of the hot path over one batch of synthetic input: 1,000 genomic windows x
+5,008 reference haplotypes x 1,030 sites (bit-packed), 2,000 query haplotypes per window, exact
+top-8 by (Hamming distance, id).  With N GPUs every rank owns its own 1,000 windows (window
+sharding, no data-path collective, weak scaling); `value` is the whole-job aggregate.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]
+  python bench.py --impl reference ...   # the reference's CPU algorithm on the host cores
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ref-haplotypes scanned/s at k=8 (window-queries/s x panel rows)"
+UNIT = "ref-haplotypes/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--windows", type=int, default=1000)
+    ap.add_argument("--refs", type=int, default=5008)
+    ap.add_argument("--sites", type=int, default=1030)
+    ap.add_argument("--queries", type=int, default=2000)
+    ap.add_argument("-k", type=int, default=8)
+    ap.add_argument("--masked", action="store_true", help="cfg 3: per-query observed-site masks")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU baseline sample budget")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"cfg2 chr21-scale sweep: {a.windows} windows x {a.refs} ref haplotypes x {a.sites} sites, "
+            f"{a.queries} queries/window, k={a.k}, bit-packed " + ("masked " if a.masked else "") + "Hamming")
+
+
+# --------------------------------------------------------------------------- synthetic data
+def gen_windows_device(torch, dev, seed, n_windows, n_rows, n_sites, founders_seed_base, chunk=25):
+    """Mosaic-of-founders haplotypes generated on the device (SURVEY.md §8d hapgen): per window
+    64 founders ~ Bernoulli(p_s), p_s ~ Beta(.25,.75); every haplotype copies a founder, switching
+    with prob 1/200 per site, alleles flipped with prob 1e-3.  Returns packed uint32-as-int32
+    [n_windows, n_rows, stride] (library pack kernel)."""
+    from rag_snvbert_b200 import _lib
+    from rag_snvbert_b200.index import pack_rows
+
+    stride = _lib.packed_stride(n_sites)
+    out = torch.empty((n_windows, n_rows, stride), dtype=torch.int32, device=dev)
+    beta = torch.distributions.Beta(torch.tensor(0.25, device=dev), torch.tensor(0.75, device=dev))
+    for w0 in range(0, n_windows, chunk):
+        nw = min(chunk, n_windows - w0)
+        gf = torch.Generator(device=dev)
+        gf.manual_seed(founders_seed_base + w0)  # founders shared by panel and queries of a window
+        torch.manual_seed(founders_seed_base + w0)
+        p = beta.sample((nw, 1, n_sites))
+        F = (torch.rand((nw, 64, n_sites), device=dev, generator=gf) < p).to(torch.uint8)
+        g = torch.Generator(device=dev)
+        g.manual_seed(seed + w0)
+        sw = torch.rand((nw, n_rows, n_sites), device=dev, generator=g) < (1.0 / 200)
+        seg = torch.cumsum(sw.to(torch.int32), dim=2)  # segment id per site
+        max_seg = int(seg.max().item()) + 1
+        choice = torch.randint(0, 64, (nw, n_rows, max_seg), device=dev, generator=g)
+        fid = torch.gather(choice, 2, seg.long())  # founder per site
+        del sw, seg, choice
+        hap = torch.gather(F, 1, fid)  # F[w, fid[w,r,s], s]
+        del fid
+        flip = torch.rand((nw, n_rows, n_sites), device=dev, generator=g) < 1e-3
+        hap ^= flip.to(torch.uint8)
+        del flip
+        out[w0:w0 + nw] = pack_rows(hap.reshape(-1, n_sites), n_sites).reshape(nw, n_rows, stride)
+        del hap
+    return out
+
+
+def gen_masks_device(torch, dev, seed, n_windows, nq, n_sites, chunk=50):
+    from rag_snvbert_b200 import _lib
+    from rag_snvbert_b200.index import pack_rows
+
+    stride = _lib.packed_stride(n_sites)
+    out = torch.empty((n_windows, nq, stride), dtype=torch.int32, device=dev)
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    for w0 in range(0, n_windows, chunk):
+        nw = min(chunk, n_windows - w0)
+        rate = 0.1 + 0.8 * torch.rand((nw, nq, 1), device=dev, generator=g)
+        obs = (torch.rand((nw, nq, n_sites), device=dev, generator=g) >= rate).to(torch.uint8)
+        out[w0:w0 + nw] = pack_rows(obs.reshape(-1, n_sites), n_sites).reshape(nw, nq, stride)
+    return out
+
+
+# --------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(prefix="clocks_", suffix=".csv")
+            os.close(fd)
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            try:
+                self.proc.kill()
+            except Exception:
+                pass
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                parts = [x.strip() for x in line.split(",")]
+                if len(parts) < 9:
+                    continue
+                try:
+                    sm.append(float(parts[1]))
+                    mx.append(float(parts[2]))
+                except ValueError:
+                    continue
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                for nm, v in zip(names, parts[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            # median over the upper half = "under load" samples
+            s = sorted(sm)
+            out["sm_mhz"] = float(np.median(s[len(s) // 2:]))
+            out["sm_max_mhz"] = float(max(mx))
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# --------------------------------------------------------------------------- CPU arm
+def cpu_reference_sample(a, seconds):
+    """The reference's CPU algorithm for this path (faiss IndexBinaryFlat-style popcount scan +
+    per-query heap, restated in oracle/snv_oracle.c: 'port'; faiss itself is absent from the
+    image and the reference has no native code to compile) on a bounded sample of the workload,
+    all host threads.  Returns (ref_haps_per_s, n_threads, sample description, seconds)."""
+    from oracle import oracle as O
+    from oracle import cbind
+
+    threads = cbind.max_threads()
+    s = (a.sites + 31) // 32
+    stride = -(-s // 4) * 4
+    P = O.pack_bits_u32(O.hapgen(2000, a.refs, a.sites), stride)[None]
+    Qfull = O.pack_bits_u32(O.hapgen(5000, a.queries, a.sites, founder_seed=2000), stride)[None]
+    M = None
+    if a.masked:
+        rng = np.random.default_rng(8000)
+        rate = rng.uniform(0.1, 0.9, size=(a.queries, 1))
+        M = O.pack_bits_u32((rng.random((a.queries, a.sites)) >= rate).astype(np.uint8), stride)[None]
+    # calibrate on a small slice, then size the sample for ~`seconds`
+    nq0 = min(a.queries, max(threads * 4, 64))
+    cbind.hamming_topk_packed(P, Qfull[:, :nq0], a.k, None if M is None else M[:, :nq0], words=s)
+    t0 = time.perf_counter()
+    cbind.hamming_topk_packed(P, Qfull[:, :nq0], a.k, None if M is None else M[:, :nq0], words=s)
+    dt0 = max(time.perf_counter() - t0, 1e-6)
+    rate0 = nq0 * a.refs / dt0
+    n_win = int(max(1, min(a.windows, seconds * rate0 / (a.queries * a.refs))))
+    Pn = np.ascontiguousarray(np.broadcast_to(P, (n_win,) + P.shape[1:]))
+    Qn = np.ascontiguousarray(np.broadcast_to(Qfull, (n_win,) + Qfull.shape[1:]))
+    Mn = None if M is None else np.ascontiguousarray(np.broadcast_to(M, (n_win,) + M.shape[1:]))
+    t0 = time.perf_counter()
+    cbind.hamming_topk_packed(Pn, Qn, a.k, Mn, words=s)
+    dt = time.perf_counter() - t0
+    val = n_win * a.queries * a.refs / dt
+    sample = (f"{n_win} of {a.windows} windows x {a.queries} queries x {a.refs} refs, k={a.k}, "
+              f"C popcount port (oracle/snv_oracle.c), {threads} OpenMP threads, {dt:.2f} s")
+    return val, threads, sample, dt
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals, times = [], []
+    sample = ""
+    threads = 1
+    per_step = max(2.0, min(a.cpu_seconds, 120.0 / max(1, a.steps + a.warmup)))
+    for i in range(a.warmup + a.steps):
+        v, threads, sample, dt = cpu_reference_sample(a, per_step)
+        if i >= a.warmup:
+            vals.append(v)
+            times.append(dt)
+    value = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": float(np.mean(times) * 1e3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32-popcount",
+        "data": "synthetic", "config": {"workload": workload_name(a), "sample_per_step": sample},
+        "window_queries_per_s": value / a.refs,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- GPU arm
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from rag_snvbert_b200 import WindowedHammingIndex, _lib
+
+    W, N, S, Q, k = a.windows, a.refs, a.sites, a.queries, a.k
+    stride = _lib.packed_stride(S)
+    # every rank owns W windows of its own (window sharding; seeds offset by rank)
+    panel = gen_windows_device(torch, dev, 2000 + 100000 * rank, W, N, S, 777 + 100000 * rank)
+    queries = gen_windows_device(torch, dev, 5000 + 100000 * rank, W, Q, S, 777 + 100000 * rank)
+    masks = gen_masks_device(torch, dev, 8000 + rank, W, Q, S) if a.masked else None
+    index = WindowedHammingIndex(S, W, local)
+    index.add(panel)
+    del panel
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        return index.search(queries, k, observed=masks)
+
+    for _ in range(max(a.warmup, 3)):
+        D, I = step()
+    barrier()
+
+    # ---- device-resident throughput (`value`) + per-launch kernel time for the roofline
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    barrier()
+    t_all0 = torch.cuda.Event(enable_timing=True)
+    t_all1 = torch.cuda.Event(enable_timing=True)
+    t_all0.record()
+    for i in range(a.steps):
+        ev[i][0].record()
+        D, I = step()
+        ev[i][1].record()
+    t_all1.record()
+    barrier()
+    launches = _lib.launch_count() - launches0
+    total_ms = t_all0.elapsed_time(t_all1)
+    kern_ms = float(np.mean([s.elapsed_time(e) for s, e in ev]))
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / a.steps
+    pairs_per_step_rank = W * Q * N
+    value = world * pairs_per_step_rank / (ms_per_step * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H in the timed region
+    e2e = None
+    if not a.no_e2e:
+        hq = torch.empty((W, Q, stride), dtype=torch.int32, pin_memory=True)
+        hq.copy_(queries)
+        hm = None
+        if masks is not None:
+            hm = torch.empty((W, Q, stride), dtype=torch.int32, pin_memory=True)
+            hm.copy_(masks)
+        hq_np = hq.numpy()
+        hm_np = None if hm is None else hm.numpy()
+        for _ in range(2):
+            Dh, Ih = index.search(hq_np, k, observed=hm_np)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            Dh, Ih = index.search(hq_np, k, observed=hm_np)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+        h2d = hq_np.nbytes + (0 if hm_np is None else hm_np.nbytes)
+        d2h = Dh.nbytes + Ih.nbytes
+        e2e = {"value": world * pairs_per_step_rank / (dt / a.steps), "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": dt / a.steps * 1e3,
+               "api": "WindowedHammingIndex.search(numpy packed uint32 [W,Q,stride]) -> numpy (D int32, I int64)"}
+        # the two paths must agree bit for bit
+        assert np.array_equal(Ih, I.cpu().numpy()) and np.array_equal(Dh, D.cpu().numpy()), "host/device result mismatch"
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (hamming_topk_kernel): scan-equivalent bandwidth
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    words = (S + 31) // 32
+    bytes_per_pair = words * 4
+    achieved = pairs_per_step_rank * bytes_per_pair / (kern_ms * 1e-3) / 1e9
+    sm_mhz = (clocks or {}).get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
+    popc_per_pair = 16 if words == 33 else words  # CSA depth 2 leaves 16 POPC for 33 words
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": None, "kernel": "hamming_topk_kernel<33,masked=%d,K=8>" % (1 if a.masked else 0),
+        "kernel_ms": kern_ms, "peak_source": peak_src,
+        "note": ("scan-equivalent bandwidth = pairs x 132 B / kernel time (SURVEY.md 8d): the panel tile is "
+                 "served from shared memory/L2, so this may exceed 1.0; the binding unit is the integer pipes"),
+        "int_pipe": {
+            "pairs_per_s": pairs_per_step_rank / (kern_ms * 1e-3),
+            "lop3_per_pair": 67 if words == 33 else None, "popc_per_pair": popc_per_pair,
+            "alu_frac_of_64_per_clk_sm": (pairs_per_step_rank / (kern_ms * 1e-3)) * 67 / (148 * 64 * sm_mhz * 1e6) if words == 33 else None,
+        },
+    }
+
+    cpu = None
+    if not a.no_cpu_baseline:
+        v, threads, sample, _ = cpu_reference_sample(a, a.cpu_seconds)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+        "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32-popcount", "data": "synthetic",
+        "config": {"workload": workload_name(a), "windows_per_gpu": W, "parallelism": f"window-sharded x{world}, no collective",
+                   "l2_policy": "inputs larger than L2 (packed panel 721 MB + queries 288 MB per GPU per step)"},
+        "window_queries_per_s": value / N,
+        "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,181 @@
+/*
+ * snvknn — C ABI of the B200-native per-window exact k-NN engine (libsnvknn.so).
+ *
+ * This is the drop-in boundary for the one hot path of wangbaonan/RAG-SNVBERT: the faiss
+ * `IndexFlatL2` / `IndexBinaryFlat` build + search (+ the gather that follows) which the
+ * reference reaches through faiss's SWIG Python API.  The reference has no C ABI of its own
+ * (it is pure Python); every entry point below cites the reference call site it replaces
+ * (paths relative to the reference tree).  The Python mirror of the faiss surface lives in
+ * rag_snvbert_b200/faiss_compat.py and binds these symbols with ctypes.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types.
+ *   - every function returns SNV_OK (0) or an snv_status; snv_last_error() gives the
+ *     thread-local message of the last failure.
+ *   - `*_on_device` / SNV_LOC_* flags say whether a pointer is host or device memory
+ *     (device pointers must belong to the index's device).  Host buffers are copied on
+ *     `stream` and the call returns after the stream has been synchronised; device buffers
+ *     are used in place and the call is asynchronous on `stream`.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).
+ *   - there is NO CPU fallback: without a usable CUDA device every compute entry point
+ *     fails with SNV_ERR_CUDA.
+ *
+ * Packed haplotype rows (the native layout): uint32 words, site s in word s/32, bit s%32,
+ * pad bits zero, row stride snv_packed_stride(d) words (a multiple of 4 => 16-byte rows for
+ * bulk async copies).
+ */
+#ifndef SNVKNN_H
+#define SNVKNN_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNVKNN_VERSION 100
+
+typedef enum snv_status {
+    SNV_OK = 0,
+    SNV_ERR_INVALID = 1,     /* bad argument (faiss: AssertionError from the SWIG wrapper) */
+    SNV_ERR_CUDA = 2,        /* CUDA runtime / driver failure, or no device                */
+    SNV_ERR_UNSUPPORTED = 3, /* valid request outside what the kernels implement           */
+    SNV_ERR_NOMEM = 4
+} snv_status;
+
+typedef enum snv_kind {
+    SNV_KIND_HAMMING = 0, /* bit-packed rows, integer Hamming / observed-site masked Hamming  */
+    SNV_KIND_L2 = 1       /* float rows, squared L2 = |q|^2 + |r|^2 - 2 q.r on tcgen05       */
+} snv_kind;
+
+typedef enum snv_dtype {
+    SNV_DT_U8 = 0,         /* one byte per site, non-zero = alt allele        [rows][d]       */
+    SNV_DT_F32 = 1,        /* HAMMING: non-zero = alt allele; L2: the vector  [rows][d]       */
+    SNV_DT_PACKED_U32 = 2, /* native packed rows            [rows][snv_packed_stride(d)]      */
+    SNV_DT_PACKED_U8 = 3,  /* np.packbits rows (faiss binary codes) [rows][(d+7)/8] bytes     */
+    SNV_DT_I64_TOKENS = 4  /* model tokens (5/6 alleles, 4 = MASK, 0/2/3 specials) [rows][d]  */
+} snv_dtype;
+
+typedef enum snv_mask_mode {
+    SNV_MASK_NONE = 0,
+    SNV_MASK_PER_WINDOW = 1, /* one mask row per window   [nw][row]      */
+    SNV_MASK_PER_QUERY = 2   /* one mask row per query    [nw][nq][row]  */
+} snv_mask_mode;
+
+/* bit flags for `flags` arguments */
+#define SNV_Q_ON_DEVICE 0x1u    /* queries (and mask) are device pointers                  */
+#define SNV_OUT_ON_DEVICE 0x2u  /* D / I (or gather output) are device pointers            */
+#define SNV_MASK_IS_MISSING 0x4u /* mask marks MISSING sites (reference convention,        */
+                                 /* partial_faiss_intersect.py:91) instead of observed ones */
+#define SNV_X_ON_DEVICE 0x8u    /* rows passed to add() are a device pointer               */
+
+/* L2 cross-term precision */
+#define SNV_L2_TF32 0   /* one tf32 pass: exact for small-integer inputs (tokens), ~1e-3 rel. otherwise */
+#define SNV_L2_TF32X3 1 /* hi/lo split, three tf32 products: fp32-faithful                               */
+
+typedef struct snv_index snv_index;
+
+const char* snv_last_error(void);
+int snv_version(void);
+/* number of visible CUDA devices (0 when there is none); SNV_ERR_CUDA if the runtime fails */
+int snv_device_count(int* count);
+
+int64_t snv_packed_words(int64_t d);  /* ceil(d/32)                     */
+int64_t snv_packed_stride(int64_t d); /* packed_words rounded up to 4   */
+
+/*
+ * faiss.IndexFlatL2(d) / faiss.IndexBinaryFlat(d_bits) constructors
+ * (build_ref_db_l2.py:89, src/dataset/rag_train_dataset.py:132, test_faiss_intersect.py:173,
+ *  src/dataset/embedding_rag_infer_dataset.py:176) — plus the windowed form: one object
+ * holding `n_windows` independent panels of the same shape so that a whole window sweep
+ * (batch_test_faiss_l2.py:80-110) is one launch.  `l2_mode` is ignored for HAMMING.
+ */
+int snv_index_create(int kind, int64_t d, int n_windows, int device, int l2_mode, snv_index** out);
+void snv_index_free(snv_index* idx);
+
+int64_t snv_index_ntotal(const snv_index* idx); /* rows per window (faiss index.ntotal) */
+int64_t snv_index_d(const snv_index* idx);      /* faiss index.d                        */
+int snv_index_kind(const snv_index* idx);
+int snv_index_n_windows(const snv_index* idx);
+int snv_index_device(const snv_index* idx);
+int snv_index_reset(snv_index* idx);            /* faiss index.reset()                  */
+
+/*
+ * index.add(x)  (build_ref_db_l2.py:90, src/dataset/rag_train_dataset.py:133-134,
+ * partial_faiss_intersect.py:103-105, test_faiss_intersect.py:152-155,173-178).
+ * Appends `n` rows to EVERY window: x is [n_windows][n][row] in `dtype`.  The index keeps
+ * its own device copy (bit-packed for HAMMING; fp32 + tf32 operand planes + |r|^2 for L2);
+ * the caller may free x on return (host x) / after the stream reaches this point (device x).
+ */
+int snv_index_add(snv_index* idx, const void* x, int64_t n, int dtype, unsigned flags, void* stream);
+
+/*
+ * index.search(q, k) -> (D, I)  (src/dataset/rag_train_dataset.py:281,
+ * batch_test_faiss_l2.py:110, test_faiss.py:135, partial_faiss_intersect.py:109,
+ * test_faiss_intersect.py:160,181, src/dataset/embedding_rag_infer_dataset.py:284-285;
+ * torch.cdist+topk at src/dataset/embedding_rag_dataset.py:397-402).
+ *
+ * Windows [w0, w0+nw) are searched with q = [nw][nq][row] (`q_dtype`).  Outputs are
+ * [nw][nq][k]: I int64 row ids (+ id_offset; -1 when fewer than k rows exist),
+ * D_i32 (HAMMING only) and/or D_f32 (squared L2 == Hamming for 0/1 rows); either D pointer may
+ * be NULL.  Results are in the canonical order (distance ascending, id ascending), ties at
+ * the k-boundary keep the lowest ids.  Padding: D_i32 = INT32_MAX, D_f32 = FLT_MAX.
+ *
+ * HAMMING only: `mask` (same dtype family as q: U8/F32/PACKED_U32) restricts the distance to
+ * observed sites, popc((q ^ r) & m) — partial_faiss_intersect.py:82-111.
+ */
+int snv_index_search(snv_index* idx, int w0, int nw, const void* q, int64_t nq, int q_dtype,
+                     const void* mask, int mask_mode, int k, int64_t id_offset, int32_t* D_i32,
+                     float* D_f32, int64_t* I, unsigned flags, void* stream);
+
+/*
+ * The gather that follows search in the V17 collate
+ * (src/dataset/rag_train_dataset.py:287-307): I -> retrieved haplotype -> tokens with an
+ * all-zero mask: out[w][q][j][:] = [SOS=2] + (5|6 per site) + [EOS=3] + PAD(0) up to seq_len.
+ * HAMMING indexes only.  n_sites: NULL (every window has d sites) or int32 [nw] real site
+ * counts (host pointer).  I: [nw][nq][k] (location per SNV_Q_ON_DEVICE), out int64
+ * [nw][nq][k][seq_len] (location per SNV_OUT_ON_DEVICE).  I == -1 -> all PAD.
+ */
+int snv_index_gather_tokens(snv_index* idx, int w0, int nw, const int64_t* I, int64_t nq, int k,
+                            const int32_t* n_sites, int seq_len, int64_t* out, unsigned flags,
+                            void* stream);
+
+/*
+ * Row gather for L2 indexes (src/dataset/embedding_rag_dataset.py:406-438,
+ * src/dataset/embedding_rag_infer_dataset.py:287-319 once re-embedding is per row):
+ * out[w][q][j][:] = panel[w][I[w][q][j]][:]  float32 [nw][nq][k][d]; I == -1 -> zeros.
+ */
+int snv_index_gather_rows(snv_index* idx, int w0, int nw, const int64_t* I, int64_t nq, int k,
+                          float* out, unsigned flags, void* stream);
+
+/*
+ * faiss.write_index / read_index support (build_ref_db_l2.py:93, batch_test_faiss_l2.py:94):
+ * copy the stored rows of window w to the HOST buffer `out`
+ * (HAMMING: uint32 [ntotal][snv_packed_stride(d)]; L2: float32 [ntotal][d]).
+ */
+int snv_index_export(snv_index* idx, int window, void* out);
+
+/*
+ * k-way merge of per-shard results (row-sharded panel; new — the reference never shards,
+ * SURVEY.md §2.2).  D/I are DEVICE arrays [parts][nq][k_in] with GLOBAL ids (what an
+ * all-gather of per-rank search outputs produces); writes the best k_out per query by
+ * (distance, id) to the device arrays Do/Io [nq][k_out].  Exactly one of D_i32/D_f32 (and
+ * the matching output) is non-NULL.
+ */
+int snv_topk_merge(int device, const int32_t* D_i32, const float* D_f32, const int64_t* I, int parts,
+                   int64_t nq, int k_in, int k_out, int32_t* Do_i32, float* Do_f32, int64_t* Io,
+                   void* stream);
+
+/* device-side pack helper: rows in `dtype` (U8 / F32 / PACKED_U8 / I64_TOKENS) ->
+ * packed uint32 [rows][snv_packed_stride(d)] (device pointers; all on `stream`).
+ * For I64_TOKENS `out_observed` (nullable) receives the observed-site plane (token in {5,6}). */
+int snv_pack_rows(int device, const void* x, int64_t rows, int64_t d, int dtype, int invert,
+                  uint32_t* out, uint32_t* out_observed, void* stream);
+
+/* number of kernels this library has launched in the calling process (bench "gpu_launches") */
+int64_t snv_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNVKNN_H */

@@ -1,0 +1,626 @@
+// C ABI of libsnvknn (include/snvknn.h): index objects, staging of host buffers, kernel dispatch.
+#include <algorithm>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace snv {
+
+static thread_local std::string t_error;
+long long g_launch_count = 0;
+void set_error(const std::string& msg) { t_error = msg; }
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; }
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// grow-only device scratch buffer
+struct Buf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes)
+    {
+        if (bytes <= cap) return SNV_OK;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 4;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            want = bytes;
+            e = cudaMalloc(&p, want);
+        }
+        if (e != cudaSuccess) {
+            p = nullptr;
+            set_error(std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
+            return SNV_ERR_NOMEM;
+        }
+        cap = want;
+        return SNV_OK;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+size_t dtype_row_bytes(int dtype, int64_t d, int stride)
+{
+    switch (dtype) {
+        case SNV_DT_U8: return (size_t)d;
+        case SNV_DT_F32: return (size_t)d * 4;
+        case SNV_DT_PACKED_U32: return (size_t)stride * 4;
+        case SNV_DT_PACKED_U8: return (size_t)((d + 7) / 8);
+        case SNV_DT_I64_TOKENS: return (size_t)d * 8;
+        default: return 0;
+    }
+}
+
+int bucket_stride(int64_t words)
+{
+    static const int buckets[] = {4, 8, 16, 24, 32, 36, 48, 68};
+    for (int b : buckets)
+        if (words <= b) return b;
+    return (int)round_up(words, 4);
+}
+
+__global__ void invert_packed_kernel(const uint32_t* __restrict__ x, int64_t rows, int64_t d, int stride,
+                                     uint32_t* __restrict__ out)
+{
+    const int64_t total = rows * stride;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t w = i % stride;
+        const int64_t lo = w * 32;
+        uint32_t valid = 0;
+        if (lo + 32 <= d) valid = 0xFFFFFFFFu;
+        else if (lo < d) valid = (1u << (d - lo)) - 1u;
+        out[i] = ~x[i] & valid;
+    }
+}
+
+}  // namespace
+}  // namespace snv
+
+using namespace snv;
+
+struct snv_index {
+    int kind = 0;
+    int64_t d = 0;
+    int n_windows = 1;
+    int device = 0;
+    int l2_mode = SNV_L2_TF32X3;
+    int words = 0, stride = 0;  // HAMMING packed geometry
+    int kp = 0;                 // L2 operand depth
+    int64_t ntotal = 0, cap = 0;
+    uint32_t* panel = nullptr;  // HAMMING [W][cap][stride]
+    float* rows = nullptr;      // L2 [W][cap][d]
+    float* ops = nullptr;       // L2 [W][cap][kp]
+    float* norms = nullptr;     // L2 [W][cap]
+    Buf ws_in, ws_q, ws_mask, ws_min, ws_partial, ws_di, ws_df, ws_i, ws_qops, ws_qnorm, ws_misc;
+};
+
+extern "C" {
+
+const char* snv_last_error(void) { return t_error.c_str(); }
+int snv_version(void) { return SNVKNN_VERSION; }
+int64_t snv_launch_count(void) { return g_launch_count; }
+
+int snv_device_count(int* count)
+{
+    if (!count) { set_error("snv_device_count: null"); return SNV_ERR_INVALID; }
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) {
+        cudaGetLastError();
+        *count = 0;
+        return SNV_OK;
+    }
+    if (e != cudaSuccess) {
+        set_error(std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+        *count = 0;
+        return SNV_ERR_CUDA;
+    }
+    *count = n;
+    return SNV_OK;
+}
+
+int64_t snv_packed_words(int64_t d) { return d <= 0 ? 0 : (d + 31) / 32; }
+int64_t snv_packed_stride(int64_t d) { return d <= 0 ? 0 : bucket_stride((d + 31) / 32); }
+
+int snv_index_create(int kind, int64_t d, int n_windows, int device, int l2_mode, snv_index** out)
+{
+    if (!out) { set_error("snv_index_create: out is null"); return SNV_ERR_INVALID; }
+    *out = nullptr;
+    if (kind != SNV_KIND_HAMMING && kind != SNV_KIND_L2) { set_error("snv_index_create: bad kind"); return SNV_ERR_INVALID; }
+    if (d <= 0) { set_error("snv_index_create: d must be positive"); return SNV_ERR_INVALID; }
+    if (n_windows < 1) { set_error("snv_index_create: n_windows must be >= 1"); return SNV_ERR_INVALID; }
+    if (kind == SNV_KIND_L2 && l2_mode != SNV_L2_TF32 && l2_mode != SNV_L2_TF32X3) { set_error("snv_index_create: bad l2_mode"); return SNV_ERR_INVALID; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("snv_index_create: no CUDA device (this engine has no CPU fallback)");
+        return SNV_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) { set_error("snv_index_create: bad device ordinal"); return SNV_ERR_INVALID; }
+    snv_index* idx = new (std::nothrow) snv_index();
+    if (!idx) { set_error("snv_index_create: out of host memory"); return SNV_ERR_NOMEM; }
+    idx->kind = kind;
+    idx->d = d;
+    idx->n_windows = n_windows;
+    idx->device = device;
+    idx->l2_mode = l2_mode;
+    if (kind == SNV_KIND_HAMMING) {
+        idx->words = (int)snv_packed_words(d);
+        idx->stride = (int)snv_packed_stride(d);
+    } else {
+        idx->kp = l2_operand_depth(d, l2_mode);
+    }
+    *out = idx;
+    return SNV_OK;
+}
+
+void snv_index_free(snv_index* idx)
+{
+    if (!idx) return;
+    DeviceGuard g(idx->device);
+    cudaDeviceSynchronize();
+    if (idx->panel) cudaFree(idx->panel);
+    if (idx->rows) cudaFree(idx->rows);
+    if (idx->ops) cudaFree(idx->ops);
+    if (idx->norms) cudaFree(idx->norms);
+    Buf* bufs[] = {&idx->ws_in, &idx->ws_q, &idx->ws_mask, &idx->ws_min, &idx->ws_partial, &idx->ws_di,
+                   &idx->ws_df, &idx->ws_i, &idx->ws_qops, &idx->ws_qnorm, &idx->ws_misc};
+    for (Buf* b : bufs) b->release();
+    delete idx;
+}
+
+int64_t snv_index_ntotal(const snv_index* idx) { return idx ? idx->ntotal : -1; }
+int64_t snv_index_d(const snv_index* idx) { return idx ? idx->d : -1; }
+int snv_index_kind(const snv_index* idx) { return idx ? idx->kind : -1; }
+int snv_index_n_windows(const snv_index* idx) { return idx ? idx->n_windows : -1; }
+int snv_index_device(const snv_index* idx) { return idx ? idx->device : -1; }
+
+int snv_index_reset(snv_index* idx)
+{
+    if (!idx) { set_error("snv_index_reset: null index"); return SNV_ERR_INVALID; }
+    idx->ntotal = 0;
+    return SNV_OK;
+}
+
+// re-layout [W][cap][row] -> [W][new_cap][row]
+static int grow_array(void** arr, size_t row_bytes, int W, int64_t ntotal, int64_t old_cap, int64_t new_cap,
+                      cudaStream_t stream)
+{
+    void* np = nullptr;
+    cudaError_t e = cudaMalloc(&np, (size_t)W * new_cap * row_bytes);
+    if (e != cudaSuccess) {
+        set_error(std::string("cudaMalloc(panel): ") + cudaGetErrorString(e));
+        return SNV_ERR_NOMEM;
+    }
+    if (*arr && ntotal > 0) {
+        SNV_CUDA_CHECK(cudaMemcpy2DAsync(np, (size_t)new_cap * row_bytes, *arr, (size_t)old_cap * row_bytes,
+                                         (size_t)ntotal * row_bytes, W, cudaMemcpyDeviceToDevice, stream));
+        SNV_CUDA_CHECK(cudaStreamSynchronize(stream));
+    }
+    if (*arr) cudaFree(*arr);
+    *arr = np;
+    return SNV_OK;
+}
+
+int snv_index_add(snv_index* idx, const void* x, int64_t n, int dtype, unsigned flags, void* stream_)
+{
+    if (!idx) { set_error("snv_index_add: null index"); return SNV_ERR_INVALID; }
+    if (n < 0) { set_error("snv_index_add: negative n"); return SNV_ERR_INVALID; }
+    if (n == 0) return SNV_OK;
+    if (!x) { set_error("snv_index_add: x is null"); return SNV_ERR_INVALID; }
+    const bool hamming = idx->kind == SNV_KIND_HAMMING;
+    if (hamming) {
+        if (dtype != SNV_DT_U8 && dtype != SNV_DT_F32 && dtype != SNV_DT_PACKED_U32 &&
+            dtype != SNV_DT_PACKED_U8 && dtype != SNV_DT_I64_TOKENS) {
+            set_error("snv_index_add: bad dtype for a HAMMING index");
+            return SNV_ERR_INVALID;
+        }
+    } else if (dtype != SNV_DT_F32) {
+        set_error("snv_index_add: an L2 index takes float32 rows");
+        return SNV_ERR_INVALID;
+    }
+    DeviceGuard g(idx->device);
+    if (!g.ok) { set_error("snv_index_add: cudaSetDevice failed"); return SNV_ERR_CUDA; }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int W = idx->n_windows;
+    const bool on_dev = flags & SNV_X_ON_DEVICE;
+
+    // capacity
+    const int64_t need = idx->ntotal + n;
+    if (need > idx->cap) {
+        int64_t new_cap = std::max<int64_t>(need, idx->cap + idx->cap / 2);
+        int rc;
+        if (hamming) {
+            rc = grow_array((void**)&idx->panel, (size_t)idx->stride * 4, W, idx->ntotal, idx->cap, new_cap, stream);
+            if (rc) return rc;
+        } else {
+            rc = grow_array((void**)&idx->rows, (size_t)idx->d * 4, W, idx->ntotal, idx->cap, new_cap, stream);
+            if (rc) return rc;
+            rc = grow_array((void**)&idx->ops, (size_t)idx->kp * 4, W, idx->ntotal, idx->cap, new_cap, stream);
+            if (rc) return rc;
+            rc = grow_array((void**)&idx->norms, 4, W, idx->ntotal, idx->cap, new_cap, stream);
+            if (rc) return rc;
+        }
+        idx->cap = new_cap;
+    }
+
+    const size_t in_row = dtype_row_bytes(dtype, idx->d, idx->stride);
+    const size_t in_bytes = (size_t)W * n * in_row;
+    const void* xd = x;
+    if (hamming && dtype == SNV_DT_PACKED_U32) {
+        // straight 2-D copy into the panel
+        const size_t rb = (size_t)idx->stride * 4;
+        SNV_CUDA_CHECK(cudaMemcpy2DAsync(idx->panel + idx->ntotal * idx->stride, (size_t)idx->cap * rb, x,
+                                         (size_t)n * rb, (size_t)n * rb, W,
+                                         on_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream));
+    } else {
+        if (!on_dev) {
+            int rc = idx->ws_in.reserve(in_bytes);
+            if (rc) return rc;
+            SNV_CUDA_CHECK(cudaMemcpyAsync(idx->ws_in.p, x, in_bytes, cudaMemcpyHostToDevice, stream));
+            xd = idx->ws_in.p;
+        }
+        if (hamming) {
+            const size_t rb = (size_t)idx->stride * 4;
+            int rc = idx->ws_q.reserve((size_t)W * n * rb);
+            if (rc) return rc;
+            rc = pack_launch(xd, (int64_t)W * n, idx->d, dtype, false, idx->stride, (uint32_t*)idx->ws_q.p, nullptr, stream);
+            if (rc) return rc;
+            SNV_CUDA_CHECK(cudaMemcpy2DAsync(idx->panel + idx->ntotal * idx->stride, (size_t)idx->cap * rb,
+                                             idx->ws_q.p, (size_t)n * rb, (size_t)n * rb, W,
+                                             cudaMemcpyDeviceToDevice, stream));
+        } else {
+            const size_t rb = (size_t)idx->d * 4;
+            SNV_CUDA_CHECK(cudaMemcpy2DAsync(idx->rows + idx->ntotal * idx->d, (size_t)idx->cap * rb, xd,
+                                             (size_t)n * rb, (size_t)n * rb, W, cudaMemcpyDeviceToDevice, stream));
+            for (int w = 0; w < W; ++w) {
+                int rc = l2_prep_launch((const float*)xd + (size_t)w * n * idx->d, n, idx->d, idx->l2_mode, false,
+                                        idx->kp, idx->ops + ((size_t)w * idx->cap + idx->ntotal) * idx->kp,
+                                        idx->norms + (size_t)w * idx->cap + idx->ntotal, stream);
+                if (rc) return rc;
+            }
+        }
+    }
+    if (!on_dev) SNV_CUDA_CHECK(cudaStreamSynchronize(stream));
+    idx->ntotal = need;
+    return SNV_OK;
+}
+
+// stage `src` ([rows][row_bytes], host or device) as packed rows in `ws`; returns device ptr
+static int stage_packed(snv_index* idx, const void* src, int64_t rows, int dtype, bool on_dev, bool invert,
+                        Buf& ws_raw, Buf& ws_packed, const uint32_t** out, uint32_t* obs_out,
+                        cudaStream_t stream)
+{
+    const size_t in_row = dtype_row_bytes(dtype, idx->d, idx->stride);
+    if (in_row == 0) { set_error("search: bad dtype"); return SNV_ERR_INVALID; }
+    const void* xd = src;
+    if (!on_dev) {
+        int rc = ws_raw.reserve((size_t)rows * in_row);
+        if (rc) return rc;
+        SNV_CUDA_CHECK(cudaMemcpyAsync(ws_raw.p, src, (size_t)rows * in_row, cudaMemcpyHostToDevice, stream));
+        xd = ws_raw.p;
+    }
+    if (dtype == SNV_DT_PACKED_U32 && !invert) {
+        *out = (const uint32_t*)xd;
+        return SNV_OK;
+    }
+    int rc = ws_packed.reserve((size_t)rows * idx->stride * 4);
+    if (rc) return rc;
+    if (dtype == SNV_DT_PACKED_U32) {
+        const int block = 256;
+        const int grid = (int)std::min<int64_t>(ceil_div(rows * idx->stride, block), (int64_t)kNumSMs * 16);
+        invert_packed_kernel<<<grid, block, 0, stream>>>((const uint32_t*)xd, rows, idx->d, idx->stride, (uint32_t*)ws_packed.p);
+        SNV_LAUNCH_CHECK();
+    } else {
+        rc = pack_launch(xd, rows, idx->d, dtype, invert, idx->stride, (uint32_t*)ws_packed.p, obs_out, stream);
+        if (rc) return rc;
+    }
+    *out = (const uint32_t*)ws_packed.p;
+    return SNV_OK;
+}
+
+static int search_hamming(snv_index* idx, int w0, int nw, const void* q, int64_t nq, int q_dtype,
+                          const void* mask, int mask_mode, int k, int64_t id_offset, int32_t* D_i32,
+                          float* D_f32, int64_t* I, unsigned flags, cudaStream_t stream)
+{
+    const bool q_dev = flags & SNV_Q_ON_DEVICE;
+    const bool out_dev = flags & SNV_OUT_ON_DEVICE;
+    const int64_t nqt = (int64_t)nw * nq;
+
+    HammingSearchParams p{};
+    p.panel = idx->panel + (int64_t)w0 * idx->cap * idx->stride;
+    p.panel_win_stride = idx->cap * idx->stride;
+    p.words = idx->words;
+    p.stride = idx->stride;
+    p.d = (int)idx->d;
+    p.n = idx->ntotal;
+    p.nq = (int)nq;
+    p.nw = nw;
+    p.k = k;
+    p.id_offset = id_offset;
+
+    // queries (tokens also yield the observed-site plane)
+    const uint32_t* qd = nullptr;
+    uint32_t* obs = nullptr;
+    if (q_dtype == SNV_DT_I64_TOKENS) {
+        if (mask_mode != SNV_MASK_NONE) { set_error("search: token queries carry their own mask"); return SNV_ERR_INVALID; }
+        int rc = idx->ws_mask.reserve((size_t)nqt * idx->stride * 4);
+        if (rc) return rc;
+        obs = (uint32_t*)idx->ws_mask.p;
+    }
+    int rc = stage_packed(idx, q, nqt, q_dtype, q_dev, false, idx->ws_in, idx->ws_q, &qd, obs, stream);
+    if (rc) return rc;
+    p.q = qd;
+    if (obs) {
+        p.mask = obs;
+        p.mask_win_stride = nq * idx->stride;
+        p.mask_q_stride = idx->stride;
+    } else if (mask_mode != SNV_MASK_NONE) {
+        if (!mask) { set_error("search: mask_mode set but mask is null"); return SNV_ERR_INVALID; }
+        if (q_dtype == SNV_DT_PACKED_U8) { set_error("search: masks are not supported with byte-packed codes"); return SNV_ERR_INVALID; }
+        const int64_t mrows = mask_mode == SNV_MASK_PER_WINDOW ? nw : nqt;
+        const uint32_t* md = nullptr;
+        rc = stage_packed(idx, mask, mrows, q_dtype, q_dev, flags & SNV_MASK_IS_MISSING, idx->ws_min, idx->ws_mask, &md, nullptr, stream);
+        if (rc) return rc;
+        p.mask = md;
+        p.mask_win_stride = mask_mode == SNV_MASK_PER_WINDOW ? idx->stride : nq * idx->stride;
+        p.mask_q_stride = mask_mode == SNV_MASK_PER_WINDOW ? 0 : idx->stride;
+    }
+
+    // outputs
+    if (out_dev) {
+        p.D_i32 = D_i32;
+        p.D_f32 = D_f32;
+        p.I = I;
+    } else {
+        if (D_i32) { rc = idx->ws_di.reserve((size_t)nqt * k * 4); if (rc) return rc; p.D_i32 = (int32_t*)idx->ws_di.p; }
+        if (D_f32) { rc = idx->ws_df.reserve((size_t)nqt * k * 4); if (rc) return rc; p.D_f32 = (float*)idx->ws_df.p; }
+        rc = idx->ws_i.reserve((size_t)nqt * k * 8);
+        if (rc) return rc;
+        p.I = (int64_t*)idx->ws_i.p;
+    }
+    const size_t part = hamming_plan(p);
+    if (part == (size_t)-1) return SNV_ERR_UNSUPPORTED;
+    if (part) {
+        rc = idx->ws_partial.reserve(part);
+        if (rc) return rc;
+        p.partial = (uint64_t*)idx->ws_partial.p;
+    }
+    rc = hamming_launch(p, stream);
+    if (rc) return rc;
+    if (!out_dev) {
+        if (D_i32) SNV_CUDA_CHECK(cudaMemcpyAsync(D_i32, p.D_i32, (size_t)nqt * k * 4, cudaMemcpyDeviceToHost, stream));
+        if (D_f32) SNV_CUDA_CHECK(cudaMemcpyAsync(D_f32, p.D_f32, (size_t)nqt * k * 4, cudaMemcpyDeviceToHost, stream));
+        SNV_CUDA_CHECK(cudaMemcpyAsync(I, p.I, (size_t)nqt * k * 8, cudaMemcpyDeviceToHost, stream));
+    }
+    if (!out_dev || !q_dev) SNV_CUDA_CHECK(cudaStreamSynchronize(stream));
+    return SNV_OK;
+}
+
+static int search_l2(snv_index* idx, int w0, int nw, const void* q, int64_t nq, int k, int64_t id_offset,
+                     float* D_f32, int64_t* I, unsigned flags, cudaStream_t stream)
+{
+    const bool q_dev = flags & SNV_Q_ON_DEVICE;
+    const bool out_dev = flags & SNV_OUT_ON_DEVICE;
+    const int64_t nqt = (int64_t)nw * nq;
+    const float* qd = (const float*)q;
+    int rc;
+    if (!q_dev) {
+        rc = idx->ws_in.reserve((size_t)nqt * idx->d * 4);
+        if (rc) return rc;
+        SNV_CUDA_CHECK(cudaMemcpyAsync(idx->ws_in.p, q, (size_t)nqt * idx->d * 4, cudaMemcpyHostToDevice, stream));
+        qd = (const float*)idx->ws_in.p;
+    }
+    rc = idx->ws_qops.reserve((size_t)nqt * idx->kp * 4);
+    if (rc) return rc;
+    rc = idx->ws_qnorm.reserve((size_t)nqt * 4);
+    if (rc) return rc;
+    rc = l2_prep_launch(qd, nqt, idx->d, idx->l2_mode, true, idx->kp, (float*)idx->ws_qops.p, (float*)idx->ws_qnorm.p, stream);
+    if (rc) return rc;
+    float* Dd = D_f32;
+    int64_t* Id = I;
+    if (!out_dev) {
+        rc = idx->ws_df.reserve((size_t)nqt * k * 4);
+        if (rc) return rc;
+        rc = idx->ws_i.reserve((size_t)nqt * k * 8);
+        if (rc) return rc;
+        Dd = (float*)idx->ws_df.p;
+        Id = (int64_t*)idx->ws_i.p;
+    } else if (!Dd) {
+        rc = idx->ws_df.reserve((size_t)nqt * k * 4);
+        if (rc) return rc;
+        Dd = (float*)idx->ws_df.p;
+    }
+    for (int w = 0; w < nw; ++w) {
+        L2SearchParams p{};
+        p.ref_ops = idx->ops + (size_t)(w0 + w) * idx->cap * idx->kp;
+        p.ref_norm = idx->norms + (size_t)(w0 + w) * idx->cap;
+        p.q_ops = (const float*)idx->ws_qops.p + (size_t)w * nq * idx->kp;
+        p.q_norm = (const float*)idx->ws_qnorm.p + (size_t)w * nq;
+        p.n = idx->ntotal;
+        p.nq = nq;
+        p.kp = idx->kp;
+        p.k = k;
+        p.id_offset = id_offset;
+        p.D_f32 = Dd + (size_t)w * nq * k;
+        p.I = Id + (size_t)w * nq * k;
+        const size_t part = l2_plan(p);
+        if (part == (size_t)-1) return SNV_ERR_UNSUPPORTED;
+        rc = idx->ws_partial.reserve(part ? part : 16);
+        if (rc) return rc;
+        p.partial = (uint64_t*)idx->ws_partial.p;
+        rc = l2_launch(p, stream);
+        if (rc) return rc;
+    }
+    if (!out_dev) {
+        if (D_f32) SNV_CUDA_CHECK(cudaMemcpyAsync(D_f32, Dd, (size_t)nqt * k * 4, cudaMemcpyDeviceToHost, stream));
+        SNV_CUDA_CHECK(cudaMemcpyAsync(I, Id, (size_t)nqt * k * 8, cudaMemcpyDeviceToHost, stream));
+    }
+    if (!out_dev || !q_dev) SNV_CUDA_CHECK(cudaStreamSynchronize(stream));
+    return SNV_OK;
+}
+
+int snv_index_search(snv_index* idx, int w0, int nw, const void* q, int64_t nq, int q_dtype,
+                     const void* mask, int mask_mode, int k, int64_t id_offset, int32_t* D_i32,
+                     float* D_f32, int64_t* I, unsigned flags, void* stream_)
+{
+    if (!idx) { set_error("snv_index_search: null index"); return SNV_ERR_INVALID; }
+    if (w0 < 0 || nw < 0 || w0 + nw > idx->n_windows) { set_error("snv_index_search: window range out of bounds"); return SNV_ERR_INVALID; }
+    if (nq < 0) { set_error("snv_index_search: negative nq"); return SNV_ERR_INVALID; }
+    if (k < 1) { set_error("snv_index_search: k must be >= 1"); return SNV_ERR_INVALID; }
+    if (nw == 0 || nq == 0) return SNV_OK;
+    if (!q || !I) { set_error("snv_index_search: q and I must not be null"); return SNV_ERR_INVALID; }
+    if (nq > 0x7fffffff) { set_error("snv_index_search: nq too large"); return SNV_ERR_INVALID; }
+    if (mask_mode < SNV_MASK_NONE || mask_mode > SNV_MASK_PER_QUERY) { set_error("snv_index_search: bad mask_mode"); return SNV_ERR_INVALID; }
+    DeviceGuard g(idx->device);
+    if (!g.ok) { set_error("snv_index_search: cudaSetDevice failed"); return SNV_ERR_CUDA; }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (idx->kind == SNV_KIND_HAMMING) {
+        return search_hamming(idx, w0, nw, q, nq, q_dtype, mask, mask_mode, k, id_offset, D_i32, D_f32, I, flags, stream);
+    }
+    if (q_dtype != SNV_DT_F32) { set_error("snv_index_search: an L2 index takes float32 queries"); return SNV_ERR_INVALID; }
+    if (mask_mode != SNV_MASK_NONE) { set_error("snv_index_search: masks apply to HAMMING indexes only"); return SNV_ERR_INVALID; }
+    if (D_i32) { set_error("snv_index_search: D_i32 applies to HAMMING indexes only"); return SNV_ERR_INVALID; }
+    return search_l2(idx, w0, nw, q, nq, k, id_offset, D_f32, I, flags, stream);
+}
+
+int snv_index_gather_tokens(snv_index* idx, int w0, int nw, const int64_t* I, int64_t nq, int k,
+                            const int32_t* n_sites, int seq_len, int64_t* out, unsigned flags, void* stream_)
+{
+    if (!idx || idx->kind != SNV_KIND_HAMMING) { set_error("snv_index_gather_tokens: needs a HAMMING index"); return SNV_ERR_INVALID; }
+    if (w0 < 0 || nw < 0 || w0 + nw > idx->n_windows || nq < 0 || k < 1 || seq_len < 1) { set_error("snv_index_gather_tokens: bad arguments"); return SNV_ERR_INVALID; }
+    if (nw == 0 || nq == 0) return SNV_OK;
+    if (!I || !out) { set_error("snv_index_gather_tokens: null buffer"); return SNV_ERR_INVALID; }
+    DeviceGuard g(idx->device);
+    if (!g.ok) { set_error("snv_index_gather_tokens: cudaSetDevice failed"); return SNV_ERR_CUDA; }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const bool i_dev = flags & SNV_Q_ON_DEVICE;
+    const bool out_dev = flags & SNV_OUT_ON_DEVICE;
+    const int64_t rows = (int64_t)nw * nq * k;
+    const int64_t* Id = I;
+    int rc;
+    if (!i_dev) {
+        rc = idx->ws_i.reserve((size_t)rows * 8);
+        if (rc) return rc;
+        SNV_CUDA_CHECK(cudaMemcpyAsync(idx->ws_i.p, I, (size_t)rows * 8, cudaMemcpyHostToDevice, stream));
+        Id = (const int64_t*)idx->ws_i.p;
+    }
+    const int32_t* nsd = nullptr;
+    if (n_sites) {
+        for (int w = 0; w < nw; ++w)
+            if (n_sites[w] < 0 || n_sites[w] > idx->d) { set_error("snv_index_gather_tokens: n_sites out of range"); return SNV_ERR_INVALID; }
+        rc = idx->ws_misc.reserve((size_t)nw * 4);
+        if (rc) return rc;
+        SNV_CUDA_CHECK(cudaMemcpyAsync(idx->ws_misc.p, n_sites, (size_t)nw * 4, cudaMemcpyHostToDevice, stream));
+        nsd = (const int32_t*)idx->ws_misc.p;
+    }
+    int64_t* od = out;
+    if (!out_dev) {
+        rc = idx->ws_in.reserve((size_t)rows * seq_len * 8);
+        if (rc) return rc;
+        od = (int64_t*)idx->ws_in.p;
+    }
+    rc = gather_tokens_launch(idx->panel + (int64_t)w0 * idx->cap * idx->stride, idx->cap * idx->stride, idx->stride,
+                              idx->ntotal, Id, 0, nw, nq, k, nsd, (int)idx->d, seq_len, od, stream);
+    if (rc) return rc;
+    if (!out_dev) SNV_CUDA_CHECK(cudaMemcpyAsync(out, od, (size_t)rows * seq_len * 8, cudaMemcpyDeviceToHost, stream));
+    if (!out_dev || !i_dev || n_sites) SNV_CUDA_CHECK(cudaStreamSynchronize(stream));
+    return SNV_OK;
+}
+
+int snv_index_gather_rows(snv_index* idx, int w0, int nw, const int64_t* I, int64_t nq, int k, float* out,
+                          unsigned flags, void* stream_)
+{
+    if (!idx || idx->kind != SNV_KIND_L2) { set_error("snv_index_gather_rows: needs an L2 index"); return SNV_ERR_INVALID; }
+    if (w0 < 0 || nw < 0 || w0 + nw > idx->n_windows || nq < 0 || k < 1) { set_error("snv_index_gather_rows: bad arguments"); return SNV_ERR_INVALID; }
+    if (nw == 0 || nq == 0) return SNV_OK;
+    if (!I || !out) { set_error("snv_index_gather_rows: null buffer"); return SNV_ERR_INVALID; }
+    DeviceGuard g(idx->device);
+    if (!g.ok) { set_error("snv_index_gather_rows: cudaSetDevice failed"); return SNV_ERR_CUDA; }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const bool i_dev = flags & SNV_Q_ON_DEVICE;
+    const bool out_dev = flags & SNV_OUT_ON_DEVICE;
+    const int64_t rows = (int64_t)nw * nq * k;
+    const int64_t* Id = I;
+    int rc;
+    if (!i_dev) {
+        rc = idx->ws_i.reserve((size_t)rows * 8);
+        if (rc) return rc;
+        SNV_CUDA_CHECK(cudaMemcpyAsync(idx->ws_i.p, I, (size_t)rows * 8, cudaMemcpyHostToDevice, stream));
+        Id = (const int64_t*)idx->ws_i.p;
+    }
+    float* od = out;
+    if (!out_dev) {
+        rc = idx->ws_in.reserve((size_t)rows * idx->d * 4);
+        if (rc) return rc;
+        od = (float*)idx->ws_in.p;
+    }
+    rc = gather_rows_launch(idx->rows + (int64_t)w0 * idx->cap * idx->d, idx->cap * idx->d, idx->d, idx->ntotal, Id,
+                            nw, nq, k, od, stream);
+    if (rc) return rc;
+    if (!out_dev) SNV_CUDA_CHECK(cudaMemcpyAsync(out, od, (size_t)rows * idx->d * 4, cudaMemcpyDeviceToHost, stream));
+    if (!out_dev || !i_dev) SNV_CUDA_CHECK(cudaStreamSynchronize(stream));
+    return SNV_OK;
+}
+
+int snv_index_export(snv_index* idx, int window, void* out)
+{
+    if (!idx || !out) { set_error("snv_index_export: null argument"); return SNV_ERR_INVALID; }
+    if (window < 0 || window >= idx->n_windows) { set_error("snv_index_export: bad window"); return SNV_ERR_INVALID; }
+    if (idx->ntotal == 0) return SNV_OK;
+    DeviceGuard g(idx->device);
+    if (!g.ok) { set_error("snv_index_export: cudaSetDevice failed"); return SNV_ERR_CUDA; }
+    SNV_CUDA_CHECK(cudaDeviceSynchronize());
+    if (idx->kind == SNV_KIND_HAMMING) {
+        const size_t rb = (size_t)idx->stride * 4;
+        SNV_CUDA_CHECK(cudaMemcpy(out, idx->panel + (size_t)window * idx->cap * idx->stride, (size_t)idx->ntotal * rb, cudaMemcpyDeviceToHost));
+    } else {
+        const size_t rb = (size_t)idx->d * 4;
+        SNV_CUDA_CHECK(cudaMemcpy(out, idx->rows + (size_t)window * idx->cap * idx->d, (size_t)idx->ntotal * rb, cudaMemcpyDeviceToHost));
+    }
+    return SNV_OK;
+}
+
+int snv_topk_merge(int device, const int32_t* D_i32, const float* D_f32, const int64_t* I, int parts,
+                   int64_t nq, int k_in, int k_out, int32_t* Do_i32, float* Do_f32, int64_t* Io, void* stream_)
+{
+    if ((D_i32 != nullptr) == (D_f32 != nullptr)) { set_error("snv_topk_merge: exactly one of D_i32 / D_f32"); return SNV_ERR_INVALID; }
+    if ((D_i32 && !Do_i32) || (D_f32 && !Do_f32) || !I || !Io) { set_error("snv_topk_merge: null buffer"); return SNV_ERR_INVALID; }
+    if (parts < 1 || nq < 0 || k_in < 1 || k_out < 1) { set_error("snv_topk_merge: bad sizes"); return SNV_ERR_INVALID; }
+    DeviceGuard g(device);
+    if (!g.ok) { set_error("snv_topk_merge: cudaSetDevice failed"); return SNV_ERR_CUDA; }
+    return merge_results_launch(D_i32, D_f32, I, parts, nq, k_in, k_out, Do_i32, Do_f32, Io, (cudaStream_t)stream_);
+}
+
+int snv_pack_rows(int device, const void* x, int64_t rows, int64_t d, int dtype, int invert, uint32_t* out,
+                  uint32_t* out_observed, void* stream_)
+{
+    if (!x || !out || rows < 0 || d <= 0) { set_error("snv_pack_rows: bad arguments"); return SNV_ERR_INVALID; }
+    DeviceGuard g(device);
+    if (!g.ok) { set_error("snv_pack_rows: cudaSetDevice failed"); return SNV_ERR_CUDA; }
+    return pack_launch(x, rows, d, dtype, invert != 0, (int)snv_packed_stride(d), out, out_observed, (cudaStream_t)stream_);
+}
+
+}  // extern "C"

@@ -1,0 +1,455 @@
+// Bit-packed Hamming / observed-site masked Hamming scan with a fused exact top-k (sm_100a).
+//
+// Replaces faiss IndexFlatL2.search on 0/1 rows and IndexBinaryFlat.search
+// (reference call sites: batch_test_faiss_l2.py:110, src/dataset/rag_train_dataset.py:281,
+// test_faiss_intersect.py:160,181, partial_faiss_intersect.py:82-111).
+//
+// Mapping: one thread = one query haplotype.  The query's packed words (and its observed-site
+// mask) live in registers for the whole scan; the window's panel streams through shared
+// memory in row tiles fetched by 1-D bulk async copies (TMA engine, mbarrier completion,
+// kStages deep) issued by one thread, and every warp reads the current panel row as a
+// shared-memory broadcast.  Distances use a carry-save-adder tree (LOP3) in front of POPC so
+// that the quarter-rate POPC pipe and the ALU pipe are balanced.
+// Candidates are ranked on ONE 32-bit key  (distance << idx_bits | row_in_split)  so the
+// result is the exact (distance, id)-lexicographic top-k, ties included.
+#include "common.cuh"
+#include "kernels.cuh"
+#include "topk.cuh"
+
+#ifndef SNV_CSA_DEPTH
+#define SNV_CSA_DEPTH 2
+#endif
+#ifndef SNV_ROW_UNROLL
+#define SNV_ROW_UNROLL 2
+#endif
+#define SNV_PRAGMA_(x) _Pragma(#x)
+#define SNV_UNROLL(n) SNV_PRAGMA_(unroll n)
+
+namespace snv {
+
+namespace {
+
+constexpr int kMaxBlock = 128;
+constexpr int kBarBytes = 128;  // smem reserved for the stage mbarriers
+
+// popcount of the multiset x[0..N): DEPTH levels of 3:2 compressors, then POPC.
+template <int N, int DEPTH>
+struct WeightedPopc {
+    static __device__ __forceinline__ uint32_t run(const uint32_t (&x)[N])
+    {
+        if constexpr (DEPTH == 0 || N < 3) {
+            uint32_t s = 0;
+#pragma unroll
+            for (int i = 0; i < N; ++i) s += __popc(x[i]);
+            return s;
+        } else {
+            constexpr int T = N / 3, R = N % 3;
+            uint32_t sum[T + R], carry[T];
+#pragma unroll
+            for (int i = 0; i < T; ++i) {
+                const uint32_t a = x[3 * i], b = x[3 * i + 1], c = x[3 * i + 2];
+                sum[i] = a ^ b ^ c;                    // LOP3 0x96
+                carry[i] = (a & b) | (c & (a ^ b));    // LOP3 0xE8 (majority)
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) sum[T + r] = x[3 * T + r];
+            return WeightedPopc<T + R, DEPTH - 1>::run(sum) +
+                   2u * WeightedPopc<T, DEPTH - 1>::run(carry);
+        }
+    }
+};
+
+template <int NW>
+__device__ __forceinline__ void load_row_regs(uint32_t (&dst)[NW], const uint32_t* __restrict__ src)
+{
+    constexpr int V = NW / 4;
+#pragma unroll
+    for (int c = 0; c < V; ++c) {
+        const uint4 v = reinterpret_cast<const uint4*>(src)[c];
+        dst[4 * c] = v.x; dst[4 * c + 1] = v.y; dst[4 * c + 2] = v.z; dst[4 * c + 3] = v.w;
+    }
+#pragma unroll
+    for (int i = 4 * V; i < NW; ++i) dst[i] = src[i];
+}
+
+template <int NW, bool MASKED, int KT>
+__global__ void __launch_bounds__(kMaxBlock)
+hamming_topk_kernel(const HammingSearchParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+    uint32_t* tiles = reinterpret_cast<uint32_t*>(smem_raw + kBarBytes);
+
+    const int tid = threadIdx.x;
+    int b = blockIdx.x;
+    const int split = b % p.nsplit;
+    b /= p.nsplit;
+    const int qt = b % p.qtiles;
+    const int w = b / p.qtiles;
+
+    const int64_t r0 = (int64_t)split * p.rows_per_split;
+    const int64_t r1 = (r0 + p.rows_per_split < p.n) ? r0 + p.rows_per_split : p.n;
+    const int nrows = (int)(r1 - r0);
+    const int TR = p.tile_rows;
+    const int ntiles = (nrows + TR - 1) / TR;
+    const int stages = p.stages;
+    const uint32_t tile_words = (uint32_t)TR * p.stride;
+    const uint32_t* pw = p.panel + (int64_t)w * p.panel_win_stride + r0 * p.stride;
+
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) mbar_init(&bars[s], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int t) {
+        const int rows = (nrows - t * TR < TR) ? nrows - t * TR : TR;
+        const uint32_t bytes = (uint32_t)rows * p.stride * 4u;
+        uint64_t* bar = &bars[t % stages];
+        mbar_arrive_expect_tx(bar, bytes);
+        bulk_g2s(tiles + (size_t)(t % stages) * tile_words, pw + (size_t)t * tile_words, bytes, bar);
+    };
+    if (tid == 0) {
+        for (int t = 0; t < stages - 1 && t < ntiles; ++t) issue(t);
+    }
+
+    // ---- this thread's query (and observed-site mask) -> registers
+    const int qi = qt * blockDim.x + tid;
+    const bool active = qi < p.nq;
+    uint32_t q[NW];
+    uint32_t m[MASKED ? NW : 1];
+    if (active) {
+        load_row_regs<NW>(q, p.q + ((int64_t)w * p.nq + qi) * p.stride);
+        if constexpr (MASKED) {
+            load_row_regs<NW>(m, p.mask + (int64_t)w * p.mask_win_stride + (int64_t)qi * p.mask_q_stride);
+#pragma unroll
+            for (int i = 0; i < NW; ++i) q[i] &= m[i];
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < NW; ++i) q[i] = 0;
+        if constexpr (MASKED) {
+#pragma unroll
+            for (int i = 0; i < NW; ++i) m[i] = 0;
+        }
+    }
+
+    uint32_t best[KT];
+#pragma unroll
+    for (int i = 0; i < KT; ++i) best[i] = kSent32;
+
+    const int idx_bits = p.idx_bits;
+    for (int t = 0; t < ntiles; ++t) {
+        if (tid == 0 && t + stages - 1 < ntiles) issue(t + stages - 1);
+        mbar_wait(&bars[t % stages], (uint32_t)(t / stages) & 1u);
+        const uint32_t* tile = tiles + (size_t)(t % stages) * tile_words;
+        const int rows = (nrows - t * TR < TR) ? nrows - t * TR : TR;
+        const uint32_t row_base = (uint32_t)(t * TR);
+SNV_UNROLL(SNV_ROW_UNROLL)
+        for (int j = 0; j < rows; ++j) {
+            uint32_t x[NW];
+            load_row_regs<NW>(x, tile + (size_t)j * p.stride);  // warp-uniform address: broadcast
+#pragma unroll
+            for (int i = 0; i < NW; ++i) {
+                if constexpr (MASKED) x[i] = (x[i] & m[i]) ^ q[i];  // == (r ^ q) & m, one LOP3
+                else                  x[i] ^= q[i];
+            }
+            const uint32_t dist = WeightedPopc<NW, SNV_CSA_DEPTH>::run(x);
+            const uint32_t key = (dist << idx_bits) | (row_base + (uint32_t)j);
+            if (key < best[KT - 1]) topk_insert<KT, uint32_t>(best, key);
+        }
+        __syncthreads();  // everyone is done with this stage before it is refilled
+    }
+
+    if (!active) return;
+    const uint32_t idx_mask = (1u << idx_bits) - 1u;
+    const int64_t qrow = (int64_t)w * p.nq + qi;
+    if (p.nsplit == 1) {
+#pragma unroll
+        for (int i = 0; i < KT; ++i) {
+            if (i < p.k) {
+                const uint32_t key = best[i];
+                const bool empty = key == kSent32;
+                const int32_t dist = empty ? 0x7FFFFFFF : (int32_t)(key >> idx_bits);
+                const int64_t id = empty ? -1 : (int64_t)(key & idx_mask) + r0 + p.id_offset;
+                const int64_t o = qrow * p.k + i;
+                if (p.D_i32) p.D_i32[o] = dist;
+                if (p.D_f32) p.D_f32[o] = empty ? 3.4028234663852886e38f : (float)dist;
+                p.I[o] = id;
+            }
+        }
+    } else {
+        uint64_t* out = p.partial + (qrow * p.nsplit + split) * KT;
+#pragma unroll
+        for (int i = 0; i < KT; ++i) {
+            const uint32_t key = best[i];
+            out[i] = key == kSent32
+                         ? kSent64
+                         : ((uint64_t)(key >> idx_bits) << 32) | (uint64_t)((key & idx_mask) + (uint32_t)r0);
+        }
+    }
+}
+
+// Generic fallback for rows wider than the register-resident instantiations: query words in
+// shared memory ([word][thread], conflict-free), plain POPC per word.
+template <bool MASKED, int KT>
+__global__ void __launch_bounds__(32)
+hamming_topk_generic_kernel(const HammingSearchParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+    uint32_t* tiles = reinterpret_cast<uint32_t*>(smem_raw + kBarBytes);
+    const int tid = threadIdx.x;
+    const int B = blockDim.x;
+    int b = blockIdx.x;
+    const int split = b % p.nsplit;
+    b /= p.nsplit;
+    const int qt = b % p.qtiles;
+    const int w = b / p.qtiles;
+    const int64_t r0 = (int64_t)split * p.rows_per_split;
+    const int64_t r1 = (r0 + p.rows_per_split < p.n) ? r0 + p.rows_per_split : p.n;
+    const int nrows = (int)(r1 - r0);
+    const int TR = p.tile_rows;
+    const int ntiles = (nrows + TR - 1) / TR;
+    const int stages = p.stages;
+    const uint32_t tile_words = (uint32_t)TR * p.stride;
+    const uint32_t* pw = p.panel + (int64_t)w * p.panel_win_stride + r0 * p.stride;
+    uint32_t* qs = tiles + (size_t)stages * tile_words;  // [words][B]
+    uint32_t* ms = qs + (size_t)p.stride * B;
+
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) mbar_init(&bars[s], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    auto issue = [&](int t) {
+        const int rows = (nrows - t * TR < TR) ? nrows - t * TR : TR;
+        const uint32_t bytes = (uint32_t)rows * p.stride * 4u;
+        uint64_t* bar = &bars[t % stages];
+        mbar_arrive_expect_tx(bar, bytes);
+        bulk_g2s(tiles + (size_t)(t % stages) * tile_words, pw + (size_t)t * tile_words, bytes, bar);
+    };
+    if (tid == 0) {
+        for (int t = 0; t < stages - 1 && t < ntiles; ++t) issue(t);
+    }
+    const int qi = qt * B + tid;
+    const bool active = qi < p.nq;
+    for (int i = 0; i < p.stride; ++i) {
+        uint32_t qv = 0, mv = 0;
+        if (active) {
+            qv = p.q[((int64_t)w * p.nq + qi) * p.stride + i];
+            if constexpr (MASKED) {
+                mv = p.mask[(int64_t)w * p.mask_win_stride + (int64_t)qi * p.mask_q_stride + i];
+                qv &= mv;
+            }
+        }
+        qs[(size_t)i * B + tid] = qv;
+        if constexpr (MASKED) ms[(size_t)i * B + tid] = mv;
+    }
+    __syncthreads();
+
+    uint32_t best[KT];
+#pragma unroll
+    for (int i = 0; i < KT; ++i) best[i] = kSent32;
+    const int idx_bits = p.idx_bits;
+    for (int t = 0; t < ntiles; ++t) {
+        if (tid == 0 && t + stages - 1 < ntiles) issue(t + stages - 1);
+        mbar_wait(&bars[t % stages], (uint32_t)(t / stages) & 1u);
+        const uint32_t* tile = tiles + (size_t)(t % stages) * tile_words;
+        const int rows = (nrows - t * TR < TR) ? nrows - t * TR : TR;
+        for (int j = 0; j < rows; ++j) {
+            const uint32_t* rp = tile + (size_t)j * p.stride;
+            uint32_t dist = 0;
+#pragma unroll 4
+            for (int i = 0; i < p.words; ++i) {
+                uint32_t x = rp[i];
+                if constexpr (MASKED) x = (x & ms[(size_t)i * B + tid]) ^ qs[(size_t)i * B + tid];
+                else                  x ^= qs[(size_t)i * B + tid];
+                dist += __popc(x);
+            }
+            const uint32_t key = (dist << idx_bits) | (uint32_t)(t * TR + j);
+            if (key < best[KT - 1]) topk_insert<KT, uint32_t>(best, key);
+        }
+        __syncthreads();
+    }
+    if (!active) return;
+    const uint32_t idx_mask = (1u << idx_bits) - 1u;
+    const int64_t qrow = (int64_t)w * p.nq + qi;
+    if (p.nsplit == 1) {
+#pragma unroll
+        for (int i = 0; i < KT; ++i) {
+            if (i < p.k) {
+                const uint32_t key = best[i];
+                const bool empty = key == kSent32;
+                const int32_t dist = empty ? 0x7FFFFFFF : (int32_t)(key >> idx_bits);
+                const int64_t id = empty ? -1 : (int64_t)(key & idx_mask) + r0 + p.id_offset;
+                const int64_t o = qrow * p.k + i;
+                if (p.D_i32) p.D_i32[o] = dist;
+                if (p.D_f32) p.D_f32[o] = empty ? 3.4028234663852886e38f : (float)dist;
+                p.I[o] = id;
+            }
+        }
+    } else {
+        uint64_t* out = p.partial + (qrow * p.nsplit + split) * KT;
+#pragma unroll
+        for (int i = 0; i < KT; ++i) {
+            const uint32_t key = best[i];
+            out[i] = key == kSent32
+                         ? kSent64
+                         : ((uint64_t)(key >> idx_bits) << 32) | (uint64_t)((key & idx_mask) + (uint32_t)r0);
+        }
+    }
+}
+
+int bit_length(int64_t v)
+{
+    int b = 0;
+    while (v > 0) { ++b; v >>= 1; }
+    return b;
+}
+
+template <int NW, bool MASKED, int KT>
+int launch_one(const HammingSearchParams& p, cudaStream_t stream)
+{
+    auto kern = hamming_topk_kernel<NW, MASKED, KT>;
+    if (p.smem_bytes > 48 * 1024) {
+        SNV_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
+    }
+    const int64_t grid = (int64_t)p.nw * p.qtiles * p.nsplit;
+    kern<<<(unsigned)grid, p.block, p.smem_bytes, stream>>>(p);
+    SNV_LAUNCH_CHECK();
+    return SNV_OK;
+}
+
+template <bool MASKED, int KT>
+int launch_generic(const HammingSearchParams& p, cudaStream_t stream)
+{
+    auto kern = hamming_topk_generic_kernel<MASKED, KT>;
+    if (p.smem_bytes > 48 * 1024) {
+        SNV_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
+    }
+    const int64_t grid = (int64_t)p.nw * p.qtiles * p.nsplit;
+    kern<<<(unsigned)grid, p.block, p.smem_bytes, stream>>>(p);
+    SNV_LAUNCH_CHECK();
+    return SNV_OK;
+}
+
+template <int NW>
+int launch_nw(const HammingSearchParams& p, cudaStream_t stream)
+{
+    const bool masked = p.mask != nullptr;
+    if (p.kt == 8) return masked ? launch_one<NW, true, 8>(p, stream) : launch_one<NW, false, 8>(p, stream);
+    return masked ? launch_one<NW, true, 32>(p, stream) : launch_one<NW, false, 32>(p, stream);
+}
+
+}  // namespace
+
+// Register-resident instantiations: words -> NW template value (0 = generic fallback)
+static int pick_nw(int words, int stride)
+{
+    if (words == 33 && stride == 36) return 33;
+    switch (stride) {
+        case 4: case 8: case 16: case 24: case 32: case 36: case 48: case 68: return stride;
+        default: return 0;
+    }
+}
+
+size_t hamming_plan(HammingSearchParams& p)
+{
+    if (p.k < 1 || p.k > 32) {
+        set_error("hamming search: k must be in [1, 32] (got " + std::to_string(p.k) + ")");
+        return (size_t)-1;
+    }
+    if (p.d >= (1 << 20)) {
+        set_error("hamming search: d too large");
+        return (size_t)-1;
+    }
+    p.kt = p.k <= 8 ? 8 : 32;
+    p.nw_templ = pick_nw(p.words, p.stride);
+    const int dist_bits = bit_length((int64_t)p.d + 1);
+    p.idx_bits = 32 - dist_bits;
+    const int64_t max_rows_per_split = (int64_t)1 << p.idx_bits;
+
+    if (p.nw_templ) {
+        p.block = p.nq >= kMaxBlock ? kMaxBlock : (int)round_up(p.nq > 0 ? p.nq : 1, 32);
+    } else {
+        p.block = 32;
+        if (p.stride > 512) {
+            set_error("hamming search: d > 16384 bits is not supported yet");
+            return (size_t)-1;
+        }
+    }
+    p.qtiles = (int)ceil_div(p.nq > 0 ? p.nq : 1, p.block);
+
+    // panel tile: ~16 KB per stage, 3 stages
+    p.stages = 3;
+    int tr = (16 * 1024) / (p.stride * 4);
+    tr = tr >= 128 ? 128 : (tr >= 64 ? 64 : (tr >= 32 ? 32 : (tr >= 16 ? 16 : 8)));
+    p.tile_rows = tr;
+
+    // row splits: enough CTAs to fill the machine (>= 4 per SM) and rows per split that fit
+    // the id field of the 32-bit key.
+    const int64_t base = (int64_t)p.nw * p.qtiles;
+    const int64_t target = (int64_t)kNumSMs * 4;
+    int64_t nsplit = 1;
+    if (p.n > 0) {
+        nsplit = base >= target ? 1 : ceil_div(target, base);
+        const int64_t max_split = ceil_div(p.n, (int64_t)tr * 2);  // at least 2 tiles per split
+        if (nsplit > max_split) nsplit = max_split;
+        if (nsplit < 1) nsplit = 1;
+        const int64_t need = ceil_div(p.n, max_rows_per_split);
+        if (nsplit < need) nsplit = need;
+        int64_t rps = round_up(ceil_div(p.n, nsplit), tr);
+        if (rps > max_rows_per_split) rps = max_rows_per_split / tr * tr;
+        if (rps < tr) {
+            set_error("hamming search: d too large for the 32-bit key");
+            return (size_t)-1;
+        }
+        nsplit = ceil_div(p.n, rps);
+        p.rows_per_split = (int)rps;
+    } else {
+        p.rows_per_split = tr;
+    }
+    if (nsplit > 65535) {
+        set_error("hamming search: panel too large for one call; shard rows");
+        return (size_t)-1;
+    }
+    p.nsplit = (int)nsplit;
+    p.smem_bytes = kBarBytes + (size_t)p.stages * p.tile_rows * p.stride * 4;
+    if (!p.nw_templ) p.smem_bytes += (size_t)p.stride * p.block * 4 * (p.mask ? 2 : 1);
+    if ((int64_t)p.nw * p.qtiles * p.nsplit > 0x7fffffffLL) {
+        set_error("hamming search: grid too large");
+        return (size_t)-1;
+    }
+    return p.nsplit > 1 ? (size_t)p.nw * p.nq * p.nsplit * p.kt * sizeof(uint64_t) : 0;
+}
+
+int hamming_launch(const HammingSearchParams& p, cudaStream_t stream)
+{
+    if (p.nw <= 0 || p.nq <= 0) return SNV_OK;
+    int rc;
+    switch (p.nw_templ) {
+        case 4: rc = launch_nw<4>(p, stream); break;
+        case 8: rc = launch_nw<8>(p, stream); break;
+        case 16: rc = launch_nw<16>(p, stream); break;
+        case 24: rc = launch_nw<24>(p, stream); break;
+        case 32: rc = launch_nw<32>(p, stream); break;
+        case 33: rc = launch_nw<33>(p, stream); break;
+        case 36: rc = launch_nw<36>(p, stream); break;
+        case 48: rc = launch_nw<48>(p, stream); break;
+        case 68: rc = launch_nw<68>(p, stream); break;
+        default: {
+            const bool masked = p.mask != nullptr;
+            if (p.kt == 8) rc = masked ? launch_generic<true, 8>(p, stream) : launch_generic<false, 8>(p, stream);
+            else rc = masked ? launch_generic<true, 32>(p, stream) : launch_generic<false, 32>(p, stream);
+        }
+    }
+    if (rc != SNV_OK) return rc;
+    if (p.nsplit > 1) {
+        return merge_keys_launch(p.partial, p.nsplit, p.kt, (int64_t)p.nw * p.nq, p.k, p.id_offset,
+                                 false, p.D_i32, p.D_f32, p.I, stream);
+    }
+    return SNV_OK;
+}
+
+}  // namespace snv

@@ -1,0 +1,89 @@
+// Host-callable launchers of the sm_100a kernels (internal; the public surface is include/snvknn.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/snvknn.h"
+
+namespace snv {
+
+// ---------------------------------------------------------------- Hamming scan + top-k
+struct HammingSearchParams {
+    // inputs (device)
+    const uint32_t* panel;     // [n_windows][cap][stride]; already offset to window w0
+    int64_t panel_win_stride;  // words between consecutive windows
+    const uint32_t* q;         // [nw][nq][stride]
+    const uint32_t* mask;      // nullptr or observed-site rows
+    int64_t mask_win_stride;   // words
+    int64_t mask_q_stride;     // words; 0 = one mask row shared by the window
+    int words;                 // ceil(d/32)
+    int stride;                // words per packed row (bucketed, multiple of 4)
+    int d;                     // sites (bits)
+    int64_t n;                 // rows per window
+    int nq;                    // queries per window
+    int nw;                    // windows in this call
+    int k;                     // neighbours requested
+    int64_t id_offset;         // added to every id written to I
+    // outputs (device) [nw][nq][k]
+    int32_t* D_i32;
+    float* D_f32;
+    int64_t* I;
+    uint64_t* partial;  // workspace, required when nsplit > 1: [nw*nq][nsplit][kt] keys
+    // plan (filled by hamming_plan)
+    int block, qtiles, nsplit, rows_per_split, idx_bits, kt, nw_templ, tile_rows, stages;
+    size_t smem_bytes;
+};
+
+// Fills the plan fields; returns the partial-key workspace bytes needed (0 when nsplit == 1),
+// or (size_t)-1 with the error set when the shape is unsupported.
+size_t hamming_plan(HammingSearchParams& p);
+int hamming_launch(const HammingSearchParams& p, cudaStream_t stream);
+
+// ---------------------------------------------------------------- key merge / finalize
+// keys [nq_total][parts][kin] (uint64: hi = distance bits, lo = id, ~0 = empty) -> top k.
+// float_dist: hi word holds float bits (L2) instead of an integer distance.
+int merge_keys_launch(const uint64_t* keys, int parts, int kin, int64_t nq_total, int k,
+                      int64_t id_offset, bool float_dist, int32_t* D_i32, float* D_f32, int64_t* I,
+                      cudaStream_t stream);
+// (D, I) [parts][nq][kin] arrays -> top k_out (row-sharded panel merge)
+int merge_results_launch(const int32_t* D_i32, const float* D_f32, const int64_t* I, int parts,
+                         int64_t nq, int kin, int kout, int32_t* Do_i32, float* Do_f32,
+                         int64_t* Io, cudaStream_t stream);
+
+// ---------------------------------------------------------------- pack
+int pack_launch(const void* x, int64_t rows, int64_t d, int dtype, bool invert, int stride,
+                uint32_t* out, uint32_t* out_observed, cudaStream_t stream);
+
+// ---------------------------------------------------------------- gather
+int gather_tokens_launch(const uint32_t* panel, int64_t panel_win_stride, int stride, int64_t n,
+                         const int64_t* I, int64_t id_offset, int nw, int64_t nq, int k,
+                         const int32_t* n_sites_dev, int d, int seq_len, int64_t* out,
+                         cudaStream_t stream);
+int gather_rows_launch(const float* panel, int64_t panel_win_stride, int64_t d, int64_t n,
+                       const int64_t* I, int nw, int64_t nq, int k, float* out, cudaStream_t stream);
+
+// ---------------------------------------------------------------- float L2 (tcgen05)
+struct L2SearchParams {
+    const float* ref_ops;   // [N][kp] tf32 operand rows of the panel (B operand, K-major)
+    const float* ref_norm;  // [N] |r|^2 (fp32, from the original fp32 rows)
+    const float* q_ops;     // [nq][kp] tf32 operand rows of the queries (A operand)
+    const float* q_norm;    // [nq]
+    int64_t n;              // panel rows
+    int64_t nq;
+    int kp;                 // padded operand depth (multiple of 32)
+    int k;
+    int64_t id_offset;
+    float* D_f32;           // [nq][k]
+    int64_t* I;             // [nq][k]
+    uint64_t* partial;      // [nq][nsplit][kt]
+    int nsplit, kt, tiles_per_split;
+};
+size_t l2_plan(L2SearchParams& p);
+int l2_launch(const L2SearchParams& p, cudaStream_t stream);
+// fp32 rows [rows][d] -> operand rows [rows][kp] (mode TF32: x | 0-pad; TF32X3 with
+// is_query: hi|lo|hi, panel: hi|hi|lo) and squared norms.
+int l2_prep_launch(const float* x, int64_t rows, int64_t d, int mode, bool is_query, int kp,
+                   float* ops, float* norms, cudaStream_t stream);
+int l2_operand_depth(int64_t d, int mode);
+
+}  // namespace snv

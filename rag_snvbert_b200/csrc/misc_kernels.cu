@@ -1,0 +1,341 @@
+// Pack, top-k merge and gather kernels (sm_100a).  All HBM-bound streaming work: coalesced
+// warp-wide accesses, no shared-memory reuse to exploit.
+#include "common.cuh"
+#include "kernels.cuh"
+#include "topk.cuh"
+
+namespace snv {
+
+namespace {
+
+// ------------------------------------------------------------------------------ merge
+// One thread per query: reselects the best k from parts*kin candidate keys.
+template <int KT>
+__global__ void __launch_bounds__(128)
+merge_keys_kernel(const uint64_t* __restrict__ keys, int parts, int kin, int64_t nq_total, int k,
+                  int64_t id_offset, bool float_dist, int32_t* __restrict__ D_i32,
+                  float* __restrict__ D_f32, int64_t* __restrict__ I)
+{
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq_total) return;
+    uint64_t best[KT];
+#pragma unroll
+    for (int i = 0; i < KT; ++i) best[i] = kSent64;
+    const uint64_t* src = keys + q * parts * kin;
+    const int total = parts * kin;
+    for (int j = 0; j < total; ++j) {
+        const uint64_t key = src[j];
+        if (key < best[KT - 1]) topk_insert<KT, uint64_t>(best, key);
+    }
+#pragma unroll
+    for (int i = 0; i < KT; ++i) {
+        if (i < k) {
+            const uint64_t key = best[i];
+            const bool empty = key == kSent64;
+            const uint32_t hi = (uint32_t)(key >> 32);
+            const int64_t o = q * k + i;
+            I[o] = empty ? -1 : (int64_t)(uint32_t)key + id_offset;
+            if (float_dist) {
+                if (D_f32) D_f32[o] = empty ? 3.4028234663852886e38f : __uint_as_float(hi);
+            } else {
+                if (D_i32) D_i32[o] = empty ? 0x7FFFFFFF : (int32_t)hi;
+                if (D_f32) D_f32[o] = empty ? 3.4028234663852886e38f : (float)hi;
+            }
+        }
+    }
+}
+
+// (D, I) [parts][nq][kin] with global 63-bit ids -> best kout by (D, I).  Ids do not fit the
+// 32-bit key half in general, so the comparison is on the (dist, id) pair explicitly.
+template <int KT, typename DT>
+__global__ void __launch_bounds__(128)
+merge_results_kernel(const DT* __restrict__ D, const int64_t* __restrict__ I, int parts, int64_t nq,
+                     int kin, int kout, DT pad, DT* __restrict__ Do, int64_t* __restrict__ Io)
+{
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    DT bd[KT];
+    int64_t bi[KT];
+    const int64_t kIdMax = 0x7FFFFFFFFFFFFFFFLL;
+#pragma unroll
+    for (int i = 0; i < KT; ++i) { bd[i] = pad; bi[i] = kIdMax; }
+    for (int part = 0; part < parts; ++part) {
+        const int64_t base = ((int64_t)part * nq + q) * kin;
+        for (int j = 0; j < kin; ++j) {
+            const int64_t id = I[base + j];
+            if (id < 0) continue;
+            const DT dv = D[base + j];
+            if (dv < bd[KT - 1] || (dv == bd[KT - 1] && id < bi[KT - 1])) {
+                // sorted insertion, branch-free over the register array
+                DT cd = dv;
+                int64_t ci = id;
+#pragma unroll
+                for (int i = 0; i < KT; ++i) {
+                    const bool lt = cd < bd[i] || (cd == bd[i] && ci < bi[i]);
+                    const DT td = bd[i];
+                    const int64_t ti = bi[i];
+                    bd[i] = lt ? cd : td;
+                    bi[i] = lt ? ci : ti;
+                    cd = lt ? td : cd;
+                    ci = lt ? ti : ci;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < KT; ++i) {
+        if (i < kout) {
+            const bool empty = bi[i] == kIdMax;
+            Do[q * kout + i] = empty ? pad : bd[i];
+            Io[q * kout + i] = empty ? -1 : bi[i];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------ pack
+// One warp per (row, 32-site group): coalesced 32-element read, ballot -> one packed word
+// (lane l <-> site 32*w + l <-> bit l: LSB-first).
+template <typename T>
+__global__ void __launch_bounds__(256)
+pack_sites_kernel(const T* __restrict__ x, int64_t rows, int64_t d, int words, int stride, bool invert,
+                  uint32_t* __restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t total = rows * stride;
+    for (int64_t item = warp; item < total; item += nwarps) {
+        const int64_t r = item / stride;
+        const int w = (int)(item % stride);
+        uint32_t word = 0;
+        if (w < words) {
+            const int64_t s = (int64_t)w * 32 + lane;
+            bool bit = false;
+            if (s < d) {
+                bit = x[r * d + s] != (T)0;
+                if (invert) bit = !bit;
+            }
+            word = __ballot_sync(0xffffffffu, bit);
+        }
+        if (lane == 0) out[item] = word;
+    }
+}
+
+// tokens: allele plane = (tok == 6), observed plane = (tok == 5 || tok == 6)
+__global__ void __launch_bounds__(256)
+pack_tokens_kernel(const int64_t* __restrict__ x, int64_t rows, int64_t d, int words, int stride,
+                   uint32_t* __restrict__ out, uint32_t* __restrict__ out_obs)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t total = rows * stride;
+    for (int64_t item = warp; item < total; item += nwarps) {
+        const int64_t r = item / stride;
+        const int w = (int)(item % stride);
+        uint32_t a = 0, o = 0;
+        if (w < words) {
+            const int64_t s = (int64_t)w * 32 + lane;
+            int64_t tok = 0;
+            if (s < d) tok = x[r * d + s];
+            a = __ballot_sync(0xffffffffu, tok == 6);
+            o = __ballot_sync(0xffffffffu, tok == 5 || tok == 6);
+        }
+        if (lane == 0) {
+            out[item] = a;
+            if (out_obs) out_obs[item] = o;
+        }
+    }
+}
+
+// np.packbits bytes -> zero padded word rows (bit order inside a byte is irrelevant to the
+// Hamming distance as long as panel and queries agree).
+__global__ void __launch_bounds__(256)
+pack_bytes_kernel(const uint8_t* __restrict__ x, int64_t rows, int64_t row_bytes, int stride,
+                  uint32_t* __restrict__ out)
+{
+    const int64_t total = rows * stride;
+    for (int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; item < total;
+         item += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = item / stride;
+        const int w = (int)(item % stride);
+        uint32_t word = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int64_t byte = (int64_t)w * 4 + b;
+            if (byte < row_bytes) word |= (uint32_t)x[r * row_bytes + byte] << (8 * b);
+        }
+        out[item] = word;
+    }
+}
+
+// ------------------------------------------------------------------------------ gather
+// out[w][q][j][0..seq_len): [SOS] + alleles(5|6) + [EOS] + PAD; one warp per retrieved row,
+// lanes stride over the sequence (coalesced int64 stores; 8 KB per row).
+__global__ void __launch_bounds__(256)
+gather_tokens_kernel(const uint32_t* __restrict__ panel, int64_t panel_win_stride, int stride, int64_t n,
+                     const int64_t* __restrict__ I, int64_t id_offset, int64_t rows_total,
+                     int64_t rows_per_window, const int32_t* __restrict__ n_sites, int d, int seq_len,
+                     int64_t* __restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t item = warp; item < rows_total; item += nwarps) {
+        const int64_t w = item / rows_per_window;
+        const int64_t id = I[item] - id_offset;
+        int64_t* o = out + item * seq_len;
+        if (id < 0 || id >= n) {
+            for (int c = lane; c < seq_len; c += 32) o[c] = 0;
+            continue;
+        }
+        const int ns = n_sites ? n_sites[w] : d;
+        const uint32_t* row = panel + w * panel_win_stride + id * stride;
+        for (int c = lane; c < seq_len; c += 32) {
+            int64_t tok;
+            if (c == 0) tok = 2;
+            else if (c <= ns) {
+                const int s = c - 1;
+                tok = 5 + ((row[s >> 5] >> (s & 31)) & 1u);
+            } else if (c == ns + 1) tok = 3;
+            else tok = 0;
+            o[c] = tok;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const float* __restrict__ panel, int64_t panel_win_stride, int64_t d, int64_t n,
+                   const int64_t* __restrict__ I, int64_t rows_total, int64_t rows_per_window,
+                   float* __restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t item = warp; item < rows_total; item += nwarps) {
+        const int64_t w = item / rows_per_window;
+        const int64_t id = I[item];
+        float* o = out + item * d;
+        if (id < 0 || id >= n) {
+            for (int64_t c = lane; c < d; c += 32) o[c] = 0.f;
+        } else {
+            const float* row = panel + w * panel_win_stride + id * d;
+            for (int64_t c = lane; c < d; c += 32) o[c] = row[c];
+        }
+    }
+}
+
+int grid_for_warps(int64_t warps, int block)
+{
+    const int64_t wpb = block / 32;
+    int64_t g = ceil_div(warps, wpb);
+    const int64_t cap = (int64_t)kNumSMs * 16;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+}  // namespace
+
+int merge_keys_launch(const uint64_t* keys, int parts, int kin, int64_t nq_total, int k,
+                      int64_t id_offset, bool float_dist, int32_t* D_i32, float* D_f32, int64_t* I,
+                      cudaStream_t stream)
+{
+    if (nq_total <= 0) return SNV_OK;
+    const int block = 128;
+    const unsigned grid = (unsigned)ceil_div(nq_total, block);
+    if (k <= 8)
+        merge_keys_kernel<8><<<grid, block, 0, stream>>>(keys, parts, kin, nq_total, k, id_offset, float_dist, D_i32, D_f32, I);
+    else if (k <= 32)
+        merge_keys_kernel<32><<<grid, block, 0, stream>>>(keys, parts, kin, nq_total, k, id_offset, float_dist, D_i32, D_f32, I);
+    else {
+        set_error("merge: k > 32 unsupported");
+        return SNV_ERR_UNSUPPORTED;
+    }
+    SNV_LAUNCH_CHECK();
+    return SNV_OK;
+}
+
+int merge_results_launch(const int32_t* D_i32, const float* D_f32, const int64_t* I, int parts,
+                         int64_t nq, int kin, int kout, int32_t* Do_i32, float* Do_f32,
+                         int64_t* Io, cudaStream_t stream)
+{
+    if (nq <= 0) return SNV_OK;
+    if (kout > 32 || kout < 1) {
+        set_error("merge: k_out must be in [1, 32]");
+        return SNV_ERR_UNSUPPORTED;
+    }
+    const int block = 128;
+    const unsigned grid = (unsigned)ceil_div(nq, block);
+    if (D_i32) {
+        if (kout <= 8)
+            merge_results_kernel<8, int32_t><<<grid, block, 0, stream>>>(D_i32, I, parts, nq, kin, kout, 0x7FFFFFFF, Do_i32, Io);
+        else
+            merge_results_kernel<32, int32_t><<<grid, block, 0, stream>>>(D_i32, I, parts, nq, kin, kout, 0x7FFFFFFF, Do_i32, Io);
+    } else {
+        if (kout <= 8)
+            merge_results_kernel<8, float><<<grid, block, 0, stream>>>(D_f32, I, parts, nq, kin, kout, 3.4028234663852886e38f, Do_f32, Io);
+        else
+            merge_results_kernel<32, float><<<grid, block, 0, stream>>>(D_f32, I, parts, nq, kin, kout, 3.4028234663852886e38f, Do_f32, Io);
+    }
+    SNV_LAUNCH_CHECK();
+    return SNV_OK;
+}
+
+int pack_launch(const void* x, int64_t rows, int64_t d, int dtype, bool invert, int stride,
+                uint32_t* out, uint32_t* out_observed, cudaStream_t stream)
+{
+    if (rows <= 0) return SNV_OK;
+    const int words = (int)ceil_div(d, 32);
+    const int block = 256;
+    const int grid = grid_for_warps(rows * stride, block);
+    switch (dtype) {
+        case SNV_DT_U8:
+            pack_sites_kernel<uint8_t><<<grid, block, 0, stream>>>((const uint8_t*)x, rows, d, words, stride, invert, out);
+            break;
+        case SNV_DT_F32:
+            pack_sites_kernel<float><<<grid, block, 0, stream>>>((const float*)x, rows, d, words, stride, invert, out);
+            break;
+        case SNV_DT_I64_TOKENS:
+            pack_tokens_kernel<<<grid, block, 0, stream>>>((const int64_t*)x, rows, d, words, stride, out, out_observed);
+            break;
+        case SNV_DT_PACKED_U8: {
+            const int g2 = (int)std::min<int64_t>(ceil_div(rows * stride, block), (int64_t)kNumSMs * 16);
+            pack_bytes_kernel<<<g2, block, 0, stream>>>((const uint8_t*)x, rows, ceil_div(d, 8), stride, out);
+            break;
+        }
+        default:
+            set_error("pack: unsupported dtype");
+            return SNV_ERR_INVALID;
+    }
+    SNV_LAUNCH_CHECK();
+    return SNV_OK;
+}
+
+int gather_tokens_launch(const uint32_t* panel, int64_t panel_win_stride, int stride, int64_t n,
+                         const int64_t* I, int64_t id_offset, int nw, int64_t nq, int k,
+                         const int32_t* n_sites_dev, int d, int seq_len, int64_t* out,
+                         cudaStream_t stream)
+{
+    const int64_t rows_total = (int64_t)nw * nq * k;
+    if (rows_total <= 0) return SNV_OK;
+    const int block = 256;
+    gather_tokens_kernel<<<grid_for_warps(rows_total, block), block, 0, stream>>>(
+        panel, panel_win_stride, stride, n, I, id_offset, rows_total, nq * k, n_sites_dev, d, seq_len, out);
+    SNV_LAUNCH_CHECK();
+    return SNV_OK;
+}
+
+int gather_rows_launch(const float* panel, int64_t panel_win_stride, int64_t d, int64_t n,
+                       const int64_t* I, int nw, int64_t nq, int k, float* out, cudaStream_t stream)
+{
+    const int64_t rows_total = (int64_t)nw * nq * k;
+    if (rows_total <= 0) return SNV_OK;
+    const int block = 256;
+    gather_rows_kernel<<<grid_for_warps(rows_total, block), block, 0, stream>>>(
+        panel, panel_win_stride, d, n, I, rows_total, nq * k, out);
+    SNV_LAUNCH_CHECK();
+    return SNV_OK;
+}
+
+}  // namespace snv

@@ -1,0 +1,354 @@
+"""Index objects over the C ABI: the host-side mirror of the faiss surface the reference calls.
+
+Reference call sites replaced (paths relative to the reference tree):
+  faiss.IndexFlatL2(d).add / .search      build_ref_db_l2.py:89-90, batch_test_faiss_l2.py:110,
+                                          src/dataset/rag_train_dataset.py:132-134,281
+  faiss.IndexBinaryFlat(d).add / .search  test_faiss_intersect.py:173-181
+  per-query observed-site search          partial_faiss_intersect.py:82-111
+  torch.cdist + topk                      src/dataset/embedding_rag_dataset.py:392-402
+  gather of retrieved haplotypes          src/dataset/rag_train_dataset.py:287-307,
+                                          src/dataset/embedding_rag_dataset.py:406-438
+
+Inputs may be numpy arrays (host; copied by the library on the call's stream) or torch CUDA
+tensors (used in place, zero copy, on torch's current stream).  Outputs come back in the same
+world as the queries.  No CPU fallback exists: without the CUDA library / device these raise.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _lib as L
+
+try:  # torch is plumbing only (device memory + streams); numpy-only use works without it
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+
+def _is_torch(x) -> bool:
+    return torch is not None and isinstance(x, torch.Tensor)
+
+
+class _Arg:
+    """A contiguous host (numpy) or device (torch.cuda) array ready to cross the C ABI."""
+
+    __slots__ = ("arr", "ptr", "on_device", "shape", "np_dtype")
+
+    def __init__(self, x):
+        if _is_torch(x):
+            if x.is_cuda:
+                x = x.contiguous()
+                self.arr, self.ptr, self.on_device = x, x.data_ptr(), True
+                self.shape = tuple(x.shape)
+                self.np_dtype = np.dtype(str(x.dtype).replace("torch.", "").replace("bool", "bool_"))
+                return
+            x = x.detach().numpy()
+        x = np.ascontiguousarray(x)
+        self.arr, self.ptr, self.on_device = x, x.ctypes.data, False
+        self.shape = x.shape
+        self.np_dtype = x.dtype
+
+
+def _current_stream(device: int) -> int:
+    if torch is not None and torch.cuda.is_available():
+        return int(torch.cuda.current_stream(device).cuda_stream)
+    return 0
+
+
+def _hamming_dtype(a: _Arg, d: int, stride: int, what: str, codes: bool = False) -> Tuple[int, "_Arg"]:
+    dt = a.np_dtype
+    last = a.shape[-1]
+    if codes:  # np.packbits rows, the input of faiss.IndexBinaryFlat (test_faiss_intersect.py:46-54)
+        if dt != np.dtype(np.uint8) or last != (d + 7) // 8:
+            raise ValueError(f"{what}: binary codes must be uint8 [.., {(d + 7) // 8}]")
+        return L.DT_PACKED_U8, a
+    if dt in (np.dtype(np.uint32), np.dtype(np.int32)):
+        if last != stride:
+            raise ValueError(f"{what}: packed rows must have {stride} uint32 words (snv_packed_stride({d})), got {last}")
+        return L.DT_PACKED_U32, a
+    if last != d:
+        raise ValueError(f"{what}: last dimension must be d={d}, got {last}")
+    if dt == np.dtype(np.float32):
+        return L.DT_F32, a
+    if dt == np.dtype(np.int64):
+        return L.DT_I64_TOKENS, a
+    if dt in (np.dtype(np.uint8), np.dtype(np.bool_), np.dtype(np.int8)):
+        if dt != np.dtype(np.uint8):
+            arr = a.arr.view(torch.uint8) if _is_torch(a.arr) else a.arr.view(np.uint8)
+            a = _Arg(arr)
+        return L.DT_U8, a
+    raise ValueError(f"{what}: unsupported dtype {dt} (use uint8/bool 0-1 sites, float32, packed uint32 or int64 tokens)")
+
+
+class _IndexBase:
+    kind = L.KIND_HAMMING
+
+    def __init__(self, d: int, n_windows: int = 1, device: Optional[int] = None, l2_mode: int = L.L2_TF32X3):
+        if int(d) <= 0:
+            raise ValueError("d must be positive")
+        lib = L.lib()
+        if device is None:
+            device = torch.cuda.current_device() if (torch is not None and torch.cuda.is_available()) else 0
+        h = ctypes.c_void_p()
+        L.check(lib.snv_index_create(self.kind, int(d), int(n_windows), int(device), int(l2_mode), ctypes.byref(h)),
+                "snv_index_create")
+        self._h = h
+        self._lib = lib
+        self.d = int(d)
+        self.n_windows = int(n_windows)
+        self.device = int(device)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                self._lib.snv_index_free(h)
+            except Exception:
+                pass
+            self._h = None
+
+    @property
+    def ntotal(self) -> int:
+        return int(self._lib.snv_index_ntotal(self._h))
+
+    def reset(self) -> None:
+        L.check(self._lib.snv_index_reset(self._h), "snv_index_reset")
+
+    # ---- helpers
+    def _win_shape(self, a: _Arg, what: str):
+        """[rows, last] for a single-window index or [W, rows, last] -> (W_in, rows)."""
+        if len(a.shape) == 2:
+            if self.n_windows != 1:
+                raise ValueError(f"{what}: a {self.n_windows}-window index takes [windows, rows, ...] arrays")
+            return 1, a.shape[0]
+        if len(a.shape) == 3:
+            return a.shape[0], a.shape[1]
+        raise ValueError(f"{what}: expected a 2-D or 3-D array, got shape {a.shape}")
+
+    def _alloc_out(self, like_device: bool, shape, np_dtype):
+        if like_device:
+            t = torch.empty(shape, dtype=getattr(torch, np.dtype(np_dtype).name), device=f"cuda:{self.device}")
+            return t, t.data_ptr()
+        arr = np.empty(shape, dtype=np_dtype)
+        return arr, arr.ctypes.data
+
+
+class WindowedHammingIndex(_IndexBase):
+    """`n_windows` independent bit-packed haplotype panels of `n_sites` sites each, searched in one
+    launch.  Distances are integer Hamming distances (== faiss squared L2 on 0/1 rows); with a
+    mask, Hamming over the observed sites of each query (partial_faiss_intersect.py:82-111)."""
+
+    kind = L.KIND_HAMMING
+
+    def __init__(self, n_sites: int, n_windows: int = 1, device: Optional[int] = None):
+        super().__init__(n_sites, n_windows, device)
+        self.stride = L.packed_stride(n_sites)
+        self.words = L.packed_words(n_sites)
+
+    def add(self, x, codes: bool = False) -> None:
+        """x: [W, n, d] (or [n, d] when W == 1) 0/1 uint8/bool/float32, int64 tokens, or packed
+        uint32 [.., stride]; codes=True: np.packbits bytes [.., ceil(d/8)].  Appends n rows to
+        every window."""
+        a = _Arg(x)
+        W, n = self._win_shape(a, "add")
+        if W != self.n_windows:
+            raise ValueError(f"add: array has {W} windows, index has {self.n_windows}")
+        dt, a = _hamming_dtype(a, self.d, self.stride, "add", codes)
+        flags = L.X_ON_DEVICE if a.on_device else 0
+        L.check(self._lib.snv_index_add(self._h, a.ptr, n, dt, flags, _current_stream(self.device)), "snv_index_add")
+
+    def search(self, q, k: int, observed=None, missing=None, w0: int = 0, id_offset: int = 0,
+               dist_dtype=np.int32, codes: bool = False):
+        """q: [nw, nq, d] (or [nq, d] for one window) in any add() dtype.  `observed` / `missing`:
+        optional site mask, [nw, nq, d] per query or [nw, d] per window ([nq, d] / [d] for one
+        window).  Returns (D [nw, nq, k] int32 or float32, I [nw, nq, k] int64); single-window
+        calls drop the leading axis."""
+        if int(k) < 1:
+            raise ValueError("k must be >= 1")
+        a = _Arg(q)
+        squeeze = len(a.shape) == 2
+        if squeeze:
+            nw, nq = 1, a.shape[0]
+        elif len(a.shape) == 3:
+            nw, nq = a.shape[0], a.shape[1]
+        else:
+            raise ValueError(f"search: expected a 2-D or 3-D query array, got shape {a.shape}")
+        dt, a = _hamming_dtype(a, self.d, self.stride, "search", codes)
+        flags = L.Q_ON_DEVICE | L.OUT_ON_DEVICE if a.on_device else 0
+        m_ptr, m_mode = None, L.MASK_NONE
+        if observed is not None and missing is not None:
+            raise ValueError("search: give observed= or missing=, not both")
+        mk = observed if observed is not None else missing
+        if mk is not None:
+            m = _Arg(mk)
+            if m.on_device != a.on_device:
+                raise ValueError("search: queries and mask must live in the same memory (both numpy or both CUDA)")
+            mshape = m.shape
+            per_query_shape = a.shape
+            if tuple(mshape) == tuple(per_query_shape):
+                m_mode = L.MASK_PER_QUERY
+            elif tuple(mshape) == tuple(per_query_shape[:-2] + per_query_shape[-1:]):
+                m_mode = L.MASK_PER_WINDOW
+            else:
+                raise ValueError(f"search: mask shape {mshape} matches neither queries {per_query_shape} nor one row per window")
+            mdt, m = _hamming_dtype(m, self.d, self.stride, "search(mask)")
+            if mdt != dt:
+                raise ValueError("search: mask and queries must use the same dtype")
+            m_ptr = m.ptr
+            if missing is not None:
+                flags |= L.MASK_IS_MISSING
+        want_f = np.dtype(dist_dtype) == np.dtype(np.float32)
+        shape = (nw, nq, int(k))
+        D, Dp = self._alloc_out(a.on_device, shape, np.float32 if want_f else np.int32)
+        I, Ip = self._alloc_out(a.on_device, shape, np.int64)
+        L.check(self._lib.snv_index_search(self._h, int(w0), nw, a.ptr, nq, dt, m_ptr, m_mode, int(k), int(id_offset),
+                                           None if want_f else Dp, Dp if want_f else None, Ip, flags,
+                                           _current_stream(self.device)), "snv_index_search")
+        if squeeze:
+            return D[0], I[0]
+        return D, I
+
+    def gather_tokens(self, I, n_sites=None, seq_len: int = 1030, w0: int = 0):
+        """I [nw, nq, k] (or [nq, k]) -> int64 tokens [.., k, seq_len] in the model's input layout
+        (src/dataset/rag_train_dataset.py:287-307): [SOS] + 5|6 per site + [EOS] + PAD."""
+        a = _Arg(I)
+        if a.np_dtype != np.dtype(np.int64):
+            raise ValueError("gather_tokens: I must be int64")
+        squeeze = len(a.shape) == 2
+        nw, nq, k = (1,) + tuple(a.shape) if squeeze else tuple(a.shape)
+        ns_ptr = None
+        if n_sites is not None:
+            ns = np.ascontiguousarray(np.broadcast_to(np.asarray(n_sites, dtype=np.int32), (nw,)))
+            ns_ptr = ns.ctypes.data
+        flags = L.Q_ON_DEVICE | L.OUT_ON_DEVICE if a.on_device else 0
+        out, op = self._alloc_out(a.on_device, (nw, nq, k, int(seq_len)), np.int64)
+        L.check(self._lib.snv_index_gather_tokens(self._h, int(w0), nw, a.ptr, nq, k, ns_ptr, int(seq_len), op, flags,
+                                                  _current_stream(self.device)), "snv_index_gather_tokens")
+        return out[0] if squeeze else out
+
+    def export_packed(self, window: int = 0) -> np.ndarray:
+        out = np.zeros((self.ntotal, self.stride), dtype=np.uint32)
+        L.check(self._lib.snv_index_export(self._h, int(window), out.ctypes.data), "snv_index_export")
+        return out
+
+
+class IndexHamming(WindowedHammingIndex):
+    """One window: the native replacement of IndexFlatL2 / IndexBinaryFlat on 0/1 haplotypes."""
+
+    def __init__(self, n_sites: int, device: Optional[int] = None):
+        super().__init__(n_sites, 1, device)
+
+
+class WindowedL2Index(_IndexBase):
+    """Float rows, squared L2 = |q|^2 + |r|^2 - 2 q.r with the cross term on tcgen05 (tf32 operands;
+    precision 'tf32x3' = hi/lo split, fp32-faithful; 'tf32' = one pass, exact for small-integer
+    inputs such as the V17 token vectors)."""
+
+    kind = L.KIND_L2
+
+    def __init__(self, d: int, n_windows: int = 1, device: Optional[int] = None, precision: str = "tf32x3"):
+        modes = {"tf32": L.L2_TF32, "tf32x3": L.L2_TF32X3}
+        if precision not in modes:
+            raise ValueError("precision must be 'tf32' or 'tf32x3'")
+        super().__init__(d, n_windows, device, modes[precision])
+        self.precision = precision
+
+    def add(self, x) -> None:
+        a = _Arg(x)
+        if a.np_dtype != np.dtype(np.float32):
+            a = _Arg(a.arr.float() if _is_torch(a.arr) else a.arr.astype(np.float32))
+        W, n = self._win_shape(a, "add")
+        if W != self.n_windows:
+            raise ValueError(f"add: array has {W} windows, index has {self.n_windows}")
+        if a.shape[-1] != self.d:
+            raise ValueError(f"add: last dimension must be d={self.d}, got {a.shape[-1]}")
+        flags = L.X_ON_DEVICE if a.on_device else 0
+        L.check(self._lib.snv_index_add(self._h, a.ptr, n, L.DT_F32, flags, _current_stream(self.device)), "snv_index_add")
+
+    def search(self, q, k: int, w0: int = 0, id_offset: int = 0):
+        if int(k) < 1:
+            raise ValueError("k must be >= 1")
+        a = _Arg(q)
+        if a.np_dtype != np.dtype(np.float32):
+            a = _Arg(a.arr.float() if _is_torch(a.arr) else a.arr.astype(np.float32))
+        squeeze = len(a.shape) == 2
+        if squeeze:
+            nw, nq = 1, a.shape[0]
+        elif len(a.shape) == 3:
+            nw, nq = a.shape[0], a.shape[1]
+        else:
+            raise ValueError(f"search: expected a 2-D or 3-D query array, got shape {a.shape}")
+        if a.shape[-1] != self.d:
+            raise ValueError(f"search: last dimension must be d={self.d}, got {a.shape[-1]}")
+        flags = L.Q_ON_DEVICE | L.OUT_ON_DEVICE if a.on_device else 0
+        shape = (nw, nq, int(k))
+        D, Dp = self._alloc_out(a.on_device, shape, np.float32)
+        I, Ip = self._alloc_out(a.on_device, shape, np.int64)
+        L.check(self._lib.snv_index_search(self._h, int(w0), nw, a.ptr, nq, L.DT_F32, None, L.MASK_NONE, int(k),
+                                           int(id_offset), None, Dp, Ip, flags, _current_stream(self.device)),
+                "snv_index_search")
+        if squeeze:
+            return D[0], I[0]
+        return D, I
+
+    def gather_rows(self, I, w0: int = 0):
+        """panel[I] -> float32 [.., k, d] (src/dataset/embedding_rag_dataset.py:406-438)."""
+        a = _Arg(I)
+        if a.np_dtype != np.dtype(np.int64):
+            raise ValueError("gather_rows: I must be int64")
+        squeeze = len(a.shape) == 2
+        nw, nq, k = (1,) + tuple(a.shape) if squeeze else tuple(a.shape)
+        flags = L.Q_ON_DEVICE | L.OUT_ON_DEVICE if a.on_device else 0
+        out, op = self._alloc_out(a.on_device, (nw, nq, k, self.d), np.float32)
+        L.check(self._lib.snv_index_gather_rows(self._h, int(w0), nw, a.ptr, nq, k, op, flags,
+                                                _current_stream(self.device)), "snv_index_gather_rows")
+        return out[0] if squeeze else out
+
+    def export_rows(self, window: int = 0) -> np.ndarray:
+        out = np.zeros((self.ntotal, self.d), dtype=np.float32)
+        L.check(self._lib.snv_index_export(self._h, int(window), out.ctypes.data), "snv_index_export")
+        return out
+
+
+def topk_merge(D, I, k: int):
+    """Merge per-shard results: D, I torch CUDA tensors [parts, nq, k_in] (global ids) ->
+    (D [nq, k], I [nq, k]) by (distance, id).  Used after the all-gather of a row-sharded search."""
+    if not (_is_torch(D) and D.is_cuda and _is_torch(I) and I.is_cuda):
+        raise ValueError("topk_merge takes CUDA tensors")
+    D = D.contiguous()
+    I = I.contiguous()
+    parts, nq, kin = D.shape
+    dev = D.device.index
+    Do = torch.empty((nq, k), dtype=D.dtype, device=D.device)
+    Io = torch.empty((nq, k), dtype=torch.int64, device=D.device)
+    is_i = D.dtype == torch.int32
+    if not is_i and D.dtype != torch.float32:
+        raise ValueError("topk_merge: D must be int32 or float32")
+    L.check(L.lib().snv_topk_merge(dev, D.data_ptr() if is_i else None, None if is_i else D.data_ptr(), I.data_ptr(),
+                                   parts, nq, kin, int(k), Do.data_ptr() if is_i else None,
+                                   None if is_i else Do.data_ptr(), Io.data_ptr(), _current_stream(dev)),
+            "snv_topk_merge")
+    return Do, Io
+
+
+def pack_rows(x, d: Optional[int] = None, invert: bool = False):
+    """Device-side bit packing (snv_pack_rows): torch CUDA tensor [rows, d] (uint8/bool 0-1 sites,
+    float32, or int64 tokens) -> packed int32 tensor [rows, snv_packed_stride(d)]."""
+    if not (_is_torch(x) and x.is_cuda):
+        raise ValueError("pack_rows takes a CUDA tensor")
+    a = _Arg(x)
+    if len(a.shape) != 2:
+        raise ValueError("pack_rows: expected [rows, d]")
+    d = a.shape[1] if d is None else int(d)
+    stride = L.packed_stride(d)
+    dt, a = _hamming_dtype(a, d, stride, "pack_rows")
+    if dt == L.DT_PACKED_U32:
+        raise ValueError("pack_rows: input is already packed")
+    dev = a.arr.device.index
+    out = torch.empty((a.shape[0], stride), dtype=torch.int32, device=a.arr.device)
+    L.check(L.lib().snv_pack_rows(dev, a.ptr, a.shape[0], d, dt, int(bool(invert)), out.data_ptr(), None,
+                                  _current_stream(dev)), "snv_pack_rows")
+    return out

@@ -1,0 +1,316 @@
+"""GPU parity: CUDA Hamming / masked-Hamming search (through the C ABI) vs the CPU oracle.
+Bit-exact on D and I, ties included."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from oracle import cbind
+
+pytestmark = pytest.mark.gpu
+
+
+def _idx(d, W=1):
+    from rag_snvbert_b200 import WindowedHammingIndex
+
+    return WindowedHammingIndex(d, W)
+
+
+def _check(panel, queries, k, observed=None, dtype="u8"):
+    """panel [W,N,d], queries [W,Q,d] uint8 0/1 -> compare with oracle per window."""
+    from rag_snvbert_b200 import _lib
+
+    W, N, d = panel.shape
+    idx = _idx(d, W)
+    stride = _lib.packed_stride(d)
+
+    def conv(x):
+        if dtype == "u8":
+            return x
+        if dtype == "f32":
+            return x.astype(np.float32)
+        if dtype == "bool":
+            return x.astype(bool)
+        if dtype == "packed":
+            return O.pack_bits_u32(x.reshape(-1, d), stride).reshape(x.shape[:-1] + (stride,))
+        raise AssertionError(dtype)
+
+    idx.add(conv(panel))
+    assert idx.ntotal == N
+    D, I = idx.search(conv(queries), k, observed=None if observed is None else conv(observed))
+    assert D.dtype == np.int32 and I.dtype == np.int64
+    for w in range(W):
+        De, Ie = O.hamming_topk(panel[w], queries[w], k, None if observed is None else observed[w])
+        np.testing.assert_array_equal(I[w], Ie, err_msg=f"window {w} ids")
+        np.testing.assert_array_equal(D[w], De, err_msg=f"window {w} distances")
+    return D, I
+
+
+@pytest.mark.parametrize("dtype", ["u8", "f32", "bool", "packed"])
+def test_small_all_dtypes(dtype):
+    rng = np.random.default_rng(0)
+    panel = (rng.random((1, 100, 50)) < 0.3).astype(np.uint8)
+    q = (rng.random((1, 7, 50)) < 0.3).astype(np.uint8)
+    _check(panel, q, 3, dtype=dtype)
+
+
+@pytest.mark.parametrize("d", [1, 31, 32, 33, 100, 128, 257, 500, 777, 1024, 1030, 1056, 1100, 1500, 2060, 2176])
+def test_site_counts(d):
+    """every register-resident word bucket plus the generic fallback (d > 68 words)."""
+    rng = np.random.default_rng(d)
+    panel = (rng.random((2, 300, d)) < 0.4).astype(np.uint8)
+    q = (rng.random((2, 37, d)) < 0.4).astype(np.uint8)
+    _check(panel, q, 8)
+
+
+def test_generic_wide_rows():
+    rng = np.random.default_rng(5)
+    d = 5000
+    panel = (rng.random((1, 200, d)) < 0.5).astype(np.uint8)
+    q = (rng.random((1, 40, d)) < 0.5).astype(np.uint8)
+    obs = (rng.random((1, 40, d)) < 0.5).astype(np.uint8)
+    _check(panel, q, 8)
+    _check(panel, q, 16, observed=obs)
+
+
+def test_chr21_window_shape_k8():
+    """one BASELINE cfg-2 window: 5008 x 1030, mosaic haplotypes (many exact ties)."""
+    panel = O.hapgen(2000, 5008, 1030)[None]
+    q = O.hapgen(5000, 300, 1030, founder_seed=2000)[None]
+    D, I = _check(panel, q, 8, dtype="packed")
+    # ties must actually occur for this to be a tie test
+    assert (D[0][:, 1:] == D[0][:, :-1]).any()
+
+
+@pytest.mark.parametrize("k", [1, 3, 5, 8, 9, 16, 32])
+def test_k_values(k):
+    panel = O.hapgen(11, 1000, 1030)[None]
+    q = O.hapgen(12, 130, 1030, founder_seed=11)[None]
+    _check(panel, q, k)
+
+
+def test_duplicates_and_ties_keep_lowest_ids():
+    rng = np.random.default_rng(3)
+    base = (rng.random((10, 200)) < 0.5).astype(np.uint8)
+    panel = np.tile(base, (40, 1))[None]  # every row appears 40 times
+    q = base[:5][None]
+    D, I = _check(panel, q, 32)
+    assert (D[0] == 0).all()
+    np.testing.assert_array_equal(I[0][0], np.arange(0, 320, 10))
+
+
+def test_planted_exact_match_returns_row_at_distance_zero():
+    panel = O.hapgen(21, 3000, 1030)[None]
+    q = panel[:, [5, 77, 2999]].copy()
+    D, I = _check(panel, q, 1)
+    np.testing.assert_array_equal(I[0][:, 0], [5, 77, 2999])
+    assert (D[0] == 0).all()
+
+
+def test_fewer_rows_than_k_pads_with_minus_one():
+    rng = np.random.default_rng(4)
+    panel = (rng.random((1, 5, 64)) < 0.5).astype(np.uint8)
+    q = (rng.random((1, 9, 64)) < 0.5).astype(np.uint8)
+    D, I = _check(panel, q, 8)
+    assert (I[0][:, 5:] == -1).all() and (D[0][:, 5:] == np.iinfo(np.int32).max).all()
+
+
+def test_per_query_observed_mask_cfg3():
+    """BASELINE cfg 3: per-query missing rate U[0.1, 0.9], masked Hamming, k=8."""
+    rng = np.random.default_rng(8000)
+    panel = O.hapgen(2001, 5008, 1030)[None]
+    q = O.hapgen(5001, 200, 1030, founder_seed=2001)[None]
+    rate = rng.uniform(0.1, 0.9, size=(1, 200, 1))
+    missing = (rng.random((1, 200, 1030)) < rate).astype(np.uint8)
+    _check(panel, q, 8, observed=1 - missing)
+    _check(panel, q, 8, observed=1 - missing, dtype="packed")
+    # reference convention: mask marks MISSING sites (partial_faiss_intersect.py:91)
+    idx = _idx(1030)
+    idx.add(panel[0])
+    D, I = idx.search(q[0], 8, missing=missing[0])
+    De, Ie = O.hamming_topk(panel[0], q[0], 8, 1 - missing[0])
+    np.testing.assert_array_equal(I, Ie)
+    np.testing.assert_array_equal(D, De)
+    # packed + missing flag exercises the device-side inversion with zeroed pad bits
+    from rag_snvbert_b200 import _lib
+
+    s = _lib.packed_stride(1030)
+    D, I = idx.search(O.pack_bits_u32(q[0], s), 8, missing=O.pack_bits_u32(missing[0], s))
+    np.testing.assert_array_equal(I, Ie)
+    np.testing.assert_array_equal(D, De)
+
+
+def test_per_window_shared_mask():
+    rng = np.random.default_rng(9)
+    panel = (rng.random((3, 400, 300)) < 0.5).astype(np.uint8)
+    q = (rng.random((3, 50, 300)) < 0.5).astype(np.uint8)
+    obs = (rng.random((3, 300)) < 0.7).astype(np.uint8)
+    idx = _idx(300, 3)
+    idx.add(panel)
+    D, I = idx.search(q, 5, observed=obs)
+    for w in range(3):
+        De, Ie = O.hamming_topk(panel[w], q[w], 5, obs[w])
+        np.testing.assert_array_equal(I[w], Ie)
+        np.testing.assert_array_equal(D[w], De)
+
+
+def test_row_split_path_small_query_batches():
+    """nq = 2 (the reference's training-time call, rag_train_dataset.py:281) and a large panel:
+    the planner splits rows across CTAs and merges partial top-k."""
+    panel = O.hapgen(31, 20000, 1030)[None]
+    q = O.hapgen(32, 2, 1030, founder_seed=31)[None]
+    _check(panel, q, 5)
+    q = O.hapgen(33, 48, 1030, founder_seed=31)[None]
+    _check(panel, q, 32)
+
+
+def test_many_windows_and_window_offset():
+    W = 12
+    panel = np.stack([O.hapgen(100 + w, 600, 1030) for w in range(W)])
+    q = np.stack([O.hapgen(200 + w, 150, 1030, founder_seed=100 + w) for w in range(W)])
+    _check(panel, q, 8)
+    idx = _idx(1030, W)
+    idx.add(panel)
+    D, I = idx.search(q[4:9], 8, w0=4, id_offset=1000)
+    for j, w in enumerate(range(4, 9)):
+        De, Ie = O.hamming_topk(panel[w], q[w], 8)
+        np.testing.assert_array_equal(I[j], Ie + 1000)
+        np.testing.assert_array_equal(D[j], De)
+
+
+def test_incremental_add_grows_panel():
+    rng = np.random.default_rng(6)
+    panel = (rng.random((2, 900, 130)) < 0.5).astype(np.uint8)
+    q = (rng.random((2, 33, 130)) < 0.5).astype(np.uint8)
+    idx = _idx(130, 2)
+    for s in (0, 100, 350):
+        e = {0: 100, 100: 350, 350: 900}[s]
+        idx.add(panel[:, s:e])
+    assert idx.ntotal == 900
+    D, I = idx.search(q, 8)
+    for w in range(2):
+        De, Ie = O.hamming_topk(panel[w], q[w], 8)
+        np.testing.assert_array_equal(I[w], Ie)
+        np.testing.assert_array_equal(D[w], De)
+    np.testing.assert_array_equal(idx.export_packed(1)[:, : idx.words], O.pack_bits_u32(panel[1]))
+
+
+def test_float_distance_output_equals_faiss_l2_on_binary_rows():
+    panel = O.hapgen(41, 500, 1030)[None]
+    q = O.hapgen(42, 20, 1030, founder_seed=41)[None]
+    idx = _idx(1030)
+    idx.add(panel[0].astype(np.float32))
+    D, I = idx.search(q[0].astype(np.float32), 4, dist_dtype=np.float32)
+    De, Ie = O.l2_topk_f32_blas(panel[0].astype(np.float32), q[0].astype(np.float32), 4)
+    np.testing.assert_array_equal(I, Ie)
+    np.testing.assert_array_equal(D, De)
+
+
+def test_torch_cuda_tensors_zero_copy():
+    import torch
+
+    panel = O.hapgen(51, 2000, 1030)
+    q = O.hapgen(52, 257, 1030, founder_seed=51)
+    idx = _idx(1030)
+    idx.add(torch.from_numpy(panel).cuda())
+    D, I = idx.search(torch.from_numpy(q).cuda(), 8)
+    assert D.is_cuda and I.is_cuda and D.dtype == torch.int32 and I.dtype == torch.int64
+    De, Ie = O.hamming_topk(panel, q, 8)
+    np.testing.assert_array_equal(I.cpu().numpy(), Ie)
+    np.testing.assert_array_equal(D.cpu().numpy(), De)
+
+
+def test_token_rows_shared_mask_equals_token_space_l2():
+    """V17 layout (rag_train_dataset.py:111-134, 262-281): tokenised panel and queries with the
+    window's mask; squared L2 over tokens == masked Hamming."""
+    rng = np.random.default_rng(7)
+    lw = 1000
+    raw_mask = (rng.random(lw) < 0.3).astype(np.int64)
+    pm = O.sequence_padding(raw_mask)
+    panel01 = O.hapgen(61, 400, lw)
+    q01 = O.hapgen(62, 30, lw, founder_seed=61)
+    ptok = O.tokenize(panel01, pm)
+    qtok = O.tokenize(q01, pm)
+    idx = _idx(O.MAX_SEQ_LEN)
+    idx.add(ptok)
+    D, I = idx.search(qtok, 3, dist_dtype=np.float32)
+    De, Ie = O.token_l2_topk(ptok, qtok, 3)
+    np.testing.assert_array_equal(I, Ie)
+    np.testing.assert_array_equal(D, De)
+
+
+def test_binary_codes_indexbinaryflat():
+    import rag_snvbert_b200.faiss_compat as faiss
+
+    rng = np.random.default_rng(10)
+    d_bits = 2 * 516
+    ref = (rng.random((700, d_bits)) < 0.5).astype(np.uint8)
+    t = (rng.random((60, d_bits)) < 0.5).astype(np.uint8)
+    index = faiss.IndexBinaryFlat(d_bits)
+    index.add(O.packbits_msb(ref))
+    D, I = index.search(O.packbits_msb(t), 5)
+    De, Ie = O.hamming_topk(ref, t, 5)
+    np.testing.assert_array_equal(I, Ie)
+    np.testing.assert_array_equal(D, De)
+    assert index.ntotal == 700 and index.d == d_bits
+
+
+def test_gather_tokens_matches_reference_layout():
+    rng = np.random.default_rng(12)
+    lw, S = 1000, 60
+    gt = (rng.random((lw, S, 2)) < 0.3).astype(np.int8)  # raw_ref_window [L_w, S, 2]
+    rows = O.panel_rows_from_gt(gt).astype(np.uint8)
+    d = 1028
+    padded = np.zeros((rows.shape[0], d), np.uint8)
+    padded[:, :lw] = rows
+    idx = _idx(d)
+    idx.add(padded)
+    I = rng.integers(0, 2 * S, size=(9, 3)).astype(np.int64)
+    I[0, 1] = -1
+    out = idx.gather_tokens(I, n_sites=lw, seq_len=O.MAX_SEQ_LEN)
+    exp = O.gather_tokens(gt, I)
+    np.testing.assert_array_equal(out, exp)
+
+
+def test_row_sharded_merge_equals_unsharded():
+    import torch
+    from rag_snvbert_b200 import topk_merge
+
+    panel = O.hapgen(71, 4000, 1030)
+    q = O.hapgen(72, 100, 1030, founder_seed=71)
+    De, Ie = O.hamming_topk(panel, q, 32)
+    parts_D, parts_I = [], []
+    for g in range(4):
+        idx = _idx(1030)
+        idx.add(torch.from_numpy(panel[g * 1000:(g + 1) * 1000]).cuda())
+        D, I = idx.search(torch.from_numpy(q).cuda(), 32, id_offset=g * 1000)
+        parts_D.append(D)
+        parts_I.append(I)
+    D, I = topk_merge(torch.stack(parts_D), torch.stack(parts_I), 32)
+    np.testing.assert_array_equal(I.cpu().numpy(), Ie)
+    np.testing.assert_array_equal(D.cpu().numpy(), De)
+
+
+def test_c_oracle_agrees_on_gpu_sized_case():
+    """the C restatement (bench's CPU baseline) against the CUDA path at 2 full cfg-2 windows."""
+    from rag_snvbert_b200 import _lib
+
+    s = _lib.packed_stride(1030)
+    P = np.stack([O.pack_bits_u32(O.hapgen(2000 + w, 5008, 1030), s) for w in range(2)])
+    Q = np.stack([O.pack_bits_u32(O.hapgen(5000 + w, 2000, 1030, founder_seed=2000 + w), s) for w in range(2)])
+    idx = _idx(1030, 2)
+    idx.add(P)
+    D, I = idx.search(Q, 8)
+    Dc, Ic = cbind.hamming_topk_packed(P, Q, 8, words=33)
+    np.testing.assert_array_equal(I, Ic)
+    np.testing.assert_array_equal(D, Dc)
+
+
+def test_error_behaviour():
+    idx = _idx(64)
+    with pytest.raises(ValueError):
+        idx.add(np.zeros((3, 65), np.uint8))
+    with pytest.raises(ValueError):
+        idx.search(np.zeros((3, 64), np.uint8), 0)
+    idx.add(np.zeros((3, 64), np.uint8))
+    with pytest.raises(Exception):
+        idx.search(np.zeros((3, 64), np.uint8), 100)  # k > 32 unsupported (stated limit)
