@@ -222,6 +222,24 @@ def cdist_topk_indices(panel: np.ndarray, queries: np.ndarray, k: int) -> np.nda
     return l2_topk_f64(panel, queries, k)[1]
 
 
+def assert_ids_match_within_tolerance(d64: np.ndarray, I_test: np.ndarray, I_ref: np.ndarray, tol_abs) -> int:
+    """Float-L2 index parity: the two id lists must select rows whose float64
+    distances agree position by position within ``tol_abs`` ([nq] or scalar) — i.e. ids may
+    differ only at ties / near-ties inside the stated tolerance.  Returns #positions that differ."""
+    tol = np.broadcast_to(np.asarray(tol_abs, dtype=np.float64).reshape(-1, 1) if np.ndim(tol_abs) else tol_abs,
+                          I_ref.shape)
+    da = np.take_along_axis(d64, np.where(I_test >= 0, I_test, 0), axis=1)
+    db = np.take_along_axis(d64, np.where(I_ref >= 0, I_ref, 0), axis=1)
+    diff = I_test != I_ref
+    bad = diff & (np.abs(da - db) > tol)
+    if bad.any():
+        q, j = np.argwhere(bad)[0]
+        raise AssertionError(
+            f"ids differ outside tolerance at query {q} rank {j}: {I_test[q, j]} (d={da[q, j]!r}) vs "
+            f"{I_ref[q, j]} (d={db[q, j]!r}), tol={tol[q, j]!r}; {int(bad.sum())} such positions")
+    return int(diff.sum())
+
+
 # --------------------------------------------------------------------------------------
 # Gather into the model's input layout
 # --------------------------------------------------------------------------------------

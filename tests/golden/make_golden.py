@@ -1,0 +1,252 @@
+#!/usr/bin/env python
+"""Generates tests/golden/*.npz by IMPORTING THE REFERENCE'S OWN PYTHON from /root/reference.
+
+Run in the build container only (the GPU box has no /root/reference):
+
+    python tests/golden/make_golden.py
+
+The reference cannot be imported as-is here: faiss, h5py, allel, vcfpy and matplotlib are absent
+(SURVEY.md §8c).  They are replaced by stub modules below; only `faiss` is ever *called*, and
+the stub implements exactly the documented contract of the two calls the reference makes
+(IndexFlatL2.add / .search: exact squared L2 in float32, results ordered by (distance, id)),
+in a few lines of numpy — so what the fixtures pin is the REFERENCE-OWNED logic around it:
+
+  g1  tokenisation          TrainDataset.tokenize + WordVocab.to_seq + sequence_padding
+                            (src/dataset/dataset.py:597-625, vocab.py:153-170, utils.py:121-132)
+  g2  V17 panel layout,     the index-side statements of RAGTrainDataset._build_faiss_indexes
+      search + gather       (rag_train_dataset.py:111-134) followed by the real
+                            rag_collate_fn_with_dataset (:232-358) -> rag_seg_h1 / rag_seg_h2
+  g3  binary packing        bitpack_2d_array (test_faiss_intersect.py:46-54)
+  g4  V18 embedding search  EmbeddingRAGDataset.process_batch_retrieval
+                            (embedding_rag_dataset.py:285-444) with the real BERTEmbedding:
+                            torch.cdist + topk ids and the gathered rag_emb tensors
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+import numpy as np
+
+REF = "/root/reference"
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+# ------------------------------------------------------------------------------- stubs
+class _ShimIndexFlatL2:
+    """The faiss.IndexFlatL2 contract in numpy (float32 exact squared L2, (distance, id) order)."""
+
+    def __init__(self, d):
+        self.d = int(d)
+        self.xb = np.zeros((0, self.d), np.float32)
+
+    @property
+    def ntotal(self):
+        return self.xb.shape[0]
+
+    def add(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        assert x.ndim == 2 and x.shape[1] == self.d
+        self.xb = np.concatenate([self.xb, x])
+
+    def search(self, x, k):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        assert x.ndim == 2 and x.shape[1] == self.d
+        diff = x[:, None, :] - self.xb[None, :, :]
+        dist = np.einsum("qnd,qnd->qn", diff, diff).astype(np.float32)
+        order = np.argsort(dist, axis=1, kind="stable")[:, :k]
+        return np.take_along_axis(dist, order, 1), order.astype(np.int64)
+
+
+def install_stubs():
+    faiss = types.ModuleType("faiss")
+    faiss.IndexFlatL2 = _ShimIndexFlatL2
+    faiss.StandardGpuResources = lambda: None
+    sys.modules["faiss"] = faiss
+    for name in ("h5py", "allel", "matplotlib", "matplotlib.pyplot", "vcfpy", "seaborn"):
+        m = types.ModuleType(name)
+        sys.modules[name] = m
+    sys.modules["vcfpy"].Header = object
+    sys.modules["vcfpy"].Reader = object
+    sys.modules["vcfpy"].Writer = object
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    sys.modules["matplotlib"].use = lambda *a, **k: None
+
+
+def main():
+    install_stubs()
+    sys.path.insert(0, REF)
+    os.chdir("/tmp")  # PanelData writes POP.json into the CWD; keep the repo clean
+    import torch
+
+    from src.dataset.dataset import TrainDataset
+    from src.dataset.utils import VCFProcessingModule
+    from src.dataset.vocab import WordVocab
+    from src.dataset import rag_train_dataset as RTD
+    from src.dataset.embedding_rag_dataset import EmbeddingRAGDataset
+    from src.model.embedding.bert import BERTEmbedding
+
+    rng = np.random.default_rng(20261018)
+    vocab = WordVocab(["AFR", "EUR", "EAS"])
+    holder = types.SimpleNamespace(vocab=vocab)
+    tokenize = lambda seq, mask=None: TrainDataset.tokenize(holder, seq, mask)  # noqa: E731
+
+    # ---- g1 tokenisation ------------------------------------------------------------------
+    g1 = {}
+    for name, lw in (("a", 1000), ("b", 1028), ("c", 37)):
+        seq = (rng.random((6, lw)) < 0.3).astype(np.int64)
+        raw_mask = (rng.random(lw) < 0.25).astype(np.int64)
+        padded = VCFProcessingModule.sequence_padding(raw_mask, dtype="int")
+        g1[f"seq_{name}"] = seq
+        g1[f"rawmask_{name}"] = raw_mask
+        g1[f"padmask_{name}"] = padded
+        g1[f"tok_masked_{name}"] = tokenize(seq, padded)
+        g1[f"tok_plain_{name}"] = tokenize(seq, np.zeros_like(padded))
+    g1["specials"] = np.array([vocab.pad_index, vocab.unk_index, vocab.sos_index, vocab.eos_index,
+                               vocab.mask_index, vocab.stoi[0], vocab.stoi[1]])
+    np.savez_compressed(os.path.join(OUT, "g1_tokenize.npz"), **g1)
+
+    # ---- g2 V17: panel layout -> index -> collate search + gather ----------------------------
+    lw, S_ref, n_samples, k = 1000, 40, 6, 3
+    founders = (rng.random((8, lw)) < 0.3).astype(np.int8)
+
+    def mosaic(n):
+        out = np.empty((n, lw), np.int8)
+        for i in range(n):
+            cuts = np.sort(rng.choice(lw, 4, replace=False))
+            f = rng.integers(0, 8, 5)
+            seg = np.searchsorted(cuts, np.arange(lw), side="right")
+            out[i] = founders[f[seg], np.arange(lw)]
+            out[i] ^= (rng.random(lw) < 0.01).astype(np.int8)
+        return out
+
+    windows = []
+    ds = types.SimpleNamespace(window_indexes=[], raw_ref_data_windows=[], raw_window_masks=[],
+                               ref_data_windows=[], vocab=vocab)
+    ds.tokenize = tokenize
+    for w in range(2):
+        ref_gt = mosaic(2 * S_ref).reshape(S_ref, 2, lw).transpose(2, 0, 1).copy()  # [L_w, S, 2]
+        raw_mask = (rng.random(lw) < 0.3).astype(np.int64)
+        padded_mask = VCFProcessingModule.sequence_padding(raw_mask, dtype="int")
+        # rag_train_dataset.py:111-134, statement for statement
+        raw_ref = ref_gt[slice(0, lw), :, :]
+        ds.raw_ref_data_windows.append(raw_ref)
+        raw_ref2 = raw_ref.reshape(raw_ref.shape[0], -1)
+        raw_ref2 = raw_ref2.T
+        ref_tokenized = tokenize(raw_ref2, padded_mask)
+        ds.ref_data_windows.append(ref_tokenized)
+        index_data = ref_tokenized.astype(np.float32)
+        index = sys.modules["faiss"].IndexFlatL2(index_data.shape[1])
+        index.add(index_data)
+        ds.window_indexes.append(index)
+        ds.raw_window_masks.append(raw_mask)
+        windows.append((ref_gt, raw_mask, padded_mask, ref_tokenized))
+    batch = []
+    q_h1, q_h2, q_win = [], [], []
+    for i in range(n_samples):
+        w = i % 2
+        padded_mask = windows[w][2]
+        h = mosaic(2)
+        if i == 0:  # planted exact match with panel row 2*7+1 (test_R_only.py:32-55 invariant)
+            h[0] = windows[w][0][:, 7, 1]
+        hap1 = tokenize(h[0].astype(np.int64), padded_mask)
+        hap2 = tokenize(h[1].astype(np.int64), padded_mask)
+        q_h1.append(hap1)
+        q_h2.append(hap2)
+        q_win.append(w)
+        batch.append({"window_idx": w, "hap_1": torch.from_numpy(hap1), "hap_2": torch.from_numpy(hap2)})
+    # record the (D, I) the collate's index.search produced
+    rec = []
+    orig_search = _ShimIndexFlatL2.search
+
+    def rec_search(self, x, k):
+        D, I = orig_search(self, x, k)
+        rec.append((np.array(x), D, I))
+        return D, I
+
+    _ShimIndexFlatL2.search = rec_search
+    out = RTD.rag_collate_fn_with_dataset(batch, ds, k)
+    _ShimIndexFlatL2.search = orig_search
+    g2 = {"k": np.array(k), "lw": np.array(lw)}
+    for w in range(2):
+        g2[f"ref_gt_{w}"] = windows[w][0]
+        g2[f"raw_mask_{w}"] = windows[w][1]
+        g2[f"padded_mask_{w}"] = windows[w][2]
+        g2[f"ref_tokenized_{w}"] = windows[w][3]
+        g2[f"search_q_{w}"] = rec[w][0]
+        g2[f"search_D_{w}"] = rec[w][1]
+        g2[f"search_I_{w}"] = rec[w][2]
+    g2["window_idx"] = np.array(out["window_idx"])
+    g2["hap_1"] = out["hap_1"].numpy()
+    g2["hap_2"] = out["hap_2"].numpy()
+    g2["rag_seg_h1"] = out["rag_seg_h1"].numpy()
+    g2["rag_seg_h2"] = out["rag_seg_h2"].numpy()
+    np.savez_compressed(os.path.join(OUT, "g2_v17_collate.npz"), **g2)
+
+    # ---- g3 bit packing ----------------------------------------------------------------------
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("ref_tfi", os.path.join(REF, "test_faiss_intersect.py"))
+    tfi = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tfi)
+    arr = (rng.random((5, 2 * 517)) < 0.5).astype(np.int8)
+    np.savez_compressed(os.path.join(OUT, "g3_bitpack.npz"), arr=arr, packed=tfi.bitpack_2d_array(arr))
+
+    # ---- g4 V18 embedding-space retrieval ------------------------------------------------------
+    torch.manual_seed(7)
+    L, D, N, B, k18 = 96, 16, 48, 10, 2
+    emb = BERTEmbedding(vocab_size=len(vocab), embed_size=D, dropout=0.0, use_af=True)
+    emb.train()  # the trainer calls it in train mode; dropout=0 keeps it deterministic
+    hap = (rng.random((N, L - 2)) < 0.3).astype(np.int64)
+    ref_tokens_complete = tokenize(hap, None)[:, :L] if False else None
+    # tokens of length L: [SOS] + L-2 sites + [EOS]
+    ref_tokens_complete = np.concatenate(
+        [np.full((N, 1), 2), np.where(hap == 0, 5, 6), np.full((N, 1), 3)], axis=1).astype(np.int64)
+    win_mask = np.zeros(L, np.int64)
+    win_mask[1:-1] = (rng.random(L - 2) < 0.3)
+    ref_af = rng.random(L).astype(np.float32)
+    qhap = hap[rng.integers(0, N, 2 * B)].copy()
+    qhap ^= (rng.random(qhap.shape) < 0.05)
+    q_tok = np.concatenate([np.full((2 * B, 1), 2), np.where(qhap == 0, 5, 6), np.full((2 * B, 1), 3)], axis=1).astype(np.int64)
+    q_tok[:, win_mask == 1] = vocab.mask_index
+    fake = types.SimpleNamespace(
+        embed_dim=D, jit_cache_win_idx=-1, jit_ref_emb_search=None, jit_ref_tokens_raw=None, jit_ref_af_raw=None,
+        ref_tokens_complete=[ref_tokens_complete], ref_af_windows=[ref_af], window_masks=[win_mask], vocab=vocab)
+    fake._apply_mask_to_tokens_gpu = lambda t, m: EmbeddingRAGDataset._apply_mask_to_tokens_gpu(fake, t, m)
+    batch = {"hap_1": torch.from_numpy(q_tok[:B]), "hap_2": torch.from_numpy(q_tok[B:]),
+             "af": torch.from_numpy(np.tile(ref_af, (B, 1))), "window_idx": [0] * B}
+    topk_rec = []
+    orig_topk = torch.Tensor.topk
+
+    def rec_topk(self, *a, **kw):
+        r = orig_topk(self, *a, **kw)
+        topk_rec.append((self.detach().numpy().copy(), r[1].numpy().copy()))
+        return r
+
+    torch.Tensor.topk = rec_topk
+    out = EmbeddingRAGDataset.process_batch_retrieval(fake, batch, emb, "cpu", k18)
+    torch.Tensor.topk = orig_topk
+    with torch.no_grad():
+        emb.eval()
+        ref_masked = ref_tokens_complete.copy()
+        ref_masked[:, win_mask == 1] = vocab.mask_index
+        af_t = torch.from_numpy(ref_af)
+        ref_emb_search = emb(torch.from_numpy(ref_masked), af=af_t.unsqueeze(0).expand(N, -1), pos=True)
+        ref_emb_complete = emb(torch.from_numpy(ref_tokens_complete), af=af_t.unsqueeze(0).expand(N, -1), pos=True)
+        q1 = emb(batch["hap_1"], af=batch["af"], pos=True)
+        q2 = emb(batch["hap_2"], af=batch["af"], pos=True)
+    np.savez_compressed(
+        os.path.join(OUT, "g4_v18_embedding.npz"),
+        ref_flat=ref_emb_search.reshape(N, L * D).numpy(), ref_complete=ref_emb_complete.numpy(),
+        q1_flat=q1.reshape(B, L * D).numpy(), q2_flat=q2.reshape(B, L * D).numpy(),
+        dists_h1=topk_rec[0][0], I1=topk_rec[0][1], dists_h2=topk_rec[1][0], I2=topk_rec[1][1],
+        rag_emb_h1=out["rag_emb_h1"].detach().numpy(), rag_emb_h2=out["rag_emb_h2"].detach().numpy(),
+        k=np.array(k18))
+    for f in sorted(os.listdir(OUT)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")
+
+
+if __name__ == "__main__":
+    main()

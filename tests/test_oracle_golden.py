@@ -1,0 +1,115 @@
+"""CPU: pins the oracle against golden vectors produced by the reference's own Python
+(tests/golden/make_golden.py, run in the build container against /root/reference)."""
+import os
+
+import numpy as np
+
+from oracle import oracle as O
+from oracle import cbind
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    return np.load(os.path.join(G, name))
+
+
+def test_g1_tokenize_matches_reference():
+    g = load("g1_tokenize.npz")
+    assert list(g["specials"]) == [O.PAD, O.UNK, O.SOS, O.EOS, O.MASK, O.ALLELE0, O.ALLELE1]
+    for name in "abc":
+        seq, raw = g[f"seq_{name}"], g[f"rawmask_{name}"]
+        padded = O.sequence_padding(raw)
+        np.testing.assert_array_equal(padded, g[f"padmask_{name}"])
+        np.testing.assert_array_equal(O.tokenize(seq, padded), g[f"tok_masked_{name}"])
+        np.testing.assert_array_equal(O.tokenize(seq, None), g[f"tok_plain_{name}"])
+
+
+def test_g2_v17_panel_layout_search_and_gather():
+    g = load("g2_v17_collate.npz")
+    k = int(g["k"])
+    h1_rows, h2_rows = [], []
+    # the collate groups samples by window (window 0 first), two queries per sample
+    for w in range(2):
+        ref_gt = g[f"ref_gt_{w}"]
+        rows = O.panel_rows_from_gt(ref_gt)
+        ref_tok = O.tokenize(rows, g[f"padded_mask_{w}"])
+        np.testing.assert_array_equal(ref_tok, g[f"ref_tokenized_{w}"])  # index-side layout
+        q = g[f"search_q_{w}"]
+        D, I = O.token_l2_topk(ref_tok, q.astype(np.int64), k)
+        np.testing.assert_array_equal(I, g[f"search_I_{w}"])
+        np.testing.assert_array_equal(D, g[f"search_D_{w}"])
+        # token-space squared L2 == masked Hamming when panel and queries share the mask
+        obs = 1 - g[f"raw_mask_{w}"]
+        lw = int(g["lw"])
+        q01 = (q[:, 1:1 + lw] == 6).astype(np.uint8)
+        Dh, Ih = O.hamming_topk(rows.astype(np.uint8), q01, k, obs)
+        np.testing.assert_array_equal(Ih, I)
+        np.testing.assert_array_equal(Dh.astype(np.float32), D)
+        seg = O.gather_tokens(ref_gt, I)
+        h1_rows.append(seg[0::2])
+        h2_rows.append(seg[1::2])
+    np.testing.assert_array_equal(np.concatenate(h1_rows), g["rag_seg_h1"])
+    np.testing.assert_array_equal(np.concatenate(h2_rows), g["rag_seg_h2"])
+    # planted exact match: sample 0 / hap 1 retrieves panel row 2*7+1 at distance 0
+    assert g["search_I_0"][0, 0] == 15 and g["search_D_0"][0, 0] == 0
+
+
+def test_g3_bitpack_matches_reference():
+    g = load("g3_bitpack.npz")
+    np.testing.assert_array_equal(O.packbits_msb(g["arr"]), g["packed"])
+
+
+def test_g4_v18_cdist_topk_ids_and_gather():
+    g = load("g4_v18_embedding.npz")
+    k = int(g["k"])
+    for qn, In, dn, out in (("q1_flat", "I1", "dists_h1", "rag_emb_h1"), ("q2_flat", "I2", "dists_h2", "rag_emb_h2")):
+        # torch.cdist + topk ran in fp32: ids may differ from the float64 ranking only at
+        # near-ties below fp32 resolution (tolerance 1e-6 * (|q|^2 + |r|^2), stated in DESIGN.md)
+        d2 = O.l2_matrix_f64(g["ref_flat"], g[qn])
+        tol = 1e-6 * ((g[qn].astype(np.float64) ** 2).sum(1) + (g["ref_flat"].astype(np.float64) ** 2).sum(1).max())
+        I = O.cdist_topk_indices(g["ref_flat"], g[qn], k)
+        n_diff = O.assert_ids_match_within_tolerance(d2, I, g[In], tol)
+        assert n_diff <= 1
+        # torch.cdist returns the NON-squared distance from the fp32 expansion; compare squares
+        np.testing.assert_allclose(g[dn].astype(np.float64) ** 2, d2, rtol=0, atol=float(tol.max()) * 4)
+        D32, I32 = O.l2_topk_f32_blas(g["ref_flat"], g[qn], k)
+        O.assert_ids_match_within_tolerance(d2, I32, g[In], tol)
+        I = g[In]
+        rows = O.gather_rows(g["ref_complete"].reshape(g["ref_complete"].shape[0], -1), I)
+        np.testing.assert_allclose(rows.reshape(g[out].shape), g[out], rtol=1e-6, atol=1e-6)
+
+
+def test_c_restatement_equals_numpy_oracle():
+    rng = np.random.default_rng(1)
+    for (n, nq, d, k) in ((300, 50, 1030, 8), (64, 9, 100, 32), (5, 4, 33, 8), (1000, 20, 2060, 1)):
+        p = (rng.random((n, d)) < 0.4).astype(np.uint8)
+        q = (rng.random((nq, d)) < 0.4).astype(np.uint8)
+        m = (rng.random((nq, d)) < 0.6).astype(np.uint8)
+        words = (d + 31) // 32
+        stride = -(-words // 4) * 4
+        P, Q, M = (O.pack_bits_u32(x, stride) for x in (p, q, m))
+        for mask01, Mp in ((None, None), (m, M)):
+            De, Ie = O.hamming_topk(p, q, k, mask01)
+            Dc, Ic = cbind.hamming_topk_packed(P, Q, k, Mp, words=words)
+            np.testing.assert_array_equal(Ic, Ie)
+            np.testing.assert_array_equal(Dc, De)
+
+
+def test_oracle_invariants():
+    p = O.hapgen(3, 500, 200)
+    q = p[[4, 99]].copy()
+    D, I = O.hamming_topk(p, q, 1)
+    assert list(I[:, 0]) == [4, 99] and (D == 0).all()
+    # row id <-> (sample, hap) convention (rag_train_dataset.py:298-299)
+    gt = np.arange(3 * 4 * 2).reshape(3, 4, 2)
+    rows = O.panel_rows_from_gt(gt)
+    for s in range(4):
+        for h in range(2):
+            np.testing.assert_array_equal(rows[2 * s + h], gt[:, s, h])
+    # sharded == unsharded
+    De, Ie = O.hamming_topk(p, O.hapgen(4, 20, 200, founder_seed=3), 8)
+    parts = [O.hamming_topk(p[s:s + 125], O.hapgen(4, 20, 200, founder_seed=3), 8) for s in range(0, 500, 125)]
+    Dm, Im = O.merge_topk([d for d, _ in parts], [i + 125 * g for g, (_, i) in enumerate(parts)], 8, O.I32_MAX)
+    np.testing.assert_array_equal(Im, Ie)
+    np.testing.assert_array_equal(Dm, De)
