@@ -1,8 +1,460 @@
+// Float squared-L2 search:  D = |q|^2 + |r|^2 - 2 q.r  with the cross term on the 5th-gen tensor
+// cores (tcgen05.mma kind::tf32, accumulators in TMEM) and the norm-add + clamp + exact top-k
+// fused into the epilogue (sm_100a).
+//
+// Replaces faiss IndexFlatL2.search on float rows (src/dataset/rag_train_dataset.py:281 token
+// vectors, src/dataset/embedding_rag_infer_dataset.py:284-285) and torch.cdist + topk
+// (src/dataset/embedding_rag_dataset.py:392-402).
+//
+// Layout of one CTA (192 threads), canonical warp-specialised Blackwell GEMM:
+//   warp 0      TMA producer: 2-D tiled loads (SWIZZLE_128B) of the query tile A [128 x 32] and the
+//               panel tile B [256 x 32] fp32 per k-block into a kStages-deep shared-memory ring
+//   warp 1      TMEM allocator + MMA issuer: one elected lane issues 4 x tcgen05.mma (M128 N256 K8)
+//               per k-block into one of two 256-column accumulator stages; tcgen05.commit frees
+//               the smem slot / publishes the accumulator
+//   warps 2..5  epilogue: thread = query row (TMEM lane); tcgen05.ld 32 columns at a time,
+//               d = fma(-2, acc, qn + rn), clamp, running register top-k on (float bits, id)
+// A CTA owns one 128-query tile and a contiguous range of panel tiles, so the running top-k
+// stays in registers across tiles; partial results go to a [nq][nsplit][kt] key buffer that
+// merge_keys_kernel reduces (same total order as everywhere else).
+//
+// Precision: operands are fp32 bit patterns read as tf32 (10-bit mantissa).  Mode TF32X3 feeds
+// the hi/lo split  A' = [q_hi | q_lo | q_hi],  B' = [r_hi | r_hi | r_lo]  so that one GEMM over
+// K' = 3d yields q_hi.r_hi + q_lo.r_hi + q_hi.r_lo (fp32-faithful: the dropped lo.lo term and
+// the truncation of lo are both ~2^-22 relative).  Small-integer inputs (tokens, genotypes) are
+// exact in either mode.
+#include <cuda.h>
+
+#include <mutex>
+
 #include "common.cuh"
 #include "kernels.cuh"
+#include "topk.cuh"
+
 namespace snv {
-size_t l2_plan(L2SearchParams&) { set_error("L2 path not built"); return (size_t)-1; }
-int l2_launch(const L2SearchParams&, cudaStream_t) { set_error("L2 path not built"); return SNV_ERR_UNSUPPORTED; }
-int l2_prep_launch(const float*, int64_t, int64_t, int, bool, int, float*, float*, cudaStream_t) { set_error("L2 path not built"); return SNV_ERR_UNSUPPORTED; }
-int l2_operand_depth(int64_t d, int mode) { int64_t k = mode == SNV_L2_TF32X3 ? 3 * d : d; return (int)((k + 31) / 32 * 32); }
+
+namespace {
+
+constexpr int BM = 128;        // queries per CTA tile (TMEM lanes)
+constexpr int BN = 256;        // panel rows per MMA tile (TMEM columns per accumulator stage)
+constexpr int BK = 32;         // fp32 elements per k-block = one 128-byte swizzle row
+constexpr int UMMA_K = 8;      // tf32: 32 bytes per MMA
+constexpr int kStages = 4;
+constexpr int kAccStages = 2;
+constexpr int kTmemCols = kAccStages * BN;  // 512
+constexpr int kThreads = 192;
+constexpr uint32_t kABytes = BM * BK * 4;   // 16 KB
+constexpr uint32_t kBBytes = BN * BK * 4;   // 32 KB
+constexpr uint32_t kStageBytes = kABytes + kBBytes;
+constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + 2 * BN * 4 /*rn*/ + 256 /*barriers*/;
+
+// ---- PTX wrappers -----------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
 }
+
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map)
+{
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t cols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T, tf32 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+// K-major operand tile, rows of 128 bytes, SWIZZLE_128B (what the TMA wrote):
+// start address >> 4 | LBO (ignored for swizzled K-major; 1) << 16 | SBO = 1024 B (8 rows) >> 4 << 32
+// | descriptor version 1 (Blackwell) << 46 | layout type SWIZZLE_128B (2) << 61
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// kind::tf32 instruction descriptor: D fp32 (1 << 4), A = B = TF32 (2 << 7, 2 << 10), both
+// K-major (bits 15, 16 = 0), N >> 3 at bit 17, M >> 4 at bit 24
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n)
+{
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+template <int KT>
+__global__ void __launch_bounds__(kThreads, 1)
+l2_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_r,
+               const L2SearchParams p)
+{
+    extern __shared__ unsigned char smem_raw[];
+    // 1024-byte alignment for SWIZZLE_128B tiles
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    unsigned char* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+    unsigned char* tiles = smem;
+    float* rn_s = reinterpret_cast<float*>(smem + (size_t)kStages * kStageBytes);  // [2][BN]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * kStageBytes + 2 * BN * 4);
+    uint64_t* full_bar = bars;                          // [kStages]   TMA -> MMA
+    uint64_t* empty_bar = bars + kStages;               // [kStages]   MMA -> TMA
+    uint64_t* tmem_full = bars + 2 * kStages;           // [2]         MMA -> epilogue
+    uint64_t* tmem_empty = bars + 2 * kStages + 2;      // [2]         epilogue -> MMA
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    const int split = blockIdx.x % p.nsplit;
+    const int mt = blockIdx.x / p.nsplit;
+    const int n_tiles_total = (int)((p.n + BN - 1) / BN);
+    const int t0 = split * p.tiles_per_split;
+    const int t1 = (t0 + p.tiles_per_split < n_tiles_total) ? t0 + p.tiles_per_split : n_tiles_total;
+    const int my_tiles = t1 - t0;  // >= 1 by construction of the plan
+    const int num_kb = p.kp / BK;
+    const int m0 = mt * BM;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&map_q);
+        prefetch_tensormap(&map_r);
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < kAccStages; ++s) {
+            mbar_init(&tmem_full[s], 1);
+            mbar_init(&tmem_empty[s], 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = 0; t < my_tiles; ++t) {
+                const int n0 = (t0 + t) * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    unsigned char* a_dst = tiles + (size_t)stage * kStageBytes;
+                    unsigned char* b_dst = a_dst + kABytes;
+                    mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+                    tma_load_2d(a_dst, &map_q, kb * BK, m0, &full_bar[stage]);
+                    tma_load_2d(b_dst, &map_r, kb * BK, n0, &full_bar[stage]);
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = 0; t < my_tiles; ++t) {
+            const int as = t & 1;
+            const uint32_t acc_phase = (uint32_t)(t >> 1) & 1u;
+            mbar_wait(&tmem_empty[as], acc_phase ^ 1u);
+            tcgen05_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
+                tcgen05_fence_after();
+                if (elect_one()) {
+                    const uint32_t a_addr = smem_u32(tiles + (size_t)stage * kStageBytes);
+                    const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t adesc = make_kmajor_sw128_desc(a_addr + k * UMMA_K * 4);
+                        const uint64_t bdesc = make_kmajor_sw128_desc(b_addr + k * UMMA_K * 4);
+                        umma_tf32(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);                   // smem slot reusable once read
+                    if (kb == num_kb - 1) umma_commit(&tmem_full[as]);  // accumulator complete
+                }
+                __syncwarp();
+                if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else {
+        // ================= epilogue: thread = query row =================
+        const int quarter = warp & 3;              // TMEM lanes [32*quarter, 32*quarter + 32)
+        const int row = quarter * 32 + lane;       // row inside the 128-query tile
+        const int et = (warp - 2) * 32 + lane;     // 0..127 among the epilogue threads
+        const int64_t q = (int64_t)m0 + row;
+        const bool active = q < p.nq;
+        const float qn = active ? p.q_norm[q] : 0.f;
+        uint64_t best[KT];
+#pragma unroll
+        for (int i = 0; i < KT; ++i) best[i] = kSent64;
+        float worst = 3.4028234663852886e38f;
+        for (int t = 0; t < my_tiles; ++t) {
+            const int as = t & 1;
+            const uint32_t acc_phase = (uint32_t)(t >> 1) & 1u;
+            const int n0 = (t0 + t) * BN;
+            // stage this tile's |r|^2 (2 per thread), visible to the 128 epilogue threads
+            float* rn = rn_s + as * BN;
+#pragma unroll
+            for (int j = 0; j < BN / 128; ++j) {
+                const int c = et + j * 128;
+                rn[c] = (n0 + c < p.n) ? p.ref_norm[n0 + c] : 0.f;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(&tmem_full[as], acc_phase);
+            tcgen05_fence_after();
+            const int ncols = (p.n - n0 < BN) ? (int)(p.n - n0) : BN;
+            for (int c0 = 0; c0 < ncols; c0 += 32) {
+                uint32_t acc[32];
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + c0), acc);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int c = c0 + j;
+                    float d = fmaf(-2.f, __uint_as_float(acc[j]), qn + rn[c]);
+                    d = d < 0.f ? 0.f : d;
+                    if (c < ncols && d < worst) {
+                        // ids ascend along the scan, so on equal distance the earlier id stays
+                        const uint64_t key = ((uint64_t)__float_as_uint(d) << 32) | (uint64_t)(uint32_t)(n0 + c);
+                        topk_insert<KT, uint64_t>(best, key);
+                        worst = __uint_as_float((uint32_t)(best[KT - 1] >> 32));
+                        if (best[KT - 1] == kSent64) worst = 3.4028234663852886e38f;
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            mbar_arrive(&tmem_empty[as]);
+        }
+        if (active) {
+            uint64_t* out = p.partial + ((int64_t)q * p.nsplit + split) * KT;
+#pragma unroll
+            for (int i = 0; i < KT; ++i) out[i] = best[i];
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ---- operand preparation: one warp per row -----------------------------------------------
+__global__ void __launch_bounds__(256)
+l2_prep_kernel(const float* __restrict__ x, int64_t rows, int64_t d, int mode, bool is_query, int kp,
+               float* __restrict__ ops, float* __restrict__ norms)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < rows; r += nwarps) {
+        const float* xr = x + r * d;
+        float* o = ops + r * kp;
+        float acc = 0.f;
+        for (int64_t c = lane; c < d; c += 32) {
+            const float v = xr[c];
+            acc = fmaf(v, v, acc);
+            if (mode == SNV_L2_TF32X3) {
+                const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+                const float lo = v - hi;
+                o[c] = hi;
+                o[d + c] = is_query ? lo : hi;
+                o[2 * d + c] = is_query ? hi : lo;
+            } else {
+                o[c] = v;
+            }
+        }
+        const int64_t used = (mode == SNV_L2_TF32X3) ? 3 * d : d;
+        for (int64_t c = used + lane; c < kp; c += 32) o[c] = 0.f;
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+        if (lane == 0) norms[r] = acc;
+    }
+}
+
+// ---- host: tensor maps ---------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    });
+    return fn;
+}
+
+int make_map(CUtensorMap* map, const float* base, int64_t rows, int kp, int box_rows)
+{
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return SNV_ERR_CUDA;
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)kp, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)kp * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+        return SNV_ERR_CUDA;
+    }
+    return SNV_OK;
+}
+
+}  // namespace
+
+int l2_operand_depth(int64_t d, int mode)
+{
+    const int64_t k = mode == SNV_L2_TF32X3 ? 3 * d : d;
+    return (int)round_up(k, BK);
+}
+
+int l2_prep_launch(const float* x, int64_t rows, int64_t d, int mode, bool is_query, int kp, float* ops,
+                   float* norms, cudaStream_t stream)
+{
+    if (rows <= 0) return SNV_OK;
+    const int block = 256;
+    int64_t grid = ceil_div(rows, block / 32);
+    if (grid > (int64_t)kNumSMs * 16) grid = (int64_t)kNumSMs * 16;
+    l2_prep_kernel<<<(unsigned)grid, block, 0, stream>>>(x, rows, d, mode, is_query, kp, ops, norms);
+    SNV_LAUNCH_CHECK();
+    return SNV_OK;
+}
+
+size_t l2_plan(L2SearchParams& p)
+{
+    if (p.k < 1 || p.k > 32) {
+        set_error("L2 search: k must be in [1, 32] (got " + std::to_string(p.k) + ")");
+        return (size_t)-1;
+    }
+    if (p.n >= ((int64_t)1 << 32)) {
+        set_error("L2 search: panel too large for 32-bit ids; shard rows");
+        return (size_t)-1;
+    }
+    p.kt = p.k <= 8 ? 8 : 32;
+    const int64_t n_tiles = p.n > 0 ? ceil_div(p.n, BN) : 0;
+    const int64_t m_tiles = ceil_div(p.nq, BM);
+    // pick the row split that minimises (waves x tiles per CTA): one CTA per SM is resident
+    int best_s = 1;
+    int64_t best_cost = -1;
+    for (int s = 1; s <= n_tiles && s <= 64; ++s) {
+        const int64_t per = ceil_div(n_tiles, s);
+        const int64_t real_s = ceil_div(n_tiles, per);
+        const int64_t waves = ceil_div(m_tiles * real_s, kNumSMs);
+        const int64_t cost = waves * (per * 8 + 1);  // +1: fixed prologue/epilogue weight per CTA
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_s = (int)real_s; }
+    }
+    p.nsplit = n_tiles > 0 ? best_s : 1;
+    p.tiles_per_split = n_tiles > 0 ? (int)ceil_div(n_tiles, p.nsplit) : 0;
+    p.nsplit = n_tiles > 0 ? (int)ceil_div(n_tiles, p.tiles_per_split) : 1;
+    return (size_t)p.nq * p.nsplit * p.kt * sizeof(uint64_t);
+}
+
+int l2_launch(const L2SearchParams& p, cudaStream_t stream)
+{
+    if (p.nq <= 0) return SNV_OK;
+    if (p.n <= 0) {
+        // empty panel: everything is padding
+        SNV_CUDA_CHECK(cudaMemsetAsync(p.partial, 0xFF, (size_t)p.nq * p.kt * 8, stream));
+        return merge_keys_launch(p.partial, 1, p.kt, p.nq, p.k, p.id_offset, true, nullptr, p.D_f32, p.I, stream);
+    }
+    CUtensorMap map_q, map_r;
+    int rc = make_map(&map_q, p.q_ops, p.nq, p.kp, BM);
+    if (rc) return rc;
+    rc = make_map(&map_r, p.ref_ops, p.n, p.kp, BN);
+    if (rc) return rc;
+    const int64_t m_tiles = ceil_div(p.nq, BM);
+    const unsigned grid = (unsigned)(m_tiles * p.nsplit);
+    if (p.kt == 8) {
+        static bool attr8 = false;
+        if (!attr8) {
+            SNV_CUDA_CHECK(cudaFuncSetAttribute(l2_topk_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+            attr8 = true;
+        }
+        l2_topk_kernel<8><<<grid, kThreads, kSmemBytes, stream>>>(map_q, map_r, p);
+    } else {
+        static bool attr32 = false;
+        if (!attr32) {
+            SNV_CUDA_CHECK(cudaFuncSetAttribute(l2_topk_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+            attr32 = true;
+        }
+        l2_topk_kernel<32><<<grid, kThreads, kSmemBytes, stream>>>(map_q, map_r, p);
+    }
+    SNV_LAUNCH_CHECK();
+    return merge_keys_launch(p.partial, p.nsplit, p.kt, p.nq, p.k, p.id_offset, true, nullptr, p.D_f32, p.I, stream);
+}
+
+}  // namespace snv

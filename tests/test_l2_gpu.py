@@ -1,0 +1,215 @@
+"""GPU parity: tcgen05 squared-L2 search (through the C ABI) vs the CPU oracle.
+
+Tolerances (stated, DESIGN.md "Parity"):
+  * integer-valued inputs (0/1 genotypes, V17 token vectors): D and I bit-exact in both modes.
+  * general fp32 inputs, mode tf32x3: |D - D_f64| <= 2e-6 * (|q|^2 + |r|^2);
+    mode tf32: |D - D_f64| <= 2e-3 * (|q|^2 + |r|^2).
+  * ids equal the float64 ranking except where the float64 distances of the two candidates
+    differ by less than twice that tolerance (ties inside the tolerance).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = {"tf32x3": 2e-6, "tf32": 2e-3}
+
+
+def _l2(d, precision="tf32x3", W=1):
+    from rag_snvbert_b200 import WindowedL2Index
+
+    return WindowedL2Index(d, W, None, precision)
+
+
+def _check_float(refs, q, k, precision):
+    idx = _l2(refs.shape[1], precision)
+    idx.add(refs)
+    assert idx.ntotal == refs.shape[0]
+    D, I = idx.search(q, k)
+    assert D.dtype == np.float32 and I.dtype == np.int64 and D.shape == (q.shape[0], k)
+    d64 = O.l2_matrix_f64(refs, q)
+    D64, I64 = O._topk_lex(d64, k, np.float64(O.F32_MAX))
+    qn = (q.astype(np.float64) ** 2).sum(1)
+    rn_max = (refs.astype(np.float64) ** 2).sum(1).max()
+    tol = TOL[precision] * (qn + rn_max)
+    valid = I >= 0
+    got = np.take_along_axis(d64, np.where(valid, I, 0), axis=1)
+    # distances returned vs float64 distances OF THE RETURNED ROWS
+    assert (np.abs(D.astype(np.float64) - got)[valid] <= np.broadcast_to(tol[:, None], D.shape)[valid]).all(), \
+        f"max |dD| = {np.abs(D - got)[valid].max()} tol {tol.max()}"
+    assert (np.diff(D, axis=1) >= 0).all(), "D not ascending"
+    n_diff = O.assert_ids_match_within_tolerance(d64, I, I64, 2 * tol)
+    return D, I, n_diff
+
+
+@pytest.mark.parametrize("precision", ["tf32x3", "tf32"])
+def test_cfg4_shape_gaussian(precision):
+    rng = np.random.default_rng(4001)
+    refs = rng.standard_normal((5008, 256)).astype(np.float32)
+    q = np.random.default_rng(4002).standard_normal((4096, 256)).astype(np.float32)
+    D, I, n_diff = _check_float(refs, q, 8, precision)
+    if precision == "tf32x3":
+        assert n_diff <= 4  # fp32-faithful: essentially the float64 ranking
+
+
+def test_cfg4_clustered_near_ties():
+    rng = np.random.default_rng(4003)
+    cent = rng.standard_normal((64, 256)).astype(np.float32)
+    refs = (cent[rng.integers(0, 64, 5008)] + 0.05 * rng.standard_normal((5008, 256))).astype(np.float32)
+    q = (cent[rng.integers(0, 64, 1000)] + 0.05 * rng.standard_normal((1000, 256))).astype(np.float32)
+    _check_float(refs, q, 8, "tf32x3")
+
+
+@pytest.mark.parametrize("n,nq,d,k", [(1000, 200, 256, 8), (300, 5, 100, 3), (257, 129, 33, 8), (256, 128, 32, 1),
+                                       (77, 300, 64, 32), (3, 10, 16, 8), (2500, 64, 1000, 16)])
+def test_ragged_shapes(n, nq, d, k):
+    rng = np.random.default_rng(n + nq + d)
+    refs = rng.standard_normal((n, d)).astype(np.float32)
+    q = rng.standard_normal((nq, d)).astype(np.float32)
+    D, I, _ = _check_float(refs, q, k, "tf32x3")
+    if n < k:
+        assert (I[:, n:] == -1).all() and (D[:, n:] == O.F32_MAX).all()
+
+
+@pytest.mark.parametrize("precision", ["tf32x3", "tf32"])
+def test_cfg1_binary_float_rows_exact(precision):
+    """BASELINE cfg 1 (batch_test_faiss_l2.py path): float 0/1 panel 5008 x 1030, 1000 queries, k=1."""
+    panel = O.hapgen(1001, 5008, 1030).astype(np.float32)
+    q = O.hapgen(1002, 1000, 1030, founder_seed=1001).astype(np.float32)
+    idx = _l2(1030, precision)
+    idx.add(panel)
+    D, I = idx.search(q, 1)
+    De, Ie = O.hamming_topk(panel, q, 1)
+    np.testing.assert_array_equal(I, Ie)
+    np.testing.assert_array_equal(D, De.astype(np.float32))
+    D8, I8 = idx.search(q[:300], 8)
+    De, Ie = O.hamming_topk(panel, q[:300], 8)
+    np.testing.assert_array_equal(I8, Ie)
+    np.testing.assert_array_equal(D8, De.astype(np.float32))
+
+
+@pytest.mark.parametrize("precision", ["tf32x3", "tf32"])
+def test_v17_token_vectors_exact_with_different_masks(precision):
+    """IndexFlatL2(1030) on tokenised rows (rag_train_dataset.py:132-134,281) where query and panel
+    masks DIFFER (dynamic mask / epoch 0): pair costs (4,5)->1, (4,6)->4, (5,6)->1 — still exact."""
+    rng = np.random.default_rng(17)
+    lw = 1000
+    pm = O.sequence_padding((rng.random(lw) < 0.3).astype(np.int64))
+    qm = O.sequence_padding((rng.random(lw) < 0.3).astype(np.int64))
+    ptok = O.tokenize(O.hapgen(171, 2008, lw), pm)
+    qtok = O.tokenize(O.hapgen(172, 64, lw, founder_seed=171), qm)
+    idx = _l2(O.MAX_SEQ_LEN, precision)
+    idx.add(ptok.astype(np.float32))
+    D, I = idx.search(qtok.astype(np.float32), 5)
+    De, Ie = O.token_l2_topk(ptok, qtok, 5)
+    np.testing.assert_array_equal(I, Ie)
+    np.testing.assert_array_equal(D, De)
+
+
+def test_golden_g2_v17_collate_through_faiss_compat():
+    """The reference's own collate outputs (tests/golden/g2): index side via faiss_compat.IndexFlatL2,
+    gather via the Hamming index's token gather."""
+    import rag_snvbert_b200.faiss_compat as faiss
+    from rag_snvbert_b200 import IndexHamming
+
+    g = np.load(os.path.join(G, "g2_v17_collate.npz"))
+    k, lw = int(g["k"]), int(g["lw"])
+    h1, h2 = [], []
+    for w in range(2):
+        index = faiss.IndexFlatL2(O.MAX_SEQ_LEN)
+        index.add(g[f"ref_tokenized_{w}"].astype(np.float32))
+        D, I = index.search(g[f"search_q_{w}"], k)
+        np.testing.assert_array_equal(I, g[f"search_I_{w}"])
+        np.testing.assert_array_equal(D, g[f"search_D_{w}"])
+        rows = O.panel_rows_from_gt(g[f"ref_gt_{w}"]).astype(np.uint8)
+        hidx = IndexHamming(lw)
+        hidx.add(rows)
+        # token rows straight into the bit-packed index give the same neighbours
+        Dh, Ih = hidx.search((g[f"search_q_{w}"][:, 1:1 + lw] == 6).astype(np.uint8), k,
+                             missing=g[f"raw_mask_{w}"].astype(np.uint8), dist_dtype=np.float32)
+        np.testing.assert_array_equal(Ih, I)
+        np.testing.assert_array_equal(Dh, D)
+        seg = hidx.gather_tokens(I, n_sites=lw)
+        h1.append(seg[0::2])
+        h2.append(seg[1::2])
+    np.testing.assert_array_equal(np.concatenate(h1), g["rag_seg_h1"])
+    np.testing.assert_array_equal(np.concatenate(h2), g["rag_seg_h2"])
+
+
+def test_golden_g4_v18_embedding_search_and_gather():
+    g = np.load(os.path.join(G, "g4_v18_embedding.npz"))
+    k = int(g["k"])
+    ref = np.ascontiguousarray(g["ref_flat"])
+    idx = _l2(ref.shape[1])
+    idx.add(ref)
+    comp = np.ascontiguousarray(g["ref_complete"].reshape(ref.shape[0], -1))
+    cidx = _l2(comp.shape[1])
+    cidx.add(comp)
+    for qn, In, out in (("q1_flat", "I1", "rag_emb_h1"), ("q2_flat", "I2", "rag_emb_h2")):
+        q = np.ascontiguousarray(g[qn])
+        D, I = idx.search(q, k)
+        d64 = O.l2_matrix_f64(ref, q)
+        tol = 2e-6 * ((q.astype(np.float64) ** 2).sum(1) + (ref.astype(np.float64) ** 2).sum(1).max())
+        O.assert_ids_match_within_tolerance(d64, I, g[In], 2 * tol)
+        rows = cidx.gather_rows(np.ascontiguousarray(g[In]))
+        np.testing.assert_array_equal(rows.reshape(g[out].shape), g[out])
+
+
+def test_faiss_compat_write_read_roundtrip(tmp_path):
+    import rag_snvbert_b200.faiss_compat as faiss
+
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((500, 96)).astype(np.float32)
+    q = rng.standard_normal((20, 96)).astype(np.float32)
+    index = faiss.IndexFlatL2(96)
+    index.add(x)
+    D, I = index.search(q, 4)
+    faiss.write_index(index, str(tmp_path / "w.faiss"))
+    again = faiss.read_index(str(tmp_path / "w.faiss"))
+    assert again.ntotal == 500 and again.d == 96
+    D2, I2 = again.search(q, 4)
+    np.testing.assert_array_equal(I, I2)
+    np.testing.assert_array_equal(D, D2)
+    res = faiss.StandardGpuResources()
+    assert faiss.index_cpu_to_gpu(res, 0, again) is again
+    with pytest.raises(AssertionError):
+        index.add(np.zeros((3, 95), np.float32))
+    b = faiss.IndexBinaryFlat(64)
+    b.add(rng.integers(0, 256, (50, 8), dtype=np.uint8))
+    faiss.write_index(b, str(tmp_path / "b.faiss"))
+    b2 = faiss.read_index(str(tmp_path / "b.faiss"))
+    qq = rng.integers(0, 256, (5, 8), dtype=np.uint8)
+    np.testing.assert_array_equal(b.search(qq, 3)[1], b2.search(qq, 3)[1])
+
+
+def test_torch_cuda_tensors_and_cdist_agreement():
+    """zero-copy device path, and agreement with the reference's live GPU path (torch.cdist+topk)."""
+    import torch
+
+    torch.manual_seed(0)
+    refs = torch.randn(2008, 512, device="cuda")
+    q = torch.randn(48, 512, device="cuda")
+    idx = _l2(512)
+    idx.add(refs)
+    D, I = idx.search(q, 4)
+    assert D.is_cuda and I.is_cuda
+    d64 = O.l2_matrix_f64(refs.cpu().numpy(), q.cpu().numpy())
+    _, Iref = torch.cdist(q, refs, p=2).topk(4, largest=False, dim=1)
+    tol = 2e-6 * (float((q ** 2).sum(1).max()) + float((refs ** 2).sum(1).max()))
+    O.assert_ids_match_within_tolerance(d64, I.cpu().numpy(), Iref.cpu().numpy(), 4 * tol)
+
+
+def test_multi_window_l2():
+    rng = np.random.default_rng(8)
+    refs = rng.standard_normal((3, 400, 64)).astype(np.float32)
+    q = rng.standard_normal((3, 50, 64)).astype(np.float32)
+    idx = _l2(64, W=3)
+    idx.add(refs)
+    D, I = idx.search(q, 5)
+    for w in range(3):
+        D64, I64 = O.l2_topk_f64(refs[w], q[w], 5)
+        np.testing.assert_array_equal(I[w], I64)
