@@ -114,6 +114,12 @@ struct snv_index {
     float* ops = nullptr;       // L2 [W][cap][kp]
     float* norms = nullptr;     // L2 [W][cap]
     Buf ws_in, ws_q, ws_mask, ws_min, ws_partial, ws_di, ws_df, ws_i, ws_qops, ws_qnorm, ws_misc;
+    // host-buffer pipeline
+    static constexpr int kPipeStreams = 3;
+    bool pipe_ready = false;
+    cudaStream_t pipe_stream[kPipeStreams] = {};
+    cudaEvent_t pipe_done[kPipeStreams] = {};
+    cudaEvent_t pipe_start = nullptr;
 };
 
 extern "C" {
@@ -188,6 +194,13 @@ void snv_index_free(snv_index* idx)
     Buf* bufs[] = {&idx->ws_in, &idx->ws_q, &idx->ws_mask, &idx->ws_min, &idx->ws_partial, &idx->ws_di,
                    &idx->ws_df, &idx->ws_i, &idx->ws_qops, &idx->ws_qnorm, &idx->ws_misc};
     for (Buf* b : bufs) b->release();
+    if (idx->pipe_ready) {
+        for (int i = 0; i < snv_index::kPipeStreams; ++i) {
+            cudaStreamDestroy(idx->pipe_stream[i]);
+            cudaEventDestroy(idx->pipe_done[i]);
+        }
+        cudaEventDestroy(idx->pipe_start);
+    }
     delete idx;
 }
 
@@ -308,36 +321,46 @@ int snv_index_add(snv_index* idx, const void* x, int64_t n, int dtype, unsigned 
     return SNV_OK;
 }
 
-// stage `src` ([rows][row_bytes], host or device) as packed rows in `ws`; returns device ptr
+// Stage `rows` rows starting at `src` (host or device, `dtype`) as packed rows.  `raw_dst` /
+// `packed_dst` are pre-reserved device slices (nullptr when not needed).  Returns the device
+// pointer of the packed rows in *out.
 static int stage_packed(snv_index* idx, const void* src, int64_t rows, int dtype, bool on_dev, bool invert,
-                        Buf& ws_raw, Buf& ws_packed, const uint32_t** out, uint32_t* obs_out,
+                        void* raw_dst, uint32_t* packed_dst, const uint32_t** out, uint32_t* obs_out,
                         cudaStream_t stream)
 {
     const size_t in_row = dtype_row_bytes(dtype, idx->d, idx->stride);
-    if (in_row == 0) { set_error("search: bad dtype"); return SNV_ERR_INVALID; }
     const void* xd = src;
     if (!on_dev) {
-        int rc = ws_raw.reserve((size_t)rows * in_row);
-        if (rc) return rc;
-        SNV_CUDA_CHECK(cudaMemcpyAsync(ws_raw.p, src, (size_t)rows * in_row, cudaMemcpyHostToDevice, stream));
-        xd = ws_raw.p;
+        SNV_CUDA_CHECK(cudaMemcpyAsync(raw_dst, src, (size_t)rows * in_row, cudaMemcpyHostToDevice, stream));
+        xd = raw_dst;
     }
     if (dtype == SNV_DT_PACKED_U32 && !invert) {
         *out = (const uint32_t*)xd;
         return SNV_OK;
     }
-    int rc = ws_packed.reserve((size_t)rows * idx->stride * 4);
-    if (rc) return rc;
     if (dtype == SNV_DT_PACKED_U32) {
         const int block = 256;
         const int grid = (int)std::min<int64_t>(ceil_div(rows * idx->stride, block), (int64_t)kNumSMs * 16);
-        invert_packed_kernel<<<grid, block, 0, stream>>>((const uint32_t*)xd, rows, idx->d, idx->stride, (uint32_t*)ws_packed.p);
+        invert_packed_kernel<<<grid, block, 0, stream>>>((const uint32_t*)xd, rows, idx->d, idx->stride, packed_dst);
         SNV_LAUNCH_CHECK();
     } else {
-        rc = pack_launch(xd, rows, idx->d, dtype, invert, idx->stride, (uint32_t*)ws_packed.p, obs_out, stream);
+        int rc = pack_launch(xd, rows, idx->d, dtype, invert, idx->stride, packed_dst, obs_out, stream);
         if (rc) return rc;
     }
-    *out = (const uint32_t*)ws_packed.p;
+    *out = packed_dst;
+    return SNV_OK;
+}
+
+// Internal streams for the host-buffer pipeline (H2D of chunk i+1 | scan of chunk i | D2H of chunk i-1)
+static int ensure_pipe(snv_index* idx)
+{
+    if (idx->pipe_ready) return SNV_OK;
+    for (int i = 0; i < snv_index::kPipeStreams; ++i) {
+        SNV_CUDA_CHECK(cudaStreamCreateWithFlags(&idx->pipe_stream[i], cudaStreamNonBlocking));
+        SNV_CUDA_CHECK(cudaEventCreateWithFlags(&idx->pipe_done[i], cudaEventDisableTiming));
+    }
+    SNV_CUDA_CHECK(cudaEventCreateWithFlags(&idx->pipe_start, cudaEventDisableTiming));
+    idx->pipe_ready = true;
     return SNV_OK;
 }
 
@@ -347,73 +370,135 @@ static int search_hamming(snv_index* idx, int w0, int nw, const void* q, int64_t
 {
     const bool q_dev = flags & SNV_Q_ON_DEVICE;
     const bool out_dev = flags & SNV_OUT_ON_DEVICE;
+    const bool invert = flags & SNV_MASK_IS_MISSING;
     const int64_t nqt = (int64_t)nw * nq;
-
-    HammingSearchParams p{};
-    p.panel = idx->panel + (int64_t)w0 * idx->cap * idx->stride;
-    p.panel_win_stride = idx->cap * idx->stride;
-    p.words = idx->words;
-    p.stride = idx->stride;
-    p.d = (int)idx->d;
-    p.n = idx->ntotal;
-    p.nq = (int)nq;
-    p.nw = nw;
-    p.k = k;
-    p.id_offset = id_offset;
-
-    // queries (tokens also yield the observed-site plane)
-    const uint32_t* qd = nullptr;
-    uint32_t* obs = nullptr;
-    if (q_dtype == SNV_DT_I64_TOKENS) {
-        if (mask_mode != SNV_MASK_NONE) { set_error("search: token queries carry their own mask"); return SNV_ERR_INVALID; }
-        int rc = idx->ws_mask.reserve((size_t)nqt * idx->stride * 4);
-        if (rc) return rc;
-        obs = (uint32_t*)idx->ws_mask.p;
-    }
-    int rc = stage_packed(idx, q, nqt, q_dtype, q_dev, false, idx->ws_in, idx->ws_q, &qd, obs, stream);
-    if (rc) return rc;
-    p.q = qd;
-    if (obs) {
-        p.mask = obs;
-        p.mask_win_stride = nq * idx->stride;
-        p.mask_q_stride = idx->stride;
-    } else if (mask_mode != SNV_MASK_NONE) {
+    const size_t row_b = (size_t)idx->stride * 4;
+    const bool tokens = q_dtype == SNV_DT_I64_TOKENS;
+    if (dtype_row_bytes(q_dtype, idx->d, idx->stride) == 0) { set_error("search: bad dtype"); return SNV_ERR_INVALID; }
+    if (tokens && mask_mode != SNV_MASK_NONE) { set_error("search: token queries carry their own mask"); return SNV_ERR_INVALID; }
+    if (mask_mode != SNV_MASK_NONE) {
         if (!mask) { set_error("search: mask_mode set but mask is null"); return SNV_ERR_INVALID; }
         if (q_dtype == SNV_DT_PACKED_U8) { set_error("search: masks are not supported with byte-packed codes"); return SNV_ERR_INVALID; }
-        const int64_t mrows = mask_mode == SNV_MASK_PER_WINDOW ? nw : nqt;
-        const uint32_t* md = nullptr;
-        rc = stage_packed(idx, mask, mrows, q_dtype, q_dev, flags & SNV_MASK_IS_MISSING, idx->ws_min, idx->ws_mask, &md, nullptr, stream);
-        if (rc) return rc;
-        p.mask = md;
-        p.mask_win_stride = mask_mode == SNV_MASK_PER_WINDOW ? idx->stride : nq * idx->stride;
-        p.mask_q_stride = mask_mode == SNV_MASK_PER_WINDOW ? 0 : idx->stride;
     }
+    const size_t in_row = dtype_row_bytes(q_dtype, idx->d, idx->stride);
+    const bool q_needs_pack = q_dtype != SNV_DT_PACKED_U32;
+    const bool m_needs_pack = mask_mode != SNV_MASK_NONE && (q_dtype != SNV_DT_PACKED_U32 || invert);
+    const int64_t mrows_total = mask_mode == SNV_MASK_PER_WINDOW ? nw : (mask_mode == SNV_MASK_PER_QUERY ? nqt : 0);
 
-    // outputs
-    if (out_dev) {
-        p.D_i32 = D_i32;
-        p.D_f32 = D_f32;
-        p.I = I;
-    } else {
-        if (D_i32) { rc = idx->ws_di.reserve((size_t)nqt * k * 4); if (rc) return rc; p.D_i32 = (int32_t*)idx->ws_di.p; }
-        if (D_f32) { rc = idx->ws_df.reserve((size_t)nqt * k * 4); if (rc) return rc; p.D_f32 = (float*)idx->ws_df.p; }
+    // ---- reserve every workspace up front (nothing is reallocated while chunks are in flight)
+    int rc;
+    if (!q_dev) { rc = idx->ws_in.reserve((size_t)nqt * in_row); if (rc) return rc; }
+    if (q_needs_pack) { rc = idx->ws_q.reserve((size_t)nqt * row_b); if (rc) return rc; }
+    if (tokens) { rc = idx->ws_mask.reserve((size_t)nqt * row_b); if (rc) return rc; }
+    if (mask_mode != SNV_MASK_NONE) {
+        if (!q_dev) { rc = idx->ws_min.reserve((size_t)mrows_total * in_row); if (rc) return rc; }
+        if (m_needs_pack) { rc = idx->ws_mask.reserve((size_t)mrows_total * row_b); if (rc) return rc; }
+    }
+    if (!out_dev) {
+        if (D_i32) { rc = idx->ws_di.reserve((size_t)nqt * k * 4); if (rc) return rc; }
+        if (D_f32) { rc = idx->ws_df.reserve((size_t)nqt * k * 4); if (rc) return rc; }
         rc = idx->ws_i.reserve((size_t)nqt * k * 8);
         if (rc) return rc;
-        p.I = (int64_t*)idx->ws_i.p;
     }
-    const size_t part = hamming_plan(p);
-    if (part == (size_t)-1) return SNV_ERR_UNSUPPORTED;
-    if (part) {
-        rc = idx->ws_partial.reserve(part);
+
+    // ---- chunking: host buffers are pipelined over internal streams, window chunk by window chunk
+    int chunk_w = nw;
+    if ((!q_dev || !out_dev) && nw >= 8) chunk_w = (int)ceil_div(nw, 16);
+    auto make_params = [&](int wb, int wc, HammingSearchParams& p) {
+        p = HammingSearchParams{};
+        p.panel = idx->panel + (int64_t)(w0 + wb) * idx->cap * idx->stride;
+        p.panel_win_stride = idx->cap * idx->stride;
+        p.words = idx->words;
+        p.stride = idx->stride;
+        p.d = (int)idx->d;
+        p.n = idx->ntotal;
+        p.nq = (int)nq;
+        p.nw = wc;
+        p.k = k;
+        p.id_offset = id_offset;
+        p.mask = mask_mode != SNV_MASK_NONE || tokens ? (const uint32_t*)1 : nullptr;  // plan only needs null-ness
+    };
+    {
+        HammingSearchParams probe;
+        make_params(0, chunk_w, probe);
+        const size_t part = hamming_plan(probe);
+        if (part == (size_t)-1) return SNV_ERR_UNSUPPORTED;
+        if (part != 0 && chunk_w != nw) {
+            chunk_w = nw;  // row-split plans share one partial buffer: run as a single chunk
+            make_params(0, nw, probe);
+        }
+        const size_t part_all = hamming_plan(probe);
+        if (part_all == (size_t)-1) return SNV_ERR_UNSUPPORTED;
+        if (part_all) { rc = idx->ws_partial.reserve(part_all); if (rc) return rc; }
+    }
+    const int nchunks = (int)ceil_div(nw, chunk_w);
+    const bool piped = nchunks > 1;
+    if (piped) {
+        rc = ensure_pipe(idx);
         if (rc) return rc;
-        p.partial = (uint64_t*)idx->ws_partial.p;
+        SNV_CUDA_CHECK(cudaEventRecord(idx->pipe_start, stream));
+        for (int i = 0; i < snv_index::kPipeStreams; ++i) SNV_CUDA_CHECK(cudaStreamWaitEvent(idx->pipe_stream[i], idx->pipe_start, 0));
     }
-    rc = hamming_launch(p, stream);
-    if (rc) return rc;
-    if (!out_dev) {
-        if (D_i32) SNV_CUDA_CHECK(cudaMemcpyAsync(D_i32, p.D_i32, (size_t)nqt * k * 4, cudaMemcpyDeviceToHost, stream));
-        if (D_f32) SNV_CUDA_CHECK(cudaMemcpyAsync(D_f32, p.D_f32, (size_t)nqt * k * 4, cudaMemcpyDeviceToHost, stream));
-        SNV_CUDA_CHECK(cudaMemcpyAsync(I, p.I, (size_t)nqt * k * 8, cudaMemcpyDeviceToHost, stream));
+
+    for (int c = 0; c < nchunks; ++c) {
+        const int wb = c * chunk_w;
+        const int wc = std::min(chunk_w, nw - wb);
+        const int64_t r0 = (int64_t)wb * nq, rows = (int64_t)wc * nq;
+        cudaStream_t cs = piped ? idx->pipe_stream[c % snv_index::kPipeStreams] : stream;
+        HammingSearchParams p;
+        make_params(wb, wc, p);
+        p.mask = nullptr;
+
+        const uint32_t* qd = nullptr;
+        uint32_t* obs = tokens ? (uint32_t*)idx->ws_mask.p + r0 * idx->stride : nullptr;
+        rc = stage_packed(idx, (const char*)q + (size_t)r0 * in_row, rows, q_dtype, q_dev, false,
+                          q_dev ? nullptr : (char*)idx->ws_in.p + (size_t)r0 * in_row,
+                          q_needs_pack ? (uint32_t*)idx->ws_q.p + r0 * idx->stride : nullptr, &qd, obs, cs);
+        if (rc) return rc;
+        p.q = qd;
+        if (tokens) {
+            p.mask = obs;
+            p.mask_win_stride = nq * idx->stride;
+            p.mask_q_stride = idx->stride;
+        } else if (mask_mode != SNV_MASK_NONE) {
+            const int64_t mr0 = mask_mode == SNV_MASK_PER_WINDOW ? wb : r0;
+            const int64_t mrows = mask_mode == SNV_MASK_PER_WINDOW ? wc : rows;
+            const uint32_t* md = nullptr;
+            rc = stage_packed(idx, (const char*)mask + (size_t)mr0 * in_row, mrows, q_dtype, q_dev, invert,
+                              q_dev ? nullptr : (char*)idx->ws_min.p + (size_t)mr0 * in_row,
+                              m_needs_pack ? (uint32_t*)idx->ws_mask.p + mr0 * idx->stride : nullptr, &md, nullptr, cs);
+            if (rc) return rc;
+            p.mask = md;
+            p.mask_win_stride = mask_mode == SNV_MASK_PER_WINDOW ? idx->stride : nq * idx->stride;
+            p.mask_q_stride = mask_mode == SNV_MASK_PER_WINDOW ? 0 : idx->stride;
+        }
+        const int64_t o0 = r0 * k;
+        if (out_dev) {
+            p.D_i32 = D_i32 ? D_i32 + o0 : nullptr;
+            p.D_f32 = D_f32 ? D_f32 + o0 : nullptr;
+            p.I = I + o0;
+        } else {
+            p.D_i32 = D_i32 ? (int32_t*)idx->ws_di.p + o0 : nullptr;
+            p.D_f32 = D_f32 ? (float*)idx->ws_df.p + o0 : nullptr;
+            p.I = (int64_t*)idx->ws_i.p + o0;
+        }
+        const size_t part = hamming_plan(p);
+        if (part == (size_t)-1) return SNV_ERR_UNSUPPORTED;
+        p.partial = part ? (uint64_t*)idx->ws_partial.p : nullptr;
+        rc = hamming_launch(p, cs);
+        if (rc) return rc;
+        if (!out_dev) {
+            const size_t cnt = (size_t)rows * k;
+            if (D_i32) SNV_CUDA_CHECK(cudaMemcpyAsync(D_i32 + o0, p.D_i32, cnt * 4, cudaMemcpyDeviceToHost, cs));
+            if (D_f32) SNV_CUDA_CHECK(cudaMemcpyAsync(D_f32 + o0, p.D_f32, cnt * 4, cudaMemcpyDeviceToHost, cs));
+            SNV_CUDA_CHECK(cudaMemcpyAsync(I + o0, p.I, cnt * 8, cudaMemcpyDeviceToHost, cs));
+        }
+    }
+    if (piped) {
+        for (int i = 0; i < snv_index::kPipeStreams; ++i) {
+            SNV_CUDA_CHECK(cudaEventRecord(idx->pipe_done[i], idx->pipe_stream[i]));
+            SNV_CUDA_CHECK(cudaStreamWaitEvent(stream, idx->pipe_done[i], 0));
+        }
     }
     if (!out_dev || !q_dev) SNV_CUDA_CHECK(cudaStreamSynchronize(stream));
     return SNV_OK;

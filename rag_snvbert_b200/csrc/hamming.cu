@@ -32,16 +32,25 @@ namespace {
 constexpr int kMaxBlock = 128;
 constexpr int kBarBytes = 128;  // smem reserved for the stage mbarriers
 
-// popcount of the multiset x[0..N): DEPTH levels of 3:2 compressors, then POPC.
-template <int N, int DEPTH>
+// acc + w * popc(x): the multiply-add goes to the FMA pipe (IMAD) because `w` is a runtime
+// register (1, 2 or 4 from the kernel parameters), keeping the saturated ALU pipe for LOP3 only.
+__device__ __forceinline__ uint32_t popc_mad(uint32_t x, uint32_t w, uint32_t acc)
+{
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"((uint32_t)__popc(x)), "r"(w), "r"(acc));
+    return r;
+}
+
+// acc + sum_i wt[LEVEL] * popcount(x[i]) over the multiset x[0..N): DEPTH levels of 3:2
+// carry-save compressors (carries move to weight level LEVEL+1), then POPC.
+template <int N, int DEPTH, int LEVEL>
 struct WeightedPopc {
-    static __device__ __forceinline__ uint32_t run(const uint32_t (&x)[N])
+    static __device__ __forceinline__ uint32_t run(const uint32_t (&x)[N], const uint32_t (&wt)[3], uint32_t acc)
     {
         if constexpr (DEPTH == 0 || N < 3) {
-            uint32_t s = 0;
 #pragma unroll
-            for (int i = 0; i < N; ++i) s += __popc(x[i]);
-            return s;
+            for (int i = 0; i < N; ++i) acc = popc_mad(x[i], wt[LEVEL], acc);
+            return acc;
         } else {
             constexpr int T = N / 3, R = N % 3;
             uint32_t sum[T + R], carry[T];
@@ -53,8 +62,8 @@ struct WeightedPopc {
             }
 #pragma unroll
             for (int r = 0; r < R; ++r) sum[T + r] = x[3 * T + r];
-            return WeightedPopc<T + R, DEPTH - 1>::run(sum) +
-                   2u * WeightedPopc<T, DEPTH - 1>::run(carry);
+            acc = WeightedPopc<T + R, DEPTH - 1, LEVEL>::run(sum, wt, acc);
+            return WeightedPopc<T, DEPTH - 1, LEVEL + 1>::run(carry, wt, acc);
         }
     }
 };
@@ -139,6 +148,8 @@ hamming_topk_kernel(const HammingSearchParams p)
     for (int i = 0; i < KT; ++i) best[i] = kSent32;
 
     const int idx_bits = p.idx_bits;
+    // popcount weights pre-scaled by 2^idx_bits (runtime values: see popc_mad)
+    const uint32_t wt[3] = {p.wt1 << idx_bits, p.wt2 << idx_bits, p.wt4 << idx_bits};
     for (int t = 0; t < ntiles; ++t) {
         if (tid == 0 && t + stages - 1 < ntiles) issue(t + stages - 1);
         mbar_wait(&bars[t % stages], (uint32_t)(t / stages) & 1u);
@@ -154,8 +165,8 @@ SNV_UNROLL(SNV_ROW_UNROLL)
                 if constexpr (MASKED) x[i] = (x[i] & m[i]) ^ q[i];  // == (r ^ q) & m, one LOP3
                 else                  x[i] ^= q[i];
             }
-            const uint32_t dist = WeightedPopc<NW, SNV_CSA_DEPTH>::run(x);
-            const uint32_t key = (dist << idx_bits) | (row_base + (uint32_t)j);
+            // key = dist * 2^idx_bits + row: one IMAD seeded with the row id
+            const uint32_t key = WeightedPopc<NW, SNV_CSA_DEPTH, 0>::run(x, wt, row_base + (uint32_t)j);
             if (key < best[KT - 1]) topk_insert<KT, uint32_t>(best, key);
         }
         __syncthreads();  // everyone is done with this stage before it is refilled
@@ -365,6 +376,7 @@ size_t hamming_plan(HammingSearchParams& p)
         return (size_t)-1;
     }
     p.kt = p.k <= 8 ? 8 : 32;
+    p.wt1 = 1; p.wt2 = 2; p.wt4 = 4;
     p.nw_templ = pick_nw(p.words, p.stride);
     const int dist_bits = bit_length((int64_t)p.d + 1);
     p.idx_bits = 32 - dist_bits;

@@ -31,6 +31,7 @@ struct HammingSearchParams {
     uint64_t* partial;  // workspace, required when nsplit > 1: [nw*nq][nsplit][kt] keys
     // plan (filled by hamming_plan)
     int block, qtiles, nsplit, rows_per_split, idx_bits, kt, nw_templ, tile_rows, stages;
+    uint32_t wt1, wt2, wt4;  // 1, 2, 4 as runtime values (keeps the popcount adds on the FMA pipe)
     size_t smem_bytes;
 };
 

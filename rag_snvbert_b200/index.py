@@ -161,11 +161,12 @@ class WindowedHammingIndex(_IndexBase):
         L.check(self._lib.snv_index_add(self._h, a.ptr, n, dt, flags, _current_stream(self.device)), "snv_index_add")
 
     def search(self, q, k: int, observed=None, missing=None, w0: int = 0, id_offset: int = 0,
-               dist_dtype=np.int32, codes: bool = False):
+               dist_dtype=np.int32, codes: bool = False, out=None):
         """q: [nw, nq, d] (or [nq, d] for one window) in any add() dtype.  `observed` / `missing`:
         optional site mask, [nw, nq, d] per query or [nw, d] per window ([nq, d] / [d] for one
         window).  Returns (D [nw, nq, k] int32 or float32, I [nw, nq, k] int64); single-window
-        calls drop the leading axis."""
+        calls drop the leading axis.  `out=(D, I)`: caller-owned result buffers (e.g. pinned host
+        arrays, so the device-to-host copies of a host-buffer call overlap the scan)."""
         if int(k) < 1:
             raise ValueError("k must be >= 1")
         a = _Arg(q)
@@ -202,8 +203,19 @@ class WindowedHammingIndex(_IndexBase):
                 flags |= L.MASK_IS_MISSING
         want_f = np.dtype(dist_dtype) == np.dtype(np.float32)
         shape = (nw, nq, int(k))
-        D, Dp = self._alloc_out(a.on_device, shape, np.float32 if want_f else np.int32)
-        I, Ip = self._alloc_out(a.on_device, shape, np.int64)
+        if out is not None:
+            Do, Io = _Arg(out[0]), _Arg(out[1])
+            want_f = Do.np_dtype == np.dtype(np.float32)
+            if (Do.on_device != a.on_device or Io.on_device != a.on_device or int(np.prod(Do.shape)) != int(np.prod(shape))
+                    or int(np.prod(Io.shape)) != int(np.prod(shape)) or Io.np_dtype != np.dtype(np.int64)
+                    or Do.np_dtype not in (np.dtype(np.int32), np.dtype(np.float32))
+                    or Do.arr is not out[0] or Io.arr is not out[1]):
+                raise ValueError("search: out=(D, I) must be contiguous int32|float32 / int64 arrays of the result size, "
+                                 "in the same memory as the queries")
+            D, Dp, I, Ip = out[0].reshape(shape), Do.ptr, out[1].reshape(shape), Io.ptr
+        else:
+            D, Dp = self._alloc_out(a.on_device, shape, np.float32 if want_f else np.int32)
+            I, Ip = self._alloc_out(a.on_device, shape, np.int64)
         L.check(self._lib.snv_index_search(self._h, int(w0), nw, a.ptr, nq, dt, m_ptr, m_mode, int(k), int(id_offset),
                                            None if want_f else Dp, Dp if want_f else None, Ip, flags,
                                            _current_stream(self.device)), "snv_index_search")

@@ -314,3 +314,37 @@ def test_error_behaviour():
     idx.add(np.zeros((3, 64), np.uint8))
     with pytest.raises(Exception):
         idx.search(np.zeros((3, 64), np.uint8), 100)  # k > 32 unsupported (stated limit)
+
+
+def test_host_pipeline_many_windows_all_mask_modes():
+    """>= 8 windows with host buffers: the library pipelines window chunks over internal streams."""
+    rng = np.random.default_rng(77)
+    W, N, Q, d = 21, 700, 90, 1030
+    panel = (rng.random((W, N, d)) < 0.4).astype(np.uint8)
+    q = (rng.random((W, Q, d)) < 0.4).astype(np.uint8)
+    obs_q = (rng.random((W, Q, d)) < 0.6).astype(np.uint8)
+    obs_w = (rng.random((W, d)) < 0.6).astype(np.uint8)
+    idx = _idx(d, W)
+    idx.add(panel)
+    outD = np.empty((W, Q, 8), np.int32)
+    outI = np.empty((W, Q, 8), np.int64)
+    for obs, kw in ((None, {}), (obs_q, {"observed": obs_q}), (obs_w, {"observed": obs_w}),
+                    (obs_q, {"missing": 1 - obs_q})):
+        D, I = idx.search(q, 8, out=(outD, outI), **kw)
+        assert D.base is outD or D is outD
+        for w in range(W):
+            m = None if obs is None else (obs[w] if obs.ndim == 3 else obs[w])
+            De, Ie = O.hamming_topk(panel[w], q[w], 8, m)
+            np.testing.assert_array_equal(I[w], Ie)
+            np.testing.assert_array_equal(D[w], De)
+    # token queries (own observed plane) through the pipelined host path
+    pm = O.sequence_padding((rng.random(1000) < 0.3).astype(np.int64))
+    ptok = np.stack([O.tokenize(O.hapgen(900 + w, 300, 1000), pm) for w in range(9)])
+    qtok = np.stack([O.tokenize(O.hapgen(950 + w, 17, 1000, founder_seed=900 + w), pm) for w in range(9)])
+    tidx = _idx(O.MAX_SEQ_LEN, 9)
+    tidx.add(ptok)
+    D, I = tidx.search(qtok, 3, dist_dtype=np.float32)
+    for w in range(9):
+        De, Ie = O.token_l2_topk(ptok[w], qtok[w], 3)
+        np.testing.assert_array_equal(I[w], Ie)
+        np.testing.assert_array_equal(D[w], De)
