@@ -10,7 +10,7 @@ import os
 import subprocess
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_PKG, "libsnvknn.so")
+_SO = os.environ.get("SNVKNN_LIB") or os.path.join(_PKG, "libsnvknn.so")  # SNVKNN_LIB: tuning builds only
 _CSRC = os.path.join(_PKG, "csrc")
 
 # enums of include/snvknn.h

@@ -12,6 +12,8 @@
 // that the quarter-rate POPC pipe and the ALU pipe are balanced.
 // Candidates are ranked on ONE 32-bit key  (distance << idx_bits | row_in_split)  so the
 // result is the exact (distance, id)-lexicographic top-k, ties included.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.cuh"
 #include "topk.cuh"
@@ -22,6 +24,15 @@
 #ifndef SNV_ROW_UNROLL
 #define SNV_ROW_UNROLL 2
 #endif
+#ifndef SNV_POPC_MODE
+#define SNV_POPC_MODE 1  // 0: plain adds (ALU pipe), 1: one IMAD chain, 2: four IMAD chains (all within 3% on B200, profiles/r1_tuning_hamming.txt)
+#endif
+#ifndef SNV_BLOCK
+#define SNV_BLOCK 128
+#endif
+#ifndef SNV_ROW_GROUP
+#define SNV_ROW_GROUP 1
+#endif
 #define SNV_PRAGMA_(x) _Pragma(#x)
 #define SNV_UNROLL(n) SNV_PRAGMA_(unroll n)
 
@@ -29,7 +40,7 @@ namespace snv {
 
 namespace {
 
-constexpr int kMaxBlock = 128;
+constexpr int kMaxBlock = SNV_BLOCK;
 constexpr int kBarBytes = 128;  // smem reserved for the stage mbarriers
 
 // acc + w * popc(x): the multiply-add goes to the FMA pipe (IMAD) because `w` is a runtime
@@ -41,16 +52,23 @@ __device__ __forceinline__ uint32_t popc_mad(uint32_t x, uint32_t w, uint32_t ac
     return r;
 }
 
-// acc + sum_i wt[LEVEL] * popcount(x[i]) over the multiset x[0..N): DEPTH levels of 3:2
-// carry-save compressors (carries move to weight level LEVEL+1), then POPC.
-template <int N, int DEPTH, int LEVEL>
+// Accumulates sum_i wt[LEVEL] * popcount(x[i]) over the multiset x[0..N) into acc[]: DEPTH levels
+// of 3:2 carry-save compressors (carries move to weight level LEVEL+1), then POPC.  The adds are
+// spread round-robin over NACC independent accumulators (short dependency chains).
+template <int N, int DEPTH, int LEVEL, int NACC>
 struct WeightedPopc {
-    static __device__ __forceinline__ uint32_t run(const uint32_t (&x)[N], const uint32_t (&wt)[3], uint32_t acc)
+    template <int SLOT>
+    static __device__ __forceinline__ void run(const uint32_t (&x)[N], const uint32_t (&wt)[3], uint32_t (&acc)[NACC])
     {
         if constexpr (DEPTH == 0 || N < 3) {
 #pragma unroll
-            for (int i = 0; i < N; ++i) acc = popc_mad(x[i], wt[LEVEL], acc);
-            return acc;
+            for (int i = 0; i < N; ++i) {
+#if SNV_POPC_MODE == 0
+                acc[(SLOT + i) % NACC] += (uint32_t)__popc(x[i]) << LEVEL;
+#else
+                acc[(SLOT + i) % NACC] = popc_mad(x[i], wt[LEVEL], acc[(SLOT + i) % NACC]);
+#endif
+            }
         } else {
             constexpr int T = N / 3, R = N % 3;
             uint32_t sum[T + R], carry[T];
@@ -62,8 +80,8 @@ struct WeightedPopc {
             }
 #pragma unroll
             for (int r = 0; r < R; ++r) sum[T + r] = x[3 * T + r];
-            acc = WeightedPopc<T + R, DEPTH - 1, LEVEL>::run(sum, wt, acc);
-            return WeightedPopc<T, DEPTH - 1, LEVEL + 1>::run(carry, wt, acc);
+            WeightedPopc<T + R, DEPTH - 1, LEVEL, NACC>::template run<SLOT>(sum, wt, acc);
+            WeightedPopc<T, DEPTH - 1, LEVEL + 1, NACC>::template run<(SLOT + T + R) % NACC>(carry, wt, acc);
         }
     }
 };
@@ -156,8 +174,7 @@ hamming_topk_kernel(const HammingSearchParams p)
         const uint32_t* tile = tiles + (size_t)(t % stages) * tile_words;
         const int rows = (nrows - t * TR < TR) ? nrows - t * TR : TR;
         const uint32_t row_base = (uint32_t)(t * TR);
-SNV_UNROLL(SNV_ROW_UNROLL)
-        for (int j = 0; j < rows; ++j) {
+        auto row_key = [&](int j) -> uint32_t {
             uint32_t x[NW];
             load_row_regs<NW>(x, tile + (size_t)j * p.stride);  // warp-uniform address: broadcast
 #pragma unroll
@@ -165,10 +182,46 @@ SNV_UNROLL(SNV_ROW_UNROLL)
                 if constexpr (MASKED) x[i] = (x[i] & m[i]) ^ q[i];  // == (r ^ q) & m, one LOP3
                 else                  x[i] ^= q[i];
             }
-            // key = dist * 2^idx_bits + row: one IMAD seeded with the row id
-            const uint32_t key = WeightedPopc<NW, SNV_CSA_DEPTH, 0>::run(x, wt, row_base + (uint32_t)j);
+            // key = dist * 2^idx_bits + row (weights are pre-scaled; accumulators sum to dist << idx_bits)
+#if SNV_POPC_MODE == 2
+            constexpr int NACC = NW >= 16 ? 4 : 1;
+#else
+            constexpr int NACC = 1;
+#endif
+            uint32_t acc[NACC];
+#pragma unroll
+            for (int a = 0; a < NACC; ++a) acc[a] = 0;
+            WeightedPopc<NW, SNV_CSA_DEPTH, 0, NACC>::template run<0>(x, wt, acc);
+#if SNV_POPC_MODE == 0
+            return (acc[0] << idx_bits) | (row_base + (uint32_t)j);
+#else
+            uint32_t key = row_base + (uint32_t)j;
+#pragma unroll
+            for (int a = 0; a < NACC; ++a) key += acc[a];
+            return key;
+#endif
+        };
+#if SNV_ROW_GROUP > 1
+        // SNV_ROW_GROUP rows are scored back to back before any (rare, divergent) insertion, so the
+        // LOP3 work of one row overlaps the POPC burst of the previous one inside a warp.
+        for (int j = 0; j < rows; j += SNV_ROW_GROUP) {
+            uint32_t keys[SNV_ROW_GROUP];
+#pragma unroll
+            for (int g = 0; g < SNV_ROW_GROUP; ++g) {
+                keys[g] = row_key(j + g);                       // rows past the tile end read stale smem...
+                if (j + g >= rows) keys[g] = kSent32;            // ...and are discarded here
+            }
+#pragma unroll
+            for (int g = 0; g < SNV_ROW_GROUP; ++g)
+                if (keys[g] < best[KT - 1]) topk_insert<KT, uint32_t>(best, keys[g]);
+        }
+#else
+SNV_UNROLL(SNV_ROW_UNROLL)
+        for (int j = 0; j < rows; ++j) {
+            const uint32_t key = row_key(j);
             if (key < best[KT - 1]) topk_insert<KT, uint32_t>(best, key);
         }
+#endif
         __syncthreads();  // everyone is done with this stage before it is refilled
     }
 
@@ -359,6 +412,9 @@ int launch_nw(const HammingSearchParams& p, cudaStream_t stream)
 static int pick_nw(int words, int stride)
 {
     if (words == 33 && stride == 36) return 33;
+#ifdef SNV_TUNE_ONLY33
+    return 0;
+#endif
     switch (stride) {
         case 4: case 8: case 16: case 24: case 32: case 36: case 48: case 68: return stride;
         default: return 0;
@@ -395,8 +451,11 @@ size_t hamming_plan(HammingSearchParams& p)
 
     // panel tile: ~16 KB per stage, 3 stages
     p.stages = 3;
-    int tr = (16 * 1024) / (p.stride * 4);
-    tr = tr >= 128 ? 128 : (tr >= 64 ? 64 : (tr >= 32 ? 32 : (tr >= 16 ? 16 : 8)));
+    if (const char* e = getenv("SNV_STAGES")) p.stages = atoi(e) >= 2 ? atoi(e) : 3;
+    int tr_budget = 16 * 1024;
+    if (const char* e = getenv("SNV_TILE_BYTES")) tr_budget = atoi(e) >= 1024 ? atoi(e) : tr_budget;
+    int tr = tr_budget / (p.stride * 4);
+    tr = tr >= 256 ? 256 : (tr >= 128 ? 128 : (tr >= 64 ? 64 : (tr >= 32 ? 32 : (tr >= 16 ? 16 : 8))));
     p.tile_rows = tr;
 
     // row splits: enough CTAs to fill the machine (>= 4 per SM) and rows per split that fit
@@ -441,15 +500,19 @@ int hamming_launch(const HammingSearchParams& p, cudaStream_t stream)
     if (p.nw <= 0 || p.nq <= 0) return SNV_OK;
     int rc;
     switch (p.nw_templ) {
+#ifndef SNV_TUNE_ONLY33
         case 4: rc = launch_nw<4>(p, stream); break;
         case 8: rc = launch_nw<8>(p, stream); break;
         case 16: rc = launch_nw<16>(p, stream); break;
         case 24: rc = launch_nw<24>(p, stream); break;
         case 32: rc = launch_nw<32>(p, stream); break;
+#endif
         case 33: rc = launch_nw<33>(p, stream); break;
+#ifndef SNV_TUNE_ONLY33
         case 36: rc = launch_nw<36>(p, stream); break;
         case 48: rc = launch_nw<48>(p, stream); break;
         case 68: rc = launch_nw<68>(p, stream); break;
+#endif
         default: {
             const bool masked = p.mask != nullptr;
             if (p.kt == 8) rc = masked ? launch_generic<true, 8>(p, stream) : launch_generic<false, 8>(p, stream);
