@@ -43,6 +43,10 @@ def parse_args():
     ap.add_argument("--queries", type=int, default=2000)
     ap.add_argument("-k", type=int, default=8)
     ap.add_argument("--masked", action="store_true", help="cfg 3: per-query observed-site masks")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4"],
+                    help="cfg2 (default, the headline), cfg3 = cfg2 + per-query masks, cfg4 = float L2 on tcgen05")
+    ap.add_argument("--dim", type=int, default=256, help="cfg4 embedding dimension")
+    ap.add_argument("--precision", default="tf32x3", choices=["tf32", "tf32x3"], help="cfg4 cross-term precision")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU baseline sample budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -50,6 +54,9 @@ def parse_args():
 
 
 def workload_name(a):
+    if a.workload == "cfg4":
+        return (f"cfg4 embedding-RAG retrieval: {a.refs} ref x {a.queries} query embeddings, dim {a.dim}, float L2 "
+                f"(tcgen05 {a.precision} cross term), k={a.k}")
     return (f"cfg2 chr21-scale sweep: {a.windows} windows x {a.refs} ref haplotypes x {a.sites} sites, "
             f"{a.queries} queries/window, k={a.k}, bit-packed " + ("masked " if a.masked else "") + "Hamming")
 
@@ -282,6 +289,7 @@ def run_ours(a):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    _lib.profile_enable(True)
     launches0 = _lib.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
     barrier()
@@ -296,7 +304,9 @@ def run_ours(a):
     barrier()
     launches = _lib.launch_count() - launches0
     total_ms = t_all0.elapsed_time(t_all1)
-    kern_ms = float(np.mean([s.elapsed_time(e) for s, e in ev]))
+    kern_ms = _lib.profile_last_ms()  # the scan kernel alone, events on its own stream (last timed step)
+    _lib.profile_enable(False)
+    step_ms_events = float(np.mean([s.elapsed_time(e) for s, e in ev]))
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -372,7 +382,7 @@ def run_ours(a):
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": traffic, "kernel": "hamming_topk_kernel<33,masked=%d,K=8>" % (1 if a.masked else 0),
-        "kernel_ms": kern_ms, "peak_source": peak_src,
+        "kernel_ms": kern_ms, "step_ms": step_ms_events, "peak_source": peak_src,
         "note": ("scan-equivalent bandwidth = pairs x 132 B / kernel time (SURVEY.md 8d): the panel tile is "
                  "served from shared memory/L2, so this may exceed 1.0; the binding unit is the integer pipes"),
         "int_pipe": {
@@ -401,8 +411,162 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
+
+# --------------------------------------------------------------------------- cfg 4: float L2 on tcgen05
+def cfg4_cpu(a, refs, q):
+    """faiss's BLAS path restated with numpy/OpenBLAS (oracle.l2_topk_f32_blas), all host threads."""
+    from oracle import oracle as O
+
+    O.l2_topk_f32_blas(refs[:512], q[:256], a.k)
+    t0 = time.perf_counter()
+    O.l2_topk_f32_blas(refs, q, a.k)
+    dt = time.perf_counter() - t0
+    threads = len(os.sched_getaffinity(0))
+    sample = (f"full step: {q.shape[0]} queries x {refs.shape[0]} refs x dim {refs.shape[1]}, k={a.k}, numpy/BLAS "
+              f"|x|^2+|y|^2-2xy restatement of faiss (oracle.l2_topk_f32_blas), {threads} host threads, {dt:.2f} s")
+    return q.shape[0] * refs.shape[0] / dt, threads, sample, dt
+
+
+def run_cfg4(a):
+    N, Q, d, k = a.refs, a.queries, a.dim, a.k
+    rank = int(os.environ.get("RANK", "0"))
+    refs_h = np.random.default_rng(4001).standard_normal((N, d)).astype(np.float32)
+    q_h = np.random.default_rng(4002).standard_normal((Q, d)).astype(np.float32)
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        vals, times = [], []
+        for i in range(a.warmup + a.steps):
+            v, threads, sample, dt = cfg4_cpu(a, refs_h, q_h)
+            if i >= a.warmup:
+                vals.append(v)
+                times.append(dt)
+        value = float(np.mean(vals))
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": float(np.mean(times) * 1e3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": workload_name(a)},
+            "window_queries_per_s": value / N,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    from rag_snvbert_b200 import WindowedL2Index, _lib
+
+    refs = torch.from_numpy(refs_h).to(dev)
+    q = torch.from_numpy(q_h).to(dev)
+    index = WindowedL2Index(d, 1, local, a.precision)
+    index.add(refs)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 3)):
+        D, I = index.search(q, k)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    _lib.profile_enable(True)
+    launches0 = _lib.launch_count()
+    step_ms, kern_ms = [], []
+    for i in range(a.steps):
+        flush.zero_()  # L2 flush between timed iterations (inputs are 9 MB)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        D, I = index.search(q, k)
+        e1.record()
+        barrier()
+        step_ms.append(e0.elapsed_time(e1))
+        kern_ms.append(_lib.profile_last_ms())
+    launches = _lib.launch_count() - launches0
+    _lib.profile_enable(False)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([float(np.sum(step_ms))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / a.steps
+    value = world * Q * N / (ms_per_step * 1e-3)
+
+    hq = torch.empty((Q, d), dtype=torch.float32, pin_memory=True)
+    hq.copy_(q)
+    hq_np = hq.numpy()
+    for _ in range(2):
+        Dh, Ih = index.search(hq_np, k)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        Dh, Ih = index.search(hq_np, k)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / a.steps
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    assert np.array_equal(Ih, I.cpu().numpy()), "host/device result mismatch"
+    e2e = {"value": world * Q * N / dt, "unit": UNIT, "h2d_bytes_per_step": int(hq_np.nbytes),
+           "d2h_bytes_per_step": int(Dh.nbytes + Ih.nbytes), "ms_per_step": dt * 1e3,
+           "api": "WindowedL2Index.search(pinned numpy float32 [Q,d]) -> numpy (D float32, I int64)"}
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    bf16 = float(peaks.get("bf16_tflops", 1590.0))
+    peak = bf16 / 2.0  # kind::tf32 issues at half the bf16 rate
+    km = float(np.mean(kern_ms))
+    flops = 2.0 * Q * N * d
+    achieved = flops / (km * 1e-3) / 1e12
+    passes = 3 if a.precision == "tf32x3" else 1
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "l2_topk_kernel<8>", "kernel_ms": km, "step_ms": float(np.mean(step_ms)),
+                "issued_tflops": achieved * passes, "issued_frac": achieved * passes / peak,
+                "peak_source": ("measured bf16_tflops / 2 (tf32 rate)" if "bf16_tflops" in peaks else "fallback 1590/2"),
+                "note": "achieved = algorithmic 2*Q*N*d FLOP / kernel time; tf32x3 issues 3x that on the tensor pipe (issued_*)"}
+    cpu = None
+    if not a.no_cpu_baseline:
+        v, threads, sample, _ = cfg4_cpu(a, refs_h, q_h)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+    print(json.dumps({
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32",
+        "data": "synthetic", "config": {"workload": workload_name(a), "parallelism": f"replicas x{world}",
+                                        "l2_policy": "256 MB buffer written between timed iterations (L2 flush)"},
+        "window_queries_per_s": value / N, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+        "cpu_baseline": cpu, "clocks": clocks}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     a = parse_args()
+    if a.workload == "cfg3":
+        a.masked = True
+    if a.workload == "cfg4":
+        if a.queries == 2000:
+            a.queries = 4096
+        return run_cfg4(a)
     if a.impl == "reference":
         run_reference(a)
     else:

@@ -175,6 +175,12 @@ int snv_pack_rows(int device, const void* x, int64_t rows, int64_t d, int dtype,
 /* number of kernels this library has launched in the calling process (bench "gpu_launches") */
 int64_t snv_launch_count(void);
 
+/* Measurement hook (bench.py roofline): when enabled, every launch of a dominant kernel
+ * (hamming_topk_kernel / l2_topk_kernel) is bracketed by CUDA events on its own stream;
+ * snv_profile_last_ms() waits for the most recent such launch and returns its duration. */
+int snv_profile_enable(int on);
+int snv_profile_last_ms(float* ms);
+
 #ifdef __cplusplus
 }
 #endif

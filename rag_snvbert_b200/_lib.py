@@ -47,6 +47,8 @@ SYMBOLS = {
     "snv_topk_merge": (_i, [_i, _vp, _vp, _vp, _i, _i64, _i, _i, _vp, _vp, _vp, _vp]),
     "snv_pack_rows": (_i, [_i, _vp, _i64, _i64, _i, _i, _vp, _vp, _vp]),
     "snv_launch_count": (_i64, []),
+    "snv_profile_enable": (_i, [_i]),
+    "snv_profile_last_ms": (_i, [_c.POINTER(_c.c_float)]),
 }
 
 _lib = None
@@ -110,3 +112,13 @@ def packed_words(d: int) -> int:
 
 def launch_count() -> int:
     return int(lib().snv_launch_count())
+
+
+def profile_enable(on: bool) -> None:
+    check(lib().snv_profile_enable(1 if on else 0), "snv_profile_enable")
+
+
+def profile_last_ms() -> float:
+    ms = _c.c_float(0.0)
+    check(lib().snv_profile_last_ms(ctypes.byref(ms)), "snv_profile_last_ms")
+    return float(ms.value)

@@ -14,6 +14,22 @@ static thread_local std::string t_error;
 long long g_launch_count = 0;
 void set_error(const std::string& msg) { t_error = msg; }
 
+static bool g_prof_on = false;
+static cudaEvent_t g_prof_e0 = nullptr, g_prof_e1 = nullptr;
+static bool g_prof_valid = false;
+void profile_begin(cudaStream_t stream)
+{
+    if (!g_prof_on) return;
+    if (!g_prof_e0) { cudaEventCreate(&g_prof_e0); cudaEventCreate(&g_prof_e1); }
+    cudaEventRecord(g_prof_e0, stream);
+}
+void profile_end(cudaStream_t stream)
+{
+    if (!g_prof_on || !g_prof_e0) return;
+    cudaEventRecord(g_prof_e1, stream);
+    g_prof_valid = true;
+}
+
 namespace {
 
 struct DeviceGuard {
@@ -127,6 +143,22 @@ extern "C" {
 const char* snv_last_error(void) { return t_error.c_str(); }
 int snv_version(void) { return SNVKNN_VERSION; }
 int64_t snv_launch_count(void) { return g_launch_count; }
+
+int snv_profile_enable(int on)
+{
+    g_prof_on = on != 0;
+    g_prof_valid = false;
+    return SNV_OK;
+}
+
+int snv_profile_last_ms(float* ms)
+{
+    if (!ms) { set_error("snv_profile_last_ms: null"); return SNV_ERR_INVALID; }
+    if (!g_prof_valid) { set_error("snv_profile_last_ms: no profiled launch"); return SNV_ERR_INVALID; }
+    SNV_CUDA_CHECK(cudaEventSynchronize(g_prof_e1));
+    SNV_CUDA_CHECK(cudaEventElapsedTime(ms, g_prof_e0, g_prof_e1));
+    return SNV_OK;
+}
 
 int snv_device_count(int* count)
 {

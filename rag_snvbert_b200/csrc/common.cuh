@@ -9,6 +9,9 @@ namespace snv {
 // ---- error plumbing -------------------------------------------------------------------
 void set_error(const std::string& msg);
 extern long long g_launch_count;  // kernels launched by this library (snv_launch_count)
+// measurement hook: events around the dominant kernel of a search (snv_profile_enable)
+void profile_begin(cudaStream_t stream);
+void profile_end(cudaStream_t stream);
 
 #define SNV_CUDA_CHECK(expr)                                                             \
     do {                                                                                 \

@@ -380,7 +380,9 @@ int launch_one(const HammingSearchParams& p, cudaStream_t stream)
         SNV_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
     }
     const int64_t grid = (int64_t)p.nw * p.qtiles * p.nsplit;
+    profile_begin(stream);
     kern<<<(unsigned)grid, p.block, p.smem_bytes, stream>>>(p);
+    profile_end(stream);
     SNV_LAUNCH_CHECK();
     return SNV_OK;
 }
@@ -393,7 +395,9 @@ int launch_generic(const HammingSearchParams& p, cudaStream_t stream)
         SNV_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
     }
     const int64_t grid = (int64_t)p.nw * p.qtiles * p.nsplit;
+    profile_begin(stream);
     kern<<<(unsigned)grid, p.block, p.smem_bytes, stream>>>(p);
+    profile_end(stream);
     SNV_LAUNCH_CHECK();
     return SNV_OK;
 }

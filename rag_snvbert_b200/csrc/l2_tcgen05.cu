@@ -449,14 +449,18 @@ int l2_launch(const L2SearchParams& p, cudaStream_t stream)
             SNV_CUDA_CHECK(cudaFuncSetAttribute(l2_topk_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
             attr8 = true;
         }
+        profile_begin(stream);
         l2_topk_kernel<8><<<grid, kThreads, kSmemBytes, stream>>>(map_q, map_r, p);
+        profile_end(stream);
     } else {
         static bool attr32 = false;
         if (!attr32) {
             SNV_CUDA_CHECK(cudaFuncSetAttribute(l2_topk_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
             attr32 = true;
         }
+        profile_begin(stream);
         l2_topk_kernel<32><<<grid, kThreads, kSmemBytes, stream>>>(map_q, map_r, p);
+        profile_end(stream);
     }
     SNV_LAUNCH_CHECK();
     return merge_keys_launch(p.partial, p.nsplit, p.kt, p.nq, p.k, p.id_offset, true, nullptr, p.D_f32, p.I, stream);
