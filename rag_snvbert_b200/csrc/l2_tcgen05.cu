@@ -41,14 +41,16 @@ constexpr int BM = 128;        // queries per CTA tile (TMEM lanes)
 constexpr int BN = 256;        // panel rows per MMA tile (TMEM columns per accumulator stage)
 constexpr int BK = 32;         // fp32 elements per k-block = one 128-byte swizzle row
 constexpr int UMMA_K = 8;      // tf32: 32 bytes per MMA
-constexpr int kStages = 4;
+constexpr int kStages = 3;
 constexpr int kAccStages = 2;
 constexpr int kTmemCols = kAccStages * BN;  // 512
 constexpr int kThreads = 192;
 constexpr uint32_t kABytes = BM * BK * 4;   // 16 KB
 constexpr uint32_t kBBytes = BN * BK * 4;   // 32 KB
 constexpr uint32_t kStageBytes = kABytes + kBBytes;
-constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + 2 * BN * 4 /*rn*/ + 256 /*barriers*/;
+constexpr int kListCap = 40;   // per-thread candidate list (epilogue), merged when more than 8 entries are pending
+constexpr size_t kListBytes = (size_t)kListCap * 128 * 8;
+constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + 2 * BN * 4 /*rn*/ + kListBytes + 256 /*barriers*/;
 
 // ---- PTX wrappers -----------------------------------------------------------------------
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar)
@@ -154,7 +156,8 @@ l2_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     unsigned char* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
     unsigned char* tiles = smem;
     float* rn_s = reinterpret_cast<float*>(smem + (size_t)kStages * kStageBytes);  // [2][BN]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * kStageBytes + 2 * BN * 4);
+    uint64_t* lists = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * kStageBytes + 2 * BN * 4);  // [kListCap][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * kStageBytes + 2 * BN * 4 + kListBytes);
     uint64_t* full_bar = bars;                          // [kStages]   TMA -> MMA
     uint64_t* empty_bar = bars + kStages;               // [kStages]   MMA -> TMA
     uint64_t* tmem_full = bars + 2 * kStages;           // [2]         MMA -> epilogue
@@ -251,17 +254,35 @@ l2_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         uint64_t best[KT];
 #pragma unroll
         for (int i = 0; i < KT; ++i) best[i] = kSent64;
-        float worst = 3.4028234663852886e38f;
+        // Selection: candidates that beat the (possibly stale, hence looser) threshold are appended
+        // to a per-thread list in shared memory; lists are folded into the sorted register top-k
+        // only when some lane has more than 8 pending — all lanes insert in lockstep, instead of
+        // one divergent ~50-instruction insertion per column.
+        uint64_t* my_list = lists + et;  // slot s at my_list[s * 128]
+        float thr = 3.4028234663852886e38f;
+        int cnt = 0;
+        auto fold = [&]() {
+            const int maxc = __reduce_max_sync(0xffffffffu, cnt);
+            for (int s2 = 0; s2 < maxc; ++s2) {
+                if (s2 < cnt) {
+                    const uint64_t key = my_list[s2 * 128];
+                    if (key < best[KT - 1]) topk_insert<KT, uint64_t>(best, key);
+                }
+            }
+            cnt = 0;
+            thr = best[KT - 1] == kSent64 ? 3.4028234663852886e38f : __uint_as_float((uint32_t)(best[KT - 1] >> 32));
+        };
         for (int t = 0; t < my_tiles; ++t) {
             const int as = t & 1;
             const uint32_t acc_phase = (uint32_t)(t >> 1) & 1u;
             const int n0 = (t0 + t) * BN;
-            // stage this tile's |r|^2 (2 per thread), visible to the 128 epilogue threads
+            // stage this tile's |r|^2 (2 per thread; +inf past the panel end so those columns never
+            // pass the threshold), visible to the 128 epilogue threads
             float* rn = rn_s + as * BN;
 #pragma unroll
             for (int j = 0; j < BN / 128; ++j) {
                 const int c = et + j * 128;
-                rn[c] = (n0 + c < p.n) ? p.ref_norm[n0 + c] : 0.f;
+                rn[c] = (n0 + c < p.n) ? p.ref_norm[n0 + c] : __int_as_float(0x7f800000);
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
             mbar_wait(&tmem_full[as], acc_phase);
@@ -276,18 +297,18 @@ l2_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                     const int c = c0 + j;
                     float d = fmaf(-2.f, __uint_as_float(acc[j]), qn + rn[c]);
                     d = d < 0.f ? 0.f : d;
-                    if (c < ncols && d < worst) {
+                    if (d < thr) {
                         // ids ascend along the scan, so on equal distance the earlier id stays
-                        const uint64_t key = ((uint64_t)__float_as_uint(d) << 32) | (uint64_t)(uint32_t)(n0 + c);
-                        topk_insert<KT, uint64_t>(best, key);
-                        worst = __uint_as_float((uint32_t)(best[KT - 1] >> 32));
-                        if (best[KT - 1] == kSent64) worst = 3.4028234663852886e38f;
+                        my_list[cnt * 128] = ((uint64_t)__float_as_uint(d) << 32) | (uint64_t)(uint32_t)(n0 + c);
+                        ++cnt;
                     }
                 }
+                if (__any_sync(0xffffffffu, cnt > kListCap - 32)) fold();
             }
             tcgen05_fence_before();
             mbar_arrive(&tmem_empty[as]);
         }
+        fold();
         if (active) {
             uint64_t* out = p.partial + ((int64_t)q * p.nsplit + split) * KT;
 #pragma unroll

@@ -9,32 +9,50 @@ namespace snv {
 namespace {
 
 // ------------------------------------------------------------------------------ merge
-// One thread per query: reselects the best k from parts*kin candidate keys.
+__device__ __forceinline__ uint64_t warp_min_u64(uint64_t v)
+{
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        const uint64_t o = __shfl_xor_sync(0xffffffffu, v, s);
+        v = o < v ? o : v;
+    }
+    return v;
+}
+
+// One WARP per query: reselects the best k from parts*kin candidate keys.  Each lane keeps the
+// best KT of its strided share in sorted registers, then k rounds of (warp-min over the lane
+// heads, owner pops).  Keys are unique (they embed the row id) except the empty sentinel.
 template <int KT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 merge_keys_kernel(const uint64_t* __restrict__ keys, int parts, int kin, int64_t nq_total, int k,
                   int64_t id_offset, bool float_dist, int32_t* __restrict__ D_i32,
                   float* __restrict__ D_f32, int64_t* __restrict__ I)
 {
-    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= nq_total) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (q >= nq_total) return;  // warp-uniform
     uint64_t best[KT];
 #pragma unroll
     for (int i = 0; i < KT; ++i) best[i] = kSent64;
     const uint64_t* src = keys + q * parts * kin;
     const int total = parts * kin;
-    for (int j = 0; j < total; ++j) {
+    for (int j = lane; j < total; j += 32) {
         const uint64_t key = src[j];
         if (key < best[KT - 1]) topk_insert<KT, uint64_t>(best, key);
     }
+    for (int i = 0; i < k; ++i) {
+        const uint64_t m = warp_min_u64(best[0]);
+        const unsigned owners = __ballot_sync(0xffffffffu, best[0] == m);
+        if (m != kSent64 && lane == __ffs(owners) - 1) {
 #pragma unroll
-    for (int i = 0; i < KT; ++i) {
-        if (i < k) {
-            const uint64_t key = best[i];
-            const bool empty = key == kSent64;
-            const uint32_t hi = (uint32_t)(key >> 32);
+            for (int j = 0; j < KT - 1; ++j) best[j] = best[j + 1];
+            best[KT - 1] = kSent64;
+        }
+        if (lane == 0) {
+            const bool empty = m == kSent64;
+            const uint32_t hi = (uint32_t)(m >> 32);
             const int64_t o = q * k + i;
-            I[o] = empty ? -1 : (int64_t)(uint32_t)key + id_offset;
+            I[o] = empty ? -1 : (int64_t)(uint32_t)m + id_offset;
             if (float_dist) {
                 if (D_f32) D_f32[o] = empty ? 3.4028234663852886e38f : __uint_as_float(hi);
             } else {
@@ -242,8 +260,8 @@ int merge_keys_launch(const uint64_t* keys, int parts, int kin, int64_t nq_total
                       cudaStream_t stream)
 {
     if (nq_total <= 0) return SNV_OK;
-    const int block = 128;
-    const unsigned grid = (unsigned)ceil_div(nq_total, block);
+    const int block = 256;
+    const unsigned grid = (unsigned)ceil_div(nq_total, block / 32);
     if (k <= 8)
         merge_keys_kernel<8><<<grid, block, 0, stream>>>(keys, parts, kin, nq_total, k, id_offset, float_dist, D_i32, D_f32, I);
     else if (k <= 32)
