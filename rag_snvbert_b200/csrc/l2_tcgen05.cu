@@ -12,8 +12,10 @@
 //   warp 1      TMEM allocator + MMA issuer: one elected lane issues 4 x tcgen05.mma (M128 N256 K8)
 //               per k-block into one of two 256-column accumulator stages; tcgen05.commit frees
 //               the smem slot / publishes the accumulator
-//   warps 2..5  epilogue: thread = query row (TMEM lane); tcgen05.ld 32 columns at a time,
-//               d = fma(-2, acc, qn + rn), clamp, running register top-k on (float bits, id)
+//   warps 2..9  epilogue: thread = query row (TMEM lane), two warps per lane quarter taking
+//               alternate 32-column chunks; tcgen05.ld (double-buffered), d = fma(-2, acc, qn + rn),
+//               clamp, candidate lists in smem folded in lockstep into a register top-k on
+//               (float bits, id)
 // A CTA owns one 128-query tile and a contiguous range of panel tiles, so the running top-k
 // stays in registers across tiles; partial results go to a [nq][nsplit][kt] key buffer that
 // merge_keys_kernel reduces (same total order as everywhere else).
@@ -44,12 +46,14 @@ constexpr int UMMA_K = 8;      // tf32: 32 bytes per MMA
 constexpr int kStages = 3;
 constexpr int kAccStages = 2;
 constexpr int kTmemCols = kAccStages * BN;  // 512
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;    // two per TMEM lane quarter, alternating 32-column chunks
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreads = 64 + kEpiThreads;
 constexpr uint32_t kABytes = BM * BK * 4;   // 16 KB
 constexpr uint32_t kBBytes = BN * BK * 4;   // 32 KB
 constexpr uint32_t kStageBytes = kABytes + kBBytes;
-constexpr int kListCap = 40;   // per-thread candidate list (epilogue), merged when more than 8 entries are pending
-constexpr size_t kListBytes = (size_t)kListCap * 128 * 8;
+constexpr int kListCap = 24;   // per-thread candidate list (epilogue): folded when > 8 are pending, checked every 16 columns
+constexpr size_t kListBytes = (size_t)kListCap * kEpiThreads * 8;
 constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + 2 * BN * 4 /*rn*/ + kListBytes + 256 /*barriers*/;
 
 // ---- PTX wrappers -----------------------------------------------------------------------
@@ -111,7 +115,19 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
         : "memory");
 }
 
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// The loaded registers are passed through the wait as in/out operands so the compiler cannot
+// schedule their consumers above it.
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.wait::ld.sync.aligned;"
+        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+          "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+          "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+          "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+        :
+        : "memory");
+}
 
 __device__ __forceinline__ bool elect_one()
 {
@@ -185,7 +201,7 @@ l2_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         }
         for (int s = 0; s < kAccStages; ++s) {
             mbar_init(&tmem_full[s], 1);
-            mbar_init(&tmem_empty[s], 128);
+            mbar_init(&tmem_empty[s], kEpiThreads);
         }
         fence_barrier_init();
     }
@@ -204,6 +220,11 @@ l2_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 const int n0 = (t0 + t) * BN;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1u);
+#ifdef L2_DEBUG_NO_TMA
+                    mbar_arrive(&full_bar[stage]);
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                    continue;
+#endif
                     unsigned char* a_dst = tiles + (size_t)stage * kStageBytes;
                     unsigned char* b_dst = a_dst + kABytes;
                     mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
@@ -228,6 +249,7 @@ l2_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 mbar_wait(&full_bar[stage], phase);
                 tcgen05_fence_after();
                 if (elect_one()) {
+#ifndef L2_DEBUG_NO_MMA
                     const uint32_t a_addr = smem_u32(tiles + (size_t)stage * kStageBytes);
                     const uint32_t b_addr = a_addr + kABytes;
 #pragma unroll
@@ -236,6 +258,7 @@ l2_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                         const uint64_t bdesc = make_kmajor_sw128_desc(b_addr + k * UMMA_K * 4);
                         umma_tf32(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
+#endif
                     umma_commit(&empty_bar[stage]);                   // smem slot reusable once read
                     if (kb == num_kb - 1) umma_commit(&tmem_full[as]);  // accumulator complete
                 }
@@ -244,10 +267,11 @@ l2_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             }
         }
     } else {
-        // ================= epilogue: thread = query row =================
+        // ================= epilogue: thread = query row, 2 warps per lane quarter =================
         const int quarter = warp & 3;              // TMEM lanes [32*quarter, 32*quarter + 32)
+        const int half = (warp - 2) >> 2;          // which alternate 32-column chunks this warp takes
         const int row = quarter * 32 + lane;       // row inside the 128-query tile
-        const int et = (warp - 2) * 32 + lane;     // 0..127 among the epilogue threads
+        const int et = (warp - 2) * 32 + lane;     // 0..255 among the epilogue threads
         const int64_t q = (int64_t)m0 + row;
         const bool active = q < p.nq;
         const float qn = active ? p.q_norm[q] : 0.f;
@@ -258,59 +282,90 @@ l2_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         // to a per-thread list in shared memory; lists are folded into the sorted register top-k
         // only when some lane has more than 8 pending — all lanes insert in lockstep, instead of
         // one divergent ~50-instruction insertion per column.
-        uint64_t* my_list = lists + et;  // slot s at my_list[s * 128]
+        uint64_t* my_list = lists + et;  // slot s at my_list[s * kEpiThreads]
         float thr = 3.4028234663852886e38f;
         int cnt = 0;
         auto fold = [&]() {
             const int maxc = __reduce_max_sync(0xffffffffu, cnt);
             for (int s2 = 0; s2 < maxc; ++s2) {
                 if (s2 < cnt) {
-                    const uint64_t key = my_list[s2 * 128];
+                    const uint64_t key = my_list[s2 * kEpiThreads];
                     if (key < best[KT - 1]) topk_insert<KT, uint64_t>(best, key);
                 }
             }
             cnt = 0;
             thr = best[KT - 1] == kSent64 ? 3.4028234663852886e38f : __uint_as_float((uint32_t)(best[KT - 1] >> 32));
         };
+        // 16 columns: distances, threshold test, append.  `bias` = |q|^2 + |r|^2 was read from shared
+        // memory before any list store (the compiler cannot hoist shared loads across those stores).
+        auto score16 = [&](const uint32_t* acc, const float* bias, int col0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float d = fmaf(-2.f, __uint_as_float(acc[j]), bias[j]);
+                if (d < thr) {
+                    // ids ascend along the scan, so on equal distance the earlier id stays;
+                    // tiny negative round-off clamps to 0 like faiss
+                    const float dc = d < 0.f ? 0.f : d;
+                    my_list[cnt * kEpiThreads] = ((uint64_t)__float_as_uint(dc) << 32) | (uint64_t)(uint32_t)(col0 + j);
+                    ++cnt;
+                }
+            }
+            if (__any_sync(0xffffffffu, cnt > kListCap - 16)) fold();
+        };
+        auto process = [&](uint32_t (&acc)[32], const float* rn, int c0, int n0) {
+            float bias[32];
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 v = reinterpret_cast<const float4*>(rn + c0)[j4];
+                bias[4 * j4] = qn + v.x; bias[4 * j4 + 1] = qn + v.y;
+                bias[4 * j4 + 2] = qn + v.z; bias[4 * j4 + 3] = qn + v.w;
+            }
+            score16(acc, bias, n0 + c0);
+            score16(acc + 16, bias + 16, n0 + c0 + 16);
+        };
+        // |r|^2 of the first tile (1 per thread; +inf past the panel end so those columns never
+        // pass the threshold); later tiles are prefetched one tile ahead
+        float rn_next = (t0 * BN + et < p.n) ? p.ref_norm[t0 * BN + et] : __int_as_float(0x7f800000);
         for (int t = 0; t < my_tiles; ++t) {
             const int as = t & 1;
             const uint32_t acc_phase = (uint32_t)(t >> 1) & 1u;
             const int n0 = (t0 + t) * BN;
-            // stage this tile's |r|^2 (2 per thread; +inf past the panel end so those columns never
-            // pass the threshold), visible to the 128 epilogue threads
             float* rn = rn_s + as * BN;
-#pragma unroll
-            for (int j = 0; j < BN / 128; ++j) {
-                const int c = et + j * 128;
-                rn[c] = (n0 + c < p.n) ? p.ref_norm[n0 + c] : __int_as_float(0x7f800000);
+            rn[et] = rn_next;
+            if (t + 1 < my_tiles) {
+                const int64_t c = (int64_t)n0 + BN + et;
+                rn_next = c < p.n ? p.ref_norm[c] : __int_as_float(0x7f800000);
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
             mbar_wait(&tmem_full[as], acc_phase);
             tcgen05_fence_after();
+#ifdef L2_DEBUG_NO_EPILOGUE
+            const int nchunks = 0;
+#else
             const int ncols = (p.n - n0 < BN) ? (int)(p.n - n0) : BN;
-            for (int c0 = 0; c0 < ncols; c0 += 32) {
-                uint32_t acc[32];
-                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + c0), acc);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int c = c0 + j;
-                    float d = fmaf(-2.f, __uint_as_float(acc[j]), qn + rn[c]);
-                    d = d < 0.f ? 0.f : d;
-                    if (d < thr) {
-                        // ids ascend along the scan, so on equal distance the earlier id stays
-                        my_list[cnt * 128] = ((uint64_t)__float_as_uint(d) << 32) | (uint64_t)(uint32_t)(n0 + c);
-                        ++cnt;
-                    }
-                }
-                if (__any_sync(0xffffffffu, cnt > kListCap - 32)) fold();
+            const int nchunks = (ncols + 31) >> 5;
+#endif
+            const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN);
+            uint32_t accA[32], accB[32];
+            int ci = half;
+            if (ci < nchunks) tmem_ld_32x32b_x32(tbase + (uint32_t)(ci * 32), accA);
+            while (ci < nchunks) {
+                tmem_ld_wait(accA);
+                if (ci + 2 < nchunks) tmem_ld_32x32b_x32(tbase + (uint32_t)((ci + 2) * 32), accB);
+                process(accA, rn, ci * 32, n0);
+                ci += 2;
+                if (ci >= nchunks) break;
+                tmem_ld_wait(accB);
+                if (ci + 2 < nchunks) tmem_ld_32x32b_x32(tbase + (uint32_t)((ci + 2) * 32), accA);
+                process(accB, rn, ci * 32, n0);
+                ci += 2;
             }
             tcgen05_fence_before();
             mbar_arrive(&tmem_empty[as]);
         }
         fold();
         if (active) {
-            uint64_t* out = p.partial + ((int64_t)q * p.nsplit + split) * KT;
+            uint64_t* out = p.partial + (((int64_t)q * p.nsplit + split) * 2 + half) * KT;
 #pragma unroll
             for (int i = 0; i < KT; ++i) out[i] = best[i];
         }
@@ -446,7 +501,7 @@ size_t l2_plan(L2SearchParams& p)
     p.nsplit = n_tiles > 0 ? best_s : 1;
     p.tiles_per_split = n_tiles > 0 ? (int)ceil_div(n_tiles, p.nsplit) : 0;
     p.nsplit = n_tiles > 0 ? (int)ceil_div(n_tiles, p.tiles_per_split) : 1;
-    return (size_t)p.nq * p.nsplit * p.kt * sizeof(uint64_t);
+    return (size_t)p.nq * p.nsplit * 2 * p.kt * sizeof(uint64_t);  // two epilogue warps per row
 }
 
 int l2_launch(const L2SearchParams& p, cudaStream_t stream)
@@ -484,7 +539,7 @@ int l2_launch(const L2SearchParams& p, cudaStream_t stream)
         profile_end(stream);
     }
     SNV_LAUNCH_CHECK();
-    return merge_keys_launch(p.partial, p.nsplit, p.kt, p.nq, p.k, p.id_offset, true, nullptr, p.D_f32, p.I, stream);
+    return merge_keys_launch(p.partial, p.nsplit * 2, p.kt, p.nq, p.k, p.id_offset, true, nullptr, p.D_f32, p.I, stream);
 }
 
 }  // namespace snv

@@ -10,14 +10,19 @@ build() {  # name, flags
   nvcc -gencode arch=compute_100a,code=sm_100a -shared -cudart static -o ../../tools/variants/libsnvknn_$name.so \
        build/api.o build/hamming_$name.o build/misc_kernels.o build/l2_tcgen05.o
 }
-build g2_adds  -DSNV_POPC_MODE=0 -DSNV_ROW_GROUP=2 &
-build g2_mad1  -DSNV_POPC_MODE=1 -DSNV_ROW_GROUP=2 &
-build g2_mad4  -DSNV_POPC_MODE=2 -DSNV_ROW_GROUP=2 &
-build g4_mad1  -DSNV_POPC_MODE=1 -DSNV_ROW_GROUP=4 &
+buildl2() {  # name, flags
+  local name=$1; shift
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --threads 2 \
+       "$@" -c l2_tcgen05.cu -o build/l2_$name.o
+  nvcc -gencode arch=compute_100a,code=sm_100a -shared -cudart static -o ../../tools/variants/libsnvknn_l2_$name.so \
+       build/api.o build/hamming.o build/misc_kernels.o build/l2_$name.o
+}
+buildl2 base &
+buildl2 noepi -DL2_DEBUG_NO_EPILOGUE &
+buildl2 nomma -DL2_DEBUG_NO_MMA &
+buildl2 notma -DL2_DEBUG_NO_TMA &
 wait
-build g4_adds  -DSNV_POPC_MODE=0 -DSNV_ROW_GROUP=4 &
-build g3_mad1  -DSNV_POPC_MODE=1 -DSNV_ROW_GROUP=3 &
-build g1_mad1  -DSNV_POPC_MODE=1 -DSNV_ROW_GROUP=1 &
-build g2_mad1_b256 -DSNV_POPC_MODE=1 -DSNV_ROW_GROUP=2 -DSNV_BLOCK=256 &
+buildl2 notma_noepi -DL2_DEBUG_NO_TMA -DL2_DEBUG_NO_EPILOGUE &
+buildl2 nomma_noepi -DL2_DEBUG_NO_MMA -DL2_DEBUG_NO_EPILOGUE &
 wait
 ls -la ../../tools/variants
