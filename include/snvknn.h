@@ -129,6 +129,18 @@ int snv_index_search(snv_index* idx, int w0, int nw, const void* q, int64_t nq, 
                      float* D_f32, int64_t* I, unsigned flags, void* stream);
 
 /*
+ * Ragged per-window batches: a training / inference batch regrouped by window_idx before the
+ * search (src/dataset/rag_train_dataset.py:239-281, src/dataset/embedding_rag_dataset.py:318-321,
+ * src/dataset/sampler.py:58-119).  q is [nq_total][row] in caller order, window_ids (HOST int32
+ * [nq_total]) names the window of every query; results come back in caller order
+ * ([nq_total][k]).  One launch for the whole batch whatever the group sizes.  HAMMING indexes;
+ * `mask` is NULL or per query ([nq_total][row]).
+ */
+int snv_index_search_grouped(snv_index* idx, const void* q, const int32_t* window_ids, int64_t nq_total,
+                             int q_dtype, const void* mask, int k, int32_t* D_i32, float* D_f32,
+                             int64_t* I, unsigned flags, void* stream);
+
+/*
  * The gather that follows search in the V17 collate
  * (src/dataset/rag_train_dataset.py:287-307): I -> retrieved haplotype -> tokens with an
  * all-zero mask: out[w][q][j][:] = [SOS=2] + (5|6 per site) + [EOS=3] + PAD(0) up to seq_len.
@@ -139,6 +151,11 @@ int snv_index_search(snv_index* idx, int w0, int nw, const void* q, int64_t nq, 
 int snv_index_gather_tokens(snv_index* idx, int w0, int nw, const int64_t* I, int64_t nq, int k,
                             const int32_t* n_sites, int seq_len, int64_t* out, unsigned flags,
                             void* stream);
+/* same for a ragged batch: I [nq_total][k] with window_ids (HOST int32 [nq_total]); n_sites is NULL
+ * or HOST int32 [n_windows] */
+int snv_index_gather_tokens_grouped(snv_index* idx, const int64_t* I, const int32_t* window_ids,
+                                    int64_t nq_total, int k, const int32_t* n_sites, int seq_len,
+                                    int64_t* out, unsigned flags, void* stream);
 
 /*
  * Row gather for L2 indexes (src/dataset/embedding_rag_dataset.py:406-438,

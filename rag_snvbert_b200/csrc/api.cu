@@ -536,6 +536,128 @@ static int search_hamming(snv_index* idx, int w0, int nw, const void* q, int64_t
     return SNV_OK;
 }
 
+static int search_hamming_grouped(snv_index* idx, const void* q, const int32_t* window_ids, int64_t nqt,
+                                  int q_dtype, const void* mask, int k, int32_t* D_i32, float* D_f32,
+                                  int64_t* I, unsigned flags, cudaStream_t stream)
+{
+    const bool q_dev = flags & SNV_Q_ON_DEVICE;
+    const bool out_dev = flags & SNV_OUT_ON_DEVICE;
+    const bool invert = flags & SNV_MASK_IS_MISSING;
+    const size_t row_b = (size_t)idx->stride * 4;
+    const bool tokens = q_dtype == SNV_DT_I64_TOKENS;
+    const size_t in_row = dtype_row_bytes(q_dtype, idx->d, idx->stride);
+    if (in_row == 0) { set_error("search_grouped: bad dtype"); return SNV_ERR_INVALID; }
+    if (tokens && mask) { set_error("search_grouped: token queries carry their own mask"); return SNV_ERR_INVALID; }
+    if (mask && q_dtype == SNV_DT_PACKED_U8) { set_error("search_grouped: masks are not supported with byte-packed codes"); return SNV_ERR_INVALID; }
+
+    // ---- host: stable counting sort of the queries by window -> permutation + work items
+    const int W = idx->n_windows;
+    std::vector<int32_t> count(W + 1, 0);
+    for (int64_t i = 0; i < nqt; ++i) {
+        const int32_t w = window_ids[i];
+        if (w < 0 || w >= W) { set_error("search_grouped: window id out of range"); return SNV_ERR_INVALID; }
+        ++count[w + 1];
+    }
+    int n_groups = 0;
+    for (int w = 0; w < W; ++w) n_groups += count[w + 1] > 0;
+    for (int w = 0; w < W; ++w) count[w + 1] += count[w];
+    std::vector<int32_t> order(nqt);
+    {
+        std::vector<int32_t> pos(count.begin(), count.end() - 1);
+        for (int64_t i = 0; i < nqt; ++i) order[pos[window_ids[i]]++] = (int32_t)i;
+    }
+    HammingSearchParams p{};
+    p.words = idx->words;
+    p.stride = idx->stride;
+    p.d = (int)idx->d;
+    const bool reg_kernel = true;
+    (void)reg_kernel;
+    const int64_t avg = n_groups ? nqt / n_groups : 0;
+    int block = avg >= 64 ? 128 : 32;
+    {   // wide rows (generic kernel) always use 32-query blocks
+        HammingSearchParams probe{};
+        probe.words = idx->words; probe.stride = idx->stride; probe.d = (int)idx->d; probe.k = k;
+        probe.n = idx->ntotal; probe.nq = 1; probe.nw = 1;
+        if (hamming_plan(probe) == (size_t)-1) return SNV_ERR_UNSUPPORTED;
+        if (!probe.nw_templ) block = 32;
+    }
+    std::vector<int32_t> work;
+    for (int w = 0; w < W; ++w) {
+        for (int32_t s0 = count[w]; s0 < count[w + 1]; s0 += block) {
+            work.push_back(w);
+            work.push_back(s0);
+            work.push_back(std::min<int32_t>(block, count[w + 1] - s0));
+        }
+    }
+    const int n_work = (int)(work.size() / 3);
+
+    int rc;
+    rc = idx->ws_misc.reserve((size_t)(nqt + work.size()) * 4);
+    if (rc) return rc;
+    int32_t* d_order = (int32_t*)idx->ws_misc.p;
+    int32_t* d_work = d_order + nqt;
+    SNV_CUDA_CHECK(cudaMemcpyAsync(d_order, order.data(), (size_t)nqt * 4, cudaMemcpyHostToDevice, stream));
+    SNV_CUDA_CHECK(cudaMemcpyAsync(d_work, work.data(), work.size() * 4, cudaMemcpyHostToDevice, stream));
+
+    const bool q_needs_pack = q_dtype != SNV_DT_PACKED_U32;
+    const bool m_needs_pack = mask && (q_dtype != SNV_DT_PACKED_U32 || invert);
+    if (!q_dev) { rc = idx->ws_in.reserve((size_t)nqt * in_row); if (rc) return rc; }
+    if (q_needs_pack) { rc = idx->ws_q.reserve((size_t)nqt * row_b); if (rc) return rc; }
+    if (tokens || m_needs_pack) { rc = idx->ws_mask.reserve((size_t)nqt * row_b); if (rc) return rc; }
+    if (mask && !q_dev) { rc = idx->ws_min.reserve((size_t)nqt * in_row); if (rc) return rc; }
+
+    const uint32_t* qd = nullptr;
+    uint32_t* obs = tokens ? (uint32_t*)idx->ws_mask.p : nullptr;
+    rc = stage_packed(idx, q, nqt, q_dtype, q_dev, false, idx->ws_in.p, (uint32_t*)idx->ws_q.p, &qd, obs, stream);
+    if (rc) return rc;
+    p.q = qd;
+    if (tokens) {
+        p.mask = obs;
+        p.mask_q_stride = idx->stride;
+    } else if (mask) {
+        const uint32_t* md = nullptr;
+        rc = stage_packed(idx, mask, nqt, q_dtype, q_dev, invert, idx->ws_min.p, (uint32_t*)idx->ws_mask.p, &md, nullptr, stream);
+        if (rc) return rc;
+        p.mask = md;
+        p.mask_q_stride = idx->stride;
+    }
+    p.panel = idx->panel;
+    p.panel_win_stride = idx->cap * idx->stride;
+    p.n = idx->ntotal;
+    p.nq = (int)std::min<int64_t>(nqt, 0x7fffffff);
+    p.nw = W;
+    p.k = k;
+    p.id_offset = 0;
+    p.work = d_work;
+    p.order = d_order;
+    p.n_work = n_work;
+    p.work_block = block;
+    p.nq_total = nqt;
+    if (out_dev) {
+        p.D_i32 = D_i32; p.D_f32 = D_f32; p.I = I;
+    } else {
+        if (D_i32) { rc = idx->ws_di.reserve((size_t)nqt * k * 4); if (rc) return rc; p.D_i32 = (int32_t*)idx->ws_di.p; }
+        if (D_f32) { rc = idx->ws_df.reserve((size_t)nqt * k * 4); if (rc) return rc; p.D_f32 = (float*)idx->ws_df.p; }
+        rc = idx->ws_i.reserve((size_t)nqt * k * 8);
+        if (rc) return rc;
+        p.I = (int64_t*)idx->ws_i.p;
+    }
+    const size_t part = hamming_plan(p);
+    if (part == (size_t)-1) return SNV_ERR_UNSUPPORTED;
+    if (part) { rc = idx->ws_partial.reserve(part); if (rc) return rc; p.partial = (uint64_t*)idx->ws_partial.p; }
+    rc = hamming_launch(p, stream);
+    if (rc) return rc;
+    if (!out_dev) {
+        const size_t cnt = (size_t)nqt * k;
+        if (D_i32) SNV_CUDA_CHECK(cudaMemcpyAsync(D_i32, p.D_i32, cnt * 4, cudaMemcpyDeviceToHost, stream));
+        if (D_f32) SNV_CUDA_CHECK(cudaMemcpyAsync(D_f32, p.D_f32, cnt * 4, cudaMemcpyDeviceToHost, stream));
+        SNV_CUDA_CHECK(cudaMemcpyAsync(I, p.I, cnt * 8, cudaMemcpyDeviceToHost, stream));
+    }
+    // order/work live in host vectors that die with this frame: always wait for their upload
+    SNV_CUDA_CHECK(cudaStreamSynchronize(stream));
+    return SNV_OK;
+}
+
 static int search_l2(snv_index* idx, int w0, int nw, const void* q, int64_t nq, int k, int64_t id_offset,
                      float* D_f32, int64_t* I, unsigned flags, cudaStream_t stream)
 {
@@ -621,6 +743,69 @@ int snv_index_search(snv_index* idx, int w0, int nw, const void* q, int64_t nq, 
     if (mask_mode != SNV_MASK_NONE) { set_error("snv_index_search: masks apply to HAMMING indexes only"); return SNV_ERR_INVALID; }
     if (D_i32) { set_error("snv_index_search: D_i32 applies to HAMMING indexes only"); return SNV_ERR_INVALID; }
     return search_l2(idx, w0, nw, q, nq, k, id_offset, D_f32, I, flags, stream);
+}
+
+int snv_index_search_grouped(snv_index* idx, const void* q, const int32_t* window_ids, int64_t nq_total,
+                             int q_dtype, const void* mask, int k, int32_t* D_i32, float* D_f32, int64_t* I,
+                             unsigned flags, void* stream_)
+{
+    if (!idx || idx->kind != SNV_KIND_HAMMING) { set_error("snv_index_search_grouped: needs a HAMMING index"); return SNV_ERR_INVALID; }
+    if (nq_total < 0 || nq_total > 0x7fffffff) { set_error("snv_index_search_grouped: bad nq_total"); return SNV_ERR_INVALID; }
+    if (k < 1) { set_error("snv_index_search_grouped: k must be >= 1"); return SNV_ERR_INVALID; }
+    if (nq_total == 0) return SNV_OK;
+    if (!q || !I || !window_ids) { set_error("snv_index_search_grouped: null buffer"); return SNV_ERR_INVALID; }
+    DeviceGuard g(idx->device);
+    if (!g.ok) { set_error("snv_index_search_grouped: cudaSetDevice failed"); return SNV_ERR_CUDA; }
+    return search_hamming_grouped(idx, q, window_ids, nq_total, q_dtype, mask, k, D_i32, D_f32, I, flags, (cudaStream_t)stream_);
+}
+
+int snv_index_gather_tokens_grouped(snv_index* idx, const int64_t* I, const int32_t* window_ids, int64_t nq_total,
+                                    int k, const int32_t* n_sites, int seq_len, int64_t* out, unsigned flags,
+                                    void* stream_)
+{
+    if (!idx || idx->kind != SNV_KIND_HAMMING) { set_error("snv_index_gather_tokens_grouped: needs a HAMMING index"); return SNV_ERR_INVALID; }
+    if (nq_total < 0 || k < 1 || seq_len < 1) { set_error("snv_index_gather_tokens_grouped: bad arguments"); return SNV_ERR_INVALID; }
+    if (nq_total == 0) return SNV_OK;
+    if (!I || !out || !window_ids) { set_error("snv_index_gather_tokens_grouped: null buffer"); return SNV_ERR_INVALID; }
+    DeviceGuard g(idx->device);
+    if (!g.ok) { set_error("snv_index_gather_tokens_grouped: cudaSetDevice failed"); return SNV_ERR_CUDA; }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const bool i_dev = flags & SNV_Q_ON_DEVICE;
+    const bool out_dev = flags & SNV_OUT_ON_DEVICE;
+    const int W = idx->n_windows;
+    // per-query (window, n_sites) pairs, uploaded once
+    std::vector<int32_t> meta((size_t)nq_total * 2);
+    for (int64_t i = 0; i < nq_total; ++i) {
+        const int32_t w = window_ids[i];
+        if (w < 0 || w >= W) { set_error("snv_index_gather_tokens_grouped: window id out of range"); return SNV_ERR_INVALID; }
+        const int32_t ns = n_sites ? n_sites[w] : (int32_t)idx->d;
+        if (ns < 0 || ns > idx->d) { set_error("snv_index_gather_tokens_grouped: n_sites out of range"); return SNV_ERR_INVALID; }
+        meta[2 * i] = w;
+        meta[2 * i + 1] = ns;
+    }
+    int rc = idx->ws_misc.reserve(meta.size() * 4);
+    if (rc) return rc;
+    SNV_CUDA_CHECK(cudaMemcpyAsync(idx->ws_misc.p, meta.data(), meta.size() * 4, cudaMemcpyHostToDevice, stream));
+    const int64_t rows = nq_total * k;
+    const int64_t* Id = I;
+    if (!i_dev) {
+        rc = idx->ws_i.reserve((size_t)rows * 8);
+        if (rc) return rc;
+        SNV_CUDA_CHECK(cudaMemcpyAsync(idx->ws_i.p, I, (size_t)rows * 8, cudaMemcpyHostToDevice, stream));
+        Id = (const int64_t*)idx->ws_i.p;
+    }
+    int64_t* od = out;
+    if (!out_dev) {
+        rc = idx->ws_in.reserve((size_t)rows * seq_len * 8);
+        if (rc) return rc;
+        od = (int64_t*)idx->ws_in.p;
+    }
+    rc = gather_tokens_grouped_launch(idx->panel, idx->cap * idx->stride, idx->stride, idx->ntotal, Id,
+                                      (const int32_t*)idx->ws_misc.p, nq_total, k, seq_len, od, stream);
+    if (rc) return rc;
+    if (!out_dev) SNV_CUDA_CHECK(cudaMemcpyAsync(out, od, (size_t)rows * seq_len * 8, cudaMemcpyDeviceToHost, stream));
+    SNV_CUDA_CHECK(cudaStreamSynchronize(stream));
+    return SNV_OK;
 }
 
 int snv_index_gather_tokens(snv_index* idx, int w0, int nw, const int64_t* I, int64_t nq, int k,

@@ -86,6 +86,39 @@ struct WeightedPopc {
     }
 };
 
+// Which (window, query, row split) a thread works on.  Uniform mode: blockIdx = ((w * qtiles) + qt)
+// * nsplit + split, queries laid out [nw][nq].  Grouped mode (p.work != nullptr): one work item
+// (window, start, count) per CTA group; queries stay in caller order and are reached through the
+// window-sorted permutation p.order (ragged per-window batches of a training step).
+struct Slot {
+    int w, split;
+    bool active;
+    int64_t qrow;    // row of this query in q / mask / outputs
+    int64_t mrow;    // word offset of its mask row
+};
+__device__ __forceinline__ Slot decode_slot(const HammingSearchParams& p)
+{
+    Slot s;
+    int b = blockIdx.x;
+    s.split = b % p.nsplit;
+    b /= p.nsplit;
+    if (p.work) {
+        const int w = p.work[3 * b], start = p.work[3 * b + 1], count = p.work[3 * b + 2];
+        s.w = w;
+        s.active = (int)threadIdx.x < count;
+        s.qrow = s.active ? p.order[start + threadIdx.x] : 0;
+        s.mrow = p.mask_q_stride ? s.qrow * p.mask_q_stride : (int64_t)w * p.mask_win_stride;
+    } else {
+        const int qt = b % p.qtiles;
+        s.w = b / p.qtiles;
+        const int qi = qt * blockDim.x + threadIdx.x;
+        s.active = qi < p.nq;
+        s.qrow = (int64_t)s.w * p.nq + (s.active ? qi : 0);
+        s.mrow = (int64_t)s.w * p.mask_win_stride + (int64_t)(s.active ? qi : 0) * p.mask_q_stride;
+    }
+    return s;
+}
+
 template <int NW>
 __device__ __forceinline__ void load_row_regs(uint32_t (&dst)[NW], const uint32_t* __restrict__ src)
 {
@@ -108,11 +141,9 @@ hamming_topk_kernel(const HammingSearchParams p)
     uint32_t* tiles = reinterpret_cast<uint32_t*>(smem_raw + kBarBytes);
 
     const int tid = threadIdx.x;
-    int b = blockIdx.x;
-    const int split = b % p.nsplit;
-    b /= p.nsplit;
-    const int qt = b % p.qtiles;
-    const int w = b / p.qtiles;
+    const Slot slot = decode_slot(p);
+    const int split = slot.split;
+    const int w = slot.w;
 
     const int64_t r0 = (int64_t)split * p.rows_per_split;
     const int64_t r1 = (r0 + p.rows_per_split < p.n) ? r0 + p.rows_per_split : p.n;
@@ -141,14 +172,13 @@ hamming_topk_kernel(const HammingSearchParams p)
     }
 
     // ---- this thread's query (and observed-site mask) -> registers
-    const int qi = qt * blockDim.x + tid;
-    const bool active = qi < p.nq;
+    const bool active = slot.active;
     uint32_t q[NW];
     uint32_t m[MASKED ? NW : 1];
     if (active) {
-        load_row_regs<NW>(q, p.q + ((int64_t)w * p.nq + qi) * p.stride);
+        load_row_regs<NW>(q, p.q + slot.qrow * p.stride);
         if constexpr (MASKED) {
-            load_row_regs<NW>(m, p.mask + (int64_t)w * p.mask_win_stride + (int64_t)qi * p.mask_q_stride);
+            load_row_regs<NW>(m, p.mask + slot.mrow);
 #pragma unroll
             for (int i = 0; i < NW; ++i) q[i] &= m[i];
         }
@@ -227,7 +257,7 @@ SNV_UNROLL(SNV_ROW_UNROLL)
 
     if (!active) return;
     const uint32_t idx_mask = (1u << idx_bits) - 1u;
-    const int64_t qrow = (int64_t)w * p.nq + qi;
+    const int64_t qrow = slot.qrow;
     if (p.nsplit == 1) {
 #pragma unroll
         for (int i = 0; i < KT; ++i) {
@@ -265,11 +295,9 @@ hamming_topk_generic_kernel(const HammingSearchParams p)
     uint32_t* tiles = reinterpret_cast<uint32_t*>(smem_raw + kBarBytes);
     const int tid = threadIdx.x;
     const int B = blockDim.x;
-    int b = blockIdx.x;
-    const int split = b % p.nsplit;
-    b /= p.nsplit;
-    const int qt = b % p.qtiles;
-    const int w = b / p.qtiles;
+    const Slot slot = decode_slot(p);
+    const int split = slot.split;
+    const int w = slot.w;
     const int64_t r0 = (int64_t)split * p.rows_per_split;
     const int64_t r1 = (r0 + p.rows_per_split < p.n) ? r0 + p.rows_per_split : p.n;
     const int nrows = (int)(r1 - r0);
@@ -296,14 +324,13 @@ hamming_topk_generic_kernel(const HammingSearchParams p)
     if (tid == 0) {
         for (int t = 0; t < stages - 1 && t < ntiles; ++t) issue(t);
     }
-    const int qi = qt * B + tid;
-    const bool active = qi < p.nq;
+    const bool active = slot.active;
     for (int i = 0; i < p.stride; ++i) {
         uint32_t qv = 0, mv = 0;
         if (active) {
-            qv = p.q[((int64_t)w * p.nq + qi) * p.stride + i];
+            qv = p.q[slot.qrow * p.stride + i];
             if constexpr (MASKED) {
-                mv = p.mask[(int64_t)w * p.mask_win_stride + (int64_t)qi * p.mask_q_stride + i];
+                mv = p.mask[slot.mrow + i];
                 qv &= mv;
             }
         }
@@ -338,7 +365,7 @@ hamming_topk_generic_kernel(const HammingSearchParams p)
     }
     if (!active) return;
     const uint32_t idx_mask = (1u << idx_bits) - 1u;
-    const int64_t qrow = (int64_t)w * p.nq + qi;
+    const int64_t qrow = slot.qrow;
     if (p.nsplit == 1) {
 #pragma unroll
         for (int i = 0; i < KT; ++i) {
@@ -379,7 +406,7 @@ int launch_one(const HammingSearchParams& p, cudaStream_t stream)
     if (p.smem_bytes > 48 * 1024) {
         SNV_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
     }
-    const int64_t grid = (int64_t)p.nw * p.qtiles * p.nsplit;
+    const int64_t grid = (p.work ? (int64_t)p.n_work : (int64_t)p.nw * p.qtiles) * p.nsplit;
     profile_begin(stream);
     kern<<<(unsigned)grid, p.block, p.smem_bytes, stream>>>(p);
     profile_end(stream);
@@ -394,7 +421,7 @@ int launch_generic(const HammingSearchParams& p, cudaStream_t stream)
     if (p.smem_bytes > 48 * 1024) {
         SNV_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
     }
-    const int64_t grid = (int64_t)p.nw * p.qtiles * p.nsplit;
+    const int64_t grid = (p.work ? (int64_t)p.n_work : (int64_t)p.nw * p.qtiles) * p.nsplit;
     profile_begin(stream);
     kern<<<(unsigned)grid, p.block, p.smem_bytes, stream>>>(p);
     profile_end(stream);
@@ -442,14 +469,17 @@ size_t hamming_plan(HammingSearchParams& p)
     p.idx_bits = 32 - dist_bits;
     const int64_t max_rows_per_split = (int64_t)1 << p.idx_bits;
 
-    if (p.nw_templ) {
+    if (p.work) {
+        p.block = p.work_block;  // chosen by the caller that built the work list
+    } else if (p.nw_templ) {
         p.block = p.nq >= kMaxBlock ? kMaxBlock : (int)round_up(p.nq > 0 ? p.nq : 1, 32);
     } else {
         p.block = 32;
-        if (p.stride > 512) {
-            set_error("hamming search: d > 16384 bits is not supported yet");
-            return (size_t)-1;
-        }
+    }
+    if (!p.nw_templ && (p.stride > 512 || p.block != 32)) {
+        set_error(p.stride > 512 ? "hamming search: d > 16384 bits is not supported yet"
+                                 : "hamming search: wide rows use 32-query blocks");
+        return (size_t)-1;
     }
     p.qtiles = (int)ceil_div(p.nq > 0 ? p.nq : 1, p.block);
 
@@ -464,7 +494,7 @@ size_t hamming_plan(HammingSearchParams& p)
 
     // row splits: enough CTAs to fill the machine (>= 4 per SM) and rows per split that fit
     // the id field of the 32-bit key.
-    const int64_t base = (int64_t)p.nw * p.qtiles;
+    const int64_t base = p.work ? (int64_t)p.n_work : (int64_t)p.nw * p.qtiles;
     const int64_t target = (int64_t)kNumSMs * 4;
     int64_t nsplit = 1;
     if (p.n > 0) {
@@ -492,16 +522,18 @@ size_t hamming_plan(HammingSearchParams& p)
     p.nsplit = (int)nsplit;
     p.smem_bytes = kBarBytes + (size_t)p.stages * p.tile_rows * p.stride * 4;
     if (!p.nw_templ) p.smem_bytes += (size_t)p.stride * p.block * 4 * (p.mask ? 2 : 1);
-    if ((int64_t)p.nw * p.qtiles * p.nsplit > 0x7fffffffLL) {
+    if (base * p.nsplit > 0x7fffffffLL) {
         set_error("hamming search: grid too large");
         return (size_t)-1;
     }
-    return p.nsplit > 1 ? (size_t)p.nw * p.nq * p.nsplit * p.kt * sizeof(uint64_t) : 0;
+    const int64_t nq_total = p.work ? p.nq_total : (int64_t)p.nw * p.nq;
+    return p.nsplit > 1 ? (size_t)nq_total * p.nsplit * p.kt * sizeof(uint64_t) : 0;
 }
 
 int hamming_launch(const HammingSearchParams& p, cudaStream_t stream)
 {
-    if (p.nw <= 0 || p.nq <= 0) return SNV_OK;
+    if (!p.work && (p.nw <= 0 || p.nq <= 0)) return SNV_OK;
+    if (p.work && p.n_work <= 0) return SNV_OK;
     int rc;
     switch (p.nw_templ) {
 #ifndef SNV_TUNE_ONLY33
@@ -525,7 +557,7 @@ int hamming_launch(const HammingSearchParams& p, cudaStream_t stream)
     }
     if (rc != SNV_OK) return rc;
     if (p.nsplit > 1) {
-        return merge_keys_launch(p.partial, p.nsplit, p.kt, (int64_t)p.nw * p.nq, p.k, p.id_offset,
+        return merge_keys_launch(p.partial, p.nsplit, p.kt, p.work ? p.nq_total : (int64_t)p.nw * p.nq, p.k, p.id_offset,
                                  false, p.D_i32, p.D_f32, p.I, stream);
     }
     return SNV_OK;

@@ -29,6 +29,11 @@ struct HammingSearchParams {
     float* D_f32;
     int64_t* I;
     uint64_t* partial;  // workspace, required when nsplit > 1: [nw*nq][nsplit][kt] keys
+    // grouped (ragged) mode: work items (window, start, count) over the window-sorted permutation `order`
+    const int32_t* work;   // device [n_work][3]; nullptr = uniform [nw][nq] mode
+    const int32_t* order;  // device [nq_total]
+    int n_work, work_block;
+    int64_t nq_total;
     // plan (filled by hamming_plan)
     int block, qtiles, nsplit, rows_per_split, idx_bits, kt, nw_templ, tile_rows, stages;
     uint32_t wt1, wt2, wt4;  // 1, 2, 4 as runtime values (keeps the popcount adds on the FMA pipe)
@@ -60,6 +65,10 @@ int gather_tokens_launch(const uint32_t* panel, int64_t panel_win_stride, int st
                          const int64_t* I, int64_t id_offset, int nw, int64_t nq, int k,
                          const int32_t* n_sites_dev, int d, int seq_len, int64_t* out,
                          cudaStream_t stream);
+// ragged batch: meta [nq][2] = (window, n_sites) per query
+int gather_tokens_grouped_launch(const uint32_t* panel, int64_t panel_win_stride, int stride, int64_t n,
+                                 const int64_t* I, const int32_t* meta, int64_t nq, int k, int seq_len,
+                                 int64_t* out, cudaStream_t stream);
 int gather_rows_launch(const float* panel, int64_t panel_win_stride, int64_t d, int64_t n,
                        const int64_t* I, int nw, int64_t nq, int k, float* out, cudaStream_t stream);
 

@@ -223,6 +223,37 @@ gather_tokens_kernel(const uint32_t* __restrict__ panel, int64_t panel_win_strid
 }
 
 __global__ void __launch_bounds__(256)
+gather_tokens_grouped_kernel(const uint32_t* __restrict__ panel, int64_t panel_win_stride, int stride, int64_t n,
+                             const int64_t* __restrict__ I, const int32_t* __restrict__ meta, int64_t rows_total,
+                             int k, int seq_len, int64_t* __restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t item = warp; item < rows_total; item += nwarps) {
+        const int64_t qi = item / k;
+        const int w = meta[2 * qi], ns = meta[2 * qi + 1];
+        const int64_t id = I[item];
+        int64_t* o = out + item * seq_len;
+        if (id < 0 || id >= n) {
+            for (int c = lane; c < seq_len; c += 32) o[c] = 0;
+            continue;
+        }
+        const uint32_t* row = panel + (int64_t)w * panel_win_stride + id * stride;
+        for (int c = lane; c < seq_len; c += 32) {
+            int64_t tok;
+            if (c == 0) tok = 2;
+            else if (c <= ns) {
+                const int s = c - 1;
+                tok = 5 + ((row[s >> 5] >> (s & 31)) & 1u);
+            } else if (c == ns + 1) tok = 3;
+            else tok = 0;
+            o[c] = tok;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
 gather_rows_kernel(const float* __restrict__ panel, int64_t panel_win_stride, int64_t d, int64_t n,
                    const int64_t* __restrict__ I, int64_t rows_total, int64_t rows_per_window,
                    float* __restrict__ out)
@@ -340,6 +371,19 @@ int gather_tokens_launch(const uint32_t* panel, int64_t panel_win_stride, int st
     const int block = 256;
     gather_tokens_kernel<<<grid_for_warps(rows_total, block), block, 0, stream>>>(
         panel, panel_win_stride, stride, n, I, id_offset, rows_total, nq * k, n_sites_dev, d, seq_len, out);
+    SNV_LAUNCH_CHECK();
+    return SNV_OK;
+}
+
+int gather_tokens_grouped_launch(const uint32_t* panel, int64_t panel_win_stride, int stride, int64_t n,
+                                 const int64_t* I, const int32_t* meta, int64_t nq, int k, int seq_len,
+                                 int64_t* out, cudaStream_t stream)
+{
+    const int64_t rows_total = nq * k;
+    if (rows_total <= 0) return SNV_OK;
+    const int block = 256;
+    gather_tokens_grouped_kernel<<<grid_for_warps(rows_total, block), block, 0, stream>>>(
+        panel, panel_win_stride, stride, n, I, meta, rows_total, k, seq_len, out);
     SNV_LAUNCH_CHECK();
     return SNV_OK;
 }

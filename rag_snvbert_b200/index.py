@@ -223,6 +223,61 @@ class WindowedHammingIndex(_IndexBase):
             return D[0], I[0]
         return D, I
 
+    def search_grouped(self, q, window_ids, k: int, observed=None, missing=None, dist_dtype=np.int32):
+        """Ragged per-window batch (a training batch regrouped by window_idx,
+        src/dataset/rag_train_dataset.py:239-281): q [nq_total, d] in caller order, window_ids
+        int [nq_total].  One launch; results [nq_total, k] in caller order."""
+        if int(k) < 1:
+            raise ValueError("k must be >= 1")
+        a = _Arg(q)
+        if len(a.shape) != 2:
+            raise ValueError("search_grouped: expected [nq_total, d] queries")
+        nq = a.shape[0]
+        wid = np.ascontiguousarray(np.asarray(window_ids.cpu() if _is_torch(window_ids) else window_ids), dtype=np.int32)
+        if wid.shape != (nq,):
+            raise ValueError("search_grouped: window_ids must have one entry per query")
+        dt, a = _hamming_dtype(a, self.d, self.stride, "search_grouped")
+        flags = L.Q_ON_DEVICE | L.OUT_ON_DEVICE if a.on_device else 0
+        if observed is not None and missing is not None:
+            raise ValueError("search_grouped: give observed= or missing=, not both")
+        mk = observed if observed is not None else missing
+        m_ptr = None
+        if mk is not None:
+            m = _Arg(mk)
+            if m.on_device != a.on_device or tuple(m.shape) != tuple(a.shape):
+                raise ValueError("search_grouped: mask must match the queries (shape and memory)")
+            mdt, m = _hamming_dtype(m, self.d, self.stride, "search_grouped(mask)")
+            if mdt != dt:
+                raise ValueError("search_grouped: mask and queries must use the same dtype")
+            m_ptr = m.ptr
+            if missing is not None:
+                flags |= L.MASK_IS_MISSING
+        want_f = np.dtype(dist_dtype) == np.dtype(np.float32)
+        D, Dp = self._alloc_out(a.on_device, (nq, int(k)), np.float32 if want_f else np.int32)
+        I, Ip = self._alloc_out(a.on_device, (nq, int(k)), np.int64)
+        L.check(self._lib.snv_index_search_grouped(self._h, a.ptr, wid.ctypes.data, nq, dt, m_ptr, int(k),
+                                                   None if want_f else Dp, Dp if want_f else None, Ip, flags,
+                                                   _current_stream(self.device)), "snv_index_search_grouped")
+        return D, I
+
+    def gather_tokens_grouped(self, I, window_ids, n_sites=None, seq_len: int = 1030):
+        """I [nq_total, k] + window_ids [nq_total] -> int64 tokens [nq_total, k, seq_len]."""
+        a = _Arg(I)
+        if a.np_dtype != np.dtype(np.int64) or len(a.shape) != 2:
+            raise ValueError("gather_tokens_grouped: I must be int64 [nq_total, k]")
+        nq, k = a.shape
+        wid = np.ascontiguousarray(np.asarray(window_ids.cpu() if _is_torch(window_ids) else window_ids), dtype=np.int32)
+        ns_ptr = None
+        if n_sites is not None:
+            ns = np.ascontiguousarray(np.broadcast_to(np.asarray(n_sites, dtype=np.int32), (self.n_windows,)))
+            ns_ptr = ns.ctypes.data
+        flags = L.Q_ON_DEVICE | L.OUT_ON_DEVICE if a.on_device else 0
+        out, op = self._alloc_out(a.on_device, (nq, k, int(seq_len)), np.int64)
+        L.check(self._lib.snv_index_gather_tokens_grouped(self._h, a.ptr, wid.ctypes.data, nq, k, ns_ptr, int(seq_len),
+                                                          op, flags, _current_stream(self.device)),
+                "snv_index_gather_tokens_grouped")
+        return out
+
     def gather_tokens(self, I, n_sites=None, seq_len: int = 1030, w0: int = 0):
         """I [nw, nq, k] (or [nq, k]) -> int64 tokens [.., k, seq_len] in the model's input layout
         (src/dataset/rag_train_dataset.py:287-307): [SOS] + 5|6 per site + [EOS] + PAD."""

@@ -348,3 +348,68 @@ def test_host_pipeline_many_windows_all_mask_modes():
         De, Ie = O.token_l2_topk(ptok[w], qtok[w], 3)
         np.testing.assert_array_equal(I[w], Ie)
         np.testing.assert_array_equal(D[w], De)
+
+
+def test_grouped_ragged_batches_one_launch():
+    """a training batch regrouped by window (rag_train_dataset.py:239-281): ragged group sizes."""
+    rng = np.random.default_rng(91)
+    W, N, d = 7, 2008, 1030
+    panel = np.stack([O.hapgen(300 + w, N, d) for w in range(W)])
+    wid = rng.integers(0, W, size=137).astype(np.int32)
+    wid[wid == 3] = 2  # leave one window without queries
+    q = np.stack([O.hapgen(400 + i, 1, d, founder_seed=300 + int(w))[0] for i, w in enumerate(wid)])
+    obs = (rng.random(q.shape) < 0.7).astype(np.uint8)
+    idx = _idx(d, W)
+    idx.add(panel)
+    from rag_snvbert_b200 import _lib
+
+    n0 = _lib.launch_count()
+    D, I = idx.search_grouped(q, wid, 5)
+    assert _lib.launch_count() - n0 <= 3  # pack + scan (+ merge): not one launch per window
+    Dm, Im = idx.search_grouped(q, wid, 5, observed=obs)
+    for i, w in enumerate(wid):
+        De, Ie = O.hamming_topk(panel[w], q[i:i + 1], 5)
+        np.testing.assert_array_equal(I[i], Ie[0])
+        np.testing.assert_array_equal(D[i], De[0])
+        De, Ie = O.hamming_topk(panel[w], q[i:i + 1], 5, obs[i:i + 1])
+        np.testing.assert_array_equal(Im[i], Ie[0])
+        np.testing.assert_array_equal(Dm[i], De[0])
+    # big groups take 128-query blocks
+    wid2 = np.repeat(np.arange(W, dtype=np.int32), 150)
+    q2 = np.concatenate([O.hapgen(500 + w, 150, d, founder_seed=300 + w) for w in range(W)])
+    perm = rng.permutation(len(wid2))
+    D2, I2 = idx.search_grouped(q2[perm], wid2[perm], 8)
+    for w in range(W):
+        sel = np.where(wid2[perm] == w)[0]
+        De, Ie = O.hamming_topk(panel[w], q2[perm][sel], 8)
+        np.testing.assert_array_equal(I2[sel], Ie)
+        np.testing.assert_array_equal(D2[sel], De)
+
+
+def test_rag_retriever_reproduces_reference_collate_golden():
+    """tests/golden/g2: the reference's own rag_collate_fn_with_dataset outputs."""
+    import os
+
+    from rag_snvbert_b200.collate import RagRetriever
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "g2_v17_collate.npz"))
+    k = int(g["k"])
+    r = RagRetriever([g["ref_gt_0"], g["ref_gt_1"]])
+    # golden rows are in the collate's regrouped order (window 0 samples, then window 1)
+    wid = g["window_idx"]
+    h1, h2 = r.retrieve(wid, g["hap_1"], g["hap_2"], k)
+    np.testing.assert_array_equal(h1, g["rag_seg_h1"])
+    np.testing.assert_array_equal(h2, g["rag_seg_h2"])
+    D, I = r.search(wid, g["hap_1"], g["hap_2"], k)
+    n0 = int((wid == 0).sum())
+    np.testing.assert_array_equal(I[:n0].reshape(-1, k), g["search_I_0"])
+    np.testing.assert_array_equal(D[:n0].reshape(-1, k), g["search_D_0"])
+    np.testing.assert_array_equal(I[n0:].reshape(-1, k), g["search_I_1"])
+    np.testing.assert_array_equal(D[n0:].reshape(-1, k), g["search_D_1"])
+    # torch CUDA inputs (the trainer-process pattern): same result, device tensors out
+    import torch
+
+    t1, t2 = r.retrieve(torch.from_numpy(wid), torch.from_numpy(g["hap_1"]).cuda(), torch.from_numpy(g["hap_2"]).cuda(), k)
+    assert t1.is_cuda
+    np.testing.assert_array_equal(t1.cpu().numpy(), g["rag_seg_h1"])
+    np.testing.assert_array_equal(t2.cpu().numpy(), g["rag_seg_h2"])
