@@ -1,0 +1,113 @@
+"""Offline reference-DB workflow on the GPU index (the callers on either side of the hot path).
+
+Mirrors, without faiss / h5py / allel:
+  * build_ref_db_l2.py:68-93       per window: slice -> [S, win_len, 2] -> rows [S, 2*win_len]
+                                   (site-major, hap-minor interleave) -> IndexFlatL2.add
+  * batch_test_faiss_l2.py:80-110  per window: target rows -> index.search(batch, top_k)
+  * test_faiss_intersect.py:128-140 ref / target position intersection before the search
+  * partial_faiss_intersect.py:46-80 expand_target_to_ref (target expanded to the ref site set
+                                   with a missing mask) + per-sample observed-site search (:82-111)
+The rows are 0/1 genotypes, so the whole sweep is ONE bit-packed Hamming search over all windows
+(D equals faiss's squared L2 on these vectors).  Windows shorter than the longest are zero padded;
+pad sites are equal in panel and queries and never contribute.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional, Tuple
+
+import numpy as np
+
+from .index import WindowedHammingIndex
+
+
+def sample_rows(gt: np.ndarray, window_info: np.ndarray, d: Optional[int] = None) -> np.ndarray:
+    """gt [V, S, 2] 0/1 (GT > 0 -> 1, build_ref_db_l2.py:50), window_info [W, 2] (start, end) ->
+    uint8 rows [W, S, d] in the scripts' layout: row = sample, columns s0h0, s0h1, s1h0, ...
+    (build_ref_db_l2.py:70-86), zero padded to d = 2 * max window length."""
+    gt = (np.asarray(gt) > 0).astype(np.uint8)
+    window_info = np.asarray(window_info)
+    W = window_info.shape[0]
+    dmax = int(2 * (window_info[:, 1] - window_info[:, 0]).max()) if W else 0
+    d = dmax if d is None else int(d)
+    if d < dmax:
+        raise ValueError("d is smaller than the longest window")
+    out = np.zeros((W, gt.shape[1], d), dtype=np.uint8)
+    for w, (a, b) in enumerate(window_info):
+        sub = np.transpose(gt[a:b], (1, 0, 2))  # [S, win_len, 2]
+        out[w, :, : 2 * (b - a)] = sub.reshape(sub.shape[0], -1)
+    return out
+
+
+def build_ref_db(ref_gt: np.ndarray, window_info: np.ndarray, device: Optional[int] = None) -> WindowedHammingIndex:
+    """build_ref_db_l2.py's loop: one windowed index instead of one .faiss file per window."""
+    rows = sample_rows(ref_gt, window_info)
+    index = WindowedHammingIndex(rows.shape[2], rows.shape[0], device)
+    index.add(rows)
+    return index
+
+
+def load_ref_db(ref_db_dir: str, n_windows: int, device: Optional[int] = None) -> WindowedHammingIndex:
+    """Reads the `window_{i}.npy` files ([S, win_len, 2]) written by build_ref_db_l2.py:77-78."""
+    cubes = [np.load(os.path.join(ref_db_dir, f"window_{w}.npy")) for w in range(n_windows)]
+    d = 2 * max(c.shape[1] for c in cubes)
+    rows = np.zeros((n_windows, cubes[0].shape[0], d), dtype=np.uint8)
+    for w, c in enumerate(cubes):
+        rows[w, :, : 2 * c.shape[1]] = (c > 0).reshape(c.shape[0], -1)
+    index = WindowedHammingIndex(d, n_windows, device)
+    index.add(rows)
+    return index
+
+
+def batch_search(index: WindowedHammingIndex, target_gt: np.ndarray, window_info: np.ndarray, top_k: int,
+                 samples=None) -> Tuple[np.ndarray, np.ndarray]:
+    """batch_test_faiss_l2.py:80-110 for every window at once -> D float32 [W, nq, k], I int64."""
+    rows = sample_rows(target_gt, window_info, index.d)
+    if samples is not None:
+        rows = np.ascontiguousarray(rows[:, list(samples)])
+    return index.search(rows, top_k, dist_dtype=np.float32)
+
+
+def expand_target_to_ref(ref_pos: np.ndarray, tgt_data: np.ndarray, tgt_pos: np.ndarray):
+    """partial_faiss_intersect.py:46-80, vectorised: target genotypes placed on the ref site set.
+    Returns (expanded [var_ref, S_t, 2] uint8, missing_mask [var_ref, S_t] uint8, 1 = missing).
+    Duplicate target positions resolve to the LAST occurrence like the reference's dict."""
+    ref_pos = np.asarray(ref_pos)
+    tgt_pos = np.asarray(tgt_pos)
+    tgt_data = np.asarray(tgt_data)
+    order = np.argsort(tgt_pos, kind="stable")
+    sp = tgt_pos[order]
+    j = np.searchsorted(sp, ref_pos, side="right") - 1  # last occurrence <= p
+    hit = (j >= 0) & (sp[np.clip(j, 0, None)] == ref_pos)
+    expanded = np.zeros((ref_pos.shape[0],) + tgt_data.shape[1:], dtype=np.uint8)
+    expanded[hit] = tgt_data[order[j[hit]]]
+    missing = np.zeros((ref_pos.shape[0], tgt_data.shape[1]), dtype=np.uint8)
+    missing[~hit] = 1
+    return expanded, missing
+
+
+def intersect_windows(ref_pos: np.ndarray, tgt_pos: np.ndarray, window_info: np.ndarray) -> np.ndarray:
+    """test_faiss_intersect.py:128-140 as a mask: observed[w, s] = 1 where ref site
+    window_info[w,0]+s is also a target position (np.intersect1d semantics)."""
+    ref_pos = np.asarray(ref_pos)
+    window_info = np.asarray(window_info)
+    shared = np.isin(ref_pos, np.asarray(tgt_pos))
+    L = int((window_info[:, 1] - window_info[:, 0]).max())
+    obs = np.zeros((window_info.shape[0], L), dtype=np.uint8)
+    for w, (a, b) in enumerate(window_info):
+        obs[w, : b - a] = shared[a:b]
+    return obs
+
+
+def partial_search(index: WindowedHammingIndex, expanded: np.ndarray, missing: np.ndarray,
+                   window_info: np.ndarray, top_k: int):
+    """Observed-site search of every target sample in every window
+    (partial_faiss_intersect.py:145-172 with build_partial_index_l2 :82-111): distance restricted to
+    sites where the sample's mask == 0, both haplotypes of a sample share its site mask.
+    expanded [var_ref, S_t, 2], missing [var_ref, S_t] -> D float32 [W, S_t, k], I int64.
+    (The script concatenates the query as [h1.., h2..] but the panel rows as s0h0,s0h1,..
+    (:94 vs :101) — a layout slip; this follows the evident intent: aligned columns.)"""
+    q = sample_rows(expanded, window_info, index.d)
+    m2 = np.repeat(np.asarray(missing)[:, :, None], 2, axis=2)  # both haplotypes share the site mask
+    miss = sample_rows(m2, window_info, index.d)
+    return index.search(q, top_k, missing=miss, dist_dtype=np.float32)

@@ -1,0 +1,73 @@
+"""GPU: offline reference-DB workflow (build_ref_db_l2 / batch_test_faiss_l2 / intersect /
+partial_faiss_intersect mirrors) against brute force in the scripts' own vector layout."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _data(seed=0, V=700, S_ref=120, S_t=9):
+    rng = np.random.default_rng(seed)
+    ref = O.hapgen(seed + 1, 2 * S_ref, V).reshape(S_ref, 2, V).transpose(2, 0, 1).copy()  # [V, S, 2]
+    tgt = O.hapgen(seed + 2, 2 * S_t, V, founder_seed=seed + 1).reshape(S_t, 2, V).transpose(2, 0, 1).copy()
+    win = np.array([[0, 250], [250, 480], [480, 700]])
+    return rng, ref, tgt, win
+
+
+def test_build_and_batch_search_match_faiss_layout(tmp_path):
+    from rag_snvbert_b200 import refdb
+
+    rng, ref, tgt, win = _data()
+    index = refdb.build_ref_db(ref, win)
+    D, I = refdb.batch_search(index, tgt, win, 4)
+    for w, (a, b) in enumerate(win):
+        # the literal vectors of build_ref_db_l2.py:86 / batch_test_faiss_l2.py:88
+        xr = np.transpose(ref[a:b], (1, 0, 2)).reshape(ref.shape[1], -1).astype(np.float32)
+        xq = np.transpose(tgt[a:b], (1, 0, 2)).reshape(tgt.shape[1], -1).astype(np.float32)
+        De, Ie = O.l2_topk_f32_blas(xr, xq, 4)
+        np.testing.assert_array_equal(I[w], Ie)
+        np.testing.assert_array_equal(D[w], De)
+    # window_{i}.npy round trip (build_ref_db_l2.py:77-78)
+    for w, (a, b) in enumerate(win):
+        np.save(tmp_path / f"window_{w}.npy", np.transpose(ref[a:b], (1, 0, 2)))
+    again = refdb.load_ref_db(str(tmp_path), len(win))
+    D2, I2 = refdb.batch_search(again, tgt, win, 4)
+    np.testing.assert_array_equal(I2, I)
+    np.testing.assert_array_equal(D2, D)
+
+
+def test_expand_target_and_partial_search():
+    from rag_snvbert_b200 import refdb
+
+    rng, ref, tgt, win = _data(5)
+    V = ref.shape[0]
+    ref_pos = np.sort(rng.choice(10 * V, V, replace=False))
+    keep = np.sort(rng.choice(V, int(0.6 * V), replace=False))
+    tgt_pos = np.concatenate([ref_pos[keep], [10 * V + 5, 10 * V + 9]])  # plus sites absent from the ref
+    tgt_data = np.concatenate([tgt[keep], np.ones((2,) + tgt.shape[1:], tgt.dtype)])
+    expanded, missing = refdb.expand_target_to_ref(ref_pos, tgt_data, tgt_pos)
+    # the reference's loop, literally (partial_faiss_intersect.py:63-78)
+    tgt_dict = {p: i for i, p in enumerate(tgt_pos)}
+    exp_e = np.zeros_like(expanded)
+    mis_e = np.zeros_like(missing)
+    for r_i, p in enumerate(ref_pos):
+        if p in tgt_dict:
+            exp_e[r_i] = tgt_data[tgt_dict[p]]
+        else:
+            mis_e[r_i] = 1
+    np.testing.assert_array_equal(expanded, exp_e)
+    np.testing.assert_array_equal(missing, mis_e)
+    np.testing.assert_array_equal(refdb.intersect_windows(ref_pos, tgt_pos, win)[0, :250], 1 - mis_e[:250, 0])
+
+    index = refdb.build_ref_db(ref, win)
+    D, I = refdb.partial_search(index, expanded, missing, win, 5)
+    for w, (a, b) in enumerate(win):
+        for s in range(tgt.shape[1]):
+            valid = np.where(missing[a:b, s] == 0)[0]
+            sub_ref = np.transpose(ref[a:b], (1, 0, 2))[:, valid, :].reshape(ref.shape[1], -1).astype(np.float32)
+            q = expanded[a:b, s][valid].reshape(1, -1).astype(np.float32)  # aligned (s0h0, s0h1, ...) columns
+            De, Ie = O.l2_topk_f32_blas(sub_ref, q, 5)
+            np.testing.assert_array_equal(I[w, s], Ie[0])
+            np.testing.assert_array_equal(D[w, s], De[0])
