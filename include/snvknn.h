@@ -72,6 +72,11 @@ typedef enum snv_mask_mode {
 /* L2 cross-term precision */
 #define SNV_L2_TF32 0   /* one tf32 pass: exact for small-integer inputs (tokens), ~1e-3 rel. otherwise */
 #define SNV_L2_TF32X3 1 /* hi/lo split, three tf32 products: fp32-faithful                               */
+/* OR-ed into l2_mode: subtract the column means of the first rows added from panel and queries
+ * before the product (squared L2 is translation invariant).  Removes the large common component
+ * of embedding vectors (position / allele-frequency terms) so that |q|^2 + |r|^2 - 2 q.r does not
+ * cancel catastrophically.  Not for integer-valued rows (it would make their products inexact). */
+#define SNV_L2_CENTER 0x10
 
 typedef struct snv_index snv_index;
 

@@ -129,6 +129,7 @@ struct snv_index {
     float* rows = nullptr;      // L2 [W][cap][d]
     float* ops = nullptr;       // L2 [W][cap][kp]
     float* norms = nullptr;     // L2 [W][cap]
+    float* mean = nullptr;      // L2 + SNV_L2_CENTER: [W][d] column means of the first add
     Buf ws_in, ws_q, ws_mask, ws_min, ws_partial, ws_di, ws_df, ws_i, ws_qops, ws_qnorm, ws_misc;
     // host-buffer pipeline
     static constexpr int kPipeStreams = 3;
@@ -189,7 +190,8 @@ int snv_index_create(int kind, int64_t d, int n_windows, int device, int l2_mode
     if (kind != SNV_KIND_HAMMING && kind != SNV_KIND_L2) { set_error("snv_index_create: bad kind"); return SNV_ERR_INVALID; }
     if (d <= 0) { set_error("snv_index_create: d must be positive"); return SNV_ERR_INVALID; }
     if (n_windows < 1) { set_error("snv_index_create: n_windows must be >= 1"); return SNV_ERR_INVALID; }
-    if (kind == SNV_KIND_L2 && l2_mode != SNV_L2_TF32 && l2_mode != SNV_L2_TF32X3) { set_error("snv_index_create: bad l2_mode"); return SNV_ERR_INVALID; }
+    if (kind == SNV_KIND_L2 && (l2_mode & 0xF) != SNV_L2_TF32 && (l2_mode & 0xF) != SNV_L2_TF32X3) { set_error("snv_index_create: bad l2_mode"); return SNV_ERR_INVALID; }
+    if (kind == SNV_KIND_L2 && (l2_mode & ~0x1F)) { set_error("snv_index_create: bad l2_mode flags"); return SNV_ERR_INVALID; }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
@@ -223,6 +225,7 @@ void snv_index_free(snv_index* idx)
     if (idx->rows) cudaFree(idx->rows);
     if (idx->ops) cudaFree(idx->ops);
     if (idx->norms) cudaFree(idx->norms);
+    if (idx->mean) cudaFree(idx->mean);
     Buf* bufs[] = {&idx->ws_in, &idx->ws_q, &idx->ws_mask, &idx->ws_min, &idx->ws_partial, &idx->ws_di,
                    &idx->ws_df, &idx->ws_i, &idx->ws_qops, &idx->ws_qnorm, &idx->ws_misc};
     for (Buf* b : bufs) b->release();
@@ -246,6 +249,7 @@ int snv_index_reset(snv_index* idx)
 {
     if (!idx) { set_error("snv_index_reset: null index"); return SNV_ERR_INVALID; }
     idx->ntotal = 0;
+    if (idx->mean) { cudaFree(idx->mean); idx->mean = nullptr; }
     return SNV_OK;
 }
 
@@ -340,8 +344,16 @@ int snv_index_add(snv_index* idx, const void* x, int64_t n, int dtype, unsigned 
             const size_t rb = (size_t)idx->d * 4;
             SNV_CUDA_CHECK(cudaMemcpy2DAsync(idx->rows + idx->ntotal * idx->d, (size_t)idx->cap * rb, xd,
                                              (size_t)n * rb, (size_t)n * rb, W, cudaMemcpyDeviceToDevice, stream));
+            const bool center = idx->l2_mode & SNV_L2_CENTER;
+            if (center && !idx->mean) {
+                if (cudaMalloc(&idx->mean, (size_t)W * idx->d * 4) != cudaSuccess) { set_error("cudaMalloc(mean)"); return SNV_ERR_NOMEM; }
+                for (int w = 0; w < W; ++w) {
+                    int rc = l2_colmean_launch((const float*)xd + (size_t)w * n * idx->d, n, idx->d, idx->mean + (size_t)w * idx->d, stream);
+                    if (rc) return rc;
+                }
+            }
             for (int w = 0; w < W; ++w) {
-                int rc = l2_prep_launch((const float*)xd + (size_t)w * n * idx->d, n, idx->d, idx->l2_mode, false,
+                int rc = l2_prep_launch((const float*)xd + (size_t)w * n * idx->d, center ? idx->mean + (size_t)w * idx->d : nullptr, n, idx->d, idx->l2_mode, false,
                                         idx->kp, idx->ops + ((size_t)w * idx->cap + idx->ntotal) * idx->kp,
                                         idx->norms + (size_t)w * idx->cap + idx->ntotal, stream);
                 if (rc) return rc;
@@ -676,8 +688,16 @@ static int search_l2(snv_index* idx, int w0, int nw, const void* q, int64_t nq, 
     if (rc) return rc;
     rc = idx->ws_qnorm.reserve((size_t)nqt * 4);
     if (rc) return rc;
-    rc = l2_prep_launch(qd, nqt, idx->d, idx->l2_mode, true, idx->kp, (float*)idx->ws_qops.p, (float*)idx->ws_qnorm.p, stream);
-    if (rc) return rc;
+    {
+        const bool center = (idx->l2_mode & SNV_L2_CENTER) && idx->mean;
+        for (int w = 0; w < (center ? nw : 1); ++w) {
+            const int64_t rows = center ? nq : nqt;
+            rc = l2_prep_launch(qd + (size_t)w * nq * idx->d, center ? idx->mean + (size_t)(w0 + w) * idx->d : nullptr, rows,
+                                idx->d, idx->l2_mode, true, idx->kp, (float*)idx->ws_qops.p + (size_t)w * nq * idx->kp,
+                                (float*)idx->ws_qnorm.p + (size_t)w * nq, stream);
+            if (rc) return rc;
+        }
+    }
     float* Dd = D_f32;
     int64_t* Id = I;
     if (!out_dev) {

@@ -87,13 +87,19 @@ struct L2SearchParams {
     int64_t* I;             // [nq][k]
     uint64_t* partial;      // [nq][nsplit][kt]
     int nsplit, kt, tiles_per_split;
+    // split-K mode (skinny problems): partial dot products accumulate into dot[nq][dot_ld]
+    float* dot;
+    int64_t dot_ld;
+    int ksplit, kb_per_split;
 };
 size_t l2_plan(L2SearchParams& p);
 int l2_launch(const L2SearchParams& p, cudaStream_t stream);
 // fp32 rows [rows][d] -> operand rows [rows][kp] (mode TF32: x | 0-pad; TF32X3 with
 // is_query: hi|lo|hi, panel: hi|hi|lo) and squared norms.
-int l2_prep_launch(const float* x, int64_t rows, int64_t d, int mode, bool is_query, int kp,
+int l2_prep_launch(const float* x, const float* mean, int64_t rows, int64_t d, int mode, bool is_query, int kp,
                    float* ops, float* norms, cudaStream_t stream);
+// column means of x [rows][d] (centering; squared L2 is translation invariant)
+int l2_colmean_launch(const float* x, int64_t rows, int64_t d, float* mean, cudaStream_t stream);
 int l2_operand_depth(int64_t d, int mode);
 
 }  // namespace snv

@@ -29,6 +29,7 @@
 // genotypes) are exact in either mode.
 #include <cuda.h>
 
+#include <algorithm>
 #include <mutex>
 
 #include "common.cuh"
@@ -161,7 +162,7 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n)
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-template <int KT>
+template <int KT, bool SPLITK>
 __global__ void __launch_bounds__(kThreads, 1)
 l2_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_r,
                const L2SearchParams p)
@@ -183,13 +184,32 @@ l2_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    const int split = blockIdx.x % p.nsplit;
-    const int mt = blockIdx.x / p.nsplit;
     const int n_tiles_total = (int)((p.n + BN - 1) / BN);
-    const int t0 = split * p.tiles_per_split;
-    const int t1 = (t0 + p.tiles_per_split < n_tiles_total) ? t0 + p.tiles_per_split : n_tiles_total;
-    const int my_tiles = t1 - t0;  // >= 1 by construction of the plan
-    const int num_kb = p.kp / BK;
+    // fused mode: CTA = (query tile, contiguous range of panel tiles), full depth.
+    // split-K mode (skinny problems, e.g. 48 x 2008 x 197,760): CTA = (query tile, ONE panel tile,
+    // a range of k-blocks); partial dot products are reduced with fp32 atomics (round-to-nearest,
+    // and the truncating tensor-core accumulation chains stay short), selection runs afterwards.
+    int split, mt, t0, my_tiles, kb0, num_kb;
+    if constexpr (SPLITK) {
+        int b = blockIdx.x;
+        const int ks = b % p.ksplit;
+        b /= p.ksplit;
+        t0 = b % n_tiles_total;
+        mt = b / n_tiles_total;
+        my_tiles = 1;
+        split = 0;
+        kb0 = ks * p.kb_per_split;
+        const int total_kb = p.kp / BK;
+        num_kb = (kb0 + p.kb_per_split < total_kb) ? p.kb_per_split : total_kb - kb0;
+    } else {
+        split = blockIdx.x % p.nsplit;
+        mt = blockIdx.x / p.nsplit;
+        t0 = split * p.tiles_per_split;
+        const int t1 = (t0 + p.tiles_per_split < n_tiles_total) ? t0 + p.tiles_per_split : n_tiles_total;
+        my_tiles = t1 - t0;  // >= 1 by construction of the plan
+        kb0 = 0;
+        num_kb = p.kp / BK;
+    }
     const int m0 = mt * BM;
 
     if (warp == 0 && lane == 0) {
@@ -228,8 +248,8 @@ l2_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                     unsigned char* a_dst = tiles + (size_t)stage * kStageBytes;
                     unsigned char* b_dst = a_dst + kABytes;
                     mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
-                    tma_load_2d(a_dst, &map_q, kb * BK, m0, &full_bar[stage]);
-                    tma_load_2d(b_dst, &map_r, kb * BK, n0, &full_bar[stage]);
+                    tma_load_2d(a_dst, &map_q, (kb0 + kb) * BK, m0, &full_bar[stage]);
+                    tma_load_2d(b_dst, &map_r, (kb0 + kb) * BK, n0, &full_bar[stage]);
                     if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -268,6 +288,29 @@ l2_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         }
     } else {
         // ================= epilogue: thread = query row, 2 warps per lane quarter =================
+        if constexpr (SPLITK) {
+            const int quarter = warp & 3;
+            const int half = (warp - 2) >> 2;
+            const int64_t q = (int64_t)m0 + quarter * 32 + lane;
+            const int n0 = t0 * BN;
+            mbar_wait(&tmem_full[0], 0);
+            tcgen05_fence_after();
+            const int ncols = (p.n - n0 < BN) ? (int)(p.n - n0) : BN;
+            const int nchunks = (ncols + 31) >> 5;
+            for (int ci = half; ci < nchunks; ci += 2) {
+                uint32_t acc[32];
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ci * 32), acc);
+                tmem_ld_wait(acc);
+                if (q < p.nq) {
+                    float* dst = p.dot + q * p.dot_ld + n0 + ci * 32;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (ci * 32 + j < ncols) atomicAdd(dst + j, __uint_as_float(acc[j]));
+                }
+            }
+            tcgen05_fence_before();
+            mbar_arrive(&tmem_empty[0]);
+        } else {
         const int quarter = warp & 3;              // TMEM lanes [32*quarter, 32*quarter + 32)
         const int half = (warp - 2) >> 2;          // which alternate 32-column chunks this warp takes
         const int row = quarter * 32 + lane;       // row inside the 128-query tile
@@ -369,6 +412,7 @@ l2_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 #pragma unroll
             for (int i = 0; i < KT; ++i) out[i] = best[i];
         }
+        }  // fused mode
     }
 
     tcgen05_fence_before();
@@ -379,10 +423,44 @@ l2_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     }
 }
 
+// ---- split-K selection input: dot products -> ordered keys ----------------------------------
+__global__ void __launch_bounds__(256)
+l2_keys_kernel(const float* __restrict__ dot, int64_t dot_ld, const float* __restrict__ q_norm,
+               const float* __restrict__ ref_norm, int64_t nq, int64_t n, uint64_t* __restrict__ keys)
+{
+    const int64_t total = nq * n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t q = i / n, c = i % n;
+        float d = fmaf(-2.f, dot[q * dot_ld + c], q_norm[q] + ref_norm[c]);
+        d = d < 0.f ? 0.f : d;
+        keys[i] = ((uint64_t)__float_as_uint(d) << 32) | (uint64_t)(uint32_t)c;
+    }
+}
+
+// ---- centering: column means of the first rows added (L2 is translation invariant) ------------
+__global__ void __launch_bounds__(256)
+l2_colsum_kernel(const float* __restrict__ x, int64_t rows, int64_t d, int rows_per_block, float* __restrict__ sums)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= d) return;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+    const int64_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+    float acc = 0.f;
+    for (int64_t r = r0; r < r1; ++r) acc += x[r * d + c];
+    atomicAdd(&sums[c], acc);
+}
+
+__global__ void __launch_bounds__(256)
+l2_scale_kernel(float* __restrict__ v, int64_t d, float scale)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < d) v[c] *= scale;
+}
+
 // ---- operand preparation: one warp per row -----------------------------------------------
 __global__ void __launch_bounds__(256)
-l2_prep_kernel(const float* __restrict__ x, int64_t rows, int64_t d, int mode, bool is_query, int kp,
-               float* __restrict__ ops, float* __restrict__ norms)
+l2_prep_kernel(const float* __restrict__ x, const float* __restrict__ mean, int64_t rows, int64_t d, int mode,
+               bool is_query, int kp, float* __restrict__ ops, float* __restrict__ norms)
 {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -392,7 +470,7 @@ l2_prep_kernel(const float* __restrict__ x, int64_t rows, int64_t d, int mode, b
         float* o = ops + r * kp;
         float acc = 0.f;
         for (int64_t c = lane; c < d; c += 32) {
-            const float v = xr[c];
+            const float v = mean ? xr[c] - mean[c] : xr[c];
             acc = fmaf(v, v, acc);
             if (mode == SNV_L2_TF32X3) {
                 const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
@@ -459,18 +537,32 @@ int make_map(CUtensorMap* map, const float* base, int64_t rows, int kp, int box_
 
 int l2_operand_depth(int64_t d, int mode)
 {
-    const int64_t k = mode == SNV_L2_TF32X3 ? 3 * d : d;
+    const int64_t k = (mode & 0xF) == SNV_L2_TF32X3 ? 3 * d : d;
     return (int)round_up(k, BK);
 }
 
-int l2_prep_launch(const float* x, int64_t rows, int64_t d, int mode, bool is_query, int kp, float* ops,
-                   float* norms, cudaStream_t stream)
+int l2_prep_launch(const float* x, const float* mean, int64_t rows, int64_t d, int mode, bool is_query, int kp,
+                   float* ops, float* norms, cudaStream_t stream)
 {
     if (rows <= 0) return SNV_OK;
     const int block = 256;
     int64_t grid = ceil_div(rows, block / 32);
     if (grid > (int64_t)kNumSMs * 16) grid = (int64_t)kNumSMs * 16;
-    l2_prep_kernel<<<(unsigned)grid, block, 0, stream>>>(x, rows, d, mode, is_query, kp, ops, norms);
+    l2_prep_kernel<<<(unsigned)grid, block, 0, stream>>>(x, mean, rows, d, mode & 0xF, is_query, kp, ops, norms);
+    SNV_LAUNCH_CHECK();
+    return SNV_OK;
+}
+
+int l2_colmean_launch(const float* x, int64_t rows, int64_t d, float* mean, cudaStream_t stream)
+{
+    SNV_CUDA_CHECK(cudaMemsetAsync(mean, 0, (size_t)d * 4, stream));
+    if (rows <= 0) return SNV_OK;
+    const int block = 256;
+    const int rpb = 64;
+    dim3 grid((unsigned)ceil_div(d, block), (unsigned)ceil_div(rows, rpb));
+    l2_colsum_kernel<<<grid, block, 0, stream>>>(x, rows, d, rpb, mean);
+    SNV_LAUNCH_CHECK();
+    l2_scale_kernel<<<(unsigned)ceil_div(d, block), block, 0, stream>>>(mean, d, 1.0f / (float)rows);
     SNV_LAUNCH_CHECK();
     return SNV_OK;
 }
@@ -501,6 +593,23 @@ size_t l2_plan(L2SearchParams& p)
     p.nsplit = n_tiles > 0 ? best_s : 1;
     p.tiles_per_split = n_tiles > 0 ? (int)ceil_div(n_tiles, p.nsplit) : 0;
     p.nsplit = n_tiles > 0 ? (int)ceil_div(n_tiles, p.tiles_per_split) : 1;
+    // split-K when the (query tile x panel tile) grid cannot fill the machine and the depth is large
+    p.ksplit = 1;
+    p.kb_per_split = p.kp / BK;
+    const int64_t total_kb = p.kp / BK;
+    const int64_t ctas = m_tiles * n_tiles;
+    if (n_tiles > 0 && ctas * 2 <= kNumSMs && total_kb >= 64 && p.nq * p.n <= ((int64_t)1 << 26)) {
+        int64_t ks = ceil_div(2 * kNumSMs, ctas);
+        const int64_t max_ks = total_kb / 16;  // at least 16 k-blocks (64 MMAs) per CTA
+        if (ks > max_ks) ks = max_ks;
+        if (ks >= 2) {
+            p.kb_per_split = (int)ceil_div(total_kb, ks);
+            p.ksplit = (int)ceil_div(total_kb, p.kb_per_split);
+            p.dot_ld = round_up(p.n, 32);
+            // workspace: dot [nq][dot_ld] fp32, then keys [nq][n] u64
+            return (size_t)p.nq * p.dot_ld * 4 + (size_t)p.nq * p.n * 8 + 256;
+        }
+    }
     return (size_t)p.nq * p.nsplit * 2 * p.kt * sizeof(uint64_t);  // two epilogue warps per row
 }
 
@@ -518,24 +627,48 @@ int l2_launch(const L2SearchParams& p, cudaStream_t stream)
     rc = make_map(&map_r, p.ref_ops, p.n, p.kp, BN);
     if (rc) return rc;
     const int64_t m_tiles = ceil_div(p.nq, BM);
+    if (p.ksplit > 1) {
+        // split-K: zero the dot matrix, accumulate partial products, then select
+        L2SearchParams ps = p;
+        ps.dot = reinterpret_cast<float*>(p.partial);
+        uint64_t* keys = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(p.partial) + round_up((size_t)p.nq * p.dot_ld * 4, 256));
+        SNV_CUDA_CHECK(cudaMemsetAsync(ps.dot, 0, (size_t)p.nq * p.dot_ld * 4, stream));
+        static bool attr_sk = false;
+        if (!attr_sk) {
+            SNV_CUDA_CHECK(cudaFuncSetAttribute(l2_topk_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+            attr_sk = true;
+        }
+        const int64_t n_tiles = ceil_div(p.n, BN);
+        const unsigned grid_sk = (unsigned)(m_tiles * n_tiles * p.ksplit);
+        profile_begin(stream);
+        l2_topk_kernel<8, true><<<grid_sk, kThreads, kSmemBytes, stream>>>(map_q, map_r, ps);
+        profile_end(stream);
+        SNV_LAUNCH_CHECK();
+        const int64_t total = p.nq * p.n;
+        const unsigned gk = (unsigned)std::min<int64_t>(ceil_div(total, 256), (int64_t)kNumSMs * 16);
+        l2_keys_kernel<<<gk, 256, 0, stream>>>(ps.dot, p.dot_ld, p.q_norm, p.ref_norm, p.nq, p.n, keys);
+        SNV_LAUNCH_CHECK();
+        if (p.n > 0x7fffffff) { set_error("L2 split-K: panel too large"); return SNV_ERR_UNSUPPORTED; }
+        return merge_keys_launch(keys, 1, (int)p.n, p.nq, p.k, p.id_offset, true, nullptr, p.D_f32, p.I, stream);
+    }
     const unsigned grid = (unsigned)(m_tiles * p.nsplit);
     if (p.kt == 8) {
         static bool attr8 = false;
         if (!attr8) {
-            SNV_CUDA_CHECK(cudaFuncSetAttribute(l2_topk_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+            SNV_CUDA_CHECK(cudaFuncSetAttribute(l2_topk_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
             attr8 = true;
         }
         profile_begin(stream);
-        l2_topk_kernel<8><<<grid, kThreads, kSmemBytes, stream>>>(map_q, map_r, p);
+        l2_topk_kernel<8, false><<<grid, kThreads, kSmemBytes, stream>>>(map_q, map_r, p);
         profile_end(stream);
     } else {
         static bool attr32 = false;
         if (!attr32) {
-            SNV_CUDA_CHECK(cudaFuncSetAttribute(l2_topk_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+            SNV_CUDA_CHECK(cudaFuncSetAttribute(l2_topk_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
             attr32 = true;
         }
         profile_begin(stream);
-        l2_topk_kernel<32><<<grid, kThreads, kSmemBytes, stream>>>(map_q, map_r, p);
+        l2_topk_kernel<32, false><<<grid, kThreads, kSmemBytes, stream>>>(map_q, map_r, p);
         profile_end(stream);
     }
     SNV_LAUNCH_CHECK();

@@ -316,12 +316,18 @@ class WindowedL2Index(_IndexBase):
 
     kind = L.KIND_L2
 
-    def __init__(self, d: int, n_windows: int = 1, device: Optional[int] = None, precision: str = "tf32x3"):
+    def __init__(self, d: int, n_windows: int = 1, device: Optional[int] = None, precision: str = "tf32x3",
+                 center: bool = False):
+        """center=True subtracts the column means of the first rows added from panel and queries
+        (squared L2 is translation invariant): use it for embedding vectors, which share a large
+        position / allele-frequency component; leave it off for integer-valued rows (tokens,
+        genotypes), whose products are exact as they are."""
         modes = {"tf32": L.L2_TF32, "tf32x3": L.L2_TF32X3}
         if precision not in modes:
             raise ValueError("precision must be 'tf32' or 'tf32x3'")
-        super().__init__(d, n_windows, device, modes[precision])
+        super().__init__(d, n_windows, device, modes[precision] | (L.L2_CENTER if center else 0))
         self.precision = precision
+        self.center = bool(center)
 
     def add(self, x) -> None:
         a = _Arg(x)

@@ -214,3 +214,43 @@ def test_multi_window_l2():
     for w in range(3):
         D64, I64 = O.l2_topk_f64(refs[w], q[w], 5)
         np.testing.assert_array_equal(I[w], I64)
+
+
+def _embedding_like(rng, n, nq, L, D):
+    """rows = per-position token embedding + a large position/AF term shared by every row
+    (src/model/embedding/bert.py:53-75): the V18 search vectors."""
+    T = rng.standard_normal((7, D)).astype(np.float32)
+    P = (3.0 * rng.standard_normal((L, D))).astype(np.float32)
+    founders = rng.random((12, L)) < 0.25
+    mask = rng.random(L) < 0.3
+
+    def emb(m):
+        h = founders[rng.integers(0, 12, m)] ^ (rng.random((m, L)) < 0.03)
+        tok = np.where(h, 6, 5)
+        tok[:, mask] = 4
+        return (T[tok] + P[None]).reshape(m, L * D).astype(np.float32)
+
+    return emb(n), emb(nq)
+
+
+@pytest.mark.parametrize("center", [False, True])
+def test_skinny_deep_problem_split_k(center):
+    """nq << 128, deep vectors (the reference's real V18 shape, scaled): split-K path."""
+    from rag_snvbert_b200 import WindowedL2Index
+
+    rng = np.random.default_rng(18)
+    refs, q = _embedding_like(rng, 2008, 24, 160, 48)  # d = 7680
+    idx = WindowedL2Index(refs.shape[1], 1, None, "tf32x3", center=center)
+    idx.add(refs)
+    D, I = idx.search(q, 4)
+    d64 = O.l2_matrix_f64(refs, q)
+    qn = (q.astype(np.float64) ** 2).sum(1)
+    rn = (refs.astype(np.float64) ** 2).sum(1).max()
+    tol = 1e-5 * (qn + rn)
+    got = np.take_along_axis(d64, I, axis=1)
+    err = np.abs(D.astype(np.float64) - got)
+    assert (err <= tol[:, None]).all(), f"max err {err.max()} tol {tol.min()}"
+    O.assert_ids_match_within_tolerance(d64, I, O._topk_lex(d64, 4, np.float64(O.F32_MAX))[1], 2 * tol)
+    if center:
+        # centring removes the shared component: errors drop by orders of magnitude
+        assert err.max() <= 1e-6 * float(qn.max() + rn) + 1e-3
