@@ -457,19 +457,26 @@ l2_scale_kernel(float* __restrict__ v, int64_t d, float scale)
     if (c < d) v[c] *= scale;
 }
 
-// ---- operand preparation: one warp per row -----------------------------------------------
+// ---- operand preparation: one warp per (row, 2048-column chunk) ------------------------------
+// (few, very long rows — 48 queries x 197,760 — must still fill the machine)
+constexpr int kPrepChunk = 2048;
 __global__ void __launch_bounds__(256)
 l2_prep_kernel(const float* __restrict__ x, const float* __restrict__ mean, int64_t rows, int64_t d, int mode,
-               bool is_query, int kp, float* __restrict__ ops, float* __restrict__ norms)
+               bool is_query, int kp, int chunks_per_row, float* __restrict__ ops, float* __restrict__ norms)
 {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t r = warp; r < rows; r += nwarps) {
+    const int64_t items = rows * chunks_per_row;
+    const int64_t used = (mode == SNV_L2_TF32X3) ? 3 * d : d;
+    for (int64_t item = warp; item < items; item += nwarps) {
+        const int64_t r = item / chunks_per_row;
+        const int64_t c0 = (item % chunks_per_row) * kPrepChunk;
+        const int64_t c1 = c0 + kPrepChunk < d ? c0 + kPrepChunk : d;
         const float* xr = x + r * d;
         float* o = ops + r * kp;
         float acc = 0.f;
-        for (int64_t c = lane; c < d; c += 32) {
+        for (int64_t c = c0 + lane; c < c1; c += 32) {
             const float v = mean ? xr[c] - mean[c] : xr[c];
             acc = fmaf(v, v, acc);
             if (mode == SNV_L2_TF32X3) {
@@ -485,11 +492,14 @@ l2_prep_kernel(const float* __restrict__ x, const float* __restrict__ mean, int6
                 o[c] = v;
             }
         }
-        const int64_t used = (mode == SNV_L2_TF32X3) ? 3 * d : d;
-        for (int64_t c = used + lane; c < kp; c += 32) o[c] = 0.f;
+        if (c1 == d)
+            for (int64_t c = used + lane; c < kp; c += 32) o[c] = 0.f;  // zero the k padding once per row
 #pragma unroll
-        for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-        if (lane == 0) norms[r] = acc;
+        for (int s2 = 16; s2 > 0; s2 >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s2);
+        if (lane == 0) {
+            if (chunks_per_row == 1) norms[r] = acc;
+            else atomicAdd(&norms[r], acc);
+        }
     }
 }
 
@@ -546,9 +556,11 @@ int l2_prep_launch(const float* x, const float* mean, int64_t rows, int64_t d, i
 {
     if (rows <= 0) return SNV_OK;
     const int block = 256;
-    int64_t grid = ceil_div(rows, block / 32);
+    const int chunks = (int)ceil_div(d, kPrepChunk);
+    if (chunks > 1) SNV_CUDA_CHECK(cudaMemsetAsync(norms, 0, (size_t)rows * 4, stream));
+    int64_t grid = ceil_div(rows * chunks, block / 32);
     if (grid > (int64_t)kNumSMs * 16) grid = (int64_t)kNumSMs * 16;
-    l2_prep_kernel<<<(unsigned)grid, block, 0, stream>>>(x, mean, rows, d, mode & 0xF, is_query, kp, ops, norms);
+    l2_prep_kernel<<<(unsigned)grid, block, 0, stream>>>(x, mean, rows, d, mode & 0xF, is_query, kp, chunks, ops, norms);
     SNV_LAUNCH_CHECK();
     return SNV_OK;
 }
