@@ -582,8 +582,6 @@ static int search_hamming_grouped(snv_index* idx, const void* q, const int32_t* 
     p.words = idx->words;
     p.stride = idx->stride;
     p.d = (int)idx->d;
-    const bool reg_kernel = true;
-    (void)reg_kernel;
     const int64_t avg = n_groups ? nqt / n_groups : 0;
     int block = avg >= 64 ? 128 : 32;
     {   // wide rows (generic kernel) always use 32-query blocks

@@ -41,6 +41,8 @@ namespace snv {
 namespace {
 
 constexpr int kMaxBlock = SNV_BLOCK;
+constexpr int kListKT = 32;    // top-k sizes from here on select through shared-memory candidate lists
+constexpr int kListCap = 24;
 constexpr int kBarBytes = 128;  // smem reserved for the stage mbarriers
 
 // acc + w * popc(x): the multiply-add goes to the FMA pipe (IMAD) because `w` is a runtime
@@ -195,6 +197,21 @@ hamming_topk_kernel(const HammingSearchParams p)
 #pragma unroll
     for (int i = 0; i < KT; ++i) best[i] = kSent32;
 
+    // candidate lists (KT >= kListKT only): [kListCap][kMaxBlock] keys after the panel tiles
+    uint32_t* my_list = tiles + (size_t)stages * tile_words + tid;
+    uint32_t thr = kSent32;
+    int cnt = 0;
+    auto fold = [&]() {
+        const int maxc = __reduce_max_sync(0xffffffffu, cnt);
+        for (int s2 = 0; s2 < maxc; ++s2) {
+            if (s2 < cnt) {
+                const uint32_t key = my_list[s2 * kMaxBlock];
+                if (key < best[KT - 1]) topk_insert<KT, uint32_t>(best, key);
+            }
+        }
+        cnt = 0;
+        thr = best[KT - 1];
+    };
     const int idx_bits = p.idx_bits;
     // popcount weights pre-scaled by 2^idx_bits (runtime values: see popc_mad)
     const uint32_t wt[3] = {p.wt1 << idx_bits, p.wt2 << idx_bits, p.wt4 << idx_bits};
@@ -246,14 +263,35 @@ hamming_topk_kernel(const HammingSearchParams p)
                 if (keys[g] < best[KT - 1]) topk_insert<KT, uint32_t>(best, keys[g]);
         }
 #else
+        if constexpr (KT >= kListKT) {
+            // Large k: a 2*KT-instruction insertion whenever ANY lane of the warp finds a candidate
+            // would cost ~30 % of the scan.  Candidates go to a per-thread list in shared memory
+            // instead and are folded into the sorted registers in lockstep, when some lane has more
+            // than kListCap - 8 pending (checked every 8 rows).  thr lags best[KT-1] between folds,
+            // which only admits extra candidates; the fold compares exact keys.
+            for (int j0 = 0; j0 < rows; j0 += 8) {
+                const int j1 = j0 + 8 < rows ? j0 + 8 : rows;
 SNV_UNROLL(SNV_ROW_UNROLL)
-        for (int j = 0; j < rows; ++j) {
-            const uint32_t key = row_key(j);
-            if (key < best[KT - 1]) topk_insert<KT, uint32_t>(best, key);
+                for (int j = j0; j < j1; ++j) {
+                    const uint32_t key = row_key(j);
+                    if (key < thr) {
+                        my_list[cnt * kMaxBlock] = key;
+                        ++cnt;
+                    }
+                }
+                if (__any_sync(0xffffffffu, cnt > kListCap - 8)) fold();
+            }
+        } else {
+SNV_UNROLL(SNV_ROW_UNROLL)
+            for (int j = 0; j < rows; ++j) {
+                const uint32_t key = row_key(j);
+                if (key < best[KT - 1]) topk_insert<KT, uint32_t>(best, key);
+            }
         }
 #endif
         __syncthreads();  // everyone is done with this stage before it is refilled
     }
+    if constexpr (KT >= kListKT) fold();
 
     if (!active) return;
     const uint32_t idx_mask = (1u << idx_bits) - 1u;
@@ -522,6 +560,7 @@ size_t hamming_plan(HammingSearchParams& p)
     p.nsplit = (int)nsplit;
     p.smem_bytes = kBarBytes + (size_t)p.stages * p.tile_rows * p.stride * 4;
     if (!p.nw_templ) p.smem_bytes += (size_t)p.stride * p.block * 4 * (p.mask ? 2 : 1);
+    else if (p.kt >= kListKT) p.smem_bytes += (size_t)kListCap * kMaxBlock * 4;
     if (base * p.nsplit > 0x7fffffffLL) {
         set_error("hamming search: grid too large");
         return (size_t)-1;

@@ -413,3 +413,36 @@ def test_rag_retriever_reproduces_reference_collate_golden():
     assert t1.is_cuda
     np.testing.assert_array_equal(t1.cpu().numpy(), g["rag_seg_h1"])
     np.testing.assert_array_equal(t2.cpu().numpy(), g["rag_seg_h2"])
+
+
+def test_empty_index_and_empty_queries():
+    idx = _idx(1030)
+    q = np.zeros((5, 1030), np.uint8)
+    D, I = idx.search(q, 8)
+    assert (I == -1).all() and (D == np.iinfo(np.int32).max).all()
+    idx.add(np.zeros((3, 1030), np.uint8))
+    D, I = idx.search(np.zeros((0, 1030), np.uint8), 8)
+    assert D.shape == (0, 8) and I.shape == (0, 8)
+    idx.reset()
+    assert idx.ntotal == 0
+    from rag_snvbert_b200 import WindowedL2Index
+
+    l2 = WindowedL2Index(64)
+    D, I = l2.search(np.zeros((4, 64), np.float32), 3)
+    assert (I == -1).all() and (D == O.F32_MAX).all()
+
+
+def test_k32_large_panel_list_selection():
+    """k = 32 selects through shared-memory candidate lists (BASELINE cfg 5 shard shape, scaled)."""
+    panel = O.hapgen(81, 25000, 1030)[None]
+    q = O.hapgen(82, 130, 1030, founder_seed=81)[None]
+    _check(panel, q, 32, dtype="packed")
+    rng = np.random.default_rng(83)
+    obs = (rng.random((1, 130, 1030)) < 0.5).astype(np.uint8)
+    _check(panel[:, :6000], q, 17, observed=obs)
+    # adversarial order for the lagging threshold: distances strictly decreasing along the scan
+    d = 1030
+    rows = np.zeros((1, 900, d), np.uint8)
+    for i in range(900):
+        rows[0, i, : 900 - i] = 1
+    _check(rows, np.zeros((1, 40, d), np.uint8), 32)
