@@ -445,9 +445,14 @@ static int search_hamming(snv_index* idx, int w0, int nw, const void* q, int64_t
         if (rc) return rc;
     }
 
-    // ---- chunking: host buffers are pipelined over internal streams, window chunk by window chunk
+    // ---- chunking: host buffers are pipelined over internal streams, window chunk by window chunk;
+    // a chunk keeps enough CTAs (>= 16 per SM) that the scan needs no row split
     int chunk_w = nw;
-    if ((!q_dev || !out_dev) && nw >= 8) chunk_w = (int)ceil_div(nw, 16);
+    if ((!q_dev || !out_dev) && nw >= 8) {
+        const int64_t qtiles = ceil_div(nq, 128);
+        chunk_w = (int)std::max<int64_t>(ceil_div(nw, 16), ceil_div((int64_t)kNumSMs * 16, qtiles));
+        if (chunk_w > nw) chunk_w = nw;
+    }
     auto make_params = [&](int wb, int wc, HammingSearchParams& p) {
         p = HammingSearchParams{};
         p.panel = idx->panel + (int64_t)(w0 + wb) * idx->cap * idx->stride;
@@ -462,18 +467,21 @@ static int search_hamming(snv_index* idx, int w0, int nw, const void* q, int64_t
         p.id_offset = id_offset;
         p.mask = mask_mode != SNV_MASK_NONE || tokens ? (const uint32_t*)1 : nullptr;  // plan only needs null-ness
     };
+    size_t part_chunk = 0;  // partial-key bytes per chunk (row-split plans); every chunk gets its own slice
     {
         HammingSearchParams probe;
         make_params(0, chunk_w, probe);
-        const size_t part = hamming_plan(probe);
-        if (part == (size_t)-1) return SNV_ERR_UNSUPPORTED;
-        if (part != 0 && chunk_w != nw) {
-            chunk_w = nw;  // row-split plans share one partial buffer: run as a single chunk
-            make_params(0, nw, probe);
+        part_chunk = hamming_plan(probe);
+        if (part_chunk == (size_t)-1) return SNV_ERR_UNSUPPORTED;
+        const int last_w = nw - (int)(ceil_div(nw, chunk_w) - 1) * chunk_w;  // the (shorter) last chunk may split rows more
+        if (last_w != chunk_w) {
+            make_params(0, last_w, probe);
+            const size_t part_last = hamming_plan(probe);
+            if (part_last == (size_t)-1) return SNV_ERR_UNSUPPORTED;
+            part_chunk = std::max(part_chunk, part_last);
         }
-        const size_t part_all = hamming_plan(probe);
-        if (part_all == (size_t)-1) return SNV_ERR_UNSUPPORTED;
-        if (part_all) { rc = idx->ws_partial.reserve(part_all); if (rc) return rc; }
+        part_chunk = (size_t)round_up((int64_t)part_chunk, 256);
+        if (part_chunk) { rc = idx->ws_partial.reserve(part_chunk * (size_t)ceil_div(nw, chunk_w)); if (rc) return rc; }
     }
     const int nchunks = (int)ceil_div(nw, chunk_w);
     const bool piped = nchunks > 1;
@@ -528,7 +536,8 @@ static int search_hamming(snv_index* idx, int w0, int nw, const void* q, int64_t
         }
         const size_t part = hamming_plan(p);
         if (part == (size_t)-1) return SNV_ERR_UNSUPPORTED;
-        p.partial = part ? (uint64_t*)idx->ws_partial.p : nullptr;
+        if (part > part_chunk) { set_error("search: internal partial-buffer sizing error"); return SNV_ERR_INVALID; }
+        p.partial = part ? (uint64_t*)((char*)idx->ws_partial.p + (size_t)c * part_chunk) : nullptr;
         rc = hamming_launch(p, cs);
         if (rc) return rc;
         if (!out_dev) {

@@ -530,10 +530,10 @@ size_t hamming_plan(HammingSearchParams& p)
     tr = tr >= 256 ? 256 : (tr >= 128 ? 128 : (tr >= 64 ? 64 : (tr >= 32 ? 32 : (tr >= 16 ? 16 : 8))));
     p.tile_rows = tr;
 
-    // row splits: enough CTAs to fill the machine (>= 4 per SM) and rows per split that fit
-    // the id field of the 32-bit key.
+    // row splits: several waves of CTAs (148 SMs x ~5-7 resident CTAs) so that the tail of the last
+    // wave is short, and rows per split that fit the id field of the 32-bit key.
     const int64_t base = p.work ? (int64_t)p.n_work : (int64_t)p.nw * p.qtiles;
-    const int64_t target = (int64_t)kNumSMs * 4;
+    const int64_t target = (int64_t)kNumSMs * 16;
     int64_t nsplit = 1;
     if (p.n > 0) {
         nsplit = base >= target ? 1 : ceil_div(target, base);
