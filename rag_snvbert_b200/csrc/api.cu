@@ -468,6 +468,7 @@ static int search_hamming(snv_index* idx, int w0, int nw, const void* q, int64_t
         p.mask = mask_mode != SNV_MASK_NONE || tokens ? (const uint32_t*)1 : nullptr;  // plan only needs null-ness
     };
     size_t part_chunk = 0;  // partial-key bytes per chunk (row-split plans); every chunk gets its own slice
+    size_t tc_chunk = 0;    // tensor-core engine workspace bytes per chunk
     {
         HammingSearchParams probe;
         make_params(0, chunk_w, probe);
@@ -482,6 +483,19 @@ static int search_hamming(snv_index* idx, int w0, int nw, const void* q, int64_t
         }
         part_chunk = (size_t)round_up((int64_t)part_chunk, 256);
         if (part_chunk) { rc = idx->ws_partial.reserve(part_chunk * (size_t)ceil_div(nw, chunk_w)); if (rc) return rc; }
+        // tensor-core engine (chosen by shape): per-chunk slice for the query operand rows, biases, partial keys
+        HammingTcPlan tplan;
+        make_params(0, chunk_w, probe);
+        tc_chunk = hamming_tc_plan(probe, tplan);
+        if (tc_chunk == (size_t)-1) return SNV_ERR_UNSUPPORTED;
+        if (last_w != chunk_w) {
+            make_params(0, last_w, probe);
+            const size_t tc_last = hamming_tc_plan(probe, tplan);
+            if (tc_last == (size_t)-1) return SNV_ERR_UNSUPPORTED;
+            tc_chunk = std::max(tc_chunk, tc_last);
+        }
+        tc_chunk = (size_t)round_up((int64_t)tc_chunk, 1024);
+        if (tc_chunk) { rc = idx->ws_qops.reserve(tc_chunk * (size_t)ceil_div(nw, chunk_w)); if (rc) return rc; }
     }
     const int nchunks = (int)ceil_div(nw, chunk_w);
     const bool piped = nchunks > 1;
@@ -534,12 +548,21 @@ static int search_hamming(snv_index* idx, int w0, int nw, const void* q, int64_t
             p.D_f32 = D_f32 ? (float*)idx->ws_df.p + o0 : nullptr;
             p.I = (int64_t*)idx->ws_i.p + o0;
         }
-        const size_t part = hamming_plan(p);
-        if (part == (size_t)-1) return SNV_ERR_UNSUPPORTED;
-        if (part > part_chunk) { set_error("search: internal partial-buffer sizing error"); return SNV_ERR_INVALID; }
-        p.partial = part ? (uint64_t*)((char*)idx->ws_partial.p + (size_t)c * part_chunk) : nullptr;
-        rc = hamming_launch(p, cs);
-        if (rc) return rc;
+        HammingTcPlan tplan;
+        const size_t tc_need = hamming_tc_plan(p, tplan);
+        if (tc_need == (size_t)-1) return SNV_ERR_UNSUPPORTED;
+        if (tplan.engine) {
+            if (tc_need > tc_chunk) { set_error("search: internal tensor-core workspace sizing error"); return SNV_ERR_INVALID; }
+            rc = hamming_tc_launch(p, tplan, (char*)idx->ws_qops.p + (size_t)c * tc_chunk, cs);
+            if (rc) return rc;
+        } else {
+            const size_t part = hamming_plan(p);
+            if (part == (size_t)-1) return SNV_ERR_UNSUPPORTED;
+            if (part > part_chunk) { set_error("search: internal partial-buffer sizing error"); return SNV_ERR_INVALID; }
+            p.partial = part ? (uint64_t*)((char*)idx->ws_partial.p + (size_t)c * part_chunk) : nullptr;
+            rc = hamming_launch(p, cs);
+            if (rc) return rc;
+        }
         if (!out_dev) {
             const size_t cnt = (size_t)rows * k;
             if (D_i32) SNV_CUDA_CHECK(cudaMemcpyAsync(D_i32 + o0, p.D_i32, cnt * 4, cudaMemcpyDeviceToHost, cs));

@@ -45,6 +45,17 @@ struct HammingSearchParams {
 size_t hamming_plan(HammingSearchParams& p);
 int hamming_launch(const HammingSearchParams& p, cudaStream_t stream);
 
+// Tensor-core engine for the same search (hamming_tc.cu): chosen per call by shape.
+struct HammingTcPlan {
+    int engine;  // 0 = popcount kernel (hamming_launch), 1 = tcgen05 with in-SM bit expansion, 2 = bring-up variant
+    int kt, kblocks, qtiles, n_tiles, nsplit, tiles_per_split, idx_bits;
+    int64_t off_bias, off_partial, off_panel;  // byte offsets inside the workspace
+};
+// Fills `plan` (p needs its shape fields and mask null-ness only); returns the workspace bytes the
+// launch needs (0 when plan.engine == 0), or (size_t)-1 with the error set.
+size_t hamming_tc_plan(const HammingSearchParams& p, HammingTcPlan& plan);
+int hamming_tc_launch(const HammingSearchParams& p, const HammingTcPlan& plan, void* ws, cudaStream_t stream);
+
 // ---------------------------------------------------------------- key merge / finalize
 // keys [nq_total][parts][kin] (uint64: hi = distance bits, lo = id, ~0 = empty) -> top k.
 // float_dist: hi word holds float bits (L2) instead of an integer distance.

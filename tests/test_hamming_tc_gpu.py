@@ -1,0 +1,175 @@
+"""GPU parity of the tensor-core Hamming engine (csrc/hamming_tc.cu) through the C ABI.
+
+The engine is forced with SNV_HAMMING_ENGINE (tc = tcgen05 with in-SM bit expansion, tc_hbm = the
+bring-up variant with the panel pre-expanded in HBM, popc = the popcount kernel); D and I must be
+bit-identical to the CPU oracle, ties included, and at sizes the oracle cannot reach the two
+engines must agree with each other."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(params=["tc", "tc_hbm"])
+def engine(request):
+    old = os.environ.get("SNV_HAMMING_ENGINE")
+    os.environ["SNV_HAMMING_ENGINE"] = request.param
+    yield request.param
+    if old is None:
+        del os.environ["SNV_HAMMING_ENGINE"]
+    else:
+        os.environ["SNV_HAMMING_ENGINE"] = old
+
+
+def _search(panel, queries, k, observed=None, id_offset=0):
+    from rag_snvbert_b200 import WindowedHammingIndex
+
+    W, N, d = panel.shape
+    idx = WindowedHammingIndex(d, W)
+    idx.add(panel)
+    return idx.search(queries, k, observed=observed)
+
+
+def _check(panel, queries, k, observed=None):
+    D, I = _search(panel, queries, k, observed)
+    for w in range(panel.shape[0]):
+        obs = None if observed is None else observed[w]  # [Q, S] per query or [S] shared by the window
+        De, Ie = O.hamming_topk(panel[w], queries[w], k, obs)
+        np.testing.assert_array_equal(D[w], De, err_msg=f"window {w} distances")
+        np.testing.assert_array_equal(I[w], Ie, err_msg=f"window {w} ids")
+    return D, I
+
+
+def test_launches_tensor_core_kernel(engine):
+    """the forced engine really runs (launch count moves by expand + search, no popcount fallback)"""
+    from rag_snvbert_b200 import _lib
+
+    rng = np.random.default_rng(1)
+    panel = (rng.random((1, 700, 200)) < 0.3).astype(np.uint8)
+    q = (rng.random((1, 64, 200)) < 0.3).astype(np.uint8)
+    _lib.profile_enable(True)
+    try:
+        _check(panel, q, 8)
+        assert _lib.profile_last_ms() > 0
+    finally:
+        _lib.profile_enable(False)
+
+
+@pytest.mark.parametrize("d", [1, 31, 32, 33, 96, 128, 129, 257, 500, 1024, 1030, 1056, 1100, 2060, 4000])
+def test_site_counts(engine, d):
+    """partial last word, partial last k-block (1-4 MMAs), many k-blocks"""
+    rng = np.random.default_rng(d)
+    panel = (rng.random((2, 300, d)) < 0.4).astype(np.uint8)
+    q = (rng.random((2, 37, d)) < 0.4).astype(np.uint8)
+    _check(panel, q, 8)
+
+
+@pytest.mark.parametrize("n", [1, 5, 255, 256, 257, 511, 513, 1000, 5008])
+def test_panel_row_tails(engine, n):
+    """last panel tile partially filled; fewer rows than k"""
+    rng = np.random.default_rng(n)
+    panel = (rng.random((1, n, 300)) < 0.5).astype(np.uint8)
+    q = (rng.random((1, 70, 300)) < 0.5).astype(np.uint8)
+    D, I = _check(panel, q, 8)
+    if n < 8:
+        assert (I[:, :, n:] == -1).all() and (D[:, :, n:] == np.iinfo(np.int32).max).all()
+
+
+@pytest.mark.parametrize("nq", [1, 31, 127, 128, 129, 300, 1000])
+def test_query_tile_tails(engine, nq):
+    rng = np.random.default_rng(nq)
+    panel = (rng.random((3, 1200, 260)) < 0.2).astype(np.uint8)
+    q = (rng.random((3, nq, 260)) < 0.2).astype(np.uint8)
+    _check(panel, q, 8)
+
+
+@pytest.mark.parametrize("k", [1, 3, 8, 9, 32])
+def test_k_values_with_ties(engine, k):
+    """mosaic haplotypes: many exact ties, lowest ids must win"""
+    panel = O.hapgen(2000, 5008, 1030)[None]
+    q = O.hapgen(5000, 200, 1030, founder_seed=2000)[None]
+    D, I = _check(panel, q, k)
+    if k >= 8:
+        assert (D[0, :, 1:] == D[0, :, :-1]).any(), "no ties in the tie test"
+
+
+def test_duplicate_rows_keep_lowest_ids(engine):
+    rng = np.random.default_rng(3)
+    base = (rng.random((1, 40, 500)) < 0.5).astype(np.uint8)
+    panel = np.tile(base, (1, 30, 1))  # every row appears 30 times
+    q = base[:, :33].copy()
+    D, I = _check(panel, q, 32)
+    assert (D[0, :, :30] == 0).all()
+
+
+def test_per_query_masks_cfg3(engine):
+    rng = np.random.default_rng(8000)
+    W, N, S, Q = 2, 5008, 1030, 200
+    panel = np.stack([O.hapgen(2000 + w, N, S) for w in range(W)])
+    q = np.stack([O.hapgen(5000 + w, Q, S, founder_seed=2000 + w) for w in range(W)])
+    observed = (rng.random((W, Q, S)) >= rng.uniform(0.1, 0.9, size=(W, Q, 1))).astype(np.uint8)
+    _check(panel, q, 8, observed=observed)
+
+
+def test_per_window_mask_and_all_masked_queries(engine):
+    rng = np.random.default_rng(11)
+    W, N, S, Q = 3, 900, 700, 50
+    panel = (rng.random((W, N, S)) < 0.3).astype(np.uint8)
+    q = (rng.random((W, Q, S)) < 0.3).astype(np.uint8)
+    shared = (rng.random((W, S)) < 0.6).astype(np.uint8)
+    shared[1] = 0  # nothing observed: every distance 0, ids 0..k-1
+    D, I = _check(panel, q, 8, observed=shared)
+    assert (D[1] == 0).all() and (I[1] == np.arange(8)).all()
+
+
+def test_row_split_when_few_items(engine):
+    """1 window x 1 query tile over a long panel: rows are split across CTAs and merged"""
+    rng = np.random.default_rng(17)
+    panel = (rng.random((1, 40000, 256)) < 0.5).astype(np.uint8)
+    q = (rng.random((1, 64, 256)) < 0.5).astype(np.uint8)
+    _check(panel, q, 8)
+    _check(panel, q[:, :40], 32)
+
+
+def test_many_windows_persistent_ctas(engine):
+    """more (window, query tile) items than SMs: every CTA loops over several items"""
+    rng = np.random.default_rng(23)
+    W, N, S, Q = 40, 600, 160, 520
+    panel = (rng.random((W, N, S)) < 0.3).astype(np.uint8)
+    q = (rng.random((W, Q, S)) < 0.3).astype(np.uint8)
+    _check(panel, q, 8)
+
+
+def test_engines_agree_at_cfg2_window_scale():
+    """size-independent property at BASELINE cfg-2 window shape: both engines return the same (D, I)"""
+    import torch
+
+    import bench
+    from rag_snvbert_b200 import WindowedHammingIndex
+
+    W, N, S, Q, k = 24, 5008, 1030, 2000, 8
+    dev = torch.device("cuda", 0)
+    panel = bench.gen_windows_device(torch, dev, 2000, W, N, S, 777)
+    queries = bench.gen_windows_device(torch, dev, 5000, W, Q, S, 777)
+    masks = bench.gen_masks_device(torch, dev, 8000, W, Q, S)
+    idx = WindowedHammingIndex(S, W, 0)
+    idx.add(panel)
+    out = {}
+    old = os.environ.get("SNV_HAMMING_ENGINE")
+    try:
+        for eng in ("popc", "tc"):
+            os.environ["SNV_HAMMING_ENGINE"] = eng
+            D, I = idx.search(queries, k)
+            Dm, Im = idx.search(queries, k, observed=masks)
+            out[eng] = [t.clone() for t in (D, I, Dm, Im)]
+    finally:
+        if old is None:
+            del os.environ["SNV_HAMMING_ENGINE"]
+        else:
+            os.environ["SNV_HAMMING_ENGINE"] = old
+    for a, b in zip(out["popc"], out["tc"]):
+        assert torch.equal(a, b)
