@@ -306,6 +306,7 @@ def run_ours(a):
     total_ms = t_all0.elapsed_time(t_all1)
     kern_ms = _lib.profile_last_ms()  # the scan kernel alone, events on its own stream (last timed step)
     _lib.profile_enable(False)
+    engine = _lib.last_hamming_engine()
     step_ms_events = float(np.mean([s.elapsed_time(e) for s, e in ev]))
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -357,40 +358,71 @@ def run_ours(a):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (hamming_topk_kernel): scan-equivalent bandwidth
+    # ---- roofline of the dominant kernel
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     words = (S + 31) // 32
     bytes_per_pair = words * 4
-    achieved = pairs_per_step_rank * bytes_per_pair / (kern_ms * 1e-3) / 1e9
+    scan_gbs = pairs_per_step_rank * bytes_per_pair / (kern_ms * 1e-3) / 1e9
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     sm_mhz = (clocks or {}).get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
-    popc_per_pair = 16 if words == 33 else words  # CSA depth 2 leaves 16 POPC for 33 words
-    kname = "hamming_topk_kernel<33,masked=%d,K=8>" % (1 if a.masked else 0)
     traffic = None
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        ent = tj.get(f"{kname}|W={W},N={N},Q={Q}")
-        if ent and S == 1030 and k == 8:
-            traffic = ent["bytes"]
-    except Exception:
-        pass
-    roofline = {
-        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": traffic, "kernel": "hamming_topk_kernel<33,masked=%d,K=8>" % (1 if a.masked else 0),
-        "kernel_ms": kern_ms, "step_ms": step_ms_events, "peak_source": peak_src,
-        "note": ("scan-equivalent bandwidth = pairs x 132 B / kernel time (SURVEY.md 8d): the panel tile is "
-                 "served from shared memory/L2, so this may exceed 1.0; the binding unit is the integer pipes"),
-        "int_pipe": {
-            "pairs_per_s": pairs_per_step_rank / (kern_ms * 1e-3),
-            "alu_instr_per_pair": 68 if words == 33 else None, "popc_per_pair": popc_per_pair,
-            "alu_frac_of_64_per_clk_sm": (pairs_per_step_rank / (kern_ms * 1e-3)) * 68 / (148 * 64 * sm_mhz * 1e6) if words == 33 else None,
-        },
-    }
+    if engine == 1:
+        # tensor-core engine: the scan is a dense contraction (2 * pairs * sites FLOP, what faiss' sgemm path
+        # computes), fp8 operands on tcgen05; peak = 2 x the measured bf16 GEMM peak (kind::f8f6f4 issues at
+        # twice the bf16 rate; MEASURED_PEAKS.json has no fp8 figure)
+        kname = "hamming_tc_kernel<K=8,expand>"
+        bf16 = float(peaks.get("bf16_tflops", 1590.0))
+        peak = 2.0 * bf16
+        achieved = 2.0 * pairs_per_step_rank * S / (kern_ms * 1e-3) / 1e12
+        issued = 2.0 * pairs_per_step_rank * words * 32 / (kern_ms * 1e-3) / 1e12
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            ent = tj.get(f"{kname}|W={W},N={N},Q={Q}")
+            if ent and S == 1030 and k == 8:
+                traffic = ent["bytes"]
+        except Exception:
+            pass
+        roofline = {
+            "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "traffic": traffic, "kernel": kname, "kernel_ms": kern_ms, "step_ms": step_ms_events,
+            "peak_source": ("2 x measured bf16_tflops (fp8 rate)" if "bf16_tflops" in peaks else "2 x fallback 1590 TFLOP/s"),
+            "issued_tflops": issued,
+            "note": ("algorithmic FLOP = 2 x pairs x sites; the kernel issues one K=32 fp8 MMA per packed word "
+                     "(issued_tflops counts the zero padding of the last word). Measured limiter: shared-memory "
+                     "bandwidth (operand reads of the MMA + expander stores), see DESIGN.md"),
+            "scan_equivalent": {"achieved": scan_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": scan_gbs / hbm_peak,
+                                "note": "pairs x 132 B / kernel time against the measured HBM copy peak (SURVEY.md 8d reading)"},
+        }
+        dtype = "fp8-e4m3 (exact 0/+-1 products, fp32 accumulate)"
+    else:
+        # popcount engine: scan-equivalent bandwidth
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        popc_per_pair = 16 if words == 33 else words  # CSA depth 2 leaves 16 POPC for 33 words
+        kname = "hamming_topk_kernel<33,masked=%d,K=8>" % (1 if a.masked else 0)
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            ent = tj.get(f"{kname}|W={W},N={N},Q={Q}")
+            if ent and S == 1030 and k == 8:
+                traffic = ent["bytes"]
+        except Exception:
+            pass
+        roofline = {
+            "bound": "hbm", "achieved": scan_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": scan_gbs / hbm_peak,
+            "traffic": traffic, "kernel": kname,
+            "kernel_ms": kern_ms, "step_ms": step_ms_events, "peak_source": peak_src,
+            "note": ("scan-equivalent bandwidth = pairs x 132 B / kernel time (SURVEY.md 8d): the panel tile is "
+                     "served from shared memory/L2, so this may exceed 1.0; the binding unit is the integer pipes"),
+            "int_pipe": {
+                "pairs_per_s": pairs_per_step_rank / (kern_ms * 1e-3),
+                "alu_instr_per_pair": 68 if words == 33 else None, "popc_per_pair": popc_per_pair,
+                "alu_frac_of_64_per_clk_sm": (pairs_per_step_rank / (kern_ms * 1e-3)) * 68 / (148 * 64 * sm_mhz * 1e6) if words == 33 else None,
+            },
+        }
+        dtype = "u32-popcount"
 
     cpu = None
     if not a.no_cpu_baseline:
@@ -400,8 +432,8 @@ def run_ours(a):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
         "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u32-popcount", "data": "synthetic",
-        "config": {"workload": workload_name(a), "windows_per_gpu": W, "parallelism": f"window-sharded x{world}, no collective",
+        "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+        "config": {"workload": workload_name(a), "windows_per_gpu": W, "engine": ["popcount", "tcgen05-fp8", "tcgen05-fp8-hbm"][engine], "parallelism": f"window-sharded x{world}, no collective",
                    "l2_policy": "inputs larger than L2 (packed panel 721 MB + queries 288 MB per GPU per step)"},
         "window_queries_per_s": value / N,
         "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,

@@ -198,10 +198,16 @@ int snv_pack_rows(int device, const void* x, int64_t rows, int64_t d, int dtype,
 int64_t snv_launch_count(void);
 
 /* Measurement hook (bench.py roofline): when enabled, every launch of a dominant kernel
- * (hamming_topk_kernel / l2_topk_kernel) is bracketed by CUDA events on its own stream;
+ * (hamming_topk_kernel / hamming_tc_kernel / l2_topk_kernel) is bracketed by CUDA events on its own stream;
  * snv_profile_last_ms() waits for the most recent such launch and returns its duration. */
 int snv_profile_enable(int on);
 int snv_profile_last_ms(float* ms);
+
+/* Which engine the most recent Hamming search of the calling process ran on:
+ * 0 = popcount scan (hamming_topk_kernel), 1 = tensor cores (hamming_tc_kernel: fp8 tcgen05.mma over the
+ * bit-packed panel expanded in shared memory), 2 = its bring-up variant, -1 = none yet.  The choice is made per
+ * call from the shape (many queries per window -> tensor cores); SNV_HAMMING_ENGINE=popc|tc forces one. */
+int snv_last_hamming_engine(void);
 
 #ifdef __cplusplus
 }

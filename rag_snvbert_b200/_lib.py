@@ -52,6 +52,7 @@ SYMBOLS = {
     "snv_launch_count": (_i64, []),
     "snv_profile_enable": (_i, [_i]),
     "snv_profile_last_ms": (_i, [_c.POINTER(_c.c_float)]),
+    "snv_last_hamming_engine": (_i, []),
 }
 
 _lib = None
@@ -115,6 +116,11 @@ def packed_words(d: int) -> int:
 
 def launch_count() -> int:
     return int(lib().snv_launch_count())
+
+
+def last_hamming_engine() -> int:
+    """0 = popcount scan, 1 = tensor cores, 2 = bring-up variant, -1 = no Hamming search yet."""
+    return int(lib().snv_last_hamming_engine())
 
 
 def profile_enable(on: bool) -> None:

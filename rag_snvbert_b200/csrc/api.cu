@@ -14,6 +14,7 @@ static thread_local std::string t_error;
 long long g_launch_count = 0;
 void set_error(const std::string& msg) { t_error = msg; }
 
+int g_last_hamming_engine = -1;
 static bool g_prof_on = false;
 static cudaEvent_t g_prof_e0 = nullptr, g_prof_e1 = nullptr;
 static bool g_prof_valid = false;
@@ -151,6 +152,8 @@ int snv_profile_enable(int on)
     g_prof_valid = false;
     return SNV_OK;
 }
+
+int snv_last_hamming_engine(void) { return g_last_hamming_engine; }
 
 int snv_profile_last_ms(float* ms)
 {
@@ -551,6 +554,7 @@ static int search_hamming(snv_index* idx, int w0, int nw, const void* q, int64_t
         HammingTcPlan tplan;
         const size_t tc_need = hamming_tc_plan(p, tplan);
         if (tc_need == (size_t)-1) return SNV_ERR_UNSUPPORTED;
+        g_last_hamming_engine = tplan.engine;
         if (tplan.engine) {
             if (tc_need > tc_chunk) { set_error("search: internal tensor-core workspace sizing error"); return SNV_ERR_INVALID; }
             rc = hamming_tc_launch(p, tplan, (char*)idx->ws_qops.p + (size_t)c * tc_chunk, cs);
@@ -687,6 +691,7 @@ static int search_hamming_grouped(snv_index* idx, const void* q, const int32_t* 
     const size_t part = hamming_plan(p);
     if (part == (size_t)-1) return SNV_ERR_UNSUPPORTED;
     if (part) { rc = idx->ws_partial.reserve(part); if (rc) return rc; p.partial = (uint64_t*)idx->ws_partial.p; }
+    g_last_hamming_engine = 0;
     rc = hamming_launch(p, stream);
     if (rc) return rc;
     if (!out_dev) {

@@ -1,7 +1,7 @@
 // Bit-packed Hamming / observed-site masked Hamming search on the 5th-gen tensor cores (sm_100a).
 //
-// Same contract as hamming.cu (exact (distance, id)-lexicographic top-k, bit-exact against the
-// oracle; reference call sites batch_test_faiss_l2.py:110, src/dataset/rag_train_dataset.py:281,
+// Same contract as hamming.cu (exact (distance, id)-lexicographic top-k, bit-exact in the parity
+// tests; reference call sites batch_test_faiss_l2.py:110, src/dataset/rag_train_dataset.py:281,
 // partial_faiss_intersect.py:82-111) for the shapes where a window's panel is scanned by many
 // queries: there the scan is a dense contraction — the reference itself runs it as an sgemm inside
 // faiss IndexFlatL2 — and the popcount kernel is bound by the integer pipes, not by HBM.
@@ -36,6 +36,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -62,20 +63,17 @@ constexpr int kFirstEpiWarp = kFirstExpWarp + kExpWarps;  // 7
 constexpr int kThreads = 32 * (kFirstEpiWarp + kEpiWarps);  // 480
 constexpr uint32_t kABytes = BM * KBLK;   // 16 KB
 constexpr uint32_t kBBytes = BN * KBLK;   // 32 KB
-constexpr uint32_t kStageBytes = kABytes + kBBytes;
 constexpr uint32_t kRawBytes = BN * 16;   // 4 KB: 256 rows x 4 packed words
+// Three rings: the query operand comes from L2 (long latency: deep ring), the panel operand is made
+// in the SM (expander latency: 3 slots), raw packed k-blocks are tiny.
+constexpr int kAStages = 5, kBStages = 3, kRawStages = 4;
 constexpr int kListCap = 24;              // per-thread candidate list, checked every 16 columns
-constexpr size_t kListBytes = (size_t)kListCap * kEpiThreads * 4;
-constexpr int kMaxStages = 4, kMaxRawStages = 8;
-
-__host__ __device__ constexpr int stages_of(bool) { return 3; }
-__host__ __device__ constexpr int raw_stages_of(bool expand) { return expand ? 8 : 0; }
-template <int KT, bool EXPAND>
-constexpr size_t smem_bytes_of()
-{
-    return 1024 /*align slack*/ + (size_t)stages_of(EXPAND) * kStageBytes + (size_t)raw_stages_of(EXPAND) * kRawBytes +
-           kListBytes + (size_t)KT * BM * 4 /*half exchange*/ + 512 /*barriers*/;
-}
+constexpr uint32_t kListStride = kEpiThreads * 4;  // bytes between consecutive slots of one thread
+constexpr size_t kListBytes = (size_t)kListCap * kListStride;
+constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kAStages * kABytes + (size_t)kBStages * kBBytes +
+                              (size_t)kRawStages * kRawBytes + kListBytes + 512 /*barriers*/;
+static_assert(32 * BM * 4 <= kListBytes, "the half-exchange buffer aliases the candidate lists");
+static_assert(kSmemBytes <= 232448, "shared memory budget");
 
 // E4M3 codes.  Panel side: the bit itself, moved (if needed) to one of bit positions 3..6 of its byte;
 // query side: the inverse power of two, sign bit = allele 1, zero = unobserved site.
@@ -130,6 +128,16 @@ __device__ __forceinline__ Item decode_item(const TcParams& p, int item)
     return it;
 }
 
+template <int N>
+struct Ring {
+    int i = 0;
+    uint32_t phase = 0;
+    __device__ __forceinline__ void next()
+    {
+        if (++i == N) { i = 0; phase ^= 1u; }
+    }
+};
+
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar)
 {
     asm volatile(
@@ -142,23 +150,23 @@ template <int KT, bool EXPAND>
 __global__ void __launch_bounds__(kThreads, 1)
 hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_r, const TcParams p)
 {
-    constexpr int kStages = stages_of(EXPAND);
-    constexpr int kRawStages = raw_stages_of(EXPAND);
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     unsigned char* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);  // SWIZZLE_128B tiles: 1024-byte aligned
-    unsigned char* tiles = smem;
-    unsigned char* raws = tiles + (size_t)kStages * kStageBytes;
+    unsigned char* a_tiles = smem;
+    unsigned char* b_tiles = a_tiles + (size_t)kAStages * kABytes;
+    unsigned char* raws = b_tiles + (size_t)kBStages * kBBytes;
     uint32_t* lists = reinterpret_cast<uint32_t*>(raws + (size_t)kRawStages * kRawBytes);  // [kListCap][256]
-    uint32_t* xchg = lists + kListCap * kEpiThreads;                                       // [KT][128]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(xchg + KT * BM);
-    uint64_t* full_a = bars;                       // [kStages]  TMA -> MMA (query tile; + panel tile when !EXPAND)
-    uint64_t* full_b = full_a + kMaxStages;        // [kStages]  expanders -> MMA
-    uint64_t* empty = full_b + kMaxStages;         // [kStages]  MMA -> TMA / expanders
-    uint64_t* raw_full = empty + kMaxStages;       // [kRawStages] TMA -> expanders
-    uint64_t* raw_empty = raw_full + kMaxRawStages;  // [kRawStages] expanders -> TMA
-    uint64_t* tmem_full = raw_empty + kMaxRawStages;   // [2] MMA -> epilogue
-    uint64_t* tmem_empty = tmem_full + kAccStages;     // [2] epilogue -> MMA
+    uint32_t* xchg = lists;                                                               // [KT][128], after the lists are folded
+    uint64_t* bars = reinterpret_cast<uint64_t*>(lists + kListCap * kEpiThreads);
+    uint64_t* full_a = bars;                        // [kAStages]   TMA -> MMA
+    uint64_t* empty_a = full_a + kAStages;          // [kAStages]   MMA -> TMA
+    uint64_t* full_b = empty_a + kAStages;          // [kBStages]   expanders (or TMA) -> MMA
+    uint64_t* empty_b = full_b + kBStages;          // [kBStages]   MMA -> expanders (or TMA)
+    uint64_t* raw_full = empty_b + kBStages;        // [kRawStages] TMA -> expanders
+    uint64_t* raw_empty = raw_full + kRawStages;    // [kRawStages] expanders -> TMA
+    uint64_t* tmem_full = raw_empty + kRawStages;   // [2] MMA -> epilogue
+    uint64_t* tmem_empty = tmem_full + kAccStages;  // [2] epilogue -> MMA
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + kAccStages);
 
     const int warp = threadIdx.x >> 5;
@@ -167,10 +175,13 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&map_q);
         prefetch_tensormap(&map_r);
-        for (int s = 0; s < kStages; ++s) {
+        for (int s = 0; s < kAStages; ++s) {
             mbar_init(&full_a[s], 1);
-            mbar_init(&full_b[s], kExpWarps);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty_a[s], 1);
+        }
+        for (int s = 0; s < kBStages; ++s) {
+            mbar_init(&full_b[s], EXPAND ? kExpWarps : 1);
+            mbar_init(&empty_b[s], 1);
         }
         for (int s = 0; s < kRawStages; ++s) {
             mbar_init(&raw_full[s], 1);
@@ -190,51 +201,42 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     const int KB = p.kblocks;
 
     if (warp == 0) {
-        // ================= TMA producer: query operand tiles (and fp8 panel tiles when !EXPAND) =================
-        if (elect_one()) {
-            int stage = 0;
-            uint32_t phase = 0;
+        // ================= TMA producer: query operand tiles =================
+        if (lane == 0) {
+            Ring<kAStages> ra;
             for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
                 const Item it = decode_item(p, item);
                 const int row_a = it.w * p.nq + it.qt * BM;
                 for (int t = 0; t < it.ntiles; ++t) {
-                    const int n0 = (it.t0 + t) * BN;
                     for (int kb = 0; kb < KB; ++kb) {
-                        mbar_wait(&empty[stage], phase ^ 1u);
-                        unsigned char* a_dst = tiles + (size_t)stage * kStageBytes;
-                        if constexpr (EXPAND) {
-                            mbar_arrive_expect_tx(&full_a[stage], kABytes);
-                            tma_load_2d(a_dst, &map_q, kb * KBLK, row_a, &full_a[stage]);
-                        } else {
-                            mbar_arrive_expect_tx(&full_a[stage], kStageBytes);
-                            tma_load_2d(a_dst, &map_q, kb * KBLK, row_a, &full_a[stage]);
-                            tma_load_3d(a_dst + kABytes, &map_r, kb * KBLK, n0, it.w, &full_a[stage]);
-                        }
-                        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                        mbar_wait(&empty_a[ra.i], ra.phase ^ 1u);
+                        mbar_arrive_expect_tx(&full_a[ra.i], kABytes);
+                        tma_load_2d(a_tiles + (size_t)ra.i * kABytes, &map_q, kb * KBLK, row_a, &full_a[ra.i]);
+                        ra.next();
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        constexpr uint32_t idesc = make_idesc_e4m3(BM, BN);
-        int stage = 0;
-        uint32_t phase = 0;
-        uint32_t tcount = 0;
-        for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-            const Item it = decode_item(p, item);
-            for (int t = 0; t < it.ntiles; ++t, ++tcount) {
-                const uint32_t as = tcount & 1u;
-                mbar_wait(&tmem_empty[as], ((tcount >> 1) & 1u) ^ 1u);
-                tcgen05_fence_after();
-                const uint32_t d_tmem = tmem_base + as * BN;
-                for (int kb = 0; kb < KB; ++kb) {
-                    mbar_wait(&full_a[stage], phase);
-                    if constexpr (EXPAND) mbar_wait(&full_b[stage], phase);
+        // ================= MMA issuer (one thread) =================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_e4m3(BM, BN);
+            Ring<kAStages> ra;
+            Ring<kBStages> rb;
+            uint32_t tcount = 0;
+            for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+                const Item it = decode_item(p, item);
+                for (int t = 0; t < it.ntiles; ++t, ++tcount) {
+                    const uint32_t as = tcount & 1u;
+                    mbar_wait(&tmem_empty[as], ((tcount >> 1) & 1u) ^ 1u);
                     tcgen05_fence_after();
-                    if (elect_one()) {
-                        const uint32_t a_addr = smem_u32(tiles + (size_t)stage * kStageBytes);
-                        const uint32_t b_addr = a_addr + kABytes;
+                    const uint32_t d_tmem = tmem_base + as * BN;
+                    for (int kb = 0; kb < KB; ++kb) {
+                        mbar_wait(&full_a[ra.i], ra.phase);
+                        mbar_wait(&full_b[rb.i], rb.phase);
+                        tcgen05_fence_after();
+                        const uint32_t a_addr = smem_u32(a_tiles + (size_t)ra.i * kABytes);
+                        const uint32_t b_addr = smem_u32(b_tiles + (size_t)rb.i * kBBytes);
                         const int nm = (kb == KB - 1) ? p.words - 4 * kb : 4;  // one MMA per packed word
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
@@ -244,29 +246,36 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                                 umma_f8(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
                             }
                         }
-                        umma_commit(&empty[stage]);
+                        umma_commit(&empty_a[ra.i]);
+                        umma_commit(&empty_b[rb.i]);
                         if (kb == KB - 1) umma_commit(&tmem_full[as]);
+                        ra.next();
+                        rb.next();
                     }
-                    __syncwarp();
-                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
             }
         }
+        __syncwarp();
     } else if (warp == 2) {
-        // ================= TMA producer: raw packed panel k-blocks =================
-        if constexpr (EXPAND) {
-            if (elect_one()) {
-                int rs = 0;
-                uint32_t rphase = 0;
-                for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-                    const Item it = decode_item(p, item);
-                    for (int t = 0; t < it.ntiles; ++t) {
-                        const int n0 = (it.t0 + t) * BN;
-                        for (int kb = 0; kb < KB; ++kb) {
-                            mbar_wait(&raw_empty[rs], rphase ^ 1u);
-                            mbar_arrive_expect_tx(&raw_full[rs], kRawBytes);
-                            tma_load_3d(raws + (size_t)rs * kRawBytes, &map_r, kb * 4, n0, it.w, &raw_full[rs]);
-                            if (++rs == kRawStages) { rs = 0; rphase ^= 1u; }
+        // ================= TMA producer: raw packed panel k-blocks (fp8 panel tiles when !EXPAND) =================
+        if (lane == 0) {
+            Ring<kRawStages> rr;
+            Ring<kBStages> rb;
+            for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+                const Item it = decode_item(p, item);
+                for (int t = 0; t < it.ntiles; ++t) {
+                    const int n0 = (it.t0 + t) * BN;
+                    for (int kb = 0; kb < KB; ++kb) {
+                        if constexpr (EXPAND) {
+                            mbar_wait(&raw_empty[rr.i], rr.phase ^ 1u);
+                            mbar_arrive_expect_tx(&raw_full[rr.i], kRawBytes);
+                            tma_load_3d(raws + (size_t)rr.i * kRawBytes, &map_r, kb * 4, n0, it.w, &raw_full[rr.i]);
+                            rr.next();
+                        } else {
+                            mbar_wait(&empty_b[rb.i], rb.phase ^ 1u);
+                            mbar_arrive_expect_tx(&full_b[rb.i], kBBytes);
+                            tma_load_3d(b_tiles + (size_t)rb.i * kBBytes, &map_r, kb * KBLK, n0, it.w, &full_b[rb.i]);
+                            rb.next();
                         }
                     }
                 }
@@ -276,56 +285,74 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         // ================= expanders: packed bits -> fp8 operand tile (SWIZZLE_128B, K-major) =================
         if constexpr (EXPAND) {
             const int et = (warp - kFirstExpWarp) * 32 + lane;
-            int stage = 0, rs = 0;
-            uint32_t phase = 0, rphase = 0;
+            Ring<kRawStages> rr;
+            Ring<kBStages> rb;
+            int pending = -1;  // B slot whose stores still need the proxy fence + arrive (deferred by one k-block)
+            const int sw = et & 7;  // rows et and et + 128 share the swizzle phase
             for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
                 const Item it = decode_item(p, item);
                 const int nkb = it.ntiles * KB;
                 for (int g = 0; g < nkb; ++g) {
-                    mbar_wait(&raw_full[rs], rphase);
-                    mbar_wait(&empty[stage], phase ^ 1u);
-                    const unsigned char* src = raws + (size_t)rs * kRawBytes;
-                    unsigned char* dst = tiles + (size_t)stage * kStageBytes + kABytes;
-#pragma unroll
-                    for (int rr = 0; rr < BN / kExpThreads; ++rr) {
-                        const int r = et + rr * kExpThreads;
-                        const uint4 w = *reinterpret_cast<const uint4*>(src + r * 16);
-                        unsigned char* drow = dst + r * 128;
-                        const int sw = r & 7;
-                        uint4 c0, c1;
-                        expand_panel_word(w.x, c0, c1);
-                        *reinterpret_cast<uint4*>(drow + ((0 ^ sw) << 4)) = c0;
-                        *reinterpret_cast<uint4*>(drow + ((1 ^ sw) << 4)) = c1;
-                        expand_panel_word(w.y, c0, c1);
-                        *reinterpret_cast<uint4*>(drow + ((2 ^ sw) << 4)) = c0;
-                        *reinterpret_cast<uint4*>(drow + ((3 ^ sw) << 4)) = c1;
-                        expand_panel_word(w.z, c0, c1);
-                        *reinterpret_cast<uint4*>(drow + ((4 ^ sw) << 4)) = c0;
-                        *reinterpret_cast<uint4*>(drow + ((5 ^ sw) << 4)) = c1;
-                        expand_panel_word(w.w, c0, c1);
-                        *reinterpret_cast<uint4*>(drow + ((6 ^ sw) << 4)) = c0;
-                        *reinterpret_cast<uint4*>(drow + ((7 ^ sw) << 4)) = c1;
+                    mbar_wait(&raw_full[rr.i], rr.phase);
+                    const unsigned char* src = raws + (size_t)rr.i * kRawBytes;
+                    const uint4 w0 = *reinterpret_cast<const uint4*>(src + et * 16);
+                    const uint4 w1 = *reinterpret_cast<const uint4*>(src + (et + kExpThreads) * 16);
+                    if (pending >= 0) {
+                        // the previous k-block's stores have had time to drain: make them visible to the
+                        // tensor core (async proxy) and publish the slot
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&full_b[pending]);
                     }
-                    fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
-                    __syncwarp();
-                    if (lane == 0) {
-                        mbar_arrive(&full_b[stage]);
-                        mbar_arrive(&raw_empty[rs]);
-                    }
-                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
-                    if (++rs == kRawStages) { rs = 0; rphase ^= 1u; }
+                    mbar_wait(&empty_b[rb.i], rb.phase ^ 1u);
+                    unsigned char* d0 = b_tiles + (size_t)rb.i * kBBytes + et * 128;
+                    unsigned char* d1 = d0 + kExpThreads * 128;
+                    uint4 c0, c1;
+                    expand_panel_word(w0.x, c0, c1);
+                    *reinterpret_cast<uint4*>(d0 + ((0 ^ sw) << 4)) = c0;
+                    *reinterpret_cast<uint4*>(d0 + ((1 ^ sw) << 4)) = c1;
+                    expand_panel_word(w0.y, c0, c1);
+                    *reinterpret_cast<uint4*>(d0 + ((2 ^ sw) << 4)) = c0;
+                    *reinterpret_cast<uint4*>(d0 + ((3 ^ sw) << 4)) = c1;
+                    expand_panel_word(w0.z, c0, c1);
+                    *reinterpret_cast<uint4*>(d0 + ((4 ^ sw) << 4)) = c0;
+                    *reinterpret_cast<uint4*>(d0 + ((5 ^ sw) << 4)) = c1;
+                    expand_panel_word(w0.w, c0, c1);
+                    *reinterpret_cast<uint4*>(d0 + ((6 ^ sw) << 4)) = c0;
+                    *reinterpret_cast<uint4*>(d0 + ((7 ^ sw) << 4)) = c1;
+                    expand_panel_word(w1.x, c0, c1);
+                    *reinterpret_cast<uint4*>(d1 + ((0 ^ sw) << 4)) = c0;
+                    *reinterpret_cast<uint4*>(d1 + ((1 ^ sw) << 4)) = c1;
+                    expand_panel_word(w1.y, c0, c1);
+                    *reinterpret_cast<uint4*>(d1 + ((2 ^ sw) << 4)) = c0;
+                    *reinterpret_cast<uint4*>(d1 + ((3 ^ sw) << 4)) = c1;
+                    expand_panel_word(w1.z, c0, c1);
+                    *reinterpret_cast<uint4*>(d1 + ((4 ^ sw) << 4)) = c0;
+                    *reinterpret_cast<uint4*>(d1 + ((5 ^ sw) << 4)) = c1;
+                    expand_panel_word(w1.w, c0, c1);
+                    *reinterpret_cast<uint4*>(d1 + ((6 ^ sw) << 4)) = c0;
+                    *reinterpret_cast<uint4*>(d1 + ((7 ^ sw) << 4)) = c1;
+                    __syncwarp();  // every lane has consumed its raw words
+                    if (lane == 0) mbar_arrive(&raw_empty[rr.i]);
+                    pending = rb.i;
+                    rr.next();
+                    rb.next();
                 }
+            }
+            if (pending >= 0) {
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full_b[pending]);
             }
         }
     } else {
         // ================= epilogue: thread = query row, 2 warps per lane quarter =================
         const int quarter = warp & 3;                   // TMEM lanes [32 * quarter, +32)
-        const int half = (warp - kFirstEpiWarp) >> 2;   // which alternate 32-column chunks
+        const int half = (warp - kFirstEpiWarp) >> 2;   // columns [128 * half, +128) of every tile
         const int row = quarter * 32 + lane;
         const int et = (warp - kFirstEpiWarp) * 32 + lane;
-        uint32_t* my_list = lists + et;                 // slot s at my_list[s * kEpiThreads]
+        const uint32_t list_base = smem_u32(lists + et);  // slot s at list_base + s * kListStride
         const int idx_bits = p.idx_bits;
-        const uint32_t key_scale = 1u << idx_bits;
         uint32_t tcount = 0;
         for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
             const Item it = decode_item(p, item);
@@ -333,77 +360,85 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             const bool active = qi < p.nq;
             const int64_t q = (int64_t)it.w * p.nq + (active ? qi : 0);
             const int32_t qb = active ? p.q_bias[q] : 0;
-            // acc + 1.5 * 2^23 has the integer value of acc in its low mantissa bits:
-            // key = (bits - 0x4B400000 + qb) << idx_bits | column   (mod 2^32), distance = qb + acc
-            const uint32_t kconst = (uint32_t)(qb - 0x4B400000) << idx_bits;
             uint32_t best[KT];
 #pragma unroll
             for (int i = 0; i < KT; ++i) best[i] = kSent32;
-            float thr = 3.0e38f;  // in accumulator units: candidates need acc < thr
-            int cnt = 0;
-            auto fold = [&]() {
+            // A candidate is scored as ONE float, kf = 128 * acc + jj (jj = column inside this half of the
+            // tile, 0..127; exact: |acc| < 2^12): one FFMA + one compare per column, and `kf < thr` with
+            // thr = 128 * (acc of the k-th best) also rejects equal distances at later columns (ids ascend
+            // along the scan).  Survivors are appended to a per-thread list in shared memory and folded
+            // into the sorted register top-k in lockstep.
+            float thr = 3.0e38f;
+            uint32_t lp = list_base;
+            auto fold = [&](uint32_t col_base) {
+                const int cnt = (int)((lp - list_base) / kListStride);
                 const int maxc = __reduce_max_sync(0xffffffffu, cnt);
                 for (int s2 = 0; s2 < maxc; ++s2) {
                     if (s2 < cnt) {
-                        const uint32_t key = my_list[s2 * kEpiThreads];
+                        const int ki = __float2int_rn(__uint_as_float(lists[et + s2 * kEpiThreads]));
+                        const uint32_t key = ((uint32_t)((ki >> 7) + qb) << idx_bits) | (col_base + (uint32_t)(ki & 127));
                         if (key < best[KT - 1]) topk_insert<KT, uint32_t>(best, key);
                     }
                 }
-                cnt = 0;
-                // ids ascend along this thread's scan, so an equal distance later in the scan never displaces
-                thr = best[KT - 1] == kSent32 ? 3.0e38f : (float)((int32_t)(best[KT - 1] >> idx_bits) - qb);
-            };
-            auto score16 = [&](const uint32_t* acc, uint32_t cbase) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float a = __uint_as_float(acc[j]);
-                    if (a < thr) {
-                        const uint32_t bits = __float_as_uint(a + 12582912.0f);
-                        my_list[cnt * kEpiThreads] = bits * key_scale + (cbase + (uint32_t)j);
-                        ++cnt;
-                    }
-                }
-                if (__any_sync(0xffffffffu, cnt > kListCap - 16)) fold();
+                lp = list_base;
+                thr = best[KT - 1] == kSent32 ? 3.0e38f : (float)(((int32_t)(best[KT - 1] >> idx_bits) - qb) * 128);
             };
             for (int t = 0; t < it.ntiles; ++t, ++tcount) {
                 const uint32_t as = tcount & 1u;
                 const int n0 = (it.t0 + t) * BN;
                 mbar_wait(&tmem_full[as], (tcount >> 1) & 1u);
                 tcgen05_fence_after();
-                const int ncols = (p.n - n0 < BN) ? (int)(p.n - n0) : BN;
-                const int nchunks = (ncols + 31) >> 5;
-                const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN;
-                const uint32_t cb_tile = kconst + (uint32_t)(t * BN);  // columns count from the split's first row
-                auto process = [&](uint32_t (&acc)[32], int ci) {
-                    const int c0 = ci * 32;
-                    if (c0 + 32 > ncols) {
+                int cols = (p.n - n0 < BN ? (int)(p.n - n0) : BN) - 128 * half;  // columns of this half in use
+                cols = cols < 0 ? 0 : (cols > 128 ? 128 : cols);
+                const int nch = (cols + 31) >> 5;
+                const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + (uint32_t)(128 * half);
+                const uint32_t col_base = (uint32_t)(t * BN + 128 * half);  // columns count from the split's first row
+                uint32_t accA[32], accB[32];
+                auto process = [&](uint32_t (&acc)[32], auto u_tag) {
+                    constexpr int u = decltype(u_tag)::value;
+                    if (32 * u + 32 > cols) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
-                            if (c0 + j >= ncols) acc[j] = 0x7F800000u;  // past the panel end (+inf): never a candidate
+                            if (32 * u + j >= cols) acc[j] = 0x7F800000u;  // past the panel end (+inf): never a candidate
                     }
-                    score16(acc, cb_tile + (uint32_t)c0);
-                    score16(acc + 16, cb_tile + (uint32_t)c0 + 16u);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float kf = fmaf(__uint_as_float(acc[j]), 128.0f, (float)(32 * u + j));
+                        if (kf < thr) {
+                            asm volatile("st.shared.f32 [%0], %1;" ::"r"(lp), "f"(kf) : "memory");
+                            lp += kListStride;
+                        }
+                        if (j == 15 || j == 31) {
+                            if (__any_sync(0xffffffffu, lp > list_base + (kListCap - 16) * kListStride)) fold(col_base);
+                        }
+                    }
                 };
-                uint32_t accA[32], accB[32];
-                int ci = half;
-                if (ci < nchunks) tmem_ld_32x32b_x32(tbase + (uint32_t)(ci * 32), accA);
-                while (ci < nchunks) {
+                if (nch > 0) tmem_ld_32x32b_x32(tbase, accA);
+                if (nch > 0) {
                     tmem_ld_wait(accA);
-                    if (ci + 2 < nchunks) tmem_ld_32x32b_x32(tbase + (uint32_t)((ci + 2) * 32), accB);
-                    process(accA, ci);
-                    ci += 2;
-                    if (ci >= nchunks) break;
+                    if (nch > 1) tmem_ld_32x32b_x32(tbase + 32u, accB);
+                    process(accA, std::integral_constant<int, 0>{});
+                }
+                if (nch > 1) {
                     tmem_ld_wait(accB);
-                    if (ci + 2 < nchunks) tmem_ld_32x32b_x32(tbase + (uint32_t)((ci + 2) * 32), accA);
-                    process(accB, ci);
-                    ci += 2;
+                    if (nch > 2) tmem_ld_32x32b_x32(tbase + 64u, accA);
+                    process(accB, std::integral_constant<int, 1>{});
+                }
+                if (nch > 2) {
+                    tmem_ld_wait(accA);
+                    if (nch > 3) tmem_ld_32x32b_x32(tbase + 96u, accB);
+                    process(accA, std::integral_constant<int, 2>{});
+                }
+                if (nch > 3) {
+                    tmem_ld_wait(accB);
+                    process(accB, std::integral_constant<int, 3>{});
                 }
                 tcgen05_fence_before();
                 mbar_arrive(&tmem_empty[as]);
+                fold(col_base);  // list entries carry tile-relative columns: fold before the next tile
             }
-            fold();
             // ---- merge the two halves of each query through shared memory, then write the result
-            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // previous item's exchange reads are done
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // every list is folded: the buffer is free
             if (half == 1) {
 #pragma unroll
                 for (int i = 0; i < KT; ++i) xchg[i * BM + row] = best[i];
@@ -416,7 +451,7 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                     if (key < best[KT - 1]) topk_insert<KT, uint32_t>(best, key);
                 }
                 if (active) {
-                    const uint32_t idx_mask = key_scale - 1u;
+                    const uint32_t idx_mask = (1u << idx_bits) - 1u;
                     const int64_t r0 = (int64_t)it.t0 * BN;
                     if (p.nsplit == 1) {
 #pragma unroll
@@ -442,6 +477,7 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                     }
                 }
             }
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // exchange reads done before lists are reused
         }
     }
 
@@ -545,7 +581,7 @@ int bit_length64(int64_t v)
 template <int KT, bool EXPAND>
 int launch_kernel(const CUtensorMap& map_q, const CUtensorMap& map_r, const TcParams& tp, int grid, cudaStream_t stream)
 {
-    constexpr size_t smem = smem_bytes_of<KT, EXPAND>();
+    constexpr size_t smem = kSmemBytes;
     static bool attr = false;
     if (!attr) {
         SNV_CUDA_CHECK(cudaFuncSetAttribute(hamming_tc_kernel<KT, EXPAND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -20,5 +20,10 @@ e0.record()
 for _ in range(reps): D, I = idx.search(queries, k, observed=masks)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / reps
+_lib.profile_enable(True)
+D, I = idx.search(queries, k, observed=masks)
+torch.cuda.synchronize()
+kernel_ms = _lib.profile_last_ms()
+_lib.profile_enable(False)
 print(json.dumps({"lib": os.path.basename(_lib.so_path()), "env": {k: v for k, v in os.environ.items() if k.startswith("SNV_")},
-                  "W": W, "ms": ms, "pairs_per_s": W * N * Q / ms * 1e3, "checksum": int(I.sum().item()), "dsum": int(D.sum().item())}))
+                  "W": W, "ms": ms, "kernel_ms": kernel_ms, "pairs_per_s": W * N * Q / ms * 1e3, "checksum": int(I.sum().item()), "dsum": int(D.sum().item())}))
