@@ -90,6 +90,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
     }
 }
 
+// For waits that are normally long and not latency critical (a producer running ahead of its
+// ring): back off between polls so the spinning warp does not take issue slots from its SM sub-partition.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) __nanosleep(128);
+}
+
 // 1-D bulk async copy global -> shared (TMA engine, SASS UBLKCP); dst/src 16-byte aligned,
 // bytes a multiple of 16; completion is signalled on `bar` as transaction bytes.
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes,

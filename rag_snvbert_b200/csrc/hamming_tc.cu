@@ -9,28 +9,32 @@
 //   d(q, r) = popc((q ^ r) & m) = popc(q & m) + sum_s a_s * r_s,   a_s = m_s * (1 - 2 q_s) in {-1, 0, +1}
 //
 // The panel stays BIT-PACKED in HBM (132 B per haplotype).  Inside the SM, expander warps turn each
-// 256-row x 128-site panel k-block into an fp8 (E4M3) operand tile directly in the SWIZZLE_128B
-// shared-memory layout the MMA reads: one LOP3 per 4 sites, because the site -> K position map is
-// free to choose (a dot product does not care about the order of K) and a set bit at ANY of bit
-// positions 3..6 of a byte is a power of two in E4M3 (2^-6, 2^-5, 2^-3, 2^1).  The query operand
-// carries the inverse magnitude (64, 32, 8, 0.5) with the sign / mask folded in, so every product
+// panel k-block into a narrow-float operand tile directly in the SWIZZLE_128B shared-memory layout
+// the MMA reads, with ONE LOP3 per output word: the site -> K position map is free to choose (a dot
+// product does not care about the order of K), and a single set bit inside a narrow-float code is
+// a power of two (E4M3 byte: bits 3..6 = 2^-6, 2^-5, 2^-3, 2^1; E2M1 nibble: bits 0..2 = 0.5, 1, 2).
+// The query operand carries the inverse magnitude with the sign / mask folded in, so every product
 // is exactly -1, 0 or +1 and the fp32 accumulation in TMEM is exact.
 //
-// K layout of one k-block (128 sites = packed words w_0..w_3 of the row): byte position
-// 32 i + 4 j + b  <->  site 32 i + 8 b + j  (word i, bit 8 b + j); MMA k-step i (32 bytes) is exactly
-// packed word i, so a row of `words` packed words costs `words` MMAs (33 for 1030 sites).
+// Two operand formats (MODE):
+//   fp8  kind::f8f6f4, E4M3, K = 32 sites per MMA, k-block = 4 packed words (128 sites), N = 256
+//        byte position 32 i + 4 j + b  <->  word i, bit 8 b + j
+//   fp4  kind::mxf4 (block scale = 1.0 everywhere), E2M1, K = 64 sites per MMA, k-block = 8 packed
+//        words (256 sites), N = 240 (TMEM: 2 x 240 accumulator columns + 32 columns of unit scales)
+//        nibble n of byte 16 i + 4 j + n / 2  <->  word i, bit 4 n + j
+// The kernel is bound by shared-memory bandwidth (MMA operand reads + expander stores), so halving
+// the bytes per site doubles the throughput.
 //
 // CTA (480 threads, one per SM, persistent over (window, query tile, row split) items):
-//   warp 0       TMA producer of the query operand tile A [128 x 128 B] (fp8, SWIZZLE_128B)
-//   warp 1       TMEM allocator + MMA issuer: tcgen05.mma kind::f8f6f4 M128 N256 K32 into one of two
-//                256-column accumulator stages
-//   warp 2       TMA producer of the raw packed panel k-blocks [256 rows x 16 B]
-//   warps 3-6    expanders: packed bits -> fp8 B tile (32 KB per k-block)
-//   warps 7-14   epilogue: thread = query (TMEM lane), two warps per lane quarter on alternate
-//                32-column chunks; threshold test on the raw accumulator, candidates appended to
-//                per-thread lists in shared memory and folded in lockstep into a register top-k of
-//                32-bit keys (distance << idx_bits | row); the two halves are merged in shared memory
-//                and the final (D, I) rows are written by the kernel itself.
+//   warp 0       TMA producer of the query operand tile A [128 x 128 B] (SWIZZLE_128B)
+//   warp 1       TMEM allocator + MMA issuer (one thread): tcgen05.mma M128 into one of two accumulator stages
+//   warp 2       TMA producer of the raw packed panel k-blocks [N rows x 16 / 32 B]
+//   warps 3-6    expanders: packed bits -> operand tile B (one 128-byte row per panel row and k-block)
+//   warps 7-14   epilogue: thread = query (TMEM lane), two warps per lane quarter on the two column
+//                halves of a tile; one FFMA + one compare per column, candidates appended to per-thread
+//                lists in shared memory and folded in lockstep into a register top-k of 32-bit keys
+//                (distance << idx_bits | row); the halves are merged in shared memory and the final
+//                (D, I) rows are written by the kernel itself.
 #include <cuda.h>
 
 #include <algorithm>
@@ -43,6 +47,10 @@
 #include "tcgen05.cuh"
 #include "topk.cuh"
 
+#ifndef SNV_TC_DEFAULT_ENGINE
+#define SNV_TC_DEFAULT_ENGINE 1  // what "auto" picks for tensor-core shapes: 1 = fp8, 3 = fp4
+#endif
+
 namespace snv {
 
 namespace {
@@ -50,10 +58,9 @@ namespace {
 using namespace tc;
 
 constexpr int BM = 128;          // queries per tile (TMEM lanes)
-constexpr int BN = 256;          // panel rows per tile (TMEM columns per accumulator stage)
-constexpr int KBLK = 128;        // sites (= fp8 bytes) per k-block: one 128-byte swizzle row
+constexpr int kRowBytes = 128;   // operand bytes per row and k-block: one 128-byte swizzle row
 constexpr int kAccStages = 2;
-constexpr int kTmemCols = kAccStages * BN;  // 512
+constexpr int kTmemCols = 512;
 constexpr int kExpWarps = 4;
 constexpr int kExpThreads = kExpWarps * 32;
 constexpr int kEpiWarps = 8;
@@ -61,33 +68,48 @@ constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kFirstExpWarp = 3;
 constexpr int kFirstEpiWarp = kFirstExpWarp + kExpWarps;  // 7
 constexpr int kThreads = 32 * (kFirstEpiWarp + kEpiWarps);  // 480
-constexpr uint32_t kABytes = BM * KBLK;   // 16 KB
-constexpr uint32_t kBBytes = BN * KBLK;   // 32 KB
-constexpr uint32_t kRawBytes = BN * 16;   // 4 KB: 256 rows x 4 packed words
+constexpr uint32_t kABytes = BM * kRowBytes;   // 16 KB
+constexpr uint32_t kBBytes = 256 * kRowBytes;  // 32 KB slot (240 or 256 rows in use)
+constexpr int kBStages = 3, kRawStages = 4;
+constexpr uint32_t kSlotStride = kEpiThreads * 4;  // bytes between the candidate slots of consecutive columns
+constexpr size_t kListBytes = (size_t)32 * kSlotStride;  // one slot per (epilogue thread, column of a 32-column chunk)
+static_assert(32 * BM * 4 <= kListBytes, "the half-exchange buffer aliases the candidate slots");
+
+enum { MODE_FP8 = 0, MODE_FP8_HBM = 1, MODE_FP4 = 2 };
+
 // Three rings: the query operand comes from L2 (long latency: deep ring), the panel operand is made
-// in the SM (expander latency: 3 slots), raw packed k-blocks are tiny.
-constexpr int kAStages = 5, kBStages = 3, kRawStages = 4;
-constexpr int kListCap = 24;              // per-thread candidate list, checked every 16 columns
-constexpr uint32_t kListStride = kEpiThreads * 4;  // bytes between consecutive slots of one thread
-constexpr size_t kListBytes = (size_t)kListCap * kListStride;
-constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kAStages * kABytes + (size_t)kBStages * kBBytes +
-                              (size_t)kRawStages * kRawBytes + kListBytes + 512 /*barriers*/;
-static_assert(32 * BM * 4 <= kListBytes, "the half-exchange buffer aliases the candidate lists");
-static_assert(kSmemBytes <= 232448, "shared memory budget");
+// in the SM (expander latency: 3 slots), raw packed k-blocks are small.
+template <int MODE>
+struct Cfg {
+    static constexpr bool kFp4 = MODE == MODE_FP4;
+    static constexpr bool kExpand = MODE != MODE_FP8_HBM;
+    static constexpr int BN = kFp4 ? 240 : 256;   // panel rows per tile = TMEM columns per accumulator stage
+    static constexpr int WPK = kFp4 ? 8 : 4;      // packed words per k-block
+    static constexpr int WPM = kFp4 ? 2 : 1;      // packed words per MMA
+    static constexpr int kAStages = kFp4 ? 4 : 5;
+    static constexpr uint32_t kRawRow = WPK * 4;                // raw bytes per panel row and k-block
+    static constexpr uint32_t kRawSlot = kExpand ? 256 * kRawRow : 0;
+    static constexpr uint32_t kRawBytes = BN * kRawRow;         // what one TMA box brings
+    static constexpr uint32_t kBBox = BN * kRowBytes;           // fp8-hbm variant: one TMA box of operand rows
+    static constexpr uint32_t kSfCol = 2 * BN;                  // fp4: first TMEM column of the unit scales
+    static constexpr size_t kSmem = 1024 /*align slack*/ + (size_t)kAStages * kABytes + (size_t)kBStages * kBBytes +
+                                    (size_t)kRawStages * kRawSlot + kListBytes + 2 * BM * 4 /*thresholds*/ + 512 /*barriers*/;
+    static_assert(kSmem <= 232448, "shared memory budget");
+};
 
 // E4M3 codes.  Panel side: the bit itself, moved (if needed) to one of bit positions 3..6 of its byte;
 // query side: the inverse power of two, sign bit = allele 1, zero = unobserved site.
 //   j (bit inside the byte):   0     1     2     3     4     5     6     7
 //   panel code              0x10  0x20  0x40  0x08  0x10  0x20  0x40  0x08   (2^-5 2^-3 2^1 2^-6 ...)
 //   query code              0x60  0x50  0x30  0x68  0x60  0x50  0x30  0x68   (32   8    0.5 64   ...)
-__device__ __forceinline__ void expand_panel_word(uint32_t w, uint4& c0, uint4& c1)
+__device__ __forceinline__ void expand_panel_word_fp8(uint32_t w, uint4& c0, uint4& c1)
 {
     const uint32_t lo = w << 4, hi = w >> 4;
     c0 = make_uint4(lo & 0x10101010u, lo & 0x20202020u, lo & 0x40404040u, w & 0x08080808u);
     c1 = make_uint4(w & 0x10101010u, w & 0x20202020u, w & 0x40404040u, hi & 0x08080808u);
 }
 
-__device__ __forceinline__ uint32_t query_code(int j)
+__device__ __forceinline__ uint32_t query_code_fp8(int j)
 {
     switch (j & 3) {
         case 0: return 0x60u;
@@ -96,6 +118,17 @@ __device__ __forceinline__ uint32_t query_code(int j)
         default: return 0x68u;
     }
 }
+
+// E2M1 codes (nibble = sign | 2 exponent bits | 1 mantissa bit: 1 = 0.5, 2 = 1.0, 4 = 2.0).
+//   j (bit inside the nibble):  0    1    2    3 (moved to bit 2)
+//   panel code                  1    2    4    4        (0.5  1  2  2)
+//   query code                  4    2    1    1        (2    1  0.5 0.5), | 8 for allele 1
+__device__ __forceinline__ uint4 expand_panel_word_fp4(uint32_t w)
+{
+    return make_uint4(w & 0x11111111u, w & 0x22222222u, w & 0x44444444u, (w >> 1) & 0x44444444u);
+}
+
+__device__ __forceinline__ uint32_t query_code_fp4(int j) { return j == 0 ? 4u : (j == 1 ? 2u : 1u); }
 
 struct TcParams {
     int nw, nq, qtiles;
@@ -146,19 +179,52 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
-template <int KT, bool EXPAND>
+// fp4: tcgen05.mma kind::mxf4 with block scaling; every scale factor in TMEM is 2^0
+__device__ __forceinline__ void umma_mxf4(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
+                                          uint32_t tmem_sfa, uint32_t tmem_sfb)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
+        : "memory");
+}
+
+// block-scaled instruction descriptor (kind::mxf4): A = B = E2M1 (format 1 at bits 7 and 10), K-major,
+// N >> 3 at bit 17, scale format UE8M0 (bit 23), M >> 4 at bit 24, scale-factor ids 0, K = 64 (bit 31 = 0)
+__host__ __device__ constexpr uint32_t make_idesc_mxf4(int m, int n)
+{
+    return (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | (1u << 23) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, uint32_t v)
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+        ::"r"(taddr), "r"(v) : "memory");
+}
+
+template <int KT, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_r, const TcParams p)
 {
+    using C = Cfg<MODE>;
+    constexpr bool EXPAND = C::kExpand;
+    constexpr bool FP4 = C::kFp4;
+    constexpr int BN = C::BN;
+    constexpr int WPK = C::WPK;
+    constexpr int kAStages = C::kAStages;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     unsigned char* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);  // SWIZZLE_128B tiles: 1024-byte aligned
     unsigned char* a_tiles = smem;
     unsigned char* b_tiles = a_tiles + (size_t)kAStages * kABytes;
     unsigned char* raws = b_tiles + (size_t)kBStages * kBBytes;
-    uint32_t* lists = reinterpret_cast<uint32_t*>(raws + (size_t)kRawStages * kRawBytes);  // [kListCap][256]
-    uint32_t* xchg = lists;                                                               // [KT][128], after the lists are folded
-    uint64_t* bars = reinterpret_cast<uint64_t*>(lists + kListCap * kEpiThreads);
+    uint32_t* lists = reinterpret_cast<uint32_t*>(raws + (size_t)kRawStages * C::kRawSlot);  // [32 columns][256 threads]
+    uint32_t* xchg = lists;                                                                 // [KT][128], after the lists are folded
+    volatile float* thrx = reinterpret_cast<float*>(lists + 32 * kEpiThreads);                     // [2 halves][128 queries] published thresholds
+    uint64_t* bars = reinterpret_cast<uint64_t*>(lists + 32 * kEpiThreads + 2 * BM);
     uint64_t* full_a = bars;                        // [kAStages]   TMA -> MMA
     uint64_t* empty_a = full_a + kAStages;          // [kAStages]   MMA -> TMA
     uint64_t* full_b = empty_a + kAStages;          // [kBStages]   expanders (or TMA) -> MMA
@@ -198,6 +264,18 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    if constexpr (FP4) {
+        // unit block scales (UE8M0 0x7F = 2^0) in the 32 TMEM columns behind the accumulators, all 128 lanes
+        if (warp >= kFirstExpWarp && warp < kFirstExpWarp + 4) {
+            const uint32_t t = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + C::kSfCol;
+            tmem_st_32x32b_x16(t, 0x7F7F7F7Fu);
+            tmem_st_32x32b_x16(t + 16u, 0x7F7F7F7Fu);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
+        tcgen05_fence_before();
+        __syncthreads();
+        tcgen05_fence_after();
+    }
     const int KB = p.kblocks;
 
     if (warp == 0) {
@@ -209,18 +287,33 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                 const int row_a = it.w * p.nq + it.qt * BM;
                 for (int t = 0; t < it.ntiles; ++t) {
                     for (int kb = 0; kb < KB; ++kb) {
-                        mbar_wait(&empty_a[ra.i], ra.phase ^ 1u);
+                        mbar_wait_relaxed(&empty_a[ra.i], ra.phase ^ 1u);
                         mbar_arrive_expect_tx(&full_a[ra.i], kABytes);
-                        tma_load_2d(a_tiles + (size_t)ra.i * kABytes, &map_q, kb * KBLK, row_a, &full_a[ra.i]);
+                        tma_load_2d(a_tiles + (size_t)ra.i * kABytes, &map_q, kb * kRowBytes, row_a, &full_a[ra.i]);
                         ra.next();
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer (one thread) =================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_e4m3(BM, BN);
+        // ================= MMA issuer: the warp loops in lockstep, one elected lane issues =================
+        {
+            constexpr uint32_t idesc = FP4 ? make_idesc_mxf4(BM, BN) : make_idesc_e4m3(BM, BN);
+            constexpr uint64_t kDescHi = (uint64_t)0x40004040u << 32;
+            // K-major SWIZZLE_128B descriptors: low word = (address >> 4) | LBO 1 << 16, high word constant
+            // (SBO 1024 B, descriptor version 1, layout SWIZZLE_128B); one MMA per 32 operand bytes = per packed
+            // word (fp8) or per two packed words (fp4)
+            const uint32_t a_lo0 = (smem_u32(a_tiles) >> 4) | 0x10000u;
+            const uint32_t b_lo0 = (smem_u32(b_tiles) >> 4) | 0x10000u;
+            const int nm_tail = (p.words - WPK * (KB - 1) + C::WPM - 1) / C::WPM;
+            const uint32_t sf_a = tmem_base + C::kSfCol, sf_b = tmem_base + C::kSfCol + 16u;
+            (void)sf_a; (void)sf_b;
+            auto mma = [&](uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t acc) {
+                const uint64_t adesc = kDescHi | (uint64_t)a_lo;
+                const uint64_t bdesc = kDescHi | (uint64_t)b_lo;
+                if constexpr (FP4) umma_mxf4(d_tmem, adesc, bdesc, idesc, acc, sf_a, sf_b);
+                else umma_f8(d_tmem, adesc, bdesc, idesc, acc);
+            };
             Ring<kAStages> ra;
             Ring<kBStages> rb;
             uint32_t tcount = 0;
@@ -235,29 +328,35 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                         mbar_wait(&full_a[ra.i], ra.phase);
                         mbar_wait(&full_b[rb.i], rb.phase);
                         tcgen05_fence_after();
-                        const uint32_t a_addr = smem_u32(a_tiles + (size_t)ra.i * kABytes);
-                        const uint32_t b_addr = smem_u32(b_tiles + (size_t)rb.i * kBBytes);
-                        const int nm = (kb == KB - 1) ? p.words - 4 * kb : 4;  // one MMA per packed word
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            if (k < nm) {
-                                const uint64_t adesc = make_kmajor_sw128_desc(a_addr + k * 32);
-                                const uint64_t bdesc = make_kmajor_sw128_desc(b_addr + k * 32);
-                                umma_f8(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                        if (elect_one()) {
+                            const uint32_t a_lo = a_lo0 + (uint32_t)ra.i * (kABytes >> 4);
+                            const uint32_t b_lo = b_lo0 + (uint32_t)rb.i * (kBBytes >> 4);
+                            if (kb != KB - 1) {
+                                mma(d_tmem, a_lo, b_lo, kb != 0 ? 1u : 0u);
+                                mma(d_tmem, a_lo + 2, b_lo + 2, 1u);
+                                mma(d_tmem, a_lo + 4, b_lo + 4, 1u);
+                                mma(d_tmem, a_lo + 6, b_lo + 6, 1u);
+                                umma_commit(&empty_a[ra.i]);
+                                umma_commit(&empty_b[rb.i]);
+                            } else {
+                                mma(d_tmem, a_lo, b_lo, kb != 0 ? 1u : 0u);
+                                if (nm_tail > 1) mma(d_tmem, a_lo + 2, b_lo + 2, 1u);
+                                if (nm_tail > 2) mma(d_tmem, a_lo + 4, b_lo + 4, 1u);
+                                if (nm_tail > 3) mma(d_tmem, a_lo + 6, b_lo + 6, 1u);
+                                umma_commit(&empty_a[ra.i]);
+                                umma_commit(&empty_b[rb.i]);
+                                umma_commit(&tmem_full[as]);
                             }
                         }
-                        umma_commit(&empty_a[ra.i]);
-                        umma_commit(&empty_b[rb.i]);
-                        if (kb == KB - 1) umma_commit(&tmem_full[as]);
+                        __syncwarp();
                         ra.next();
                         rb.next();
                     }
                 }
             }
         }
-        __syncwarp();
     } else if (warp == 2) {
-        // ================= TMA producer: raw packed panel k-blocks (fp8 panel tiles when !EXPAND) =================
+        // ================= TMA producer: raw packed panel k-blocks (fp8 panel tiles in the bring-up variant) =================
         if (lane == 0) {
             Ring<kRawStages> rr;
             Ring<kBStages> rb;
@@ -267,14 +366,14 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                     const int n0 = (it.t0 + t) * BN;
                     for (int kb = 0; kb < KB; ++kb) {
                         if constexpr (EXPAND) {
-                            mbar_wait(&raw_empty[rr.i], rr.phase ^ 1u);
-                            mbar_arrive_expect_tx(&raw_full[rr.i], kRawBytes);
-                            tma_load_3d(raws + (size_t)rr.i * kRawBytes, &map_r, kb * 4, n0, it.w, &raw_full[rr.i]);
+                            mbar_wait_relaxed(&raw_empty[rr.i], rr.phase ^ 1u);
+                            mbar_arrive_expect_tx(&raw_full[rr.i], C::kRawBytes);
+                            tma_load_3d(raws + (size_t)rr.i * C::kRawSlot, &map_r, kb * WPK, n0, it.w, &raw_full[rr.i]);
                             rr.next();
                         } else {
-                            mbar_wait(&empty_b[rb.i], rb.phase ^ 1u);
-                            mbar_arrive_expect_tx(&full_b[rb.i], kBBytes);
-                            tma_load_3d(b_tiles + (size_t)rb.i * kBBytes, &map_r, kb * KBLK, n0, it.w, &full_b[rb.i]);
+                            mbar_wait_relaxed(&empty_b[rb.i], rb.phase ^ 1u);
+                            mbar_arrive_expect_tx(&full_b[rb.i], C::kBBox);
+                            tma_load_3d(b_tiles + (size_t)rb.i * kBBytes, &map_r, kb * kRowBytes, n0, it.w, &full_b[rb.i]);
                             rb.next();
                         }
                     }
@@ -282,61 +381,92 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             }
         }
     } else if (warp < kFirstEpiWarp) {
-        // ================= expanders: packed bits -> fp8 operand tile (SWIZZLE_128B, K-major) =================
+        // ================= expanders: packed bits -> operand tile (SWIZZLE_128B, K-major) =================
         if constexpr (EXPAND) {
+            // thread et expands panel rows et and et + BN / 2 of every k-block (BN / 2 is a multiple of 8, so both
+            // rows share the swizzle phase): 16-byte chunk c of a row lands at row * 128 + ((c ^ (row & 7)) << 4)
             const int et = (warp - kFirstExpWarp) * 32 + lane;
+            constexpr int kHalfRows = BN / 2;
+            const bool act = et < kHalfRows;
+            const int sw = et & 7;
+            uint32_t off[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) off[c] = (uint32_t)(et * kRowBytes + ((c ^ sw) << 4));
+            const uint32_t b_base = smem_u32(b_tiles);
+            const uint32_t raw_base = smem_u32(raws) + (uint32_t)et * C::kRawRow;
             Ring<kRawStages> rr;
             Ring<kBStages> rb;
             int pending = -1;  // B slot whose stores still need the proxy fence + arrive (deferred by one k-block)
-            const int sw = et & 7;  // rows et and et + 128 share the swizzle phase
+            const int tail_words = p.words - WPK * (KB - 1);  // packed words of the last k-block that an MMA reads
+            const int tail_chunks = FP4 ? ((tail_words + 1) & ~1) : 2 * tail_words;  // 16-byte chunks to write there
+            auto lds128 = [](uint32_t addr) {
+                uint4 v;
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+                return v;
+            };
+            auto sts128 = [](uint32_t addr, const uint4& v) {
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+            };
+            // chunks [0, nchunk) of one row; NCHUNK = 8 is the branch-free hot path
+            auto expand_row = [&](const uint4 (&w)[WPK / 4], uint32_t dst, int nchunk) {
+#pragma unroll
+                for (int v = 0; v < WPK / 4; ++v) {
+                    const uint32_t ww[4] = {w[v].x, w[v].y, w[v].z, w[v].w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if constexpr (FP4) {
+                            const int c = 4 * v + i;
+                            if (c < nchunk) sts128(dst + off[c], expand_panel_word_fp4(ww[i]));
+                        } else {
+                            const int c = 2 * i;
+                            if (c < nchunk) {
+                                uint4 c0, c1;
+                                expand_panel_word_fp8(ww[i], c0, c1);
+                                sts128(dst + off[c], c0);
+                                sts128(dst + off[c + 1], c1);
+                            }
+                        }
+                    }
+                }
+            };
             for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
                 const Item it = decode_item(p, item);
-                const int nkb = it.ntiles * KB;
-                for (int g = 0; g < nkb; ++g) {
-                    mbar_wait(&raw_full[rr.i], rr.phase);
-                    const unsigned char* src = raws + (size_t)rr.i * kRawBytes;
-                    const uint4 w0 = *reinterpret_cast<const uint4*>(src + et * 16);
-                    const uint4 w1 = *reinterpret_cast<const uint4*>(src + (et + kExpThreads) * 16);
-                    if (pending >= 0) {
-                        // the previous k-block's stores have had time to drain: make them visible to the
-                        // tensor core (async proxy) and publish the slot
-                        fence_proxy_async();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&full_b[pending]);
+                for (int t = 0; t < it.ntiles; ++t) {
+                    for (int kb = 0; kb < KB; ++kb) {
+                        mbar_wait(&raw_full[rr.i], rr.phase);
+                        uint4 w0[WPK / 4], w1[WPK / 4];
+                        if (act) {
+                            const uint32_t src = raw_base + (uint32_t)rr.i * C::kRawSlot;
+#pragma unroll
+                            for (int v = 0; v < WPK / 4; ++v) {
+                                w0[v] = lds128(src + v * 16);
+                                w1[v] = lds128(src + kHalfRows * C::kRawRow + v * 16);
+                            }
+                        }
+                        if (pending >= 0) {
+                            // the previous k-block's stores have had time to drain: make them visible to the
+                            // tensor core (async proxy) and publish the slot
+                            fence_proxy_async();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&full_b[pending]);
+                        }
+                        mbar_wait(&empty_b[rb.i], rb.phase ^ 1u);
+                        if (act) {
+                            const uint32_t dst = b_base + (uint32_t)rb.i * kBBytes;
+                            if (kb != KB - 1 || tail_chunks == 8) {
+                                expand_row(w0, dst, 8);
+                                expand_row(w1, dst + kHalfRows * kRowBytes, 8);
+                            } else {
+                                expand_row(w0, dst, tail_chunks);
+                                expand_row(w1, dst + kHalfRows * kRowBytes, tail_chunks);
+                            }
+                        }
+                        __syncwarp();  // every lane has consumed its raw words
+                        if (lane == 0) mbar_arrive(&raw_empty[rr.i]);
+                        pending = rb.i;
+                        rr.next();
+                        rb.next();
                     }
-                    mbar_wait(&empty_b[rb.i], rb.phase ^ 1u);
-                    unsigned char* d0 = b_tiles + (size_t)rb.i * kBBytes + et * 128;
-                    unsigned char* d1 = d0 + kExpThreads * 128;
-                    uint4 c0, c1;
-                    expand_panel_word(w0.x, c0, c1);
-                    *reinterpret_cast<uint4*>(d0 + ((0 ^ sw) << 4)) = c0;
-                    *reinterpret_cast<uint4*>(d0 + ((1 ^ sw) << 4)) = c1;
-                    expand_panel_word(w0.y, c0, c1);
-                    *reinterpret_cast<uint4*>(d0 + ((2 ^ sw) << 4)) = c0;
-                    *reinterpret_cast<uint4*>(d0 + ((3 ^ sw) << 4)) = c1;
-                    expand_panel_word(w0.z, c0, c1);
-                    *reinterpret_cast<uint4*>(d0 + ((4 ^ sw) << 4)) = c0;
-                    *reinterpret_cast<uint4*>(d0 + ((5 ^ sw) << 4)) = c1;
-                    expand_panel_word(w0.w, c0, c1);
-                    *reinterpret_cast<uint4*>(d0 + ((6 ^ sw) << 4)) = c0;
-                    *reinterpret_cast<uint4*>(d0 + ((7 ^ sw) << 4)) = c1;
-                    expand_panel_word(w1.x, c0, c1);
-                    *reinterpret_cast<uint4*>(d1 + ((0 ^ sw) << 4)) = c0;
-                    *reinterpret_cast<uint4*>(d1 + ((1 ^ sw) << 4)) = c1;
-                    expand_panel_word(w1.y, c0, c1);
-                    *reinterpret_cast<uint4*>(d1 + ((2 ^ sw) << 4)) = c0;
-                    *reinterpret_cast<uint4*>(d1 + ((3 ^ sw) << 4)) = c1;
-                    expand_panel_word(w1.z, c0, c1);
-                    *reinterpret_cast<uint4*>(d1 + ((4 ^ sw) << 4)) = c0;
-                    *reinterpret_cast<uint4*>(d1 + ((5 ^ sw) << 4)) = c1;
-                    expand_panel_word(w1.w, c0, c1);
-                    *reinterpret_cast<uint4*>(d1 + ((6 ^ sw) << 4)) = c0;
-                    *reinterpret_cast<uint4*>(d1 + ((7 ^ sw) << 4)) = c1;
-                    __syncwarp();  // every lane has consumed its raw words
-                    if (lane == 0) mbar_arrive(&raw_empty[rr.i]);
-                    pending = rb.i;
-                    rr.next();
-                    rb.next();
                 }
             }
             if (pending >= 0) {
@@ -351,9 +481,11 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         const int half = (warp - kFirstEpiWarp) >> 2;   // columns [128 * half, +128) of every tile
         const int row = quarter * 32 + lane;
         const int et = (warp - kFirstEpiWarp) * 32 + lane;
-        const uint32_t list_base = smem_u32(lists + et);  // slot s at list_base + s * kListStride
+        const uint32_t slot_base = smem_u32(lists + et);  // this thread's slot of column j at slot_base + j * kSlotStride
         const int idx_bits = p.idx_bits;
         uint32_t tcount = 0;
+        thrx[half * BM + row] = 3.0e38f;
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
             const Item it = decode_item(p, item);
             const int qi = it.qt * BM + row;
@@ -363,25 +495,40 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             uint32_t best[KT];
 #pragma unroll
             for (int i = 0; i < KT; ++i) best[i] = kSent32;
-            // A candidate is scored as ONE float, kf = 128 * acc + jj (jj = column inside this half of the
-            // tile, 0..127; exact: |acc| < 2^12): one FFMA + one compare per column, and `kf < thr` with
-            // thr = 128 * (acc of the k-th best) also rejects equal distances at later columns (ids ascend
-            // along the scan).  Survivors are appended to a per-thread list in shared memory and folded
-            // into the sorted register top-k in lockstep.
-            float thr = 3.0e38f;
-            uint32_t lp = list_base;
-            auto fold = [&](uint32_t col_base) {
-                const int cnt = (int)((lp - list_base) / kListStride);
-                const int maxc = __reduce_max_sync(0xffffffffu, cnt);
-                for (int s2 = 0; s2 < maxc; ++s2) {
-                    if (s2 < cnt) {
-                        const int ki = __float2int_rn(__uint_as_float(lists[et + s2 * kEpiThreads]));
-                        const uint32_t key = ((uint32_t)((ki >> 7) + qb) << idx_bits) | (col_base + (uint32_t)(ki & 127));
-                        if (key < best[KT - 1]) topk_insert<KT, uint32_t>(best, key);
+            // Selection.  Per column: one compare of the raw accumulator against the threshold (strict, so equal
+            // distances at later columns never displace: ids ascend along the scan), a predicated store into the
+            // column's own slot in shared memory and a predicated bit in a 32-column mask - no serial pointer
+            // chain.  After each 32-column chunk the lanes pop their mask bits in lockstep (two per round) and
+            // insert into the sorted register top-k.  acc + 1.5 * 2^23 has the integer value of acc in its low
+            // mantissa bits:  key = (bits - 0x4B400000 + qb) << idx_bits | column  (mod 2^32), distance = qb + acc.
+            // The two warps of a query (column halves) publish their thresholds to each other: a candidate must
+            // also not exceed the other half's k-th best (non-strict: ids interleave between the halves).
+            const uint32_t kconst = (uint32_t)(qb - 0x4B400000) << idx_bits;
+            float thr_mine = 3.0e38f, thr = 3.0e38f;
+            auto key_of = [&](float a, uint32_t col) { return (__float_as_uint(a + 12582912.0f) << idx_bits) + kconst + col; };
+            auto refresh_thr = [&]() {
+                thr_mine = best[KT - 1] == kSent32 ? 3.0e38f : (float)((int32_t)(best[KT - 1] >> idx_bits) - qb);
+                thrx[half * BM + row] = thr_mine;
+                thr = fminf(thr_mine, thrx[(half ^ 1) * BM + row] + 1.0f);
+            };
+            auto fold = [&](uint32_t mask, uint32_t col0) {
+                while (__any_sync(0xffffffffu, mask != 0u)) {
+                    if (mask != 0u) {
+                        const int j1 = __ffs((int)mask) - 1;
+                        mask &= mask - 1u;
+                        const bool two = mask != 0u;
+                        const int j2 = two ? __ffs((int)mask) - 1 : j1;
+                        mask &= mask - 1u;
+                        float a1, a2;
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a1) : "r"(slot_base + (uint32_t)j1 * kSlotStride));
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a2) : "r"(slot_base + (uint32_t)j2 * kSlotStride));
+                        const uint32_t key1 = key_of(a1, col0 + (uint32_t)j1);
+                        const uint32_t key2 = two ? key_of(a2, col0 + (uint32_t)j2) : kSent32;
+                        if (key1 < best[KT - 1]) topk_insert<KT, uint32_t>(best, key1);
+                        if (key2 < best[KT - 1]) topk_insert<KT, uint32_t>(best, key2);
                     }
                 }
-                lp = list_base;
-                thr = best[KT - 1] == kSent32 ? 3.0e38f : (float)(((int32_t)(best[KT - 1] >> idx_bits) - qb) * 128);
+                refresh_thr();
             };
             for (int t = 0; t < it.ntiles; ++t, ++tcount) {
                 const uint32_t as = tcount & 1u;
@@ -394,51 +541,61 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                 const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + (uint32_t)(128 * half);
                 const uint32_t col_base = (uint32_t)(t * BN + 128 * half);  // columns count from the split's first row
                 uint32_t accA[32], accB[32];
-                auto process = [&](uint32_t (&acc)[32], auto u_tag) {
-                    constexpr int u = decltype(u_tag)::value;
+                auto process = [&](uint32_t (&acc)[32], int u) {
                     if (32 * u + 32 > cols) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
                             if (32 * u + j >= cols) acc[j] = 0x7F800000u;  // past the panel end (+inf): never a candidate
                     }
+                    const uint32_t col0 = col_base + (uint32_t)(32 * u);
+                    if (t == 0 && u == 0) {
+                        // first chunk of an item: no threshold yet, every column is a candidate - insert in lockstep
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float a = __uint_as_float(acc[j]);
+                            const uint32_t key = a < 3.0e38f ? key_of(a, col0 + (uint32_t)j) : kSent32;
+                            if (key < best[KT - 1]) topk_insert<KT, uint32_t>(best, key);
+                        }
+                        refresh_thr();
+                        return;
+                    }
+                    uint32_t mask = 0;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        const float kf = fmaf(__uint_as_float(acc[j]), 128.0f, (float)(32 * u + j));
-                        if (kf < thr) {
-                            asm volatile("st.shared.f32 [%0], %1;" ::"r"(lp), "f"(kf) : "memory");
-                            lp += kListStride;
-                        }
-                        if (j == 15 || j == 31) {
-                            if (__any_sync(0xffffffffu, lp > list_base + (kListCap - 16) * kListStride)) fold(col_base);
+                        const float a = __uint_as_float(acc[j]);
+                        if (a < thr) {
+                            asm volatile("st.shared.f32 [%0], %1;" ::"r"(slot_base + (uint32_t)j * kSlotStride), "f"(a) : "memory");
+                            mask |= 1u << j;
                         }
                     }
+                    fold(mask, col0);
                 };
                 if (nch > 0) tmem_ld_32x32b_x32(tbase, accA);
                 if (nch > 0) {
                     tmem_ld_wait(accA);
                     if (nch > 1) tmem_ld_32x32b_x32(tbase + 32u, accB);
-                    process(accA, std::integral_constant<int, 0>{});
+                    process(accA, 0);
                 }
                 if (nch > 1) {
                     tmem_ld_wait(accB);
                     if (nch > 2) tmem_ld_32x32b_x32(tbase + 64u, accA);
-                    process(accB, std::integral_constant<int, 1>{});
+                    process(accB, 1);
                 }
                 if (nch > 2) {
                     tmem_ld_wait(accA);
                     if (nch > 3) tmem_ld_32x32b_x32(tbase + 96u, accB);
-                    process(accA, std::integral_constant<int, 2>{});
+                    process(accA, 2);
                 }
                 if (nch > 3) {
                     tmem_ld_wait(accB);
-                    process(accB, std::integral_constant<int, 3>{});
+                    process(accB, 3);
                 }
                 tcgen05_fence_before();
                 mbar_arrive(&tmem_empty[as]);
-                fold(col_base);  // list entries carry tile-relative columns: fold before the next tile
             }
             // ---- merge the two halves of each query through shared memory, then write the result
-            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // every list is folded: the buffer is free
+            thrx[half * BM + row] = 3.0e38f;  // reset for the next item (ordered by the barriers below)
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // every chunk is folded: the buffer is free
             if (half == 1) {
 #pragma unroll
                 for (int i = 0; i < KT; ++i) xchg[i * BM + row] = best[i];
@@ -477,7 +634,7 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                     }
                 }
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // exchange reads done before lists are reused
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // exchange reads done before the slots are reused
         }
     }
 
@@ -489,7 +646,8 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     }
 }
 
-// ---- query operand: packed (q, observed mask) -> fp8 rows [rows][kblocks * 128] + popc(q & m) ----------------
+// ---- query operand: packed (q, observed mask) -> operand rows [rows][kblocks * 128 B] + popc(q & m) ----------------
+template <bool FP4>
 __global__ void __launch_bounds__(256)
 tc_expand_queries_kernel(const uint32_t* __restrict__ q, const uint32_t* __restrict__ mask, int64_t mask_win_stride,
                          int64_t mask_q_stride, int nq, int64_t rows, int stride, int words, int d, int kblocks,
@@ -500,7 +658,8 @@ tc_expand_queries_kernel(const uint32_t* __restrict__ q, const uint32_t* __restr
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
         const int64_t row = idx / cpr;
         const int ch = (int)(idx % cpr);
-        const int wi = (ch >> 3) * 4 + ((ch & 7) >> 1);
+        // fp8: chunk pair (2 i, 2 i + 1) of a k-block <- packed word i; fp4: chunk i <- packed word i
+        const int wi = FP4 ? ch : (ch >> 3) * 4 + ((ch & 7) >> 1);
         const int h = ch & 1;
         const uint32_t* qr = q + row * stride;
         const uint32_t* mr = mask ? mask + (row / nq) * mask_win_stride + (row % nq) * mask_q_stride : nullptr;
@@ -517,10 +676,16 @@ tc_expand_queries_kernel(const uint32_t* __restrict__ q, const uint32_t* __restr
         uint32_t out[4];
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
-            const int j = 4 * h + jj;
-            const uint32_t mb = (wm >> j) & 0x01010101u;
-            const uint32_t sb = (wq >> j) & 0x01010101u;
-            out[jj] = mb * query_code(j) | sb * 0x80u;
+            if constexpr (FP4) {
+                const uint32_t mb = (wm >> jj) & 0x11111111u;
+                const uint32_t sb = (wq >> jj) & 0x11111111u;
+                out[jj] = mb * query_code_fp4(jj) | sb * 8u;
+            } else {
+                const int j = 4 * h + jj;
+                const uint32_t mb = (wm >> j) & 0x01010101u;
+                const uint32_t sb = (wq >> j) & 0x01010101u;
+                out[jj] = mb * query_code_fp8(j) | sb * 0x80u;
+            }
         }
         *reinterpret_cast<uint4*>(ops + (row * cpr + ch) * 16) = make_uint4(out[0], out[1], out[2], out[3]);
         if (ch == 0) {
@@ -535,7 +700,7 @@ tc_expand_queries_kernel(const uint32_t* __restrict__ q, const uint32_t* __restr
     }
 }
 
-// ---- bring-up variant (EXPAND = false): the panel expanded to fp8 rows in HBM ------------------------------
+// ---- bring-up variant (MODE_FP8_HBM): the panel expanded to fp8 rows in HBM ------------------------------
 __global__ void __launch_bounds__(256)
 tc_expand_panel_kernel(const uint32_t* __restrict__ panel, int64_t panel_win_stride, int nw, int64_t n, int stride,
                        int words, int kblocks, uint8_t* __restrict__ ops)
@@ -548,7 +713,7 @@ tc_expand_panel_kernel(const uint32_t* __restrict__ panel, int64_t panel_win_str
         const int wi = (ch >> 3) * 4 + ((ch & 7) >> 1);
         const uint32_t w = wi < words ? panel[(row / n) * panel_win_stride + (row % n) * stride + wi] : 0u;
         uint4 c0, c1;
-        expand_panel_word(w, c0, c1);
+        expand_panel_word_fp8(w, c0, c1);
         *reinterpret_cast<uint4*>(ops + (row * cpr + ch) * 16) = (ch & 1) ? c1 : c0;
     }
 }
@@ -578,39 +743,44 @@ int bit_length64(int64_t v)
     return b;
 }
 
-template <int KT, bool EXPAND>
+template <int KT, int MODE>
 int launch_kernel(const CUtensorMap& map_q, const CUtensorMap& map_r, const TcParams& tp, int grid, cudaStream_t stream)
 {
-    constexpr size_t smem = kSmemBytes;
+    constexpr size_t smem = Cfg<MODE>::kSmem;
     static bool attr = false;
     if (!attr) {
-        SNV_CUDA_CHECK(cudaFuncSetAttribute(hamming_tc_kernel<KT, EXPAND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SNV_CUDA_CHECK(cudaFuncSetAttribute(hamming_tc_kernel<KT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = true;
     }
     profile_begin(stream);
-    hamming_tc_kernel<KT, EXPAND><<<grid, kThreads, smem, stream>>>(map_q, map_r, tp);
+    hamming_tc_kernel<KT, MODE><<<grid, kThreads, smem, stream>>>(map_q, map_r, tp);
     profile_end(stream);
     SNV_LAUNCH_CHECK();
     return SNV_OK;
 }
 
+int mode_of_engine(int engine) { return engine == 3 ? MODE_FP4 : (engine == 2 ? MODE_FP8_HBM : MODE_FP8); }
+int bn_of_engine(int engine) { return engine == 3 ? Cfg<MODE_FP4>::BN : 256; }
+int wpk_of_engine(int engine) { return engine == 3 ? Cfg<MODE_FP4>::WPK : 4; }
+
 }  // namespace
 
-// 0 = popcount kernel, 1 = tensor cores with in-SM expansion, 2 = tensor cores, panel pre-expanded (bring-up)
+// 0 = popcount kernel, 1 = tensor cores fp8, 2 = fp8 with the panel pre-expanded in HBM (bring-up), 3 = tensor cores fp4
 int hamming_engine_for(const HammingSearchParams& p)
 {
     int mode = -1;  // auto
     if (const char* e = getenv("SNV_HAMMING_ENGINE")) {
         if (!strcmp(e, "popc")) mode = 0;
-        else if (!strcmp(e, "tc")) mode = 1;
+        else if (!strcmp(e, "tc") || !strcmp(e, "tc8")) mode = 1;
         else if (!strcmp(e, "tc_hbm")) mode = 2;
+        else if (!strcmp(e, "tc4")) mode = 3;
     }
     const bool can = !p.work && p.n > 0 && p.nq > 0 && p.k >= 1 && p.k <= 32 && p.d < (1 << 12) &&
                      (int64_t)p.nw * p.nq < ((int64_t)1 << 31) && p.n < ((int64_t)1 << 31);
     if (!can || mode == 0) return 0;
     if (mode > 0) return mode;
     // auto: enough queries per window to fill a useful part of the 128-lane tile, and a panel worth a tile
-    return (p.nq >= 32 && p.n >= 2 * BN) ? 1 : 0;
+    return (p.nq >= 32 && p.n >= 512) ? SNV_TC_DEFAULT_ENGINE : 0;
 }
 
 size_t hamming_tc_plan(const HammingSearchParams& p, HammingTcPlan& plan)
@@ -618,8 +788,9 @@ size_t hamming_tc_plan(const HammingSearchParams& p, HammingTcPlan& plan)
     plan = HammingTcPlan{};
     plan.engine = hamming_engine_for(p);
     if (!plan.engine) return 0;
+    const int BN = bn_of_engine(plan.engine);
     plan.kt = p.k <= 8 ? 8 : 32;
-    plan.kblocks = (int)ceil_div(p.words, 4);
+    plan.kblocks = (int)ceil_div(p.words, wpk_of_engine(plan.engine));
     plan.qtiles = (int)ceil_div(p.nq, BM);
     plan.n_tiles = (int)ceil_div(p.n, BN);
     plan.idx_bits = 32 - bit_length64((int64_t)p.d + 1);
@@ -636,12 +807,12 @@ size_t hamming_tc_plan(const HammingSearchParams& p, HammingTcPlan& plan)
         return (size_t)-1;
     }
     const int64_t rows = (int64_t)p.nw * p.nq;
-    plan.off_bias = round_up(rows * plan.kblocks * KBLK, 256);
+    plan.off_bias = round_up(rows * plan.kblocks * kRowBytes, 256);
     plan.off_partial = plan.off_bias + round_up(rows * 4, 256);
     plan.off_panel = plan.off_partial + (plan.nsplit > 1 ? round_up(rows * plan.nsplit * plan.kt * 8, 256) : 0);
     size_t total = plan.off_panel;
-    if (plan.engine == 2) total += (size_t)p.nw * p.n * plan.kblocks * KBLK;
-    return total + 1024;  // + slack so that the last query tile's TMA box stays inside the allocation
+    if (plan.engine == 2) total += (size_t)p.nw * p.n * plan.kblocks * kRowBytes;
+    return total + 1024;
 }
 
 int hamming_tc_launch(const HammingSearchParams& p, const HammingTcPlan& plan, void* ws, cudaStream_t stream)
@@ -652,27 +823,32 @@ int hamming_tc_launch(const HammingSearchParams& p, const HammingTcPlan& plan, v
     int32_t* q_bias = reinterpret_cast<int32_t*>(q_ops + plan.off_bias);
     uint64_t* partial = reinterpret_cast<uint64_t*>(q_ops + plan.off_partial);
     uint8_t* panel_ops = q_ops + plan.off_panel;
-    const int kbytes = plan.kblocks * KBLK;
+    const int kbytes = plan.kblocks * kRowBytes;
+    const int BN = bn_of_engine(plan.engine);
     {
         const int64_t total = rows * plan.kblocks * 8;
         const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(total, 256), (int64_t)kNumSMs * 32);
-        tc_expand_queries_kernel<<<grid, 256, 0, stream>>>(p.q, p.mask, p.mask_win_stride, p.mask_q_stride, p.nq, rows, p.stride,
-                                                          p.words, p.d, plan.kblocks, q_ops, q_bias);
+        if (plan.engine == 3)
+            tc_expand_queries_kernel<true><<<grid, 256, 0, stream>>>(p.q, p.mask, p.mask_win_stride, p.mask_q_stride, p.nq, rows, p.stride,
+                                                                    p.words, p.d, plan.kblocks, q_ops, q_bias);
+        else
+            tc_expand_queries_kernel<false><<<grid, 256, 0, stream>>>(p.q, p.mask, p.mask_win_stride, p.mask_q_stride, p.nq, rows, p.stride,
+                                                                     p.words, p.d, plan.kblocks, q_ops, q_bias);
         SNV_LAUNCH_CHECK();
     }
     CUtensorMap map_q, map_r;
     {
         const cuuint64_t gdim[2] = {(cuuint64_t)kbytes, (cuuint64_t)rows};
         const cuuint64_t gstride[1] = {(cuuint64_t)kbytes};
-        const cuuint32_t box[2] = {KBLK, BM};
+        const cuuint32_t box[2] = {kRowBytes, BM};
         int rc = encode_map(&map_q, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, q_ops, gdim, gstride, box, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
     }
-    if (plan.engine == 1) {
-        // raw packed panel [nw][n][stride] words: box = 4 words x 256 rows of one window
+    if (plan.engine != 2) {
+        // raw packed panel [nw][n][stride] words: box = one k-block of words x one tile of rows of one window
         const cuuint64_t gdim[3] = {(cuuint64_t)p.stride, (cuuint64_t)p.n, (cuuint64_t)p.nw};
         const cuuint64_t gstride[2] = {(cuuint64_t)p.stride * 4, (cuuint64_t)p.panel_win_stride * 4};
-        const cuuint32_t box[3] = {4, BN, 1};
+        const cuuint32_t box[3] = {(cuuint32_t)wpk_of_engine(plan.engine), (cuuint32_t)BN, 1};
         int rc = encode_map(&map_r, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, p.panel, gdim, gstride, box, CU_TENSOR_MAP_SWIZZLE_NONE);
         if (rc) return rc;
     } else {
@@ -682,7 +858,7 @@ int hamming_tc_launch(const HammingSearchParams& p, const HammingTcPlan& plan, v
         SNV_LAUNCH_CHECK();
         const cuuint64_t gdim[3] = {(cuuint64_t)kbytes, (cuuint64_t)p.n, (cuuint64_t)p.nw};
         const cuuint64_t gstride[2] = {(cuuint64_t)kbytes, (cuuint64_t)p.n * kbytes};
-        const cuuint32_t box[3] = {KBLK, BN, 1};
+        const cuuint32_t box[3] = {kRowBytes, (cuuint32_t)BN, 1};
         int rc = encode_map(&map_r, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, panel_ops, gdim, gstride, box, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
     }
@@ -699,8 +875,12 @@ int hamming_tc_launch(const HammingSearchParams& p, const HammingTcPlan& plan, v
     tp.partial = partial;
     const int grid = std::min(tp.items, kNumSMs);
     int rc;
-    if (plan.engine == 1) rc = plan.kt == 8 ? launch_kernel<8, true>(map_q, map_r, tp, grid, stream) : launch_kernel<32, true>(map_q, map_r, tp, grid, stream);
-    else rc = plan.kt == 8 ? launch_kernel<8, false>(map_q, map_r, tp, grid, stream) : launch_kernel<32, false>(map_q, map_r, tp, grid, stream);
+    const bool k8 = plan.kt == 8;
+    switch (mode_of_engine(plan.engine)) {
+        case MODE_FP4: rc = k8 ? launch_kernel<8, MODE_FP4>(map_q, map_r, tp, grid, stream) : launch_kernel<32, MODE_FP4>(map_q, map_r, tp, grid, stream); break;
+        case MODE_FP8_HBM: rc = k8 ? launch_kernel<8, MODE_FP8_HBM>(map_q, map_r, tp, grid, stream) : launch_kernel<32, MODE_FP8_HBM>(map_q, map_r, tp, grid, stream); break;
+        default: rc = k8 ? launch_kernel<8, MODE_FP8>(map_q, map_r, tp, grid, stream) : launch_kernel<32, MODE_FP8>(map_q, map_r, tp, grid, stream); break;
+    }
     if (rc) return rc;
     if (plan.nsplit > 1)
         return merge_keys_launch(partial, plan.nsplit, plan.kt, rows, p.k, p.id_offset, false, p.D_i32, p.D_f32, p.I, stream);

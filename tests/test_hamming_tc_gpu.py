@@ -1,7 +1,8 @@
 """GPU parity of the tensor-core Hamming engine (csrc/hamming_tc.cu) through the C ABI.
 
-The engine is forced with SNV_HAMMING_ENGINE (tc = tcgen05 with in-SM bit expansion, tc_hbm = the
-bring-up variant with the panel pre-expanded in HBM, popc = the popcount kernel); D and I must be
+The engine is forced with SNV_HAMMING_ENGINE (tc = tcgen05 fp8 with in-SM bit expansion, tc4 = the same
+with fp4 operands, tc_hbm = the bring-up variant with the panel pre-expanded in HBM, popc = the popcount
+kernel); D and I must be
 bit-identical to the CPU oracle, ties included, and at sizes the oracle cannot reach the two
 engines must agree with each other."""
 import os
@@ -14,7 +15,7 @@ from oracle import oracle as O
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["tc", "tc_hbm"])
+@pytest.fixture(params=["tc", "tc_hbm", "tc4"])
 def engine(request):
     old = os.environ.get("SNV_HAMMING_ENGINE")
     os.environ["SNV_HAMMING_ENGINE"] = request.param
@@ -161,7 +162,7 @@ def test_engines_agree_at_cfg2_window_scale():
     out = {}
     old = os.environ.get("SNV_HAMMING_ENGINE")
     try:
-        for eng in ("popc", "tc"):
+        for eng in ("popc", "tc", "tc4"):
             os.environ["SNV_HAMMING_ENGINE"] = eng
             D, I = idx.search(queries, k)
             Dm, Im = idx.search(queries, k, observed=masks)
@@ -171,5 +172,6 @@ def test_engines_agree_at_cfg2_window_scale():
             del os.environ["SNV_HAMMING_ENGINE"]
         else:
             os.environ["SNV_HAMMING_ENGINE"] = old
-    for a, b in zip(out["popc"], out["tc"]):
-        assert torch.equal(a, b)
+    for eng in ("tc", "tc4"):
+        for a, b in zip(out["popc"], out[eng]):
+            assert torch.equal(a, b), eng
