@@ -47,8 +47,11 @@
 #include "tcgen05.cuh"
 #include "topk.cuh"
 
+#ifndef SNV_TC_EPI16
+#define SNV_TC_EPI16 0  // 1: 16 epilogue warps for k <= 8 (measured slower on B200: they take issue slots from the expanders)
+#endif
 #ifndef SNV_TC_DEFAULT_ENGINE
-#define SNV_TC_DEFAULT_ENGINE 1  // what "auto" picks for tensor-core shapes: 1 = fp8, 3 = fp4
+#define SNV_TC_DEFAULT_ENGINE 3  // what "auto" picks for tensor-core shapes: 1 = fp8, 3 = fp4
 #endif
 
 namespace snv {
@@ -63,17 +66,29 @@ constexpr int kAccStages = 2;
 constexpr int kTmemCols = 512;
 constexpr int kExpWarps = 4;
 constexpr int kExpThreads = kExpWarps * 32;
-constexpr int kEpiWarps = 8;
-constexpr int kEpiThreads = kEpiWarps * 32;
+// Epilogue shape by top-k width: k <= 8 runs 16 epilogue warps (4 per SM sub-partition: the selection is bound
+// by instruction latency, not throughput, so more warps hide it) on 64-column parts in 16-column groups; k <= 32
+// keeps 8 warps (register budget) on 128-column parts in 32-column groups.
+template <int KT>
+struct Epi {
+    static constexpr int kWarps = (KT == 8 && SNV_TC_EPI16) ? 16 : 8;
+    static constexpr int kThreads = kWarps * 32;
+    static constexpr int kParts = kWarps / 4;          // warps per TMEM lane quarter = column parts of a tile
+    static constexpr int kPartCols = 256 / kParts;     // 64 or 128
+    static constexpr int kGroup = kPartCols / 4;       // columns scored between two folds: 16 or 32
+    static constexpr uint32_t kSlotStride = kThreads * 4;  // bytes between the candidate slots of consecutive columns
+};
 constexpr int kFirstExpWarp = 3;
 constexpr int kFirstEpiWarp = kFirstExpWarp + kExpWarps;  // 7
-constexpr int kThreads = 32 * (kFirstEpiWarp + kEpiWarps);  // 480
+template <int KT>
+constexpr int threads_of() { return 32 * (kFirstEpiWarp + Epi<KT>::kWarps); }  // 736 or 480
 constexpr uint32_t kABytes = BM * kRowBytes;   // 16 KB
 constexpr uint32_t kBBytes = 256 * kRowBytes;  // 32 KB slot (240 or 256 rows in use)
 constexpr int kBStages = 3, kRawStages = 4;
-constexpr uint32_t kSlotStride = kEpiThreads * 4;  // bytes between the candidate slots of consecutive columns
-constexpr size_t kListBytes = (size_t)32 * kSlotStride;  // one slot per (epilogue thread, column of a 32-column chunk)
-static_assert(32 * BM * 4 <= kListBytes, "the half-exchange buffer aliases the candidate slots");
+constexpr size_t kListBytes = 32 * 1024;  // one slot per (epilogue thread, column of a group): 16 x 512 or 32 x 256 floats
+static_assert((size_t)Epi<8>::kGroup * Epi<8>::kThreads * 4 == kListBytes && (size_t)Epi<32>::kGroup * Epi<32>::kThreads * 4 == kListBytes, "slot area");
+static_assert((Epi<8>::kParts - 1) * 8 * BM * 4 <= kListBytes && (Epi<32>::kParts - 1) * 32 * BM * 4 <= kListBytes,
+              "the part-exchange buffer aliases the candidate slots");
 
 enum { MODE_FP8 = 0, MODE_FP8_HBM = 1, MODE_FP4 = 2 };
 
@@ -86,14 +101,14 @@ struct Cfg {
     static constexpr int BN = kFp4 ? 240 : 256;   // panel rows per tile = TMEM columns per accumulator stage
     static constexpr int WPK = kFp4 ? 8 : 4;      // packed words per k-block
     static constexpr int WPM = kFp4 ? 2 : 1;      // packed words per MMA
-    static constexpr int kAStages = kFp4 ? 4 : 5;
+    static constexpr int kAStages = 4;
     static constexpr uint32_t kRawRow = WPK * 4;                // raw bytes per panel row and k-block
     static constexpr uint32_t kRawSlot = kExpand ? 256 * kRawRow : 0;
     static constexpr uint32_t kRawBytes = BN * kRawRow;         // what one TMA box brings
     static constexpr uint32_t kBBox = BN * kRowBytes;           // fp8-hbm variant: one TMA box of operand rows
     static constexpr uint32_t kSfCol = 2 * BN;                  // fp4: first TMEM column of the unit scales
     static constexpr size_t kSmem = 1024 /*align slack*/ + (size_t)kAStages * kABytes + (size_t)kBStages * kBBytes +
-                                    (size_t)kRawStages * kRawSlot + kListBytes + 2 * BM * 4 /*thresholds*/ + 512 /*barriers*/;
+                                    (size_t)kRawStages * kRawSlot + kListBytes + 2 * BM * 4 * (SNV_TC_EPI16 ? 2 : 1) /*thresholds*/ + 256 /*barriers*/;
     static_assert(kSmem <= 232448, "shared memory budget");
 };
 
@@ -136,7 +151,7 @@ struct TcParams {
     int words, kblocks;      // packed words in use (= MMAs per tile), k-blocks of 4 words
     int n_tiles, nsplit, tiles_per_split;
     int items;               // nw * qtiles * nsplit
-    int idx_bits, k;
+    int idx_bits, k, one;
     int64_t id_offset;
     const int32_t* q_bias;   // [nw * nq] popc(q & m)
     int32_t* D_i32;
@@ -159,6 +174,16 @@ __device__ __forceinline__ Item decode_item(const TcParams& p, int item)
     const int t1 = it.t0 + p.tiles_per_split < p.n_tiles ? it.t0 + p.tiles_per_split : p.n_tiles;
     it.ntiles = t1 - it.t0;
     return it;
+}
+
+// compile-time unrolled loop: f(std::integral_constant<int, 0>{}), ..., f(std::integral_constant<int, N - 1>{})
+template <int N, int I = 0, typename F>
+__device__ __forceinline__ void static_for(F&& f)
+{
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<N, I + 1>(f);
+    }
 }
 
 template <int N>
@@ -205,8 +230,40 @@ __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, uint32_t v)
         ::"r"(taddr), "r"(v) : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&r)[16])
+{
+    asm volatile(
+        "tcgen05.wait::ld.sync.aligned;"
+        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+          "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+        :
+        : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[N])
+{
+    if constexpr (N == 16) tmem_ld_32x32b_x16(taddr, r);
+    else tmem_ld_32x32b_x32(taddr, r);
+}
+template <int N>
+__device__ __forceinline__ void tmem_ld_wait_cols(uint32_t (&r)[N])
+{
+    if constexpr (N == 16) tmem_ld_wait16(r);
+    else tmem_ld_wait(r);
+}
+
 template <int KT, int MODE>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(threads_of<KT>(), 1)
 hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_r, const TcParams p)
 {
     using C = Cfg<MODE>;
@@ -221,10 +278,12 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     unsigned char* a_tiles = smem;
     unsigned char* b_tiles = a_tiles + (size_t)kAStages * kABytes;
     unsigned char* raws = b_tiles + (size_t)kBStages * kBBytes;
-    uint32_t* lists = reinterpret_cast<uint32_t*>(raws + (size_t)kRawStages * C::kRawSlot);  // [32 columns][256 threads]
-    uint32_t* xchg = lists;                                                                 // [KT][128], after the lists are folded
-    volatile float* thrx = reinterpret_cast<float*>(lists + 32 * kEpiThreads);                     // [2 halves][128 queries] published thresholds
-    uint64_t* bars = reinterpret_cast<uint64_t*>(lists + 32 * kEpiThreads + 2 * BM);
+    uint32_t* lists = reinterpret_cast<uint32_t*>(raws + (size_t)kRawStages * C::kRawSlot);  // [group columns][epilogue threads]
+    using E = Epi<KT>;
+    constexpr int kEpiThreads = E::kThreads;
+    uint32_t* xchg = lists;                                                                 // [parts - 1][KT][128], after the slots are folded
+    volatile float* thrx = reinterpret_cast<float*>(lists + kListBytes / 4);               // [parts][128 queries] published thresholds
+    uint64_t* bars = reinterpret_cast<uint64_t*>(lists + kListBytes / 4 + 2 * BM * (SNV_TC_EPI16 ? 2 : 1));
     uint64_t* full_a = bars;                        // [kAStages]   TMA -> MMA
     uint64_t* empty_a = full_a + kAStages;          // [kAStages]   MMA -> TMA
     uint64_t* full_b = empty_a + kAStages;          // [kBStages]   expanders (or TMA) -> MMA
@@ -260,6 +319,7 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
+    if (warp == 2 && lane == 0) tmem_ptr[1] = (uint32_t)p.one;
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
@@ -309,6 +369,9 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             const uint32_t sf_a = tmem_base + C::kSfCol, sf_b = tmem_base + C::kSfCol + 16u;
             (void)sf_a; (void)sf_b;
             auto mma = [&](uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t acc) {
+#ifdef TC_DEBUG_NO_MMA
+                return;
+#endif
                 const uint64_t adesc = kDescHi | (uint64_t)a_lo;
                 const uint64_t bdesc = kDescHi | (uint64_t)b_lo;
                 if constexpr (FP4) umma_mxf4(d_tmem, adesc, bdesc, idesc, acc, sf_a, sf_b);
@@ -405,6 +468,9 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                 return v;
             };
             auto sts128 = [](uint32_t addr, const uint4& v) {
+#ifdef TC_DEBUG_NO_EXPAND_STS
+                if (v.x != 0xdeadbeefu) return;
+#endif
                 asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
             };
             // chunks [0, nchunk) of one row; NCHUNK = 8 is the branch-free hot path
@@ -476,15 +542,20 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             }
         }
     } else {
-        // ================= epilogue: thread = query row, 2 warps per lane quarter =================
+        // ================= epilogue: thread = query row (TMEM lane), kParts warps per lane quarter =================
+        constexpr int kParts = E::kParts, kPartCols = E::kPartCols, G = E::kGroup;
+        constexpr uint32_t kSlotStride = E::kSlotStride;
         const int quarter = warp & 3;                   // TMEM lanes [32 * quarter, +32)
-        const int half = (warp - kFirstEpiWarp) >> 2;   // columns [128 * half, +128) of every tile
+        const int part = (warp - kFirstEpiWarp) >> 2;   // columns [kPartCols * part, +kPartCols) of every tile
         const int row = quarter * 32 + lane;
         const int et = (warp - kFirstEpiWarp) * 32 + lane;
         const uint32_t slot_base = smem_u32(lists + et);  // this thread's slot of column j at slot_base + j * kSlotStride
         const int idx_bits = p.idx_bits;
+        // a runtime 1 the compiler cannot see through (read back from shared memory): keeps the mask adds on the
+        // FMA pipe as IMAD with a register multiplier instead of ALU-pipe LOP3
+        const uint32_t one = *reinterpret_cast<volatile uint32_t*>(tmem_ptr + 1);
         uint32_t tcount = 0;
-        thrx[half * BM + row] = 3.0e38f;
+        thrx[part * BM + row] = 3.0e38f;
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
             const Item it = decode_item(p, item);
@@ -497,61 +568,74 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             for (int i = 0; i < KT; ++i) best[i] = kSent32;
             // Selection.  Per column: one compare of the raw accumulator against the threshold (strict, so equal
             // distances at later columns never displace: ids ascend along the scan), a predicated store into the
-            // column's own slot in shared memory and a predicated bit in a 32-column mask - no serial pointer
-            // chain.  After each 32-column chunk the lanes pop their mask bits in lockstep (two per round) and
+            // column's own slot in shared memory and a predicated bit in a per-group mask - no serial pointer
+            // chain.  After each group of G columns the lanes pop their mask bits in lockstep (two per round) and
             // insert into the sorted register top-k.  acc + 1.5 * 2^23 has the integer value of acc in its low
             // mantissa bits:  key = (bits - 0x4B400000 + qb) << idx_bits | column  (mod 2^32), distance = qb + acc.
-            // The two warps of a query (column halves) publish their thresholds to each other: a candidate must
-            // also not exceed the other half's k-th best (non-strict: ids interleave between the halves).
+            // The warps of a query (column parts) publish their thresholds to each other: a candidate must
+            // also not exceed the other parts' k-th best (non-strict: ids interleave between the parts).
             const uint32_t kconst = (uint32_t)(qb - 0x4B400000) << idx_bits;
             float thr_mine = 3.0e38f, thr = 3.0e38f;
             auto key_of = [&](float a, uint32_t col) { return (__float_as_uint(a + 12582912.0f) << idx_bits) + kconst + col; };
+            float thr_other = 3.0e38f;  // min over the other parts of (published threshold + 1), re-read once per tile
             auto refresh_thr = [&]() {
-                thr_mine = best[KT - 1] == kSent32 ? 3.0e38f : (float)((int32_t)(best[KT - 1] >> idx_bits) - qb);
-                thrx[half * BM + row] = thr_mine;
-                thr = fminf(thr_mine, thrx[(half ^ 1) * BM + row] + 1.0f);
+                // (float)(k-th best distance - qb) without a conversion instruction (|value| < 2^22)
+                const int32_t x = (int32_t)(best[KT - 1] >> idx_bits) - qb;
+                thr_mine = best[KT - 1] == kSent32 ? 3.0e38f : __uint_as_float(0x4B400000u + (uint32_t)x) - 12582912.0f;
+                thr = fminf(thr_mine, thr_other);
             };
             auto fold = [&](uint32_t mask, uint32_t col0) {
-                while (__any_sync(0xffffffffu, mask != 0u)) {
-                    if (mask != 0u) {
-                        const int j1 = __ffs((int)mask) - 1;
-                        mask &= mask - 1u;
-                        const bool two = mask != 0u;
-                        const int j2 = two ? __ffs((int)mask) - 1 : j1;
-                        mask &= mask - 1u;
-                        float a1, a2;
-                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a1) : "r"(slot_base + (uint32_t)j1 * kSlotStride));
-                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a2) : "r"(slot_base + (uint32_t)j2 * kSlotStride));
-                        const uint32_t key1 = key_of(a1, col0 + (uint32_t)j1);
-                        const uint32_t key2 = two ? key_of(a2, col0 + (uint32_t)j2) : kSent32;
-                        if (key1 < best[KT - 1]) topk_insert<KT, uint32_t>(best, key1);
-                        if (key2 < best[KT - 1]) topk_insert<KT, uint32_t>(best, key2);
-                    }
+                if (__any_sync(0xffffffffu, mask != 0u)) {
+                    do {
+                        if (mask != 0u) {
+                            const int j1 = __ffs((int)mask) - 1;
+                            mask &= mask - 1u;
+                            const bool two = mask != 0u;
+                            const int j2 = two ? __ffs((int)mask) - 1 : j1;
+                            mask &= mask - 1u;
+                            float a1, a2;
+                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a1) : "r"(slot_base + (uint32_t)j1 * kSlotStride));
+                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a2) : "r"(slot_base + (uint32_t)j2 * kSlotStride));
+                            const uint32_t key1 = key_of(a1, col0 + (uint32_t)j1);
+                            const uint32_t key2 = two ? key_of(a2, col0 + (uint32_t)j2) : kSent32;
+                            if (key1 < best[KT - 1]) topk_insert<KT, uint32_t>(best, key1);
+                            if (key2 < best[KT - 1]) topk_insert<KT, uint32_t>(best, key2);
+                        }
+                    } while (__any_sync(0xffffffffu, mask != 0u));
+                    refresh_thr();
                 }
-                refresh_thr();
             };
             for (int t = 0; t < it.ntiles; ++t, ++tcount) {
                 const uint32_t as = tcount & 1u;
                 const int n0 = (it.t0 + t) * BN;
                 mbar_wait(&tmem_full[as], (tcount >> 1) & 1u);
                 tcgen05_fence_after();
-                int cols = (p.n - n0 < BN ? (int)(p.n - n0) : BN) - 128 * half;  // columns of this half in use
-                cols = cols < 0 ? 0 : (cols > 128 ? 128 : cols);
-                const int nch = (cols + 31) >> 5;
-                const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + (uint32_t)(128 * half);
-                const uint32_t col_base = (uint32_t)(t * BN + 128 * half);  // columns count from the split's first row
-                uint32_t accA[32], accB[32];
-                auto process = [&](uint32_t (&acc)[32], int u) {
-                    if (32 * u + 32 > cols) {
+                int cols = (p.n - n0 < BN ? (int)(p.n - n0) : BN) - kPartCols * part;  // columns of this part in use
+                cols = cols < 0 ? 0 : (cols > kPartCols ? kPartCols : cols);
+                const int nch = (cols + G - 1) / G;
+                const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + (uint32_t)(kPartCols * part);
+                const uint32_t col_base = (uint32_t)(t * BN + kPartCols * part);  // columns count from the split's first row
+                // exchange thresholds with the other column parts of this query (once per tile; stale is safe)
+                thrx[part * BM + row] = thr_mine;
+                thr_other = 3.0e38f;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (32 * u + j >= cols) acc[j] = 0x7F800000u;  // past the panel end (+inf): never a candidate
+                for (int o = 1; o < kParts; ++o) thr_other = fminf(thr_other, thrx[((part + o) % kParts) * BM + row] + 1.0f);
+                thr = fminf(thr_mine, thr_other);
+                uint32_t accA[G], accB[G];
+                auto process = [&](uint32_t (&acc)[G], int u) {
+                    if (G * u + G > cols) {
+#pragma unroll
+                        for (int j = 0; j < G; ++j)
+                            if (G * u + j >= cols) acc[j] = 0x7F800000u;  // past the panel end (+inf): never a candidate
                     }
-                    const uint32_t col0 = col_base + (uint32_t)(32 * u);
+                    const uint32_t col0 = col_base + (uint32_t)(G * u);
+#ifdef TC_DEBUG_NO_EPI
+                    return;
+#endif
                     if (t == 0 && u == 0) {
-                        // first chunk of an item: no threshold yet, every column is a candidate - insert in lockstep
+                        // first group of an item: no threshold yet, every column is a candidate - insert in lockstep
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
+                        for (int j = 0; j < G; ++j) {
                             const float a = __uint_as_float(acc[j]);
                             const uint32_t key = a < 3.0e38f ? key_of(a, col0 + (uint32_t)j) : kSent32;
                             if (key < best[KT - 1]) topk_insert<KT, uint32_t>(best, key);
@@ -559,51 +643,57 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                         refresh_thr();
                         return;
                     }
-                    uint32_t mask = 0;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
+                    // four independent partial masks (short dependency chains); the bit is added with a
+                    // multiply-add by a runtime 1 so that it issues on the FMA pipe, not the busier ALU pipe
+                    uint32_t m4[4] = {0u, 0u, 0u, 0u};
+                    static_for<G>([&](auto jc) {
+                        constexpr int j = decltype(jc)::value;
                         const float a = __uint_as_float(acc[j]);
                         if (a < thr) {
                             asm volatile("st.shared.f32 [%0], %1;" ::"r"(slot_base + (uint32_t)j * kSlotStride), "f"(a) : "memory");
-                            mask |= 1u << j;
+                            asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(m4[j & 3]) : "r"(one), "n"(1u << j));
                         }
-                    }
-                    fold(mask, col0);
+                    });
+#ifdef TC_DEBUG_NO_FOLD
+                    if (((m4[0] | m4[1]) | (m4[2] | m4[3])) == 0xdeadbeefu) fold(1u, col0);
+#else
+                    fold((m4[0] | m4[1]) | (m4[2] | m4[3]), col0);
+#endif
                 };
-                if (nch > 0) tmem_ld_32x32b_x32(tbase, accA);
+                if (nch > 0) tmem_ld_cols<G>(tbase, accA);
                 if (nch > 0) {
-                    tmem_ld_wait(accA);
-                    if (nch > 1) tmem_ld_32x32b_x32(tbase + 32u, accB);
+                    tmem_ld_wait_cols<G>(accA);
+                    if (nch > 1) tmem_ld_cols<G>(tbase + (uint32_t)G, accB);
                     process(accA, 0);
                 }
                 if (nch > 1) {
-                    tmem_ld_wait(accB);
-                    if (nch > 2) tmem_ld_32x32b_x32(tbase + 64u, accA);
+                    tmem_ld_wait_cols<G>(accB);
+                    if (nch > 2) tmem_ld_cols<G>(tbase + (uint32_t)(2 * G), accA);
                     process(accB, 1);
                 }
                 if (nch > 2) {
-                    tmem_ld_wait(accA);
-                    if (nch > 3) tmem_ld_32x32b_x32(tbase + 96u, accB);
+                    tmem_ld_wait_cols<G>(accA);
+                    if (nch > 3) tmem_ld_cols<G>(tbase + (uint32_t)(3 * G), accB);
                     process(accA, 2);
                 }
                 if (nch > 3) {
-                    tmem_ld_wait(accB);
+                    tmem_ld_wait_cols<G>(accB);
                     process(accB, 3);
                 }
                 tcgen05_fence_before();
                 mbar_arrive(&tmem_empty[as]);
             }
-            // ---- merge the two halves of each query through shared memory, then write the result
-            thrx[half * BM + row] = 3.0e38f;  // reset for the next item (ordered by the barriers below)
-            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // every chunk is folded: the buffer is free
-            if (half == 1) {
+            // ---- merge the parts of each query through shared memory, then write the result
+            thrx[part * BM + row] = 3.0e38f;  // reset for the next item (ordered by the barriers below)
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // every group is folded: the buffer is free
+            if (part != 0) {
 #pragma unroll
-                for (int i = 0; i < KT; ++i) xchg[i * BM + row] = best[i];
+                for (int i = 0; i < KT; ++i) xchg[((part - 1) * KT + i) * BM + row] = best[i];
             }
             asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-            if (half == 0) {
+            if (part == 0) {
 #pragma unroll 1
-                for (int i = 0; i < KT; ++i) {
+                for (int i = 0; i < (kParts - 1) * KT; ++i) {
                     const uint32_t key = xchg[i * BM + row];
                     if (key < best[KT - 1]) topk_insert<KT, uint32_t>(best, key);
                 }
@@ -647,55 +737,54 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 }
 
 // ---- query operand: packed (q, observed mask) -> operand rows [rows][kblocks * 128 B] + popc(q & m) ----------------
+// One warp per query row: lane l owns packed word l (and l + 32, ...) for the bias, and writes the row's 16-byte
+// chunks l, l + 32, ... (coalesced); no integer divisions on the hot path.
 template <bool FP4>
 __global__ void __launch_bounds__(256)
 tc_expand_queries_kernel(const uint32_t* __restrict__ q, const uint32_t* __restrict__ mask, int64_t mask_win_stride,
                          int64_t mask_q_stride, int nq, int64_t rows, int stride, int words, int d, int kblocks,
                          uint8_t* __restrict__ ops, int32_t* __restrict__ bias)
 {
+    const int lane = threadIdx.x & 31;
     const int cpr = kblocks * 8;  // 16-byte chunks per row
-    const int64_t total = rows * cpr;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t row = idx / cpr;
-        const int ch = (int)(idx % cpr);
-        // fp8: chunk pair (2 i, 2 i + 1) of a k-block <- packed word i; fp4: chunk i <- packed word i
-        const int wi = FP4 ? ch : (ch >> 3) * 4 + ((ch & 7) >> 1);
-        const int h = ch & 1;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = warp0; row < rows; row += nwarps) {
         const uint32_t* qr = q + row * stride;
         const uint32_t* mr = mask ? mask + (row / nq) * mask_win_stride + (row % nq) * mask_q_stride : nullptr;
-        auto valid_bits = [&](int w) -> uint32_t {
+        auto observed = [&](int w) -> uint32_t {  // observed-site bits of packed word w (0 past the row end)
             const int lo = w * 32;
-            return lo + 32 <= d ? 0xFFFFFFFFu : (lo < d ? (1u << (d - lo)) - 1u : 0u);
+            uint32_t m = lo + 32 <= d ? 0xFFFFFFFFu : (lo < d ? (1u << (d - lo)) - 1u : 0u);
+            if (mr && w < words) m &= mr[w];
+            return w < words ? m : 0u;
         };
-        uint32_t wm = 0, wq = 0;
-        if (wi < words) {
-            wm = valid_bits(wi);
-            if (mr) wm &= mr[wi];
-            wq = qr[wi] & wm;
-        }
-        uint32_t out[4];
+        int32_t b = 0;
+        for (int w = lane; w < words; w += 32) b += __popc(qr[w] & observed(w));
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-            if constexpr (FP4) {
-                const uint32_t mb = (wm >> jj) & 0x11111111u;
-                const uint32_t sb = (wq >> jj) & 0x11111111u;
-                out[jj] = mb * query_code_fp4(jj) | sb * 8u;
-            } else {
-                const int j = 4 * h + jj;
-                const uint32_t mb = (wm >> j) & 0x01010101u;
-                const uint32_t sb = (wq >> j) & 0x01010101u;
-                out[jj] = mb * query_code_fp8(j) | sb * 0x80u;
+        for (int o = 16; o > 0; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+        if (lane == 0) bias[row] = b;
+        uint4* out_row = reinterpret_cast<uint4*>(ops + row * (int64_t)cpr * 16);
+        for (int ch = lane; ch < cpr; ch += 32) {
+            // fp8: chunk pair (2 i, 2 i + 1) of a k-block <- packed word i; fp4: chunk i <- packed word i
+            const int wi = FP4 ? ch : (ch >> 3) * 4 + ((ch & 7) >> 1);
+            const int h = ch & 1;
+            const uint32_t wm = observed(wi);
+            const uint32_t wq = wi < words ? qr[wi] & wm : 0u;
+            uint32_t out[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                if constexpr (FP4) {
+                    const uint32_t mb = (wm >> jj) & 0x11111111u;
+                    const uint32_t sb = (wq >> jj) & 0x11111111u;
+                    out[jj] = mb * query_code_fp4(jj) | sb * 8u;
+                } else {
+                    const int j = 4 * h + jj;
+                    const uint32_t mb = (wm >> j) & 0x01010101u;
+                    const uint32_t sb = (wq >> j) & 0x01010101u;
+                    out[jj] = mb * query_code_fp8(j) | sb * 0x80u;
+                }
             }
-        }
-        *reinterpret_cast<uint4*>(ops + (row * cpr + ch) * 16) = make_uint4(out[0], out[1], out[2], out[3]);
-        if (ch == 0) {
-            int32_t b = 0;
-            for (int w = 0; w < words; ++w) {
-                uint32_t m = valid_bits(w);
-                if (mr) m &= mr[w];
-                b += __popc(qr[w] & m);
-            }
-            bias[row] = b;
+            out_row[ch] = make_uint4(out[0], out[1], out[2], out[3]);
         }
     }
 }
@@ -753,7 +842,7 @@ int launch_kernel(const CUtensorMap& map_q, const CUtensorMap& map_r, const TcPa
         attr = true;
     }
     profile_begin(stream);
-    hamming_tc_kernel<KT, MODE><<<grid, kThreads, smem, stream>>>(map_q, map_r, tp);
+    hamming_tc_kernel<KT, MODE><<<grid, threads_of<KT>(), smem, stream>>>(map_q, map_r, tp);
     profile_end(stream);
     SNV_LAUNCH_CHECK();
     return SNV_OK;
@@ -826,8 +915,7 @@ int hamming_tc_launch(const HammingSearchParams& p, const HammingTcPlan& plan, v
     const int kbytes = plan.kblocks * kRowBytes;
     const int BN = bn_of_engine(plan.engine);
     {
-        const int64_t total = rows * plan.kblocks * 8;
-        const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(total, 256), (int64_t)kNumSMs * 32);
+        const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(rows, 8), (int64_t)kNumSMs * 32);  // 8 warps = 8 rows per block
         if (plan.engine == 3)
             tc_expand_queries_kernel<true><<<grid, 256, 0, stream>>>(p.q, p.mask, p.mask_win_stride, p.mask_q_stride, p.nq, rows, p.stride,
                                                                     p.words, p.d, plan.kblocks, q_ops, q_bias);
@@ -868,7 +956,7 @@ int hamming_tc_launch(const HammingSearchParams& p, const HammingTcPlan& plan, v
     tp.words = p.words; tp.kblocks = plan.kblocks;
     tp.n_tiles = plan.n_tiles; tp.nsplit = plan.nsplit; tp.tiles_per_split = plan.tiles_per_split;
     tp.items = p.nw * plan.qtiles * plan.nsplit;
-    tp.idx_bits = plan.idx_bits; tp.k = p.k;
+    tp.idx_bits = plan.idx_bits; tp.k = p.k; tp.one = 1;
     tp.id_offset = p.id_offset;
     tp.q_bias = q_bias;
     tp.D_i32 = p.D_i32; tp.D_f32 = p.D_f32; tp.I = p.I;
