@@ -71,15 +71,17 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// try_wait suspends the warp in hardware until the phase completes or the time hint (ns) expires, so a waiting
+// warp does not poll: it takes no issue slots from the other warps of its SM sub-partition while it waits.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
 {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.b32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)
         : "memory");
     return ok != 0;
 }

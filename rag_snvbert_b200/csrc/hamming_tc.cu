@@ -84,24 +84,40 @@ template <int KT>
 constexpr int threads_of() { return 32 * (kFirstEpiWarp + Epi<KT>::kWarps); }  // 736 or 480
 constexpr uint32_t kABytes = BM * kRowBytes;   // 16 KB
 constexpr uint32_t kBBytes = 256 * kRowBytes;  // 32 KB slot (240 or 256 rows in use)
-constexpr int kBStages = 3, kRawStages = 4;
+#ifndef SNV_TC_BSTAGES
+#define SNV_TC_BSTAGES 3
+#endif
+#ifndef SNV_TC_ASTAGES
+#define SNV_TC_ASTAGES 4
+#endif
+#ifndef SNV_TC_RAWSTAGES
+#define SNV_TC_RAWSTAGES 4
+#endif
+#ifndef SNV_TC_RESIDENT
+#define SNV_TC_RESIDENT 0  // 1: keep the query tile resident in shared memory when it fits (measured no faster: the raw ring shrinks)
+#endif
+constexpr int kBStages = SNV_TC_BSTAGES;
 constexpr size_t kListBytes = 32 * 1024;  // one slot per (epilogue thread, column of a group): 16 x 512 or 32 x 256 floats
 static_assert((size_t)Epi<8>::kGroup * Epi<8>::kThreads * 4 == kListBytes && (size_t)Epi<32>::kGroup * Epi<32>::kThreads * 4 == kListBytes, "slot area");
 static_assert((Epi<8>::kParts - 1) * 8 * BM * 4 <= kListBytes && (Epi<32>::kParts - 1) * 32 * BM * 4 <= kListBytes,
               "the part-exchange buffer aliases the candidate slots");
 
-enum { MODE_FP8 = 0, MODE_FP8_HBM = 1, MODE_FP4 = 2 };
+enum { MODE_FP8 = 0, MODE_FP8_HBM = 1, MODE_FP4 = 2, MODE_FP4_RES = 3 };
 
 // Three rings: the query operand comes from L2 (long latency: deep ring), the panel operand is made
 // in the SM (expander latency: 3 slots), raw packed k-blocks are small.
 template <int MODE>
 struct Cfg {
-    static constexpr bool kFp4 = MODE == MODE_FP4;
+    static constexpr bool kFp4 = MODE == MODE_FP4 || MODE == MODE_FP4_RES;
+    // resident query tile: the whole A operand of an item (<= 5 k-blocks) stays in shared memory for all of the
+    // item's panel tiles instead of being re-streamed from L2 for each of them
+    static constexpr bool kResident = MODE == MODE_FP4_RES;
     static constexpr bool kExpand = MODE != MODE_FP8_HBM;
     static constexpr int BN = kFp4 ? 240 : 256;   // panel rows per tile = TMEM columns per accumulator stage
     static constexpr int WPK = kFp4 ? 8 : 4;      // packed words per k-block
     static constexpr int WPM = kFp4 ? 2 : 1;      // packed words per MMA
-    static constexpr int kAStages = 4;
+    static constexpr int kAStages = kResident ? 5 : SNV_TC_ASTAGES;
+    static constexpr int kRawStages = kResident ? 2 : SNV_TC_RAWSTAGES;
     static constexpr uint32_t kRawRow = WPK * 4;                // raw bytes per panel row and k-block
     static constexpr uint32_t kRawSlot = kExpand ? 256 * kRawRow : 0;
     static constexpr uint32_t kRawBytes = BN * kRawRow;         // what one TMA box brings
@@ -240,7 +256,7 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
         : "r"(taddr)
         : "memory");
 }
-__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&r)[16])
+[[maybe_unused]] __device__ __forceinline__ void tmem_ld_wait16(uint32_t (&r)[16])
 {
     asm volatile(
         "tcgen05.wait::ld.sync.aligned;"
@@ -272,6 +288,8 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     constexpr int BN = C::BN;
     constexpr int WPK = C::WPK;
     constexpr int kAStages = C::kAStages;
+    constexpr int kRawStages = C::kRawStages;
+    constexpr bool RES = C::kResident;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     unsigned char* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);  // SWIZZLE_128B tiles: 1024-byte aligned
@@ -341,16 +359,31 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     if (warp == 0) {
         // ================= TMA producer: query operand tiles =================
         if (lane == 0) {
-            Ring<kAStages> ra;
-            for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-                const Item it = decode_item(p, item);
-                const int row_a = it.w * p.nq + it.qt * BM;
-                for (int t = 0; t < it.ntiles; ++t) {
+            if constexpr (RES) {
+                // resident: slot kb holds k-block kb of the item's query tile; it is reloaded for the next item as
+                // soon as the last panel tile's MMAs on it have completed
+                uint32_t icount = 0;
+                for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++icount) {
+                    const Item it = decode_item(p, item);
+                    const int row_a = it.w * p.nq + it.qt * BM;
                     for (int kb = 0; kb < KB; ++kb) {
-                        mbar_wait_relaxed(&empty_a[ra.i], ra.phase ^ 1u);
-                        mbar_arrive_expect_tx(&full_a[ra.i], kABytes);
-                        tma_load_2d(a_tiles + (size_t)ra.i * kABytes, &map_q, kb * kRowBytes, row_a, &full_a[ra.i]);
-                        ra.next();
+                        mbar_wait_relaxed(&empty_a[kb], (icount & 1u) ^ 1u);
+                        mbar_arrive_expect_tx(&full_a[kb], kABytes);
+                        tma_load_2d(a_tiles + (size_t)kb * kABytes, &map_q, kb * kRowBytes, row_a, &full_a[kb]);
+                    }
+                }
+            } else {
+                Ring<kAStages> ra;
+                for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+                    const Item it = decode_item(p, item);
+                    const int row_a = it.w * p.nq + it.qt * BM;
+                    for (int t = 0; t < it.ntiles; ++t) {
+                        for (int kb = 0; kb < KB; ++kb) {
+                            mbar_wait_relaxed(&empty_a[ra.i], ra.phase ^ 1u);
+                            mbar_arrive_expect_tx(&full_a[ra.i], kABytes);
+                            tma_load_2d(a_tiles + (size_t)ra.i * kABytes, &map_q, kb * kRowBytes, row_a, &full_a[ra.i]);
+                            ra.next();
+                        }
                     }
                 }
             }
@@ -379,37 +412,41 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             };
             Ring<kAStages> ra;
             Ring<kBStages> rb;
-            uint32_t tcount = 0;
-            for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+            uint32_t tcount = 0, icount = 0;
+            for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++icount) {
                 const Item it = decode_item(p, item);
                 for (int t = 0; t < it.ntiles; ++t, ++tcount) {
                     const uint32_t as = tcount & 1u;
                     mbar_wait(&tmem_empty[as], ((tcount >> 1) & 1u) ^ 1u);
                     tcgen05_fence_after();
                     const uint32_t d_tmem = tmem_base + as * BN;
+                    const bool last_tile = t == it.ntiles - 1;
                     for (int kb = 0; kb < KB; ++kb) {
-                        mbar_wait(&full_a[ra.i], ra.phase);
+                        const int sa = RES ? kb : ra.i;  // A slot: k-block index when the query tile is resident
+                        if constexpr (RES) {
+                            if (t == 0) mbar_wait(&full_a[sa], icount & 1u);
+                        } else {
+                            mbar_wait(&full_a[sa], ra.phase);
+                        }
                         mbar_wait(&full_b[rb.i], rb.phase);
                         tcgen05_fence_after();
                         if (elect_one()) {
-                            const uint32_t a_lo = a_lo0 + (uint32_t)ra.i * (kABytes >> 4);
+                            const uint32_t a_lo = a_lo0 + (uint32_t)sa * (kABytes >> 4);
                             const uint32_t b_lo = b_lo0 + (uint32_t)rb.i * (kBBytes >> 4);
                             if (kb != KB - 1) {
                                 mma(d_tmem, a_lo, b_lo, kb != 0 ? 1u : 0u);
                                 mma(d_tmem, a_lo + 2, b_lo + 2, 1u);
                                 mma(d_tmem, a_lo + 4, b_lo + 4, 1u);
                                 mma(d_tmem, a_lo + 6, b_lo + 6, 1u);
-                                umma_commit(&empty_a[ra.i]);
-                                umma_commit(&empty_b[rb.i]);
                             } else {
                                 mma(d_tmem, a_lo, b_lo, kb != 0 ? 1u : 0u);
                                 if (nm_tail > 1) mma(d_tmem, a_lo + 2, b_lo + 2, 1u);
                                 if (nm_tail > 2) mma(d_tmem, a_lo + 4, b_lo + 4, 1u);
                                 if (nm_tail > 3) mma(d_tmem, a_lo + 6, b_lo + 6, 1u);
-                                umma_commit(&empty_a[ra.i]);
-                                umma_commit(&empty_b[rb.i]);
-                                umma_commit(&tmem_full[as]);
                             }
+                            if (!RES || last_tile) umma_commit(&empty_a[sa]);
+                            umma_commit(&empty_b[rb.i]);
+                            if (kb == KB - 1) umma_commit(&tmem_full[as]);
                         }
                         __syncwarp();
                         ra.next();
@@ -848,7 +885,11 @@ int launch_kernel(const CUtensorMap& map_q, const CUtensorMap& map_r, const TcPa
     return SNV_OK;
 }
 
-int mode_of_engine(int engine) { return engine == 3 ? MODE_FP4 : (engine == 2 ? MODE_FP8_HBM : MODE_FP8); }
+int mode_of_engine(int engine, int kblocks)
+{
+    if (engine == 3) return (SNV_TC_RESIDENT && kblocks <= Cfg<MODE_FP4_RES>::kAStages) ? MODE_FP4_RES : MODE_FP4;
+    return engine == 2 ? MODE_FP8_HBM : MODE_FP8;
+}
 int bn_of_engine(int engine) { return engine == 3 ? Cfg<MODE_FP4>::BN : 256; }
 int wpk_of_engine(int engine) { return engine == 3 ? Cfg<MODE_FP4>::WPK : 4; }
 
@@ -884,11 +925,24 @@ size_t hamming_tc_plan(const HammingSearchParams& p, HammingTcPlan& plan)
     plan.n_tiles = (int)ceil_div(p.n, BN);
     plan.idx_bits = 32 - bit_length64((int64_t)p.d + 1);
     const int64_t max_tiles_per_split = ((int64_t)1 << plan.idx_bits) / BN;
-    // row splits only when (window, query tile) items cannot fill the machine, or for the key's id field
+    // Row splits: the persistent CTAs take (window, query tile, row split) items round-robin, so the step lasts
+    // ceil(items / SMs) rounds of one item each.  Pick the split count that minimises rounds x tiles per item (a few
+    // long items leave most SMs idle in the last round); every split costs a partial top-k and the merge kernel, so
+    // ties go to fewer splits and a split must keep at least two tiles.  The key's id field bounds the tiles per item.
     const int64_t base = (int64_t)p.nw * plan.qtiles;
-    int64_t nsplit = 1;
-    if (base < kNumSMs) nsplit = std::min<int64_t>(ceil_div(kNumSMs, base), std::max<int64_t>(1, plan.n_tiles / 2));
-    nsplit = std::max<int64_t>(nsplit, ceil_div(plan.n_tiles, max_tiles_per_split));
+    const int64_t min_split = ceil_div(plan.n_tiles, max_tiles_per_split);
+    int64_t nsplit = min_split;
+    {
+        int64_t best_cost = -1;
+        const int64_t max_split = std::max<int64_t>(min_split, std::min<int64_t>(32, plan.n_tiles / 2));
+        for (int64_t s = min_split; s <= max_split; ++s) {
+            const int64_t per = ceil_div(plan.n_tiles, s);
+            const int64_t real = ceil_div(plan.n_tiles, per);
+            const int64_t rounds = ceil_div(base * real, kNumSMs);
+            const int64_t cost = rounds * (per * 64 + 16) + (real > 1 ? rounds : 0);  // +16: per-item prologue / merge weight
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; nsplit = real; }
+        }
+    }
     plan.tiles_per_split = (int)ceil_div(plan.n_tiles, nsplit);
     plan.nsplit = (int)ceil_div(plan.n_tiles, plan.tiles_per_split);
     if (base * plan.nsplit > 0x7fffffffLL) {
@@ -964,7 +1018,8 @@ int hamming_tc_launch(const HammingSearchParams& p, const HammingTcPlan& plan, v
     const int grid = std::min(tp.items, kNumSMs);
     int rc;
     const bool k8 = plan.kt == 8;
-    switch (mode_of_engine(plan.engine)) {
+    switch (mode_of_engine(plan.engine, plan.kblocks)) {
+        case MODE_FP4_RES: rc = k8 ? launch_kernel<8, MODE_FP4_RES>(map_q, map_r, tp, grid, stream) : launch_kernel<32, MODE_FP4_RES>(map_q, map_r, tp, grid, stream); break;
         case MODE_FP4: rc = k8 ? launch_kernel<8, MODE_FP4>(map_q, map_r, tp, grid, stream) : launch_kernel<32, MODE_FP4>(map_q, map_r, tp, grid, stream); break;
         case MODE_FP8_HBM: rc = k8 ? launch_kernel<8, MODE_FP8_HBM>(map_q, map_r, tp, grid, stream) : launch_kernel<32, MODE_FP8_HBM>(map_q, map_r, tp, grid, stream); break;
         default: rc = k8 ? launch_kernel<8, MODE_FP8>(map_q, map_r, tp, grid, stream) : launch_kernel<32, MODE_FP8>(map_q, map_r, tp, grid, stream); break;
