@@ -629,7 +629,7 @@ def run_cfg5(a):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     from rag_snvbert_b200 import WindowedHammingIndex, _lib, topk_merge
-    from rag_snvbert_b200.sharding import shard_range
+    from rag_snvbert_b200.sharding import search_row_sharded, shard_range
 
     N = a.refs if a.refs != 5008 else 200000
     Q = a.queries if a.queries != 2000 else 10000
@@ -651,15 +651,11 @@ def run_cfg5(a):
         torch.cuda.synchronize()
 
     def step():
-        D, I = index.search(queries, k, id_offset=lo)           # [W, Q, k], global ids
-        if world == 1:
-            return D, I
-        Dg = torch.empty((world,) + tuple(D.shape), dtype=D.dtype, device=dev)
-        Ig = torch.empty((world,) + tuple(I.shape), dtype=I.dtype, device=dev)
-        dist.all_gather_into_tensor(Dg, D)
-        dist.all_gather_into_tensor(Ig, I)
-        Dm, Im = topk_merge(Dg.reshape(world, W * Q, k), Ig.reshape(world, W * Q, k), k)
-        return Dm.reshape(W, Q, k), Im.reshape(W, Q, k)
+        # local scan with global ids, then ONE all-to-all: rank r receives every rank's candidates for its 1/G of
+        # the (window, query) rows and merges them (the merged result stays sharded by query)
+        _, _, D, I = search_row_sharded(lambda qq, kk, off: index.search(qq, kk, id_offset=off), topk_merge, queries, k, lo,
+                                        world=world, distribute="scatter")
+        return D, I
 
     for _ in range(max(a.warmup, 3)):
         D, I = step()
@@ -680,12 +676,10 @@ def run_cfg5(a):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = float(t.item()) / a.steps
     value = W * Q * N / (ms_per_step * 1e-3)
-    # cross-check: rank-independent result checksum
+    # cross-check: checksum of the whole (query-sharded) result, comparable between GPU counts
     chk = torch.stack([I.sum(), D.sum().to(torch.int64)])
     if world > 1:
-        ref = chk.clone()
-        dist.broadcast(ref, 0)
-        assert bool((ref == chk).all()), "ranks disagree on the merged result"
+        dist.all_reduce(chk, op=dist.ReduceOp.SUM)
     if rank == 0:
         peaks = {}
         try:
@@ -715,7 +709,7 @@ def run_cfg5(a):
             "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": dtype, "data": "synthetic",
             "config": {"workload": f"cfg5 biobank-scale: {W} of 500 windows x {N} ref haplotypes x {S} sites, {Q} queries/window, "
-                                   f"k={k}, panel row-sharded over {world} GPU(s) + all-gather top-k merge",
+                                   f"k={k}, panel row-sharded over {world} GPU(s) + all-to-all of the per-shard top-k + on-device merge (result sharded by query)",
                        "engine": ["popcount", "tcgen05-fp8", "tcgen05-fp8-hbm", "tcgen05-fp4"][engine],
                        "rows_per_gpu": hi - lo, "l2_policy": "panel shard larger than L2"},
             "window_queries_per_s": value / N, "gpu_launches": int(launches),

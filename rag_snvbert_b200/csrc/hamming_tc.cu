@@ -39,6 +39,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <type_traits>
 
@@ -926,20 +927,30 @@ size_t hamming_tc_plan(const HammingSearchParams& p, HammingTcPlan& plan)
     plan.idx_bits = 32 - bit_length64((int64_t)p.d + 1);
     const int64_t max_tiles_per_split = ((int64_t)1 << plan.idx_bits) / BN;
     // Row splits: the persistent CTAs take (window, query tile, row split) items round-robin, so the step lasts
-    // ceil(items / SMs) rounds of one item each.  Pick the split count that minimises rounds x tiles per item (a few
-    // long items leave most SMs idle in the last round); every split costs a partial top-k and the merge kernel, so
-    // ties go to fewer splits and a split must keep at least two tiles.  The key's id field bounds the tiles per item.
+    // ceil(items / SMs) rounds of one item each.  Pick the split count that minimises rounds x (tiles per item +
+    // per-item overhead): a few long items leave most SMs idle in the last round, but every item re-learns its
+    // top-k threshold from scratch - about kt (1 + ln(rows / kt)) insertions per query, each a lockstep round
+    // of the epilogue - and a split adds partial keys for the merge kernel.  The key's id field bounds the tiles
+    // per item.
     const int64_t base = (int64_t)p.nw * plan.qtiles;
     const int64_t min_split = ceil_div(plan.n_tiles, max_tiles_per_split);
     int64_t nsplit = min_split;
     {
-        int64_t best_cost = -1;
+        double best_cost = -1.0;
         const int64_t max_split = std::max<int64_t>(min_split, std::min<int64_t>(32, plan.n_tiles / 2));
+        // tiles of time per candidate insertion round, and per partial key merged afterwards (fitted on B200:
+        // cfg 5 at 1-8 GPUs, profiles/r1_bench_cfg5_*)
+        double ins = plan.kt == 8 ? 0.04 : 0.3;
+        const double merge_per_key = 3.5e-5;
+        if (const char* e = getenv("SNV_TC_INS")) ins = atof(e) > 0 ? atof(e) : ins;  // tuning override
         for (int64_t s = min_split; s <= max_split; ++s) {
             const int64_t per = ceil_div(plan.n_tiles, s);
             const int64_t real = ceil_div(plan.n_tiles, per);
             const int64_t rounds = ceil_div(base * real, kNumSMs);
-            const int64_t cost = rounds * (per * 64 + 16) + (real > 1 ? rounds : 0);  // +16: per-item prologue / merge weight
+            const double rows_item = (double)per * BN;
+            const double cand = plan.kt * (1.0 + std::log(std::max(1.0, rows_item / plan.kt)));
+            const double cost = (double)rounds * ((double)per + 0.25 + ins * cand) +
+                                (real > 1 ? merge_per_key * (double)p.nw * p.nq * real * plan.kt : 0.0);
             if (best_cost < 0 || cost < best_cost) { best_cost = cost; nsplit = real; }
         }
     }

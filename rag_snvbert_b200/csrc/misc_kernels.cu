@@ -110,6 +110,91 @@ merge_results_kernel(const DT* __restrict__ D, const int64_t* __restrict__ I, in
     }
 }
 
+// Warp-cooperative variant (parts * kin <= 32 * SHARE candidates per query): each lane keeps a sorted share of the
+// candidates in registers, then kout rounds of a lexicographic warp minimum over the lane heads (three 32-bit
+// reductions: distance, id high word, id low word) pop the winners in (D, I) order.  One warp per query instead
+// of one thread per query: coalescing-friendly and ~50x fewer serial steps for k = 32 over 8 shards.
+template <typename DT>
+__device__ __forceinline__ uint32_t dist_key(DT d);
+template <>
+__device__ __forceinline__ uint32_t dist_key<int32_t>(int32_t d) { return (uint32_t)d ^ 0x80000000u; }
+template <>
+__device__ __forceinline__ uint32_t dist_key<float>(float d)
+{
+    const uint32_t u = __float_as_uint(d);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+template <typename DT>
+__device__ __forceinline__ DT dist_unkey(uint32_t k);
+template <>
+__device__ __forceinline__ int32_t dist_unkey<int32_t>(uint32_t k) { return (int32_t)(k ^ 0x80000000u); }
+template <>
+__device__ __forceinline__ float dist_unkey<float>(uint32_t k)
+{
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
+
+template <int SHARE, typename DT>
+__global__ void __launch_bounds__(256)
+merge_results_warp_kernel(const DT* __restrict__ D, const int64_t* __restrict__ I, int parts, int64_t nq, int kin,
+                          int kout, DT pad, DT* __restrict__ Do, int64_t* __restrict__ Io)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int total = parts * kin;
+    const int64_t kIdMax = 0x7FFFFFFFFFFFFFFFLL;
+    for (int64_t q = warp0; q < nq; q += nwarps) {
+        uint32_t kd[SHARE];
+        int64_t ki[SHARE];
+#pragma unroll
+        for (int i = 0; i < SHARE; ++i) { kd[i] = 0xFFFFFFFFu; ki[i] = kIdMax; }
+#pragma unroll
+        for (int s = 0; s < SHARE; ++s) {
+            const int c = lane + 32 * s;
+            if (c < total) {
+                const int part = c / kin, j = c - part * kin;
+                const int64_t o = ((int64_t)part * nq + q) * kin + j;
+                int64_t ci = I[o];
+                if (ci >= 0) {
+                    uint32_t cd = dist_key<DT>(D[o]);
+#pragma unroll
+                    for (int i = 0; i < SHARE; ++i) {  // sorted insertion, branch-free over the register array
+                        const bool lt = cd < kd[i] || (cd == kd[i] && ci < ki[i]);
+                        const uint32_t td = kd[i];
+                        const int64_t ti = ki[i];
+                        kd[i] = lt ? cd : td;
+                        ki[i] = lt ? ci : ti;
+                        cd = lt ? td : cd;
+                        ci = lt ? ti : ci;
+                    }
+                }
+            }
+        }
+        for (int r = 0; r < kout; ++r) {
+            const uint32_t hd = kd[0];
+            const uint32_t hh = (uint32_t)((uint64_t)ki[0] >> 32), hl = (uint32_t)ki[0];
+            const uint32_t md = __reduce_min_sync(0xffffffffu, hd);
+            const uint32_t mh = __reduce_min_sync(0xffffffffu, hd == md ? hh : 0xFFFFFFFFu);
+            const uint32_t ml = __reduce_min_sync(0xffffffffu, (hd == md && hh == mh) ? hl : 0xFFFFFFFFu);
+            const bool win = hd == md && hh == mh && hl == ml;
+            const uint32_t winners = __ballot_sync(0xffffffffu, win);
+            const int64_t mi = (int64_t)(((uint64_t)mh << 32) | ml);
+            if (lane == 0) {
+                const bool empty = mi == kIdMax;
+                Do[q * kout + r] = empty ? pad : dist_unkey<DT>(md);
+                Io[q * kout + r] = empty ? -1 : mi;
+            }
+            if (win && lane == __ffs((int)winners) - 1) {
+#pragma unroll
+                for (int i = 0; i + 1 < SHARE; ++i) { kd[i] = kd[i + 1]; ki[i] = ki[i + 1]; }
+                kd[SHARE - 1] = 0xFFFFFFFFu;
+                ki[SHARE - 1] = kIdMax;
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------ pack
 // One warp per (row, 32-site group): coalesced 32-element read, ballot -> one packed word
 // (lane l <-> site 32*w + l <-> bit l: LSB-first).
@@ -313,6 +398,20 @@ int merge_results_launch(const int32_t* D_i32, const float* D_f32, const int64_t
     if (kout > 32 || kout < 1) {
         set_error("merge: k_out must be in [1, 32]");
         return SNV_ERR_UNSUPPORTED;
+    }
+    if ((int64_t)parts * kin <= 32 * 32) {
+        const int blockw = 256;
+        const unsigned gridw = (unsigned)std::min<int64_t>(ceil_div(nq, blockw / 32), (int64_t)kNumSMs * 32);
+        const bool small = (int64_t)parts * kin <= 32 * 8;
+        if (D_i32) {
+            if (small) merge_results_warp_kernel<8, int32_t><<<gridw, blockw, 0, stream>>>(D_i32, I, parts, nq, kin, kout, 0x7FFFFFFF, Do_i32, Io);
+            else merge_results_warp_kernel<32, int32_t><<<gridw, blockw, 0, stream>>>(D_i32, I, parts, nq, kin, kout, 0x7FFFFFFF, Do_i32, Io);
+        } else {
+            if (small) merge_results_warp_kernel<8, float><<<gridw, blockw, 0, stream>>>(D_f32, I, parts, nq, kin, kout, 3.4028234663852886e38f, Do_f32, Io);
+            else merge_results_warp_kernel<32, float><<<gridw, blockw, 0, stream>>>(D_f32, I, parts, nq, kin, kout, 3.4028234663852886e38f, Do_f32, Io);
+        }
+        SNV_LAUNCH_CHECK();
+        return SNV_OK;
     }
     const int block = 128;
     const unsigned grid = (unsigned)ceil_div(nq, block);

@@ -7,9 +7,11 @@ src/dataset/embedding_rag_infer_dataset.py:218), so both modes 
     src/dataset/rag_train_dataset.py:52-136), so rank g owns a contiguous window range and
     searches it with NO data-path collective; results live in disjoint slices.
   * row-sharded panel (BASELINE cfg 5): rank g holds panel rows [g*N/G, (g+1)*N/G) of every
-    window, searches its rows with GLOBAL ids (id_offset), then ONE all-gather of the per-rank
-    (D, I) [Q, k] (NCCL over NVLink on the GPU box, gloo in the CPU tests) and an on-device
-    k-way merge on the (distance, id) order.  Result == unsharded search by construction.
+    window, searches its rows with GLOBAL ids (id_offset), then ONE exchange of the per-rank
+    (D, I) [Q, k] (NCCL over NVLink on the GPU box, gloo in the CPU tests) - an all-gather (every rank
+    gets the full result) or an all-to-all (the result stays sharded by query: 1/G of the traffic and of
+    the merge work) - and an on-device k-way merge on the (distance, id) order.  Result == unsharded
+    search by construction.
 
 `search_fn` / `merge_fn` are injected so the plumbing (offsets, gather order, shapes) is testable
 on CPU with world_size 2 over gloo; on the GPU they are the CUDA index's search and
@@ -40,22 +42,45 @@ def window_owner(window: int, n_windows: int, world: int) -> int:
 
 
 def search_row_sharded(search_fn: Callable, merge_fn: Callable, queries, k: int, row_lo: int,
-                       group=None, world: Optional[int] = None):
+                       group=None, world: Optional[int] = None, distribute: str = "all"):
     """Row-sharded exact k-NN for one window batch.
 
     search_fn(queries, k, id_offset) -> (D, I) tensors [.., nq, k] over THIS rank's rows, ids
     already global; merge_fn(D_parts [G, nq, k], I_parts [G, nq, k], k) -> (D, I).
-    Every rank passes the same `queries` and gets the same full result."""
+    Every rank passes the same `queries`.
+
+    distribute="all": one all-gather of the per-rank (D, I); every rank merges and returns the full result.
+    distribute="scatter": one all-to-all instead - rank r receives, from every rank, only the rows of the
+    flattened query range shard_range(n_queries, G, r), merges those and returns (q_lo, q_hi, D, I) for its
+    slice: 1/G of the bytes on the wire and 1/G of the merge work per rank (the merged result stays
+    query-sharded, which is what a data-parallel consumer wants)."""
     import torch
     import torch.distributed as dist
 
     D, I = search_fn(queries, k, row_lo)
     if world is None:
         world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if distribute not in ("all", "scatter"):
+        raise ValueError("distribute must be 'all' or 'scatter'")
     if world == 1:
+        if distribute == "scatter":  # one shard: its top-k already is the result
+            D2, I2 = D.reshape(-1, k), I.reshape(-1, k)
+            return 0, D2.shape[0], D2, I2
         return merge_fn(D.unsqueeze(0), I.unsqueeze(0), k)
     D = D.contiguous()
     I = I.contiguous()
+    if distribute == "scatter":
+        rank = dist.get_rank(group)
+        D2, I2 = D.reshape(-1, k), I.reshape(-1, k)
+        nqt = D2.shape[0]
+        cuts = [shard_range(nqt, world, r) for r in range(world)]
+        lo, hi = cuts[rank]
+        Dg = torch.empty((world, hi - lo, k), dtype=D.dtype, device=D.device)
+        Ig = torch.empty((world, hi - lo, k), dtype=I.dtype, device=I.device)
+        dist.all_to_all(list(Dg.unbind(0)), [D2[a:b] for a, b in cuts], group=group)
+        dist.all_to_all(list(Ig.unbind(0)), [I2[a:b] for a, b in cuts], group=group)
+        Dm, Im = merge_fn(Dg, Ig, k)
+        return lo, hi, Dm, Im
     Dg = torch.empty((world,) + tuple(D.shape), dtype=D.dtype, device=D.device)
     Ig = torch.empty((world,) + tuple(I.shape), dtype=I.dtype, device=I.device)
     # list-of-views form: same call on nccl (GPU box) and gloo (CPU tests)

@@ -446,3 +446,37 @@ def test_k32_large_panel_list_selection():
     for i in range(900):
         rows[0, i, : 900 - i] = 1
     _check(rows, np.zeros((1, 40, d), np.uint8), 32)
+
+
+@pytest.mark.parametrize("parts,kin,kout,dt", [(2, 8, 8, "i32"), (8, 32, 32, "i32"), (8, 32, 32, "f32"), (3, 5, 4, "f32"),
+                                             (20, 32, 32, "i32"), (40, 32, 16, "i32")])
+def test_topk_merge_arbitrary_order_and_padding(parts, kin, kout, dt):
+    """snv_topk_merge against a numpy lexsort: unsorted per-part lists, -1 padding, ties on D broken by id;
+    covers the warp-cooperative kernels (<= 256 and <= 1024 candidates per query) and the generic one."""
+    import torch
+
+    from rag_snvbert_b200 import topk_merge
+
+    rng = np.random.default_rng(parts * 1000 + kin)
+    nq = 777
+    D = rng.integers(0, 50, size=(parts, nq, kin)).astype(np.int32)
+    I = rng.permuted(np.tile(np.arange(parts * kin, dtype=np.int64) * 7 + (1 << 33), (nq, 1)), axis=1).reshape(nq, parts, kin).transpose(1, 0, 2).copy()
+    pad = rng.random((parts, nq, kin)) < 0.15
+    I[pad] = -1
+    Dx = D.astype(np.float32) * 0.5 - 3.0 if dt == "f32" else D
+    padv = np.float32(3.4028234663852886e38) if dt == "f32" else np.int32(2**31 - 1)
+    Dx = np.where(pad, padv, Dx).astype(Dx.dtype)
+    Dm, Im = topk_merge(torch.from_numpy(Dx).cuda(), torch.from_numpy(I).cuda(), kout)
+    Dm, Im = Dm.cpu().numpy(), Im.cpu().numpy()
+    for q in range(0, nq, 37):
+        d = Dx[:, q, :].reshape(-1)
+        i = I[:, q, :].reshape(-1)
+        keep = i >= 0
+        d, i = d[keep], i[keep]
+        order = np.lexsort((i, d))[:kout]
+        exp_d = np.full(kout, padv, dtype=Dx.dtype)
+        exp_i = np.full(kout, -1, dtype=np.int64)
+        exp_d[: len(order)] = d[order]
+        exp_i[: len(order)] = i[order]
+        np.testing.assert_array_equal(Im[q], exp_i)
+        np.testing.assert_array_equal(Dm[q], exp_d)

@@ -57,6 +57,14 @@ def _worker(rank, world, port, out):
         D, I = search_row_sharded(search_fn, merge_fn, torch.from_numpy(q), k, lo)
         De, Ie = O.hamming_topk(panel, q, k)
         ok_rows = bool((I.numpy() == Ie).all() and (D.numpy() == De).all())
+        # scatter mode: every rank merges only its slice of the queries (all-to-all)
+        try:
+            qlo, qhi, Ds, Is = search_row_sharded(search_fn, merge_fn, torch.from_numpy(q), k, lo, distribute="scatter")
+            ok_rows = ok_rows and (qlo, qhi) == shard_range(Q, world, rank)
+            ok_rows = ok_rows and bool((Is.numpy() == Ie[qlo:qhi]).all() and (Ds.numpy() == De[qlo:qhi]).all())
+        except RuntimeError as e:  # a gloo build without all_to_all: the NCCL path is exercised on the GPU box
+            if "alltoall" not in str(e).lower() and "all_to_all" not in str(e).lower():
+                raise
 
         # window sharding: disjoint ranges, no collective on the data path
         W = 5
