@@ -360,7 +360,7 @@ def run_ours(a):
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": dt / a.steps * 1e3,
                "api": "WindowedHammingIndex.search(pinned numpy packed uint32 [W,Q,stride], out=pinned (D int32, I int64)); "
-                      "16 window chunks pipelined over 3 streams inside libsnvknn"}
+                      "window chunks pipelined over 3 streams inside libsnvknn (H2D | expand + scan | D2H)"}
         # the two paths must agree bit for bit
         assert np.array_equal(Ih, I.cpu().numpy()) and np.array_equal(Dh, D.cpu().numpy()), "host/device result mismatch"
 
