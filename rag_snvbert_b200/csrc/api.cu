@@ -449,13 +449,8 @@ static int search_hamming(snv_index* idx, int w0, int nw, const void* q, int64_t
     }
 
     // ---- chunking: host buffers are pipelined over internal streams, window chunk by window chunk;
-    // a chunk keeps enough CTAs (>= 16 per SM) that the scan needs no row split
+    // (popcount engine) a chunk keeps enough CTAs (>= 16 per SM) that the scan needs no row split
     int chunk_w = nw;
-    if ((!q_dev || !out_dev) && nw >= 8) {
-        const int64_t qtiles = ceil_div(nq, 128);
-        chunk_w = (int)std::max<int64_t>(ceil_div(nw, 16), ceil_div((int64_t)kNumSMs * 16, qtiles));
-        if (chunk_w > nw) chunk_w = nw;
-    }
     auto make_params = [&](int wb, int wc, HammingSearchParams& p) {
         p = HammingSearchParams{};
         p.panel = idx->panel + (int64_t)(w0 + wb) * idx->cap * idx->stride;
@@ -470,6 +465,26 @@ static int search_hamming(snv_index* idx, int w0, int nw, const void* q, int64_t
         p.id_offset = id_offset;
         p.mask = mask_mode != SNV_MASK_NONE || tokens ? (const uint32_t*)1 : nullptr;  // plan only needs null-ness
     };
+    if ((!q_dev || !out_dev) && nw >= 8) {
+        const int64_t qtiles = ceil_div(nq, 128);
+        HammingSearchParams probe;
+        HammingTcPlan tprobe;
+        make_params(0, nw, probe);
+        if (hamming_tc_plan(probe, tprobe) == (size_t)-1) return SNV_ERR_UNSUPPORTED;
+        if (tprobe.engine) {
+            // tensor-core engine: persistent CTAs take (window, query tile) items round-robin, so a chunk should hold
+            // a whole number of items per SM; ~24 chunks keep the pipeline's fill (first H2D) and drain (last D2H) short
+            int64_t a = kNumSMs, b = qtiles;
+            while (b) { const int64_t t = a % b; a = b; b = t; }
+            const int64_t unit = kNumSMs / a;  // windows per chunk so that windows x qtiles is a multiple of the SM count
+            int64_t cw = std::max<int64_t>(unit, nw / 24 / unit * unit);
+            if (cw * qtiles < 2 * kNumSMs) cw = ceil_div(2 * kNumSMs, qtiles);
+            chunk_w = (int)std::min<int64_t>(cw, nw);
+        } else {
+            chunk_w = (int)std::max<int64_t>(ceil_div(nw, 16), ceil_div((int64_t)kNumSMs * 16, qtiles));
+            if (chunk_w > nw) chunk_w = nw;
+        }
+    }
     size_t part_chunk = 0;  // partial-key bytes per chunk (row-split plans); every chunk gets its own slice
     size_t tc_chunk = 0;    // tensor-core engine workspace bytes per chunk
     {
