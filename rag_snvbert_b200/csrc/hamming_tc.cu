@@ -94,34 +94,32 @@ constexpr uint32_t kBBytes = 256 * kRowBytes;  // 32 KB slot (240 or 256 rows in
 #ifndef SNV_TC_RAWSTAGES
 #define SNV_TC_RAWSTAGES 4
 #endif
-#ifndef SNV_TC_RESIDENT
-#define SNV_TC_RESIDENT 0  // 1: keep the query tile resident in shared memory when it fits (measured no faster: the raw ring shrinks)
-#endif
 constexpr int kBStages = SNV_TC_BSTAGES;
 constexpr size_t kListBytes = 32 * 1024;  // one slot per (epilogue thread, column of a group): 16 x 512 or 32 x 256 floats
 static_assert((size_t)Epi<8>::kGroup * Epi<8>::kThreads * 4 == kListBytes && (size_t)Epi<32>::kGroup * Epi<32>::kThreads * 4 == kListBytes, "slot area");
 static_assert((Epi<8>::kParts - 1) * 8 * BM * 4 <= kListBytes && (Epi<32>::kParts - 1) * 32 * BM * 4 <= kListBytes,
               "the part-exchange buffer aliases the candidate slots");
 
-enum { MODE_FP8 = 0, MODE_FP8_HBM = 1, MODE_FP4 = 2, MODE_FP4_RES = 3 };
+enum { MODE_FP8 = 0, MODE_FP8_HBM = 1, MODE_FP4 = 2, MODE_FP4_2CTA = 3 };
 
 // Three rings: the query operand comes from L2 (long latency: deep ring), the panel operand is made
 // in the SM (expander latency: 3 slots), raw packed k-blocks are small.
 template <int MODE>
 struct Cfg {
-    static constexpr bool kFp4 = MODE == MODE_FP4 || MODE == MODE_FP4_RES;
-    // resident query tile: the whole A operand of an item (<= 5 k-blocks) stays in shared memory for all of the
-    // item's panel tiles instead of being re-streamed from L2 for each of them
-    static constexpr bool kResident = MODE == MODE_FP4_RES;
+    static constexpr bool kFp4 = MODE == MODE_FP4 || MODE == MODE_FP4_2CTA;
+    // CTA pair (cta_group::2): two CTAs of a cluster hold 128 queries each (M = 256) and each expands HALF of every
+    // panel tile; the pair's MMA reads both halves.  Halves the expander work and the B operand bytes per SM.
+    static constexpr bool kTwoCta = MODE == MODE_FP4_2CTA;
     static constexpr bool kExpand = MODE != MODE_FP8_HBM;
     static constexpr int BN = kFp4 ? 240 : 256;   // panel rows per tile = TMEM columns per accumulator stage
     static constexpr int WPK = kFp4 ? 8 : 4;      // packed words per k-block
     static constexpr int WPM = kFp4 ? 2 : 1;      // packed words per MMA
-    static constexpr int kAStages = kResident ? 5 : SNV_TC_ASTAGES;
-    static constexpr int kRawStages = kResident ? 2 : SNV_TC_RAWSTAGES;
+    static constexpr int kAStages = SNV_TC_ASTAGES;
+    static constexpr int kRawStages = SNV_TC_RAWSTAGES;
+    static constexpr int kBRows = kTwoCta ? BN / 2 : BN;          // panel rows this CTA expands per tile
     static constexpr uint32_t kRawRow = WPK * 4;                // raw bytes per panel row and k-block
     static constexpr uint32_t kRawSlot = kExpand ? 256 * kRawRow : 0;
-    static constexpr uint32_t kRawBytes = BN * kRawRow;         // what one TMA box brings
+    static constexpr uint32_t kRawBytes = kBRows * kRawRow;     // what one TMA box brings
     static constexpr uint32_t kBBox = BN * kRowBytes;           // fp8-hbm variant: one TMA box of operand rows
     static constexpr uint32_t kSfCol = 2 * BN;                  // fp4: first TMEM column of the unit scales
     static constexpr size_t kSmem = 1024 /*align slack*/ + (size_t)kAStages * kABytes + (size_t)kBStages * kBBytes +
@@ -163,7 +161,7 @@ __device__ __forceinline__ uint4 expand_panel_word_fp4(uint32_t w)
 __device__ __forceinline__ uint32_t query_code_fp4(int j) { return j == 0 ? 4u : (j == 1 ? 2u : 1u); }
 
 struct TcParams {
-    int nw, nq, qtiles;
+    int nw, nq, qtiles;      // qtiles: query tiles per window (tile PAIRS in the 2-CTA mode)
     int64_t n;               // panel rows per window
     int words, kblocks;      // packed words in use (= MMAs per tile), k-blocks of 4 words
     int n_tiles, nsplit, tiles_per_split;
@@ -180,17 +178,71 @@ struct TcParams {
 struct Item {
     int w, qt, split, t0, ntiles;
 };
-__device__ __forceinline__ Item decode_item(const TcParams& p, int item)
+__device__ __forceinline__ Item decode_item(const TcParams& p, int item, int qt_mul = 1, int qt_add = 0)
 {
     Item it;
     it.split = item % p.nsplit;
     item /= p.nsplit;
-    it.qt = item % p.qtiles;
+    it.qt = (item % p.qtiles) * qt_mul + qt_add;
     it.w = item / p.qtiles;
     it.t0 = it.split * p.tiles_per_split;
     const int t1 = it.t0 + p.tiles_per_split < p.n_tiles ? it.t0 + p.tiles_per_split : p.n_tiles;
     it.ntiles = t1 - it.t0;
     return it;
+}
+
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
+{
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(smem_u32(bar)), "r"(cta)
+        : "memory");
+}
+// 2-CTA TMA load: data lands in THIS CTA's shared memory, the transaction bytes complete on the LEADER CTA's barrier
+__device__ __forceinline__ void tma_load_2d_2cta(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t* smem_result, uint32_t cols)
+{
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t addr, uint32_t cols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// completion of all prior MMAs of this thread -> one arrival on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma_mxf4_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
+                                               uint32_t tmem_sfa, uint32_t tmem_sfb)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
+        : "memory");
 }
 
 // compile-time unrolled loop: f(std::integral_constant<int, 0>{}), ..., f(std::integral_constant<int, N - 1>{})
@@ -290,7 +342,7 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     constexpr int WPK = C::WPK;
     constexpr int kAStages = C::kAStages;
     constexpr int kRawStages = C::kRawStages;
-    constexpr bool RES = C::kResident;
+    constexpr bool TWO = C::kTwoCta;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     unsigned char* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);  // SWIZZLE_128B tiles: 1024-byte aligned
@@ -315,6 +367,14 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    // CTA pair: rank 0 is the leader (issues the MMAs; its barriers collect both CTAs' operands), items are
+    // (window, query-tile PAIR, row split) and CTA r takes query tile 2 * pair + r
+    const uint32_t cta_rank = TWO ? cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0u;
+    const int item0 = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int item_step = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    constexpr int kQtMul = TWO ? 2 : 1;
+    constexpr uint32_t kPair = TWO ? 2u : 1u;
 
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&map_q);
@@ -324,7 +384,7 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             mbar_init(&empty_a[s], 1);
         }
         for (int s = 0; s < kBStages; ++s) {
-            mbar_init(&full_b[s], EXPAND ? kExpWarps : 1);
+            mbar_init(&full_b[s], EXPAND ? kPair * kExpWarps : 1);
             mbar_init(&empty_b[s], 1);
         }
         for (int s = 0; s < kRawStages; ++s) {
@@ -333,14 +393,18 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         }
         for (int s = 0; s < kAccStages; ++s) {
             mbar_init(&tmem_full[s], 1);
-            mbar_init(&tmem_empty[s], kEpiThreads);
+            mbar_init(&tmem_empty[s], kPair * kEpiThreads);
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
+    if (warp == 1) {
+        if constexpr (TWO) tmem_alloc_2cta(tmem_ptr, kTmemCols);
+        else tmem_alloc(tmem_ptr, kTmemCols);
+    }
     if (warp == 2 && lane == 0) tmem_ptr[1] = (uint32_t)p.one;
     tcgen05_fence_before();
     __syncthreads();
+    if constexpr (TWO) cluster_sync();  // the peer's barriers are initialised before anything arrives on them
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     if constexpr (FP4) {
@@ -360,39 +424,31 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     if (warp == 0) {
         // ================= TMA producer: query operand tiles =================
         if (lane == 0) {
-            if constexpr (RES) {
-                // resident: slot kb holds k-block kb of the item's query tile; it is reloaded for the next item as
-                // soon as the last panel tile's MMAs on it have completed
-                uint32_t icount = 0;
-                for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++icount) {
-                    const Item it = decode_item(p, item);
-                    const int row_a = it.w * p.nq + it.qt * BM;
+            Ring<kAStages> ra;
+            for (int item = item0; item < p.items; item += item_step) {
+                const Item it = decode_item(p, item, kQtMul, (int)cta_rank);
+                const int row_a = it.w * p.nq + it.qt * BM;
+                for (int t = 0; t < it.ntiles; ++t) {
                     for (int kb = 0; kb < KB; ++kb) {
-                        mbar_wait_relaxed(&empty_a[kb], (icount & 1u) ^ 1u);
-                        mbar_arrive_expect_tx(&full_a[kb], kABytes);
-                        tma_load_2d(a_tiles + (size_t)kb * kABytes, &map_q, kb * kRowBytes, row_a, &full_a[kb]);
-                    }
-                }
-            } else {
-                Ring<kAStages> ra;
-                for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-                    const Item it = decode_item(p, item);
-                    const int row_a = it.w * p.nq + it.qt * BM;
-                    for (int t = 0; t < it.ntiles; ++t) {
-                        for (int kb = 0; kb < KB; ++kb) {
-                            mbar_wait_relaxed(&empty_a[ra.i], ra.phase ^ 1u);
+                        mbar_wait_relaxed(&empty_a[ra.i], ra.phase ^ 1u);
+                        if constexpr (TWO) {
+                            // both CTAs' tiles complete on the leader's barrier; only the leader arms it
+                            if (leader) mbar_arrive_expect_tx(&full_a[ra.i], 2 * kABytes);
+                            tma_load_2d_2cta(a_tiles + (size_t)ra.i * kABytes, &map_q, kb * kRowBytes, row_a, &full_a[ra.i]);
+                        } else {
                             mbar_arrive_expect_tx(&full_a[ra.i], kABytes);
                             tma_load_2d(a_tiles + (size_t)ra.i * kABytes, &map_q, kb * kRowBytes, row_a, &full_a[ra.i]);
-                            ra.next();
                         }
+                        ra.next();
                     }
                 }
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer: the warp loops in lockstep, one elected lane issues =================
-        {
-            constexpr uint32_t idesc = FP4 ? make_idesc_mxf4(BM, BN) : make_idesc_e4m3(BM, BN);
+        if (leader) {
+            constexpr int MM = TWO ? 2 * BM : BM;
+            constexpr uint32_t idesc = FP4 ? make_idesc_mxf4(MM, BN) : make_idesc_e4m3(MM, BN);
             constexpr uint64_t kDescHi = (uint64_t)0x40004040u << 32;
             // K-major SWIZZLE_128B descriptors: low word = (address >> 4) | LBO 1 << 16, high word constant
             // (SBO 1024 B, descriptor version 1, layout SWIZZLE_128B); one MMA per 32 operand bytes = per packed
@@ -408,46 +464,47 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 #endif
                 const uint64_t adesc = kDescHi | (uint64_t)a_lo;
                 const uint64_t bdesc = kDescHi | (uint64_t)b_lo;
-                if constexpr (FP4) umma_mxf4(d_tmem, adesc, bdesc, idesc, acc, sf_a, sf_b);
+                if constexpr (TWO) umma_mxf4_2cta(d_tmem, adesc, bdesc, idesc, acc, sf_a, sf_b);
+                else if constexpr (FP4) umma_mxf4(d_tmem, adesc, bdesc, idesc, acc, sf_a, sf_b);
                 else umma_f8(d_tmem, adesc, bdesc, idesc, acc);
+            };
+            auto commit = [&](uint64_t* bar) {
+                if constexpr (TWO) umma_commit_2cta(bar);
+                else umma_commit(bar);
             };
             Ring<kAStages> ra;
             Ring<kBStages> rb;
-            uint32_t tcount = 0, icount = 0;
-            for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++icount) {
-                const Item it = decode_item(p, item);
+            uint32_t tcount = 0;
+            for (int item = item0; item < p.items; item += item_step) {
+                const Item it = decode_item(p, item, kQtMul, (int)cta_rank);
                 for (int t = 0; t < it.ntiles; ++t, ++tcount) {
                     const uint32_t as = tcount & 1u;
                     mbar_wait(&tmem_empty[as], ((tcount >> 1) & 1u) ^ 1u);
                     tcgen05_fence_after();
                     const uint32_t d_tmem = tmem_base + as * BN;
-                    const bool last_tile = t == it.ntiles - 1;
                     for (int kb = 0; kb < KB; ++kb) {
-                        const int sa = RES ? kb : ra.i;  // A slot: k-block index when the query tile is resident
-                        if constexpr (RES) {
-                            if (t == 0) mbar_wait(&full_a[sa], icount & 1u);
-                        } else {
-                            mbar_wait(&full_a[sa], ra.phase);
-                        }
+                        mbar_wait(&full_a[ra.i], ra.phase);
                         mbar_wait(&full_b[rb.i], rb.phase);
                         tcgen05_fence_after();
                         if (elect_one()) {
-                            const uint32_t a_lo = a_lo0 + (uint32_t)sa * (kABytes >> 4);
+                            const uint32_t a_lo = a_lo0 + (uint32_t)ra.i * (kABytes >> 4);
                             const uint32_t b_lo = b_lo0 + (uint32_t)rb.i * (kBBytes >> 4);
                             if (kb != KB - 1) {
                                 mma(d_tmem, a_lo, b_lo, kb != 0 ? 1u : 0u);
                                 mma(d_tmem, a_lo + 2, b_lo + 2, 1u);
                                 mma(d_tmem, a_lo + 4, b_lo + 4, 1u);
                                 mma(d_tmem, a_lo + 6, b_lo + 6, 1u);
+                                commit(&empty_a[ra.i]);
+                                commit(&empty_b[rb.i]);
                             } else {
                                 mma(d_tmem, a_lo, b_lo, kb != 0 ? 1u : 0u);
                                 if (nm_tail > 1) mma(d_tmem, a_lo + 2, b_lo + 2, 1u);
                                 if (nm_tail > 2) mma(d_tmem, a_lo + 4, b_lo + 4, 1u);
                                 if (nm_tail > 3) mma(d_tmem, a_lo + 6, b_lo + 6, 1u);
+                                commit(&empty_a[ra.i]);
+                                commit(&empty_b[rb.i]);
+                                commit(&tmem_full[as]);
                             }
-                            if (!RES || last_tile) umma_commit(&empty_a[sa]);
-                            umma_commit(&empty_b[rb.i]);
-                            if (kb == KB - 1) umma_commit(&tmem_full[as]);
                         }
                         __syncwarp();
                         ra.next();
@@ -461,10 +518,10 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         if (lane == 0) {
             Ring<kRawStages> rr;
             Ring<kBStages> rb;
-            for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-                const Item it = decode_item(p, item);
+            for (int item = item0; item < p.items; item += item_step) {
+                const Item it = decode_item(p, item, kQtMul, (int)cta_rank);
                 for (int t = 0; t < it.ntiles; ++t) {
-                    const int n0 = (it.t0 + t) * BN;
+                    const int n0 = (it.t0 + t) * BN + (int)cta_rank * C::kBRows;  // this CTA's rows of the tile
                     for (int kb = 0; kb < KB; ++kb) {
                         if constexpr (EXPAND) {
                             mbar_wait_relaxed(&raw_empty[rr.i], rr.phase ^ 1u);
@@ -487,7 +544,8 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             // thread et expands panel rows et and et + BN / 2 of every k-block (BN / 2 is a multiple of 8, so both
             // rows share the swizzle phase): 16-byte chunk c of a row lands at row * 128 + ((c ^ (row & 7)) << 4)
             const int et = (warp - kFirstExpWarp) * 32 + lane;
-            constexpr int kHalfRows = BN / 2;
+            constexpr bool kTwoRows = C::kBRows > kExpThreads;     // two rows per thread, or one (CTA pair: 120 rows)
+            constexpr int kHalfRows = kTwoRows ? C::kBRows / 2 : C::kBRows;
             const bool act = et < kHalfRows;
             const int sw = et & 7;
             uint32_t off[8];
@@ -533,8 +591,14 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                     }
                 }
             };
-            for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-                const Item it = decode_item(p, item);
+            auto publish = [&](int slot) {  // the slot's stores are fenced: one arrival per warp on the (leader's) full barrier
+                if (lane == 0) {
+                    if (TWO && !leader) mbar_arrive_cluster(&full_b[slot], 0u);
+                    else mbar_arrive(&full_b[slot]);
+                }
+            };
+            for (int item = item0; item < p.items; item += item_step) {
+                const Item it = decode_item(p, item, kQtMul, (int)cta_rank);
                 for (int t = 0; t < it.ntiles; ++t) {
                     for (int kb = 0; kb < KB; ++kb) {
                         mbar_wait(&raw_full[rr.i], rr.phase);
@@ -544,7 +608,7 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 #pragma unroll
                             for (int v = 0; v < WPK / 4; ++v) {
                                 w0[v] = lds128(src + v * 16);
-                                w1[v] = lds128(src + kHalfRows * C::kRawRow + v * 16);
+                                if constexpr (kTwoRows) w1[v] = lds128(src + kHalfRows * C::kRawRow + v * 16);
                             }
                         }
                         if (pending >= 0) {
@@ -552,17 +616,17 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                             // tensor core (async proxy) and publish the slot
                             fence_proxy_async();
                             __syncwarp();
-                            if (lane == 0) mbar_arrive(&full_b[pending]);
+                            publish(pending);
                         }
                         mbar_wait(&empty_b[rb.i], rb.phase ^ 1u);
                         if (act) {
                             const uint32_t dst = b_base + (uint32_t)rb.i * kBBytes;
                             if (kb != KB - 1 || tail_chunks == 8) {
                                 expand_row(w0, dst, 8);
-                                expand_row(w1, dst + kHalfRows * kRowBytes, 8);
+                                if constexpr (kTwoRows) expand_row(w1, dst + kHalfRows * kRowBytes, 8);
                             } else {
                                 expand_row(w0, dst, tail_chunks);
-                                expand_row(w1, dst + kHalfRows * kRowBytes, tail_chunks);
+                                if constexpr (kTwoRows) expand_row(w1, dst + kHalfRows * kRowBytes, tail_chunks);
                             }
                         }
                         __syncwarp();  // every lane has consumed its raw words
@@ -576,7 +640,7 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             if (pending >= 0) {
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&full_b[pending]);
+                publish(pending);
             }
         }
     } else {
@@ -595,8 +659,8 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         uint32_t tcount = 0;
         thrx[part * BM + row] = 3.0e38f;
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-        for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-            const Item it = decode_item(p, item);
+        for (int item = item0; item < p.items; item += item_step) {
+            const Item it = decode_item(p, item, kQtMul, (int)cta_rank);
             const int qi = it.qt * BM + row;
             const bool active = qi < p.nq;
             const int64_t q = (int64_t)it.w * p.nq + (active ? qi : 0);
@@ -719,7 +783,8 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                     process(accB, 3);
                 }
                 tcgen05_fence_before();
-                mbar_arrive(&tmem_empty[as]);
+                if (TWO && !leader) mbar_arrive_cluster(&tmem_empty[as], 0u);
+                else mbar_arrive(&tmem_empty[as]);
             }
             // ---- merge the parts of each query through shared memory, then write the result
             thrx[part * BM + row] = 3.0e38f;  // reset for the next item (ordered by the barriers below)
@@ -768,9 +833,11 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 
     tcgen05_fence_before();
     __syncthreads();
+    if constexpr (TWO) cluster_sync();  // the peer may still read this CTA's operands / arrive on its barriers
     if (warp == 1) {
         tcgen05_fence_after();
-        tmem_dealloc(tmem_base, kTmemCols);
+        if constexpr (TWO) tmem_dealloc_2cta(tmem_base, kTmemCols);
+        else tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
@@ -880,23 +947,37 @@ int launch_kernel(const CUtensorMap& map_q, const CUtensorMap& map_r, const TcPa
         attr = true;
     }
     profile_begin(stream);
-    hamming_tc_kernel<KT, MODE><<<grid, threads_of<KT>(), smem, stream>>>(map_q, map_r, tp);
+    if constexpr (Cfg<MODE>::kTwoCta) {
+        // CTA pairs: a cluster of two CTAs on the two SMs of a TPC
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3((unsigned)threads_of<KT>());
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        SNV_CUDA_CHECK(cudaLaunchKernelEx(&cfg, hamming_tc_kernel<KT, MODE>, map_q, map_r, tp));
+    } else {
+        hamming_tc_kernel<KT, MODE><<<grid, threads_of<KT>(), smem, stream>>>(map_q, map_r, tp);
+    }
     profile_end(stream);
     SNV_LAUNCH_CHECK();
     return SNV_OK;
 }
 
-int mode_of_engine(int engine, int kblocks)
-{
-    if (engine == 3) return (SNV_TC_RESIDENT && kblocks <= Cfg<MODE_FP4_RES>::kAStages) ? MODE_FP4_RES : MODE_FP4;
-    return engine == 2 ? MODE_FP8_HBM : MODE_FP8;
-}
-int bn_of_engine(int engine) { return engine == 3 ? Cfg<MODE_FP4>::BN : 256; }
-int wpk_of_engine(int engine) { return engine == 3 ? Cfg<MODE_FP4>::WPK : 4; }
+int mode_of_engine(int engine) { return engine == 4 ? MODE_FP4_2CTA : (engine == 3 ? MODE_FP4 : (engine == 2 ? MODE_FP8_HBM : MODE_FP8)); }
+int bn_of_engine(int engine) { return engine >= 3 ? Cfg<MODE_FP4>::BN : 256; }
+int wpk_of_engine(int engine) { return engine >= 3 ? Cfg<MODE_FP4>::WPK : 4; }
 
 }  // namespace
 
-// 0 = popcount kernel, 1 = tensor cores fp8, 2 = fp8 with the panel pre-expanded in HBM (bring-up), 3 = tensor cores fp4
+// 0 = popcount kernel, 1 = tensor cores fp8, 2 = fp8 with the panel pre-expanded in HBM (bring-up), 3 = tensor cores fp4,
+// 4 = fp4 on CTA pairs (cta_group::2)
 int hamming_engine_for(const HammingSearchParams& p)
 {
     int mode = -1;  // auto
@@ -905,6 +986,7 @@ int hamming_engine_for(const HammingSearchParams& p)
         else if (!strcmp(e, "tc") || !strcmp(e, "tc8")) mode = 1;
         else if (!strcmp(e, "tc_hbm")) mode = 2;
         else if (!strcmp(e, "tc4")) mode = 3;
+        else if (!strcmp(e, "tc4x2")) mode = 4;
     }
     const bool can = !p.work && p.n > 0 && p.nq > 0 && p.k >= 1 && p.k <= 32 && p.d < (1 << 12) &&
                      (int64_t)p.nw * p.nq < ((int64_t)1 << 31) && p.n < ((int64_t)1 << 31);
@@ -932,7 +1014,9 @@ size_t hamming_tc_plan(const HammingSearchParams& p, HammingTcPlan& plan)
     // top-k threshold from scratch - about kt (1 + ln(rows / kt)) insertions per query, each a lockstep round
     // of the epilogue - and a split adds partial keys for the merge kernel.  The key's id field bounds the tiles
     // per item.
-    const int64_t base = (int64_t)p.nw * plan.qtiles;
+    // CTA-pair engine: an item is a PAIR of query tiles and runs on a pair of SMs
+    const int64_t units = plan.engine == 4 ? kNumSMs / 2 : kNumSMs;
+    const int64_t base = (int64_t)p.nw * (plan.engine == 4 ? ceil_div(plan.qtiles, 2) : plan.qtiles);
     const int64_t min_split = ceil_div(plan.n_tiles, max_tiles_per_split);
     int64_t nsplit = min_split;
     {
@@ -946,7 +1030,7 @@ size_t hamming_tc_plan(const HammingSearchParams& p, HammingTcPlan& plan)
         for (int64_t s = min_split; s <= max_split; ++s) {
             const int64_t per = ceil_div(plan.n_tiles, s);
             const int64_t real = ceil_div(plan.n_tiles, per);
-            const int64_t rounds = ceil_div(base * real, kNumSMs);
+            const int64_t rounds = ceil_div(base * real, units);
             const double rows_item = (double)per * BN;
             const double cand = plan.kt * (1.0 + std::log(std::max(1.0, rows_item / plan.kt)));
             const double cost = (double)rounds * ((double)per + 0.25 + ins * cand) +
@@ -981,7 +1065,7 @@ int hamming_tc_launch(const HammingSearchParams& p, const HammingTcPlan& plan, v
     const int BN = bn_of_engine(plan.engine);
     {
         const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(rows, 8), (int64_t)kNumSMs * 32);  // 8 warps = 8 rows per block
-        if (plan.engine == 3)
+        if (plan.engine >= 3)
             tc_expand_queries_kernel<true><<<grid, 256, 0, stream>>>(p.q, p.mask, p.mask_win_stride, p.mask_q_stride, p.nq, rows, p.stride,
                                                                     p.words, p.d, plan.kblocks, q_ops, q_bias);
         else
@@ -1001,7 +1085,7 @@ int hamming_tc_launch(const HammingSearchParams& p, const HammingTcPlan& plan, v
         // raw packed panel [nw][n][stride] words: box = one k-block of words x one tile of rows of one window
         const cuuint64_t gdim[3] = {(cuuint64_t)p.stride, (cuuint64_t)p.n, (cuuint64_t)p.nw};
         const cuuint64_t gstride[2] = {(cuuint64_t)p.stride * 4, (cuuint64_t)p.panel_win_stride * 4};
-        const cuuint32_t box[3] = {(cuuint32_t)wpk_of_engine(plan.engine), (cuuint32_t)BN, 1};
+        const cuuint32_t box[3] = {(cuuint32_t)wpk_of_engine(plan.engine), (cuuint32_t)(plan.engine == 4 ? BN / 2 : BN), 1};
         int rc = encode_map(&map_r, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, p.panel, gdim, gstride, box, CU_TENSOR_MAP_SWIZZLE_NONE);
         if (rc) return rc;
     } else {
@@ -1016,21 +1100,22 @@ int hamming_tc_launch(const HammingSearchParams& p, const HammingTcPlan& plan, v
         if (rc) return rc;
     }
     TcParams tp{};
-    tp.nw = p.nw; tp.nq = p.nq; tp.qtiles = plan.qtiles;
+    const bool pair = plan.engine == 4;
+    tp.nw = p.nw; tp.nq = p.nq; tp.qtiles = pair ? (int)ceil_div(plan.qtiles, 2) : plan.qtiles;
     tp.n = p.n;
     tp.words = p.words; tp.kblocks = plan.kblocks;
     tp.n_tiles = plan.n_tiles; tp.nsplit = plan.nsplit; tp.tiles_per_split = plan.tiles_per_split;
-    tp.items = p.nw * plan.qtiles * plan.nsplit;
+    tp.items = p.nw * tp.qtiles * plan.nsplit;
     tp.idx_bits = plan.idx_bits; tp.k = p.k; tp.one = 1;
     tp.id_offset = p.id_offset;
     tp.q_bias = q_bias;
     tp.D_i32 = p.D_i32; tp.D_f32 = p.D_f32; tp.I = p.I;
     tp.partial = partial;
-    const int grid = std::min(tp.items, kNumSMs);
+    const int grid = pair ? 2 * std::min(tp.items, kNumSMs / 2) : std::min(tp.items, kNumSMs);
     int rc;
     const bool k8 = plan.kt == 8;
-    switch (mode_of_engine(plan.engine, plan.kblocks)) {
-        case MODE_FP4_RES: rc = k8 ? launch_kernel<8, MODE_FP4_RES>(map_q, map_r, tp, grid, stream) : launch_kernel<32, MODE_FP4_RES>(map_q, map_r, tp, grid, stream); break;
+    switch (mode_of_engine(plan.engine)) {
+        case MODE_FP4_2CTA: rc = k8 ? launch_kernel<8, MODE_FP4_2CTA>(map_q, map_r, tp, grid, stream) : launch_kernel<32, MODE_FP4_2CTA>(map_q, map_r, tp, grid, stream); break;
         case MODE_FP4: rc = k8 ? launch_kernel<8, MODE_FP4>(map_q, map_r, tp, grid, stream) : launch_kernel<32, MODE_FP4>(map_q, map_r, tp, grid, stream); break;
         case MODE_FP8_HBM: rc = k8 ? launch_kernel<8, MODE_FP8_HBM>(map_q, map_r, tp, grid, stream) : launch_kernel<32, MODE_FP8_HBM>(map_q, map_r, tp, grid, stream); break;
         default: rc = k8 ? launch_kernel<8, MODE_FP8>(map_q, map_r, tp, grid, stream) : launch_kernel<32, MODE_FP8>(map_q, map_r, tp, grid, stream); break;

@@ -15,7 +15,7 @@ from oracle import oracle as O
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["tc", "tc_hbm", "tc4"])
+@pytest.fixture(params=["tc", "tc_hbm", "tc4", "tc4x2"])
 def engine(request):
     old = os.environ.get("SNV_HAMMING_ENGINE")
     os.environ["SNV_HAMMING_ENGINE"] = request.param
@@ -162,7 +162,7 @@ def test_engines_agree_at_cfg2_window_scale():
     out = {}
     old = os.environ.get("SNV_HAMMING_ENGINE")
     try:
-        for eng in ("popc", "tc", "tc4"):
+        for eng in ("popc", "tc", "tc4", "tc4x2"):
             os.environ["SNV_HAMMING_ENGINE"] = eng
             D, I = idx.search(queries, k)
             Dm, Im = idx.search(queries, k, observed=masks)
@@ -172,6 +172,6 @@ def test_engines_agree_at_cfg2_window_scale():
             del os.environ["SNV_HAMMING_ENGINE"]
         else:
             os.environ["SNV_HAMMING_ENGINE"] = old
-    for eng in ("tc", "tc4"):
+    for eng in ("tc", "tc4", "tc4x2"):
         for a, b in zip(out["popc"], out[eng]):
             assert torch.equal(a, b), eng
