@@ -49,10 +49,10 @@
 #include "topk.cuh"
 
 #ifndef SNV_TC_EPI16
-#define SNV_TC_EPI16 0  // 1: 16 epilogue warps for k <= 8 (measured slower on B200: they take issue slots from the expanders)
+#define SNV_TC_EPI16 0  // 1: 16 epilogue warps for k <= 8 in the CTA-pair kernel (measured slower on B200 in both kernels: 1.94 vs 1.71 ms)
 #endif
 #ifndef SNV_TC_DEFAULT_ENGINE
-#define SNV_TC_DEFAULT_ENGINE 3  // what "auto" picks for tensor-core shapes: 1 = fp8, 3 = fp4
+#define SNV_TC_DEFAULT_ENGINE 4  // what "auto" picks for tensor-core shapes: 1 = fp8, 3 = fp4, 4 = fp4 on CTA pairs
 #endif
 
 namespace snv {
@@ -70,9 +70,9 @@ constexpr int kExpThreads = kExpWarps * 32;
 // Epilogue shape by top-k width: k <= 8 runs 16 epilogue warps (4 per SM sub-partition: the selection is bound
 // by instruction latency, not throughput, so more warps hide it) on 64-column parts in 16-column groups; k <= 32
 // keeps 8 warps (register budget) on 128-column parts in 32-column groups.
-template <int KT>
+template <int KT, bool PAIR = false>
 struct Epi {
-    static constexpr int kWarps = (KT == 8 && SNV_TC_EPI16) ? 16 : 8;
+    static constexpr int kWarps = (KT == 8 && PAIR && SNV_TC_EPI16) ? 16 : 8;
     static constexpr int kThreads = kWarps * 32;
     static constexpr int kParts = kWarps / 4;          // warps per TMEM lane quarter = column parts of a tile
     static constexpr int kPartCols = 256 / kParts;     // 64 or 128
@@ -81,8 +81,8 @@ struct Epi {
 };
 constexpr int kFirstExpWarp = 3;
 constexpr int kFirstEpiWarp = kFirstExpWarp + kExpWarps;  // 7
-template <int KT>
-constexpr int threads_of() { return 32 * (kFirstEpiWarp + Epi<KT>::kWarps); }  // 736 or 480
+template <int KT, bool PAIR>
+constexpr int threads_of() { return 32 * (kFirstEpiWarp + Epi<KT, PAIR>::kWarps); }  // 736 or 480
 constexpr uint32_t kABytes = BM * kRowBytes;   // 16 KB
 constexpr uint32_t kBBytes = 256 * kRowBytes;  // 32 KB slot (240 or 256 rows in use)
 #ifndef SNV_TC_BSTAGES
@@ -96,8 +96,8 @@ constexpr uint32_t kBBytes = 256 * kRowBytes;  // 32 KB slot (240 or 256 rows in
 #endif
 constexpr int kBStages = SNV_TC_BSTAGES;
 constexpr size_t kListBytes = 32 * 1024;  // one slot per (epilogue thread, column of a group): 16 x 512 or 32 x 256 floats
-static_assert((size_t)Epi<8>::kGroup * Epi<8>::kThreads * 4 == kListBytes && (size_t)Epi<32>::kGroup * Epi<32>::kThreads * 4 == kListBytes, "slot area");
-static_assert((Epi<8>::kParts - 1) * 8 * BM * 4 <= kListBytes && (Epi<32>::kParts - 1) * 32 * BM * 4 <= kListBytes,
+static_assert((size_t)Epi<8, true>::kGroup * Epi<8, true>::kThreads * 4 == kListBytes && (size_t)Epi<32>::kGroup * Epi<32>::kThreads * 4 == kListBytes, "slot area");
+static_assert((Epi<8, true>::kParts - 1) * 8 * BM * 4 <= kListBytes && (Epi<32>::kParts - 1) * 32 * BM * 4 <= kListBytes,
               "the part-exchange buffer aliases the candidate slots");
 
 enum { MODE_FP8 = 0, MODE_FP8_HBM = 1, MODE_FP4 = 2, MODE_FP4_2CTA = 3 };
@@ -118,12 +118,13 @@ struct Cfg {
     static constexpr int kRawStages = SNV_TC_RAWSTAGES;
     static constexpr int kBRows = kTwoCta ? BN / 2 : BN;          // panel rows this CTA expands per tile
     static constexpr uint32_t kRawRow = WPK * 4;                // raw bytes per panel row and k-block
-    static constexpr uint32_t kRawSlot = kExpand ? 256 * kRawRow : 0;
+    static constexpr uint32_t kRawSlot = kExpand ? (kTwoCta ? 128 : 256) * kRawRow : 0;
+    static constexpr uint32_t kBSlot = kTwoCta ? kBBytes / 2 : kBBytes;  // 16 KB holds the pair kernel's 120 rows
     static constexpr uint32_t kRawBytes = kBRows * kRawRow;     // what one TMA box brings
     static constexpr uint32_t kBBox = BN * kRowBytes;           // fp8-hbm variant: one TMA box of operand rows
     static constexpr uint32_t kSfCol = 2 * BN;                  // fp4: first TMEM column of the unit scales
-    static constexpr size_t kSmem = 1024 /*align slack*/ + (size_t)kAStages * kABytes + (size_t)kBStages * kBBytes +
-                                    (size_t)kRawStages * kRawSlot + kListBytes + 2 * BM * 4 * (SNV_TC_EPI16 ? 2 : 1) /*thresholds*/ + 256 /*barriers*/;
+    static constexpr size_t kSmem = 1024 /*align slack*/ + (size_t)kAStages * kABytes + (size_t)kBStages * kBSlot +
+                                    (size_t)kRawStages * kRawSlot + kListBytes + (kTwoCta ? 4 : 2) * BM * 4 /*thresholds*/ + 256 /*barriers*/;
     static_assert(kSmem <= 232448, "shared memory budget");
 };
 
@@ -332,7 +333,7 @@ __device__ __forceinline__ void tmem_ld_wait_cols(uint32_t (&r)[N])
 }
 
 template <int KT, int MODE>
-__global__ void __launch_bounds__(threads_of<KT>(), 1)
+__global__ void __launch_bounds__(threads_of<KT, MODE == MODE_FP4_2CTA>(), 1)
 hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_r, const TcParams p)
 {
     using C = Cfg<MODE>;
@@ -348,13 +349,13 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     unsigned char* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);  // SWIZZLE_128B tiles: 1024-byte aligned
     unsigned char* a_tiles = smem;
     unsigned char* b_tiles = a_tiles + (size_t)kAStages * kABytes;
-    unsigned char* raws = b_tiles + (size_t)kBStages * kBBytes;
+    unsigned char* raws = b_tiles + (size_t)kBStages * C::kBSlot;
     uint32_t* lists = reinterpret_cast<uint32_t*>(raws + (size_t)kRawStages * C::kRawSlot);  // [group columns][epilogue threads]
-    using E = Epi<KT>;
+    using E = Epi<KT, C::kTwoCta>;
     constexpr int kEpiThreads = E::kThreads;
     uint32_t* xchg = lists;                                                                 // [parts - 1][KT][128], after the slots are folded
     volatile float* thrx = reinterpret_cast<float*>(lists + kListBytes / 4);               // [parts][128 queries] published thresholds
-    uint64_t* bars = reinterpret_cast<uint64_t*>(lists + kListBytes / 4 + 2 * BM * (SNV_TC_EPI16 ? 2 : 1));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(lists + kListBytes / 4 + (C::kTwoCta ? 4 : 2) * BM);
     uint64_t* full_a = bars;                        // [kAStages]   TMA -> MMA
     uint64_t* empty_a = full_a + kAStages;          // [kAStages]   MMA -> TMA
     uint64_t* full_b = empty_a + kAStages;          // [kBStages]   expanders (or TMA) -> MMA
@@ -488,7 +489,7 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                         tcgen05_fence_after();
                         if (elect_one()) {
                             const uint32_t a_lo = a_lo0 + (uint32_t)ra.i * (kABytes >> 4);
-                            const uint32_t b_lo = b_lo0 + (uint32_t)rb.i * (kBBytes >> 4);
+                            const uint32_t b_lo = b_lo0 + (uint32_t)rb.i * (C::kBSlot >> 4);
                             if (kb != KB - 1) {
                                 mma(d_tmem, a_lo, b_lo, kb != 0 ? 1u : 0u);
                                 mma(d_tmem, a_lo + 2, b_lo + 2, 1u);
@@ -531,7 +532,7 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                         } else {
                             mbar_wait_relaxed(&empty_b[rb.i], rb.phase ^ 1u);
                             mbar_arrive_expect_tx(&full_b[rb.i], C::kBBox);
-                            tma_load_3d(b_tiles + (size_t)rb.i * kBBytes, &map_r, kb * kRowBytes, n0, it.w, &full_b[rb.i]);
+                            tma_load_3d(b_tiles + (size_t)rb.i * C::kBSlot, &map_r, kb * kRowBytes, n0, it.w, &full_b[rb.i]);
                             rb.next();
                         }
                     }
@@ -620,7 +621,7 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                         }
                         mbar_wait(&empty_b[rb.i], rb.phase ^ 1u);
                         if (act) {
-                            const uint32_t dst = b_base + (uint32_t)rb.i * kBBytes;
+                            const uint32_t dst = b_base + (uint32_t)rb.i * C::kBSlot;
                             if (kb != KB - 1 || tail_chunks == 8) {
                                 expand_row(w0, dst, 8);
                                 if constexpr (kTwoRows) expand_row(w1, dst + kHalfRows * kRowBytes, 8);
@@ -951,7 +952,7 @@ int launch_kernel(const CUtensorMap& map_q, const CUtensorMap& map_r, const TcPa
         // CTA pairs: a cluster of two CTAs on the two SMs of a TPC
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)grid);
-        cfg.blockDim = dim3((unsigned)threads_of<KT>());
+        cfg.blockDim = dim3((unsigned)threads_of<KT, true>());
         cfg.dynamicSmemBytes = smem;
         cfg.stream = stream;
         cudaLaunchAttribute at[1];
@@ -963,7 +964,7 @@ int launch_kernel(const CUtensorMap& map_q, const CUtensorMap& map_r, const TcPa
         cfg.numAttrs = 1;
         SNV_CUDA_CHECK(cudaLaunchKernelEx(&cfg, hamming_tc_kernel<KT, MODE>, map_q, map_r, tp));
     } else {
-        hamming_tc_kernel<KT, MODE><<<grid, threads_of<KT>(), smem, stream>>>(map_q, map_r, tp);
+        hamming_tc_kernel<KT, MODE><<<grid, threads_of<KT, false>(), smem, stream>>>(map_q, map_r, tp);
     }
     profile_end(stream);
     SNV_LAUNCH_CHECK();
@@ -993,7 +994,9 @@ int hamming_engine_for(const HammingSearchParams& p)
     if (!can || mode == 0) return 0;
     if (mode > 0) return mode;
     // auto: enough queries per window to fill a useful part of the 128-lane tile, and a panel worth a tile
-    return (p.nq >= 32 && p.n >= 512) ? SNV_TC_DEFAULT_ENGINE : 0;
+    if (!(p.nq >= 32 && p.n >= 512)) return 0;
+    // CTA pairs need two query tiles per window to keep both SMs of a pair busy
+    return (SNV_TC_DEFAULT_ENGINE == 4 && p.nq <= BM) ? 3 : SNV_TC_DEFAULT_ENGINE;
 }
 
 size_t hamming_tc_plan(const HammingSearchParams& p, HammingTcPlan& plan)
