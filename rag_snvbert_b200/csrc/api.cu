@@ -472,13 +472,18 @@ static int search_hamming(snv_index* idx, int w0, int nw, const void* q, int64_t
         make_params(0, nw, probe);
         if (hamming_tc_plan(probe, tprobe) == (size_t)-1) return SNV_ERR_UNSUPPORTED;
         if (tprobe.engine) {
-            // tensor-core engine: persistent CTAs take (window, query tile) items round-robin, so a chunk should hold
-            // a whole number of items per SM; ~24 chunks keep the pipeline's fill (first H2D) and drain (last D2H) short
-            int64_t a = kNumSMs, b = qtiles;
+            // tensor-core engine: persistent CTAs (or CTA pairs) take (window, query tile [pair]) items round-robin,
+            // so a chunk should hold a whole number of items per SM (pair); ~24 chunks keep the pipeline's fill
+            // (first H2D) and drain (last D2H) short.  (Chunking device-resident searches to overlap the query
+            // expansion with the previous chunk's scan was measured: < 1 %, not worth the extra launches.)
+            const int64_t per_w = tprobe.engine == 4 ? ceil_div(qtiles, 2) : qtiles;
+            const int64_t units = tprobe.engine == 4 ? kNumSMs / 2 : kNumSMs;
+            int64_t a = units, b = per_w;
             while (b) { const int64_t t = a % b; a = b; b = t; }
-            const int64_t unit = kNumSMs / a;  // windows per chunk so that windows x qtiles is a multiple of the SM count
-            int64_t cw = std::max<int64_t>(unit, nw / 24 / unit * unit);
-            if (cw * qtiles < 2 * kNumSMs) cw = ceil_div(2 * kNumSMs, qtiles);
+            const int64_t unit = units / a;  // windows per chunk so that items per chunk is a multiple of the units
+            const int64_t target = 24;
+            int64_t cw = std::max<int64_t>(unit, nw / target / unit * unit);
+            if (cw * per_w < 2 * units) cw = ceil_div(2 * units, per_w);
             chunk_w = (int)std::min<int64_t>(cw, nw);
         } else {
             chunk_w = (int)std::max<int64_t>(ceil_div(nw, 16), ceil_div((int64_t)kNumSMs * 16, qtiles));

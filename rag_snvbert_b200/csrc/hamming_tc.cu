@@ -844,9 +844,11 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 
 // ---- query operand: packed (q, observed mask) -> operand rows [rows][kblocks * 128 B] + popc(q & m) ----------------
 // One warp per query row: lane l owns packed word l (and l + 32, ...) for the bias, and writes the row's 16-byte
-// chunks l, l + 32, ... (coalesced); no integer divisions on the hot path.
+// chunks l, l + 32, ... (coalesced); no integer divisions on the hot path.  128-thread blocks at 32 registers fit
+// in the 4096 registers the resident scan CTA (480 x 128) leaves free on an SM, so the expansion of the next window
+// chunk overlaps the scan of the current one.
 template <bool FP4>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 tc_expand_queries_kernel(const uint32_t* __restrict__ q, const uint32_t* __restrict__ mask, int64_t mask_win_stride,
                          int64_t mask_q_stride, int nq, int64_t rows, int stride, int words, int d, int kblocks,
                          uint8_t* __restrict__ ops, int32_t* __restrict__ bias)
@@ -1067,12 +1069,12 @@ int hamming_tc_launch(const HammingSearchParams& p, const HammingTcPlan& plan, v
     const int kbytes = plan.kblocks * kRowBytes;
     const int BN = bn_of_engine(plan.engine);
     {
-        const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(rows, 8), (int64_t)kNumSMs * 32);  // 8 warps = 8 rows per block
+        const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(rows, 4), (int64_t)kNumSMs * 64);  // 4 warps = 4 rows per block
         if (plan.engine >= 3)
-            tc_expand_queries_kernel<true><<<grid, 256, 0, stream>>>(p.q, p.mask, p.mask_win_stride, p.mask_q_stride, p.nq, rows, p.stride,
+            tc_expand_queries_kernel<true><<<grid, 128, 0, stream>>>(p.q, p.mask, p.mask_win_stride, p.mask_q_stride, p.nq, rows, p.stride,
                                                                     p.words, p.d, plan.kblocks, q_ops, q_bias);
         else
-            tc_expand_queries_kernel<false><<<grid, 256, 0, stream>>>(p.q, p.mask, p.mask_win_stride, p.mask_q_stride, p.nq, rows, p.stride,
+            tc_expand_queries_kernel<false><<<grid, 128, 0, stream>>>(p.q, p.mask, p.mask_win_stride, p.mask_q_stride, p.nq, rows, p.stride,
                                                                      p.words, p.d, plan.kblocks, q_ops, q_bias);
         SNV_LAUNCH_CHECK();
     }

@@ -175,3 +175,29 @@ def test_engines_agree_at_cfg2_window_scale():
     for eng in ("tc", "tc4", "tc4x2"):
         for a, b in zip(out["popc"], out[eng]):
             assert torch.equal(a, b), eng
+
+
+def test_auto_engine_choice_by_shape():
+    """batched queries -> tensor cores (CTA pairs when a window has two query tiles), the reference's training-time
+    nq = 2 call and very wide rows -> popcount scan; results identical either way (checked elsewhere)"""
+    from rag_snvbert_b200 import WindowedHammingIndex, _lib
+
+    old = os.environ.pop("SNV_HAMMING_ENGINE", None)
+    try:
+        rng = np.random.default_rng(5)
+        panel = (rng.random((1, 2000, 1030)) < 0.3).astype(np.uint8)
+        idx = WindowedHammingIndex(1030, 1)
+        idx.add(panel)
+        idx.search((rng.random((1, 300, 1030)) < 0.3).astype(np.uint8), 8)
+        assert _lib.last_hamming_engine() == 4
+        idx.search((rng.random((1, 100, 1030)) < 0.3).astype(np.uint8), 8)
+        assert _lib.last_hamming_engine() == 3
+        idx.search((rng.random((1, 2, 1030)) < 0.3).astype(np.uint8), 8)
+        assert _lib.last_hamming_engine() == 0
+        wide = WindowedHammingIndex(5000, 1)
+        wide.add((rng.random((1, 600, 5000)) < 0.3).astype(np.uint8))
+        wide.search((rng.random((1, 64, 5000)) < 0.3).astype(np.uint8), 8)
+        assert _lib.last_hamming_engine() == 0
+    finally:
+        if old is not None:
+            os.environ["SNV_HAMMING_ENGINE"] = old
