@@ -30,6 +30,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -59,7 +60,7 @@ constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kStages * kStageByt
 
 using namespace tc;
 
-template <int KT, bool SPLITK>
+template <int KT, bool SPLITK, bool PAIR = false>
 __global__ void __launch_bounds__(kThreads, 1)
 l2_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_r,
                const L2SearchParams p)
@@ -99,8 +100,11 @@ l2_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         const int total_kb = p.kp / BK;
         num_kb = (kb0 + p.kb_per_split < total_kb) ? p.kb_per_split : total_kb - kb0;
     } else {
-        split = blockIdx.x % p.nsplit;
-        mt = blockIdx.x / p.nsplit;
+        // CTA pair (PAIR): the two CTAs of a cluster take query tiles 2 m and 2 m + 1 against the same panel tiles;
+        // each loads half (128 rows) of every panel tile and the leader issues one M = 256 MMA over both halves
+        const int b = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+        split = b % p.nsplit;
+        mt = PAIR ? 2 * (b / p.nsplit) + (int)cluster_ctarank() : b / p.nsplit;
         t0 = split * p.tiles_per_split;
         const int t1 = (t0 + p.tiles_per_split < n_tiles_total) ? t0 + p.tiles_per_split : n_tiles_total;
         my_tiles = t1 - t0;  // >= 1 by construction of the plan
@@ -108,6 +112,8 @@ l2_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         num_kb = p.kp / BK;
     }
     const int m0 = mt * BM;
+    const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0u;
 
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&map_q);
@@ -118,13 +124,17 @@ l2_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         }
         for (int s = 0; s < kAccStages; ++s) {
             mbar_init(&tmem_full[s], 1);
-            mbar_init(&tmem_empty[s], kEpiThreads);
+            mbar_init(&tmem_empty[s], (PAIR ? 2 : 1) * kEpiThreads);
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
+    if (warp == 1) {
+        if constexpr (PAIR) tmem_alloc_2cta(tmem_ptr, kTmemCols);
+        else tmem_alloc(tmem_ptr, kTmemCols);
+    }
     tcgen05_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync();  // the peer's barriers exist before anything arrives on them
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
@@ -144,16 +154,24 @@ l2_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 #endif
                     unsigned char* a_dst = tiles + (size_t)stage * kStageBytes;
                     unsigned char* b_dst = a_dst + kABytes;
-                    mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
-                    tma_load_2d(a_dst, &map_q, (kb0 + kb) * BK, m0, &full_bar[stage]);
-                    tma_load_2d(b_dst, &map_r, (kb0 + kb) * BK, n0, &full_bar[stage]);
+                    if constexpr (PAIR) {
+                        // both CTAs' bytes (query tile + half panel tile each) complete on the leader's barrier
+                        if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * (kABytes + kBBytes / 2));
+                        tma_load_2d_2cta(a_dst, &map_q, (kb0 + kb) * BK, m0, &full_bar[stage]);
+                        tma_load_2d_2cta(b_dst, &map_r, (kb0 + kb) * BK, n0 + (int)cta_rank * (BN / 2), &full_bar[stage]);
+                    } else {
+                        mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+                        tma_load_2d(a_dst, &map_q, (kb0 + kb) * BK, m0, &full_bar[stage]);
+                        tma_load_2d(b_dst, &map_r, (kb0 + kb) * BK, n0, &full_bar[stage]);
+                    }
                     if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
+        // ================= MMA issuer (the leader CTA of a pair) =================
+        constexpr uint32_t idesc = make_idesc_tf32(PAIR ? 2 * BM : BM, BN);
+        if (leader) {
         int stage = 0;
         uint32_t phase = 0;
         for (int t = 0; t < my_tiles; ++t) {
@@ -173,16 +191,23 @@ l2_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint64_t adesc = make_kmajor_sw128_desc(a_addr + k * UMMA_K * 4);
                         const uint64_t bdesc = make_kmajor_sw128_desc(b_addr + k * UMMA_K * 4);
-                        umma_tf32(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                        if constexpr (PAIR) umma_tf32_2cta(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                        else umma_tf32(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
 #endif
-                    umma_commit(&empty_bar[stage]);                   // smem slot reusable once read
-                    if (kb == num_kb - 1) umma_commit(&tmem_full[as]);  // accumulator complete
+                    if constexpr (PAIR) {
+                        umma_commit_2cta(&empty_bar[stage]);                   // both CTAs' slots reusable once read
+                        if (kb == num_kb - 1) umma_commit_2cta(&tmem_full[as]);  // both CTAs' accumulators complete
+                    } else {
+                        umma_commit(&empty_bar[stage]);                   // smem slot reusable once read
+                        if (kb == num_kb - 1) umma_commit(&tmem_full[as]);  // accumulator complete
+                    }
                 }
                 __syncwarp();
                 if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
         }
+        }  // leader
     } else {
         // ================= epilogue: thread = query row, 2 warps per lane quarter =================
         if constexpr (SPLITK) {
@@ -301,7 +326,8 @@ l2_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 ci += 2;
             }
             tcgen05_fence_before();
-            mbar_arrive(&tmem_empty[as]);
+            if (PAIR && !leader) mbar_arrive_cluster(&tmem_empty[as], 0u);
+            else mbar_arrive(&tmem_empty[as]);
         }
         fold();
         if (active) {
@@ -314,9 +340,11 @@ l2_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 
     tcgen05_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync();  // the leader's MMAs may still read this CTA's operands
     if (warp == 1) {
         tcgen05_fence_after();
-        tmem_dealloc(tmem_base, kTmemCols);
+        if constexpr (PAIR) tmem_dealloc_2cta(tmem_base, kTmemCols);
+        else tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
@@ -471,13 +499,20 @@ size_t l2_plan(L2SearchParams& p)
     p.kt = p.k <= 8 ? 8 : 32;
     const int64_t n_tiles = p.n > 0 ? ceil_div(p.n, BN) : 0;
     const int64_t m_tiles = ceil_div(p.nq, BM);
+    // CTA pairs (cta_group::2; SNV_L2_PAIR=1, needs two query tiles): each CTA of a pair streams only half of every
+    // panel tile.  Measured on B200: no gain (cfg 4: 59.4 us either way; 8192 x 50000 x 256 tf32x3: 875 vs 885 us, where
+    // the single-CTA kernel already runs at 86 % of the tf32 rate), so the single-CTA kernel stays the default.
+    p.pair = false;
+    if (const char* e = getenv("SNV_L2_PAIR")) p.pair = m_tiles >= 2 && atoi(e) != 0;
+    const int64_t m_items = p.pair ? ceil_div(m_tiles, 2) : m_tiles;
+    const int64_t units = p.pair ? kNumSMs / 2 : kNumSMs;
     // pick the row split that minimises (waves x tiles per CTA): one CTA per SM is resident
     int best_s = 1;
     int64_t best_cost = -1;
     for (int s = 1; s <= n_tiles && s <= 64; ++s) {
         const int64_t per = ceil_div(n_tiles, s);
         const int64_t real_s = ceil_div(n_tiles, per);
-        const int64_t waves = ceil_div(m_tiles * real_s, kNumSMs);
+        const int64_t waves = ceil_div(m_items * real_s, units);
         const int64_t cost = waves * (per * 8 + 1);  // +1: fixed prologue/epilogue weight per CTA
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_s = (int)real_s; }
     }
@@ -497,6 +532,7 @@ size_t l2_plan(L2SearchParams& p)
             p.kb_per_split = (int)ceil_div(total_kb, ks);
             p.ksplit = (int)ceil_div(total_kb, p.kb_per_split);
             p.dot_ld = round_up(p.n, 32);
+            p.pair = false;  // split-K runs on single CTAs
             // workspace: dot [nq][dot_ld] fp32, then keys [nq][n] u64
             return (size_t)p.nq * p.dot_ld * 4 + (size_t)p.nq * p.n * 8 + 256;
         }
@@ -515,7 +551,7 @@ int l2_launch(const L2SearchParams& p, cudaStream_t stream)
     CUtensorMap map_q, map_r;
     int rc = make_map(&map_q, p.q_ops, p.nq, p.kp, BM);
     if (rc) return rc;
-    rc = make_map(&map_r, p.ref_ops, p.n, p.kp, BN);
+    rc = make_map(&map_r, p.ref_ops, p.n, p.kp, p.pair && p.ksplit <= 1 ? BN / 2 : BN);
     if (rc) return rc;
     const int64_t m_tiles = ceil_div(p.nq, BM);
     if (p.ksplit > 1) {
@@ -542,26 +578,37 @@ int l2_launch(const L2SearchParams& p, cudaStream_t stream)
         if (p.n > 0x7fffffff) { set_error("L2 split-K: panel too large"); return SNV_ERR_UNSUPPORTED; }
         return merge_keys_launch(keys, 1, (int)p.n, p.nq, p.k, p.id_offset, true, nullptr, p.D_f32, p.I, stream);
     }
-    const unsigned grid = (unsigned)(m_tiles * p.nsplit);
-    if (p.kt == 8) {
-        static bool attr8 = false;
-        if (!attr8) {
-            SNV_CUDA_CHECK(cudaFuncSetAttribute(l2_topk_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-            attr8 = true;
+    const unsigned grid = p.pair ? (unsigned)(2 * ceil_div(m_tiles, 2) * p.nsplit) : (unsigned)(m_tiles * p.nsplit);
+    auto launch = [&](auto kern, bool& attr_done) -> int {
+        if (!attr_done) {
+            SNV_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+            attr_done = true;
         }
         profile_begin(stream);
-        l2_topk_kernel<8, false><<<grid, kThreads, kSmemBytes, stream>>>(map_q, map_r, p);
-        profile_end(stream);
-    } else {
-        static bool attr32 = false;
-        if (!attr32) {
-            SNV_CUDA_CHECK(cudaFuncSetAttribute(l2_topk_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-            attr32 = true;
+        if (p.pair) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(grid);
+            cfg.blockDim = dim3(kThreads);
+            cfg.dynamicSmemBytes = kSmemBytes;
+            cfg.stream = stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            SNV_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, map_q, map_r, p));
+        } else {
+            kern<<<grid, kThreads, kSmemBytes, stream>>>(map_q, map_r, p);
         }
-        profile_begin(stream);
-        l2_topk_kernel<32, false><<<grid, kThreads, kSmemBytes, stream>>>(map_q, map_r, p);
         profile_end(stream);
-    }
+        return SNV_OK;
+    };
+    static bool attr8 = false, attr32 = false, attr8p = false, attr32p = false;
+    if (p.kt == 8) rc = p.pair ? launch(l2_topk_kernel<8, false, true>, attr8p) : launch(l2_topk_kernel<8, false, false>, attr8);
+    else rc = p.pair ? launch(l2_topk_kernel<32, false, true>, attr32p) : launch(l2_topk_kernel<32, false, false>, attr32);
+    if (rc) return rc;
     SNV_LAUNCH_CHECK();
     return merge_keys_launch(p.partial, p.nsplit * 2, p.kt, p.nq, p.k, p.id_offset, true, nullptr, p.D_f32, p.I, stream);
 }

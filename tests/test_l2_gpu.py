@@ -254,3 +254,29 @@ def test_skinny_deep_problem_split_k(center):
     if center:
         # centring removes the shared component: errors drop by orders of magnitude
         assert err.max() <= 1e-6 * float(qn.max() + rn) + 1e-3
+
+
+def test_l2_cta_pair_kernel_matches_default():
+    """the optional CTA-pair (cta_group::2) L2 kernel returns what the default kernel returns"""
+    import os
+
+    import torch
+
+    from rag_snvbert_b200 import WindowedL2Index
+
+    torch.manual_seed(3)
+    refs = torch.randn(3000, 200, device="cuda")
+    q = torch.randn(700, 200, device="cuda")  # 6 query tiles: 3 pairs
+    idx = WindowedL2Index(200, 1, 0)
+    idx.add(refs)
+    D0, I0 = idx.search(q, 8)
+    old = os.environ.get("SNV_L2_PAIR")
+    os.environ["SNV_L2_PAIR"] = "1"
+    try:
+        D1, I1 = idx.search(q, 8)
+    finally:
+        if old is None:
+            del os.environ["SNV_L2_PAIR"]
+        else:
+            os.environ["SNV_L2_PAIR"] = old
+    assert torch.equal(I0, I1) and torch.equal(D0, D1)
