@@ -194,6 +194,19 @@ int snv_topk_merge(int device, const int32_t* D_i32, const float* D_f32, const i
 int snv_pack_rows(int device, const void* x, int64_t rows, int64_t d, int dtype, int invert,
                   uint32_t* out, uint32_t* out_observed, void* stream);
 
+/*
+ * Observed-site masks from a position intersection (replaces the host-side
+ * np.intersect1d of test_faiss_intersect.py:128-140 and the searchsorted of
+ * src/dataset/embedding_rag_dataset.py:117-128).  All pointers are DEVICE pointers:
+ * ref_pos int64 [n_ref] (the panel's site positions), tgt_pos int64 [n_tgt] ASCENDING,
+ * window_info int64 [n_windows][2] = (start, end) site indices into ref_pos.  Writes packed
+ * uint32 [n_windows][snv_packed_stride(d)]: bit c of window w is set when site start + c / ploidy
+ * (< end) is also a target position.  ploidy 1 = haplotype rows, 2 = the offline scripts' sample rows
+ * (s0h0, s0h1, ...).  The result is what snv_index_search takes as a PER_WINDOW observed mask.
+ */
+int snv_intersect_masks(int device, const int64_t* ref_pos, int64_t n_ref, const int64_t* tgt_pos, int64_t n_tgt,
+                        const int64_t* window_info, int n_windows, int64_t d, int ploidy, uint32_t* out, void* stream);
+
 /* number of kernels this library has launched in the calling process (bench "gpu_launches") */
 int64_t snv_launch_count(void);
 

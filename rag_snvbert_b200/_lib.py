@@ -49,6 +49,7 @@ SYMBOLS = {
     "snv_index_export": (_i, [_vp, _i, _vp]),
     "snv_topk_merge": (_i, [_i, _vp, _vp, _vp, _i, _i64, _i, _i, _vp, _vp, _vp, _vp]),
     "snv_pack_rows": (_i, [_i, _vp, _i64, _i64, _i, _i, _vp, _vp, _vp]),
+    "snv_intersect_masks": (_i, [_i, _vp, _i64, _vp, _i64, _vp, _i, _i64, _i, _vp, _vp]),
     "snv_launch_count": (_i64, []),
     "snv_profile_enable": (_i, [_i]),
     "snv_profile_last_ms": (_i, [_c.POINTER(_c.c_float)]),

@@ -991,6 +991,17 @@ int snv_topk_merge(int device, const int32_t* D_i32, const float* D_f32, const i
     return merge_results_launch(D_i32, D_f32, I, parts, nq, k_in, k_out, Do_i32, Do_f32, Io, (cudaStream_t)stream_);
 }
 
+int snv_intersect_masks(int device, const int64_t* ref_pos, int64_t n_ref, const int64_t* tgt_pos, int64_t n_tgt,
+                        const int64_t* window_info, int n_windows, int64_t d, int ploidy, uint32_t* out, void* stream_)
+{
+    if (!ref_pos || !window_info || !out || (!tgt_pos && n_tgt > 0)) { set_error("snv_intersect_masks: null buffer"); return SNV_ERR_INVALID; }
+    if (n_ref < 0 || n_tgt < 0 || n_windows < 0 || d <= 0 || (ploidy != 1 && ploidy != 2)) { set_error("snv_intersect_masks: bad arguments"); return SNV_ERR_INVALID; }
+    DeviceGuard g(device);
+    if (!g.ok) { set_error("snv_intersect_masks: cudaSetDevice failed"); return SNV_ERR_CUDA; }
+    return intersect_masks_launch(ref_pos, n_ref, tgt_pos, n_tgt, window_info, n_windows, d, ploidy, (int)snv_packed_stride(d), out,
+                                  (cudaStream_t)stream_);
+}
+
 int snv_pack_rows(int device, const void* x, int64_t rows, int64_t d, int dtype, int invert, uint32_t* out,
                   uint32_t* out_observed, void* stream_)
 {

@@ -71,6 +71,11 @@ int merge_results_launch(const int32_t* D_i32, const float* D_f32, const int64_t
 int pack_launch(const void* x, int64_t rows, int64_t d, int dtype, bool invert, int stride,
                 uint32_t* out, uint32_t* out_observed, cudaStream_t stream);
 
+// ---------------------------------------------------------------- position intersection -> observed-site masks
+int intersect_masks_launch(const int64_t* ref_pos, int64_t n_ref, const int64_t* tgt_pos, int64_t n_tgt,
+                           const int64_t* window_info, int n_windows, int64_t d, int ploidy, int stride, uint32_t* out,
+                           cudaStream_t stream);
+
 // ---------------------------------------------------------------- gather
 int gather_tokens_launch(const uint32_t* panel, int64_t panel_win_stride, int stride, int64_t n,
                          const int64_t* I, int64_t id_offset, int nw, int64_t nq, int k,

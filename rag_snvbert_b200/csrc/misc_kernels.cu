@@ -195,6 +195,44 @@ merge_results_warp_kernel(const DT* __restrict__ D, const int64_t* __restrict__ 
     }
 }
 
+// ------------------------------------------------------------------------------ position intersection
+// Observed-site masks of a ref / target position intersection (test_faiss_intersect.py:128-140 keeps only the
+// shared sites of a window): thread = one packed mask word of one window; every bit's ref site is
+// looked up in the ascending target positions by binary search.  `ploidy` 1: bit s <-> site s (haplotype rows);
+// 2: bits 2s, 2s+1 <-> site s (the offline scripts' sample rows s0h0, s0h1, ...).
+__global__ void __launch_bounds__(256)
+intersect_mask_kernel(const int64_t* __restrict__ ref_pos, int64_t n_ref, const int64_t* __restrict__ tgt_pos, int64_t n_tgt,
+                      const int64_t* __restrict__ window_info, int n_windows, int64_t d, int ploidy, int stride,
+                      uint32_t* __restrict__ out)
+{
+    const int64_t total = (int64_t)n_windows * stride;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int w = (int)(i / stride);
+        const int word = (int)(i % stride);
+        const int64_t start = window_info[2 * w], end = window_info[2 * w + 1];
+        uint32_t bits = 0;
+        for (int b = 0; b < 32; ++b) {
+            const int64_t col = (int64_t)word * 32 + b;
+            if (col >= d) break;
+            const int64_t site = start + col / ploidy;
+            if (site >= end || site >= n_ref || site < 0) continue;
+            if (ploidy == 2 && (b & 1)) {  // second haplotype of the same site: copy the bit just computed
+                bits |= ((bits >> (b - 1)) & 1u) << b;
+                continue;
+            }
+            const int64_t key = ref_pos[site];
+            int64_t lo = 0, hi = n_tgt;
+            while (lo < hi) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (tgt_pos[mid] < key) lo = mid + 1;
+                else hi = mid;
+            }
+            if (lo < n_tgt && tgt_pos[lo] == key) bits |= 1u << b;
+        }
+        out[i] = bits;
+    }
+}
+
 // ------------------------------------------------------------------------------ pack
 // One warp per (row, 32-site group): coalesced 32-element read, ballot -> one packed word
 // (lane l <-> site 32*w + l <-> bit l: LSB-first).
@@ -495,6 +533,18 @@ int gather_rows_launch(const float* panel, int64_t panel_win_stride, int64_t d, 
     const int block = 256;
     gather_rows_kernel<<<grid_for_warps(rows_total, block), block, 0, stream>>>(
         panel, panel_win_stride, d, n, I, rows_total, nq * k, out);
+    SNV_LAUNCH_CHECK();
+    return SNV_OK;
+}
+
+int intersect_masks_launch(const int64_t* ref_pos, int64_t n_ref, const int64_t* tgt_pos, int64_t n_tgt,
+                           const int64_t* window_info, int n_windows, int64_t d, int ploidy, int stride, uint32_t* out,
+                           cudaStream_t stream)
+{
+    if (n_windows <= 0) return SNV_OK;
+    const int block = 256;
+    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div((int64_t)n_windows * stride, block), (int64_t)kNumSMs * 16);
+    intersect_mask_kernel<<<grid, block, 0, stream>>>(ref_pos, n_ref, tgt_pos, n_tgt, window_info, n_windows, d, ploidy, stride, out);
     SNV_LAUNCH_CHECK();
     return SNV_OK;
 }

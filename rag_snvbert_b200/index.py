@@ -407,6 +407,27 @@ def topk_merge(D, I, k: int):
     return Do, Io
 
 
+def intersect_masks(ref_pos, tgt_pos, window_info, d: int, ploidy: int = 1):
+    """Device-side position intersection (snv_intersect_masks): CUDA int64 tensors ref_pos [n_ref], tgt_pos [n_tgt]
+    (any order; sorted here on the device), window_info [W, 2] (start, end) -> packed int32 observed masks
+    [W, snv_packed_stride(d)], usable as `observed=` of a search over packed queries (one mask per window)."""
+    for t in (ref_pos, tgt_pos, window_info):
+        if not (_is_torch(t) and t.is_cuda and t.dtype == torch.int64):
+            raise ValueError("intersect_masks takes CUDA int64 tensors")
+    if window_info.dim() != 2 or window_info.shape[1] != 2:
+        raise ValueError("intersect_masks: window_info must be [W, 2]")
+    dev = ref_pos.device.index
+    ref_pos = ref_pos.contiguous()
+    tgt_sorted = torch.sort(tgt_pos.contiguous()).values
+    window_info = window_info.contiguous()
+    W = int(window_info.shape[0])
+    out = torch.empty((W, L.packed_stride(int(d))), dtype=torch.int32, device=ref_pos.device)
+    L.check(L.lib().snv_intersect_masks(dev, ref_pos.data_ptr(), int(ref_pos.numel()), tgt_sorted.data_ptr(), int(tgt_sorted.numel()),
+                                        window_info.data_ptr(), W, int(d), int(ploidy), out.data_ptr(), _current_stream(dev)),
+            "snv_intersect_masks")
+    return out
+
+
 def pack_rows(x, d: Optional[int] = None, invert: bool = False):
     """Device-side bit packing (snv_pack_rows): torch CUDA tensor [rows, d] (uint8/bool 0-1 sites,
     float32, or int64 tokens) -> packed int32 tensor [rows, snv_packed_stride(d)]."""

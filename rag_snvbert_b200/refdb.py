@@ -99,6 +99,16 @@ def intersect_windows(ref_pos: np.ndarray, tgt_pos: np.ndarray, window_info: np.
     return obs
 
 
+def intersect_windows_device(ref_pos, tgt_pos, window_info, d: int, ploidy: int = 2):
+    """intersect_windows on the device (snv_intersect_masks): CUDA int64 tensors in, packed per-window observed
+    masks [W, snv_packed_stride(d)] out - what `index.search(packed_queries, k, observed=...)` takes, so the
+    intersect workflow (test_faiss_intersect.py:128-181) needs no host round trip per window.  ploidy 2 = the
+    scripts' sample rows (s0h0, s0h1, ...), 1 = haplotype rows."""
+    from .index import intersect_masks
+
+    return intersect_masks(ref_pos, tgt_pos, window_info, d, ploidy)
+
+
 def partial_search(index: WindowedHammingIndex, expanded: np.ndarray, missing: np.ndarray,
                    window_info: np.ndarray, top_k: int):
     """Observed-site search of every target sample in every window

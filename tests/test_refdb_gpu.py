@@ -71,3 +71,39 @@ def test_expand_target_and_partial_search():
             De, Ie = O.l2_topk_f32_blas(sub_ref, q, 5)
             np.testing.assert_array_equal(I[w, s], Ie[0])
             np.testing.assert_array_equal(D[w, s], De[0])
+
+
+def test_intersect_masks_on_device_match_host_and_drive_the_masked_search():
+    """the ref/target position intersection as a device kernel -> per-window observed masks that feed
+    the masked Hamming search (no host round trip); equals the numpy intersect1d mask and the host-mask search."""
+    import torch
+
+    from rag_snvbert_b200 import _lib
+    from rag_snvbert_b200.index import pack_rows
+    from rag_snvbert_b200.refdb import build_ref_db, intersect_windows, intersect_windows_device, sample_rows
+
+    rng = np.random.default_rng(21)
+    V, S_ref, S_tgt = 900, 120, 40
+    ref_pos = np.sort(rng.choice(50000, size=V, replace=False)).astype(np.int64)
+    tgt_pos = rng.permutation(np.concatenate([rng.choice(ref_pos, size=500, replace=False),
+                                              rng.choice(50000, size=200)])).astype(np.int64)
+    window_info = np.array([[0, 250], [250, 400], [400, 900]], dtype=np.int64)
+    ref_gt = (rng.random((V, S_ref, 2)) < 0.3).astype(np.uint8)
+    tgt_gt = (rng.random((V, S_tgt, 2)) < 0.3).astype(np.uint8)
+    index = build_ref_db(ref_gt, window_info)
+    d = index.d
+    obs_host = intersect_windows(ref_pos, tgt_pos, window_info)            # [W, Lmax] per site
+    obs_rows = np.zeros((3, d), dtype=np.uint8)
+    obs_rows[:, : 2 * obs_host.shape[1]] = np.repeat(obs_host, 2, axis=1)  # both haplotypes share the site mask
+    dev = torch.device("cuda", 0)
+    masks = intersect_windows_device(torch.from_numpy(ref_pos).to(dev), torch.from_numpy(tgt_pos).to(dev),
+                                     torch.from_numpy(window_info).to(dev), d, ploidy=2)
+    exp = O.pack_bits_u32(obs_rows, _lib.packed_stride(d))
+    np.testing.assert_array_equal(masks.cpu().numpy().view(np.uint32), exp)
+    # drive the masked search with the device masks
+    q = sample_rows(tgt_gt, window_info, d)
+    qd = pack_rows(torch.from_numpy(q.reshape(-1, d)).to(dev), d).reshape(3, S_tgt, -1)
+    Dd, Id = index.search(qd, 5, observed=masks)
+    Dh, Ih = index.search(q, 5, observed=obs_rows)
+    np.testing.assert_array_equal(Id.cpu().numpy(), Ih)
+    np.testing.assert_array_equal(Dd.cpu().numpy(), Dh)
