@@ -22,19 +22,25 @@
 //   fp4  kind::mxf4 (block scale = 1.0 everywhere), E2M1, K = 64 sites per MMA, k-block = 8 packed
 //        words (256 sites), N = 240 (TMEM: 2 x 240 accumulator columns + 32 columns of unit scales)
 //        nibble n of byte 16 i + 4 j + n / 2  <->  word i, bit 4 n + j
-// The kernel is bound by shared-memory bandwidth (MMA operand reads + expander stores), so halving
-// the bytes per site doubles the throughput.
+// Halving the operand bytes per site (fp4) is what pays: the single-CTA kernels are bound by shared-memory
+// bandwidth (MMA operand reads + expander stores), not by the tensor pipe.
 //
-// CTA (480 threads, one per SM, persistent over (window, query tile, row split) items):
+// CTA pairs (MODE_FP4_2CTA, the default when a window has two query tiles): two CTAs of a cluster hold 128 queries
+// each (M = 256, tcgen05.mma.cta_group::2 issued by the leader) and each expands only half (120 rows) of every panel
+// tile; slots are released and accumulators published with multicast tcgen05.commit, the peer's TMA completes on the
+// leader's barrier, the peer's expanders / epilogue arrive on the leader's barriers through mapa.
+//
+// CTA (480 threads, one per SM, persistent over (window, query tile [pair], row split) items):
 //   warp 0       TMA producer of the query operand tile A [128 x 128 B] (SWIZZLE_128B)
-//   warp 1       TMEM allocator + MMA issuer (one thread): tcgen05.mma M128 into one of two accumulator stages
-//   warp 2       TMA producer of the raw packed panel k-blocks [N rows x 16 / 32 B]
+//   warp 1       TMEM allocator + MMA issuer (one elected lane): tcgen05.mma M128 / M256 into one of two accumulator stages
+//   warp 2       TMA producer of the raw packed panel k-blocks [rows x 16 / 32 B]
 //   warps 3-6    expanders: packed bits -> operand tile B (one 128-byte row per panel row and k-block)
-//   warps 7-14   epilogue: thread = query (TMEM lane), two warps per lane quarter on the two column
-//                halves of a tile; one FFMA + one compare per column, candidates appended to per-thread
-//                lists in shared memory and folded in lockstep into a register top-k of 32-bit keys
-//                (distance << idx_bits | row); the halves are merged in shared memory and the final
-//                (D, I) rows are written by the kernel itself.
+//   warps 7-14   epilogue: thread = query (TMEM lane), two warps per lane quarter on the two column halves of a
+//                tile; per column one compare of the raw accumulator with the threshold, a predicated store into
+//                the column's slot in shared memory and a predicated bit in a 32-column mask; after each chunk
+//                the lanes pop their mask bits in lockstep and insert 32-bit keys (distance << idx_bits | row) into
+//                a sorted register top-k; the halves exchange thresholds, are merged in shared memory and the
+//                final (D, I) rows are written by the kernel itself.
 #include <cuda.h>
 
 #include <algorithm>
