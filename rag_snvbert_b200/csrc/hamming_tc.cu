@@ -55,7 +55,7 @@
 #include "topk.cuh"
 
 #ifndef SNV_TC_EPI16
-#define SNV_TC_EPI16 0  // 1: 16 epilogue warps for k <= 8 in the CTA-pair kernel (measured slower on B200 in both kernels: 1.94 vs 1.71 ms)
+#define SNV_TC_EPI16 0  // 1: 16 epilogue warps for k <= 8 in the CTA-pair kernel (measured slower on B200: 1.98 vs 1.76 ms per 296 windows)
 #endif
 #ifndef SNV_TC_DEFAULT_ENGINE
 #define SNV_TC_DEFAULT_ENGINE 4  // what "auto" picks for tensor-core shapes: 1 = fp8, 3 = fp4, 4 = fp4 on CTA pairs
@@ -82,7 +82,7 @@ struct Epi {
     static constexpr int kThreads = kWarps * 32;
     static constexpr int kParts = kWarps / 4;          // warps per TMEM lane quarter = column parts of a tile
     static constexpr int kPartCols = 256 / kParts;     // 64 or 128
-    static constexpr int kGroup = kPartCols / 4;       // columns scored between two folds: 16 or 32
+    static constexpr int kGroup = 32;                  // columns scored between two folds
     static constexpr uint32_t kSlotStride = kThreads * 4;  // bytes between the candidate slots of consecutive columns
 };
 constexpr int kFirstExpWarp = 3;
@@ -101,8 +101,8 @@ constexpr uint32_t kBBytes = 256 * kRowBytes;  // 32 KB slot (240 or 256 rows in
 #define SNV_TC_RAWSTAGES 4
 #endif
 constexpr int kBStages = SNV_TC_BSTAGES;
-constexpr size_t kListBytes = 32 * 1024;  // one slot per (epilogue thread, column of a group): 16 x 512 or 32 x 256 floats
-static_assert((size_t)Epi<8, true>::kGroup * Epi<8, true>::kThreads * 4 == kListBytes && (size_t)Epi<32>::kGroup * Epi<32>::kThreads * 4 == kListBytes, "slot area");
+constexpr size_t kListBytes = 32 * 1024;  // one slot per (epilogue thread, column of a group): 32 x 256 floats
+constexpr size_t kListBytes16 = 64 * 1024; // 16 epilogue warps: 32 x 512 floats
 static_assert((Epi<8, true>::kParts - 1) * 8 * BM * 4 <= kListBytes && (Epi<32>::kParts - 1) * 32 * BM * 4 <= kListBytes,
               "the part-exchange buffer aliases the candidate slots");
 
@@ -130,7 +130,7 @@ struct Cfg {
     static constexpr uint32_t kBBox = BN * kRowBytes;           // fp8-hbm variant: one TMA box of operand rows
     static constexpr uint32_t kSfCol = 2 * BN;                  // fp4: first TMEM column of the unit scales
     static constexpr size_t kSmem = 1024 /*align slack*/ + (size_t)kAStages * kABytes + (size_t)kBStages * kBSlot +
-                                    (size_t)kRawStages * kRawSlot + kListBytes + (kTwoCta ? 4 : 2) * BM * 4 /*thresholds*/ + 256 /*barriers*/;
+                                    (size_t)kRawStages * kRawSlot + ((kTwoCta && SNV_TC_EPI16) ? kListBytes16 : kListBytes) + (kTwoCta ? 4 : 2) * BM * 4 /*thresholds*/ + 256 /*barriers*/;
     static_assert(kSmem <= 232448, "shared memory budget");
 };
 
@@ -317,8 +317,9 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     using E = Epi<KT, C::kTwoCta>;
     constexpr int kEpiThreads = E::kThreads;
     uint32_t* xchg = lists;                                                                 // [parts - 1][KT][128], after the slots are folded
-    volatile float* thrx = reinterpret_cast<float*>(lists + kListBytes / 4);               // [parts][128 queries] published thresholds
-    uint64_t* bars = reinterpret_cast<uint64_t*>(lists + kListBytes / 4 + (C::kTwoCta ? 4 : 2) * BM);
+    constexpr size_t kSlots = (KT == 8 && C::kTwoCta && SNV_TC_EPI16) ? kListBytes16 : kListBytes;
+    volatile float* thrx = reinterpret_cast<float*>(lists + kSlots / 4);               // [parts][128 queries] published thresholds
+    uint64_t* bars = reinterpret_cast<uint64_t*>(lists + kSlots / 4 + (C::kTwoCta ? 4 : 2) * BM);
     uint64_t* full_a = bars;                        // [kAStages]   TMA -> MMA
     uint64_t* empty_a = full_a + kAStages;          // [kAStages]   MMA -> TMA
     uint64_t* full_b = empty_a + kAStages;          // [kBStages]   expanders (or TMA) -> MMA
