@@ -280,3 +280,39 @@ def test_l2_cta_pair_kernel_matches_default():
         else:
             os.environ["SNV_L2_PAIR"] = old
     assert torch.equal(I0, I1) and torch.equal(D0, D1)
+
+
+def test_indexflatl2_binary_fast_path_equals_float_kernel():
+    """BASELINE cfg 1 through the faiss-shaped surface: 0/1 float rows take the bit-packed Hamming engine and
+    return exactly what the float L2 kernel returns (same D, same I, ties included); anything non-binary falls
+    back to the float kernel."""
+    import rag_snvbert_b200.faiss_compat as faiss
+
+    panel = O.hapgen(1001, 5008, 1030).astype(np.float32)
+    q = O.hapgen(1002, 1000, 1030, founder_seed=1001).astype(np.float32)
+    fast = faiss.IndexFlatL2(1030)
+    fast.binary_min_work = 0  # force the Hamming engine at this (small) size
+    slow = faiss.IndexFlatL2(1030, binary_fast_path=False)
+    fast.add(panel[:3000])
+    fast.add(panel[3000:])
+    slow.add(panel)
+    for k in (1, 8):
+        Df, If = fast.search(q, k)
+        Ds, Is = slow.search(q, k)
+        assert fast.last_search_path == "hamming" and slow.last_search_path == "l2"
+        assert Df.dtype == np.float32 and If.dtype == np.int64
+        np.testing.assert_array_equal(If, Is)
+        np.testing.assert_array_equal(Df, Ds)
+    De, Ie = O.hamming_topk(panel.astype(np.uint8), q.astype(np.uint8), 8)
+    np.testing.assert_array_equal(If, Ie)
+    np.testing.assert_array_equal(Df, De.astype(np.float32))
+    # non-binary queries: float kernel
+    q2 = q.copy()
+    q2[0, 0] = 0.5
+    D2, I2 = fast.search(q2, 8)
+    assert fast.last_search_path == "l2"
+    np.testing.assert_array_equal(I2[1:], Is[1:])
+    # a non-binary row switches the index to the float kernel for good
+    fast.add(np.full((1, 1030), 0.25, dtype=np.float32))
+    fast.search(q, 8)
+    assert fast.last_search_path == "l2"
