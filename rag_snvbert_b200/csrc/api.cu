@@ -490,37 +490,51 @@ static int search_hamming(snv_index* idx, int w0, int nw, const void* q, int64_t
             if (chunk_w > nw) chunk_w = nw;
         }
     }
+    // chunk boundaries: uniform chunks of chunk_w windows; with many chunks the first and the last one are cut
+    // short (an eighth) so that the pipeline fills (first H2D + expansion) and drains (last scan + D2H) quickly
+    std::vector<int> bounds;
+    bounds.push_back(0);
+    {
+        const int nfull = (int)ceil_div(nw, chunk_w);
+        const int small = std::max(1, chunk_w / 8);
+        if (chunk_w < nw && nfull >= 8 && small < chunk_w) {
+            bounds.push_back(small);
+            int at = small;
+            while (nw - at > chunk_w + small) { at += chunk_w; bounds.push_back(at); }
+            if (nw - at > small) { at = nw - small; bounds.push_back(at); }
+        } else {
+            for (int at = chunk_w; at < nw; at += chunk_w) bounds.push_back(at);
+        }
+        bounds.push_back(nw);
+    }
+    const int nchunks = (int)bounds.size() - 1;
     size_t part_chunk = 0;  // partial-key bytes per chunk (row-split plans); every chunk gets its own slice
     size_t tc_chunk = 0;    // tensor-core engine workspace bytes per chunk
     {
         HammingSearchParams probe;
-        make_params(0, chunk_w, probe);
-        part_chunk = hamming_plan(probe);
-        if (part_chunk == (size_t)-1) return SNV_ERR_UNSUPPORTED;
-        const int last_w = nw - (int)(ceil_div(nw, chunk_w) - 1) * chunk_w;  // the (shorter) last chunk may split rows more
-        if (last_w != chunk_w) {
-            make_params(0, last_w, probe);
-            const size_t part_last = hamming_plan(probe);
-            if (part_last == (size_t)-1) return SNV_ERR_UNSUPPORTED;
-            part_chunk = std::max(part_chunk, part_last);
+        HammingTcPlan tplan;
+        int seen[4] = {0, 0, 0, 0};  // distinct chunk sizes (at most: short, full, remainder)
+        int nseen = 0;
+        for (int c = 0; c < nchunks; ++c) {
+            const int wc = bounds[c + 1] - bounds[c];
+            bool dup = false;
+            for (int i = 0; i < nseen; ++i) dup = dup || seen[i] == wc;
+            if (dup) continue;
+            if (nseen < 4) seen[nseen++] = wc;
+            make_params(0, wc, probe);
+            const size_t part = hamming_plan(probe);
+            if (part == (size_t)-1) return SNV_ERR_UNSUPPORTED;
+            part_chunk = std::max(part_chunk, part);
+            // tensor-core engine (chosen by shape): per-chunk slice for the query operand rows, biases, partial keys
+            const size_t tcb = hamming_tc_plan(probe, tplan);
+            if (tcb == (size_t)-1) return SNV_ERR_UNSUPPORTED;
+            tc_chunk = std::max(tc_chunk, tcb);
         }
         part_chunk = (size_t)round_up((int64_t)part_chunk, 256);
-        if (part_chunk) { rc = idx->ws_partial.reserve(part_chunk * (size_t)ceil_div(nw, chunk_w)); if (rc) return rc; }
-        // tensor-core engine (chosen by shape): per-chunk slice for the query operand rows, biases, partial keys
-        HammingTcPlan tplan;
-        make_params(0, chunk_w, probe);
-        tc_chunk = hamming_tc_plan(probe, tplan);
-        if (tc_chunk == (size_t)-1) return SNV_ERR_UNSUPPORTED;
-        if (last_w != chunk_w) {
-            make_params(0, last_w, probe);
-            const size_t tc_last = hamming_tc_plan(probe, tplan);
-            if (tc_last == (size_t)-1) return SNV_ERR_UNSUPPORTED;
-            tc_chunk = std::max(tc_chunk, tc_last);
-        }
+        if (part_chunk) { rc = idx->ws_partial.reserve(part_chunk * (size_t)nchunks); if (rc) return rc; }
         tc_chunk = (size_t)round_up((int64_t)tc_chunk, 1024);
-        if (tc_chunk) { rc = idx->ws_qops.reserve(tc_chunk * (size_t)ceil_div(nw, chunk_w)); if (rc) return rc; }
+        if (tc_chunk) { rc = idx->ws_qops.reserve(tc_chunk * (size_t)nchunks); if (rc) return rc; }
     }
-    const int nchunks = (int)ceil_div(nw, chunk_w);
     const bool piped = nchunks > 1;
     if (piped) {
         rc = ensure_pipe(idx);
@@ -530,8 +544,8 @@ static int search_hamming(snv_index* idx, int w0, int nw, const void* q, int64_t
     }
 
     for (int c = 0; c < nchunks; ++c) {
-        const int wb = c * chunk_w;
-        const int wc = std::min(chunk_w, nw - wb);
+        const int wb = bounds[c];
+        const int wc = bounds[c + 1] - wb;
         const int64_t r0 = (int64_t)wb * nq, rows = (int64_t)wc * nq;
         cudaStream_t cs = piped ? idx->pipe_stream[c % snv_index::kPipeStreams] : stream;
         HammingSearchParams p;
