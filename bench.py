@@ -197,7 +197,7 @@ def cpu_reference_sample(a, seconds):
         rate = rng.uniform(0.1, 0.9, size=(a.queries, 1))
         M = O.pack_bits_u32((rng.random((a.queries, a.sites)) >= rate).astype(np.uint8), stride)[None]
     # calibrate on a small slice, then size the sample for ~`seconds`
-    nq0 = min(a.queries, max(threads * 4, 64))
+    nq0 = a.queries  # one full window: a smaller slice under-reports the rate and the sample comes out short
     cbind.hamming_topk_packed(P, Qfull[:, :nq0], a.k, None if M is None else M[:, :nq0], words=s)
     t0 = time.perf_counter()
     cbind.hamming_topk_packed(P, Qfull[:, :nq0], a.k, None if M is None else M[:, :nq0], words=s)
