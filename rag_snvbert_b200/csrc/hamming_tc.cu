@@ -172,7 +172,11 @@ struct TcParams {
     int64_t n;               // panel rows per window
     int words, kblocks;      // packed words in use (= MMAs per tile), k-blocks of 4 words
     int n_tiles, nsplit, tiles_per_split;
-    int items;               // nw * qtiles * nsplit
+    int items;               // nw * qtiles * nsplit (+ the extra pieces of the tail items)
+    // tail split (nsplit == 1 only): the last `items - items_a` pieces belong to trailing (window, query tile) items
+    // that are cut into tail_split row ranges of tail_tiles tiles, so that the last round of items fills every SM
+    int items_a, tail_split, tail_tiles;
+    int64_t tail_row0;       // first query row of the tail items (their partial keys are indexed from it)
     int idx_bits, k, one;
     int64_t id_offset;
     const int32_t* q_bias;   // [nw * nq] popc(q & m)
@@ -184,10 +188,23 @@ struct TcParams {
 
 struct Item {
     int w, qt, split, t0, ntiles;
+    int out_split;  // 1: this piece covers the whole panel and writes final results; > 1: partial keys [row][out_split][kt]
 };
 __device__ __forceinline__ Item decode_item(const TcParams& p, int item, int qt_mul = 1, int qt_add = 0)
 {
     Item it;
+    if (p.tail_split > 1 && item >= p.items_a) {
+        const int piece = item - p.items_a;
+        it.split = piece % p.tail_split;
+        const int base_item = p.items_a + piece / p.tail_split;
+        it.qt = (base_item % p.qtiles) * qt_mul + qt_add;
+        it.w = base_item / p.qtiles;
+        it.t0 = it.split * p.tail_tiles;
+        const int t1 = it.t0 + p.tail_tiles < p.n_tiles ? it.t0 + p.tail_tiles : p.n_tiles;
+        it.ntiles = t1 - it.t0;
+        it.out_split = p.tail_split;
+        return it;
+    }
     it.split = item % p.nsplit;
     item /= p.nsplit;
     it.qt = (item % p.qtiles) * qt_mul + qt_add;
@@ -195,6 +212,7 @@ __device__ __forceinline__ Item decode_item(const TcParams& p, int item, int qt_
     it.t0 = it.split * p.tiles_per_split;
     const int t1 = it.t0 + p.tiles_per_split < p.n_tiles ? it.t0 + p.tiles_per_split : p.n_tiles;
     it.ntiles = t1 - it.t0;
+    it.out_split = p.nsplit;
     return it;
 }
 
@@ -768,7 +786,7 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                 if (active) {
                     const uint32_t idx_mask = (1u << idx_bits) - 1u;
                     const int64_t r0 = (int64_t)it.t0 * BN;
-                    if (p.nsplit == 1) {
+                    if (it.out_split == 1) {
 #pragma unroll
                         for (int i = 0; i < KT; ++i) {
                             if (i < p.k) {
@@ -782,7 +800,9 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                             }
                         }
                     } else {
-                        uint64_t* out = p.partial + (q * p.nsplit + it.split) * KT;
+                        // tail pieces index their partial keys from the first tail row
+                        const int64_t qrel = (p.tail_split > 1 && p.nsplit == 1) ? q - p.tail_row0 : q;
+                        uint64_t* out = p.partial + (qrel * it.out_split + it.split) * KT;
 #pragma unroll
                         for (int i = 0; i < KT; ++i) {
                             const uint32_t key = best[i];
@@ -1013,10 +1033,36 @@ size_t hamming_tc_plan(const HammingSearchParams& p, HammingTcPlan& plan)
         set_error("hamming search: grid too large");
         return (size_t)-1;
     }
+    // Tail split: with unsplit items, `base mod units` items are left for a last round that keeps only that many
+    // SMs (pairs) busy for a whole item.  Cutting just those trailing items into floor(units / rem) row ranges makes
+    // the last round short instead (cfg 5: 320 pair items on 74 pairs = 4 rounds + 24 items -> 4.33 rounds, not 5).
+    plan.tail_items = 0;
+    plan.tail_split = 0;
+    plan.tail_tiles = 0;
+    const char* no_tail = getenv("SNV_TC_NO_TAIL_SPLIT");
+    if (plan.nsplit == 1 && base > units && base % units != 0 && !(no_tail && no_tail[0] == '1')) {
+        const int64_t R = base / units, rem = base % units;
+        int64_t s2 = std::min<int64_t>(std::min<int64_t>(units / rem, plan.n_tiles / 2), 32);
+        if (s2 >= 2) {
+            const int64_t per = ceil_div(plan.n_tiles, s2);
+            s2 = ceil_div(plan.n_tiles, per);
+            const double ins = plan.kt == 8 ? 0.04 : 0.3;
+            auto item_cost = [&](double tiles) { return tiles + 0.25 + ins * plan.kt * (1.0 + std::log(std::max(1.0, tiles * BN / plan.kt))); };
+            const double now = (double)(R + 1) * item_cost((double)plan.n_tiles);
+            const double then = (double)R * item_cost((double)plan.n_tiles) + item_cost((double)per) +
+                                3.5e-5 * (double)rem * (plan.engine == 4 ? 2 * BM : BM) * s2 * plan.kt;
+            if (s2 >= 2 && then < 0.97 * now) {
+                plan.tail_items = (int)rem;
+                plan.tail_split = (int)s2;
+                plan.tail_tiles = (int)per;
+            }
+        }
+    }
     const int64_t rows = (int64_t)p.nw * p.nq;
     plan.off_bias = round_up(rows * plan.kblocks * kRowBytes, 256);
     plan.off_partial = plan.off_bias + round_up(rows * 4, 256);
-    plan.off_panel = plan.off_partial + (plan.nsplit > 1 ? round_up(rows * plan.nsplit * plan.kt * 8, 256) : 0);
+    plan.off_panel = plan.off_partial + (plan.nsplit > 1 ? round_up(rows * plan.nsplit * plan.kt * 8, 256)
+                                                          : round_up((int64_t)plan.tail_items * (plan.engine == 4 ? 2 * BM : BM) * plan.tail_split * plan.kt * 8, 256));
     size_t total = plan.off_panel;
     if (plan.engine == 2) total += (size_t)p.nw * p.n * plan.kblocks * kRowBytes;
     return total + 1024;
@@ -1075,6 +1121,20 @@ int hamming_tc_launch(const HammingSearchParams& p, const HammingTcPlan& plan, v
     tp.words = p.words; tp.kblocks = plan.kblocks;
     tp.n_tiles = plan.n_tiles; tp.nsplit = plan.nsplit; tp.tiles_per_split = plan.tiles_per_split;
     tp.items = p.nw * tp.qtiles * plan.nsplit;
+    tp.items_a = tp.items;
+    tp.tail_split = 0;
+    tp.tail_tiles = 0;
+    tp.tail_row0 = 0;
+    int64_t tail_rows = 0;
+    if (plan.tail_split > 1) {
+        tp.items_a = tp.items - plan.tail_items;
+        tp.tail_split = plan.tail_split;
+        tp.tail_tiles = plan.tail_tiles;
+        tp.items = tp.items_a + plan.tail_items * plan.tail_split;
+        const int64_t w_a = tp.items_a / tp.qtiles, qt_a = tp.items_a % tp.qtiles;
+        tp.tail_row0 = w_a * p.nq + qt_a * (pair ? 2 * BM : BM);
+        tail_rows = rows - tp.tail_row0;
+    }
     tp.idx_bits = plan.idx_bits; tp.k = p.k; tp.one = 1;
     tp.id_offset = p.id_offset;
     tp.q_bias = q_bias;
@@ -1092,6 +1152,11 @@ int hamming_tc_launch(const HammingSearchParams& p, const HammingTcPlan& plan, v
     if (rc) return rc;
     if (plan.nsplit > 1)
         return merge_keys_launch(partial, plan.nsplit, plan.kt, rows, p.k, p.id_offset, false, p.D_i32, p.D_f32, p.I, stream);
+    if (plan.tail_split > 1 && tail_rows > 0) {
+        const int64_t o = tp.tail_row0 * p.k;
+        return merge_keys_launch(partial, plan.tail_split, plan.kt, tail_rows, p.k, p.id_offset, false, p.D_i32 ? p.D_i32 + o : nullptr,
+                                 p.D_f32 ? p.D_f32 + o : nullptr, p.I + o, stream);
+    }
     return SNV_OK;
 }
 

@@ -49,6 +49,7 @@ int hamming_launch(const HammingSearchParams& p, cudaStream_t stream);
 struct HammingTcPlan {
     int engine;  // 0 = popcount kernel (hamming_launch), 1 = tcgen05 with in-SM bit expansion, 2 = bring-up variant
     int kt, kblocks, qtiles, n_tiles, nsplit, tiles_per_split, idx_bits;
+    int tail_items, tail_split, tail_tiles;     // trailing items cut into row ranges so that the last round fills the machine
     int64_t off_bias, off_partial, off_panel;  // byte offsets inside the workspace
 };
 // Fills `plan` (p needs its shape fields and mask null-ness only); returns the workspace bytes the

@@ -215,3 +215,36 @@ def test_randomised_shapes_all_engines_agree():
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_engines.py")], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert '"mismatches": 0' in r.stdout
+
+
+@pytest.mark.parametrize("eng", ["tc4x2", "tc4"])
+def test_tail_split_of_trailing_items(eng):
+    """80 (window, query-tile pair) items on 74 SM pairs (160 items on 148 SMs for the single-CTA kernel): the
+    trailing items are cut into row ranges (partial keys + merge) - results must equal the popcount scan."""
+    import torch
+
+    import bench
+    from rag_snvbert_b200 import WindowedHammingIndex
+
+    W, N, S, Q, k = 10, 5008, 1030, 2000, 8
+    dev = torch.device("cuda", 0)
+    panel = bench.gen_windows_device(torch, dev, 2000, W, N, S, 777)
+    queries = bench.gen_windows_device(torch, dev, 5000, W, Q, S, 777)
+    masks = bench.gen_masks_device(torch, dev, 8000, W, Q, S)
+    idx = WindowedHammingIndex(S, W, 0)
+    idx.add(panel)
+    out = {}
+    old = os.environ.get("SNV_HAMMING_ENGINE")
+    try:
+        for e in ("popc", eng):
+            os.environ["SNV_HAMMING_ENGINE"] = e
+            D, I = idx.search(queries, k)
+            Dm, Im = idx.search(queries, 32, observed=masks)
+            out[e] = [t.clone() for t in (D, I, Dm, Im)]
+    finally:
+        if old is None:
+            del os.environ["SNV_HAMMING_ENGINE"]
+        else:
+            os.environ["SNV_HAMMING_ENGINE"] = old
+    for a, b in zip(out["popc"], out[eng]):
+        assert torch.equal(a, b)
