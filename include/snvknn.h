@@ -217,10 +217,25 @@ int snv_profile_enable(int on);
 int snv_profile_last_ms(float* ms);
 
 /* Which engine the most recent Hamming search of the calling process ran on:
- * 0 = popcount scan (hamming_topk_kernel), 1 = tensor cores (hamming_tc_kernel: fp8 tcgen05.mma over the
- * bit-packed panel expanded in shared memory), 2 = its bring-up variant, -1 = none yet.  The choice is made per
- * call from the shape (many queries per window -> tensor cores); SNV_HAMMING_ENGINE=popc|tc forces one. */
+ * 0 = popcount scan (hamming_topk_kernel); 1 = tensor cores, fp8 operands (hamming_tc_kernel: tcgen05.mma over the
+ * bit-packed panel expanded in shared memory); 2 = its bring-up variant (panel expanded in HBM); 3 = tensor cores,
+ * fp4 block-scaled operands; 4 = fp4 on CTA pairs (cta_group::2); -1 = none yet.  The choice is made per call from
+ * the shape (many queries per window -> tensor cores); SNV_HAMMING_ENGINE=popc|tc|tc_hbm|tc4|tc4x2 forces one. */
 int snv_last_hamming_engine(void);
+
+/* Host-only view of the tensor-core engine's planner (no device work; test hook for tests/test_planner.py): for a
+ * uniform search of n_windows x nq queries against n rows of d sites at top-k, writes
+ * plan_out[12] = (engine, k capacity, k-blocks, query tiles, panel tiles, row splits, tiles per split, id bits,
+ * tail items, tail split, tail tiles, workspace KiB) and up to `cap` work items
+ * items_out[i][8] = (window, query tile, first panel tile, tiles, piece, pieces, partial-key row base, CTA slot),
+ * enumerated with the decoder the kernel itself uses; *n_items = how many there are (may exceed cap). */
+int snv_debug_hamming_plan(int n_windows, int nq, int64_t n, int d, int k, int32_t* plan_out, int64_t* items_out,
+                           int64_t cap, int64_t* n_items);
+
+/* Host-only: the window-chunk boundaries snv_index_search would pipeline that search over (host_io != 0: queries or
+ * results in host memory; 0: everything device resident = one chunk).  bounds_out[0 .. *n_bounds) = 0 < ... < n_windows. */
+int snv_debug_hamming_chunks(int n_windows, int nq, int64_t n, int d, int k, int host_io, int32_t* bounds_out, int cap,
+                             int* n_bounds);
 
 #ifdef __cplusplus
 }

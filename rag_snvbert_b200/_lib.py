@@ -54,6 +54,8 @@ SYMBOLS = {
     "snv_profile_enable": (_i, [_i]),
     "snv_profile_last_ms": (_i, [_c.POINTER(_c.c_float)]),
     "snv_last_hamming_engine": (_i, []),
+    "snv_debug_hamming_plan": (_i, [_i, _i, _i64, _i, _i, _vp, _vp, _i64, _vp]),
+    "snv_debug_hamming_chunks": (_i, [_i, _i, _i64, _i, _i, _i, _vp, _i, _vp]),
 }
 
 _lib = None
@@ -120,8 +122,37 @@ def launch_count() -> int:
 
 
 def last_hamming_engine() -> int:
-    """0 = popcount scan, 1 = tensor cores, 2 = bring-up variant, -1 = no Hamming search yet."""
+    """0 = popcount scan, 1 = tcgen05 fp8, 2 = its bring-up variant, 3 = tcgen05 fp4, 4 = fp4 on CTA pairs, -1 = none yet."""
     return int(lib().snv_last_hamming_engine())
+
+
+def debug_hamming_plan(n_windows: int, nq: int, n: int, d: int, k: int, cap: int = 1 << 16):
+    """Planner of the tensor-core engine, host only (no GPU needed): (plan dict, items int64 [n_items, 8]).
+    items columns: window, query tile, first panel tile, tiles, piece, pieces, partial-key row base, CTA slot."""
+    import numpy as np
+
+    plan = np.zeros(12, np.int32)
+    items = np.zeros((cap, 8), np.int64)
+    cnt = _c.c_int64(0)
+    check(lib().snv_debug_hamming_plan(n_windows, nq, n, d, k, plan.ctypes.data, items.ctypes.data, cap, _c.addressof(cnt)),
+          "snv_debug_hamming_plan")
+    if cnt.value > cap:
+        return debug_hamming_plan(n_windows, nq, n, d, k, cap=int(cnt.value))
+    names = ["engine", "kt", "kblocks", "qtiles", "n_tiles", "nsplit", "tiles_per_split", "idx_bits", "tail_items",
+             "tail_split", "tail_tiles", "workspace_kib"]
+    return dict(zip(names, (int(v) for v in plan))), items[: cnt.value]
+
+
+def debug_hamming_chunks(n_windows: int, nq: int, n: int, d: int, k: int, host_io: bool = True):
+    """Window-chunk boundaries the host-buffer pipeline of snv_index_search uses for that search (host only)."""
+    import numpy as np
+
+    cap = n_windows + 2
+    out = np.zeros(cap, np.int32)
+    cnt = _c.c_int(0)
+    check(lib().snv_debug_hamming_chunks(n_windows, nq, n, d, k, 1 if host_io else 0, out.ctypes.data, cap, _c.addressof(cnt)),
+          "snv_debug_hamming_chunks")
+    return out[: cnt.value].copy()
 
 
 def profile_enable(on: bool) -> None:

@@ -155,6 +155,56 @@ int snv_profile_enable(int on)
 
 int snv_last_hamming_engine(void) { return g_last_hamming_engine; }
 
+static int hamming_chunk_bounds(const HammingSearchParams& p, bool host_io, std::vector<int>& bounds);
+
+int snv_debug_hamming_plan(int n_windows, int nq, int64_t n, int d, int k, int32_t* plan_out, int64_t* items_out,
+                           int64_t cap, int64_t* n_items)
+{
+    if (n_windows < 0 || nq < 0 || n < 0 || d < 1 || k < 1 || !plan_out || !n_items || (cap > 0 && !items_out)) {
+        set_error("snv_debug_hamming_plan: bad arguments");
+        return SNV_ERR_INVALID;
+    }
+    HammingSearchParams p{};
+    p.d = d;
+    p.words = (d + 31) / 32;
+    p.stride = snv_packed_stride(d);
+    p.n = n;
+    p.nq = nq;
+    p.nw = n_windows;
+    p.k = k;
+    HammingTcPlan plan;
+    const size_t ws = hamming_tc_plan(p, plan);
+    if (ws == (size_t)-1) return SNV_ERR_INVALID;
+    const int32_t f[12] = {plan.engine, plan.kt, plan.kblocks, plan.qtiles, plan.n_tiles, plan.nsplit, plan.tiles_per_split,
+                           plan.idx_bits, plan.tail_items, plan.tail_split, plan.tail_tiles, (int32_t)std::min<size_t>(ws >> 10, 0x7fffffff)};
+    for (int i = 0; i < 12; ++i) plan_out[i] = f[i];
+    *n_items = hamming_tc_debug_items(p, plan, items_out, cap);
+    return SNV_OK;
+}
+
+int snv_debug_hamming_chunks(int n_windows, int nq, int64_t n, int d, int k, int host_io, int32_t* bounds_out, int cap,
+                             int* n_bounds)
+{
+    if (n_windows < 1 || nq < 1 || n < 0 || d < 1 || k < 1 || !n_bounds || (cap > 0 && !bounds_out)) {
+        set_error("snv_debug_hamming_chunks: bad arguments");
+        return SNV_ERR_INVALID;
+    }
+    HammingSearchParams p{};
+    p.d = d;
+    p.words = (d + 31) / 32;
+    p.stride = snv_packed_stride(d);
+    p.n = n;
+    p.nq = nq;
+    p.nw = n_windows;
+    p.k = k;
+    std::vector<int> bounds;
+    const int rc = hamming_chunk_bounds(p, host_io != 0, bounds);
+    if (rc) return rc;
+    *n_bounds = (int)bounds.size();
+    for (int i = 0; i < (int)bounds.size() && i < cap; ++i) bounds_out[i] = bounds[i];
+    return SNV_OK;
+}
+
 int snv_profile_last_ms(float* ms)
 {
     if (!ms) { set_error("snv_profile_last_ms: null"); return SNV_ERR_INVALID; }
@@ -411,6 +461,57 @@ static int ensure_pipe(snv_index* idx)
     return SNV_OK;
 }
 
+// Window-chunk boundaries of one uniform Hamming search (p: the whole call, p.nw windows).  Host buffers are pipelined
+// over internal streams chunk by chunk (H2D of chunk i+1 | scan of chunk i | D2H of chunk i-1); device-resident
+// searches run as one chunk.  bounds = 0 = b_0 < b_1 < ... = p.nw.
+static int hamming_chunk_bounds(const HammingSearchParams& p, bool host_io, std::vector<int>& bounds)
+{
+    const int nw = p.nw;
+    const int64_t nq = p.nq;
+    int chunk_w = nw;
+    if (host_io && nw >= 8) {
+        const int64_t qtiles = ceil_div(nq, 128);
+        HammingTcPlan tprobe;
+        if (hamming_tc_plan(p, tprobe) == (size_t)-1) return SNV_ERR_UNSUPPORTED;
+        if (tprobe.engine) {
+            // tensor-core engine: persistent CTAs (or CTA pairs) take (window, query tile [pair]) items round-robin,
+            // so a chunk should hold a whole number of items per SM (pair); ~24 chunks keep the pipeline's fill
+            // (first H2D) and drain (last D2H) short.  (Chunking device-resident searches to overlap the query
+            // expansion with the previous chunk's scan was measured: < 1 %, not worth the extra launches.)
+            const int64_t per_w = tprobe.engine == 4 ? ceil_div(qtiles, 2) : qtiles;
+            const int64_t units = tprobe.engine == 4 ? kNumSMs / 2 : kNumSMs;
+            int64_t a = units, b = per_w;
+            while (b) { const int64_t t = a % b; a = b; b = t; }
+            const int64_t unit = units / a;  // windows per chunk so that items per chunk is a multiple of the units
+            const int64_t target = 24;
+            int64_t cw = std::max<int64_t>(unit, nw / target / unit * unit);
+            if (cw * per_w < 2 * units) cw = ceil_div(2 * units, per_w);
+            chunk_w = (int)std::min<int64_t>(cw, nw);
+        } else {
+            // popcount engine: a chunk keeps enough CTAs (>= 16 per SM) that the scan needs no row split
+            chunk_w = (int)std::max<int64_t>(ceil_div(nw, 16), ceil_div((int64_t)kNumSMs * 16, qtiles));
+            if (chunk_w > nw) chunk_w = nw;
+        }
+    }
+    // uniform chunks of chunk_w windows; with many chunks the first and the last one are cut short (an eighth) so
+    // that the pipeline fills (first H2D + expansion) and drains (last scan + D2H) quickly
+    bounds.clear();
+    bounds.push_back(0);
+    if (nw <= 0) { bounds.push_back(0); return SNV_OK; }
+    const int nfull = (int)ceil_div(nw, chunk_w);
+    const int small = std::max(1, chunk_w / 8);
+    if (chunk_w < nw && nfull >= 8 && small < chunk_w) {
+        bounds.push_back(small);
+        int at = small;
+        while (nw - at > chunk_w + small) { at += chunk_w; bounds.push_back(at); }
+        if (nw - at > small) { at = nw - small; bounds.push_back(at); }
+    } else {
+        for (int at = chunk_w; at < nw; at += chunk_w) bounds.push_back(at);
+    }
+    bounds.push_back(nw);
+    return SNV_OK;
+}
+
 static int search_hamming(snv_index* idx, int w0, int nw, const void* q, int64_t nq, int q_dtype,
                           const void* mask, int mask_mode, int k, int64_t id_offset, int32_t* D_i32,
                           float* D_f32, int64_t* I, unsigned flags, cudaStream_t stream)
@@ -450,7 +551,6 @@ static int search_hamming(snv_index* idx, int w0, int nw, const void* q, int64_t
 
     // ---- chunking: host buffers are pipelined over internal streams, window chunk by window chunk;
     // (popcount engine) a chunk keeps enough CTAs (>= 16 per SM) that the scan needs no row split
-    int chunk_w = nw;
     auto make_params = [&](int wb, int wc, HammingSearchParams& p) {
         p = HammingSearchParams{};
         p.panel = idx->panel + (int64_t)(w0 + wb) * idx->cap * idx->stride;
@@ -465,47 +565,12 @@ static int search_hamming(snv_index* idx, int w0, int nw, const void* q, int64_t
         p.id_offset = id_offset;
         p.mask = mask_mode != SNV_MASK_NONE || tokens ? (const uint32_t*)1 : nullptr;  // plan only needs null-ness
     };
-    if ((!q_dev || !out_dev) && nw >= 8) {
-        const int64_t qtiles = ceil_div(nq, 128);
-        HammingSearchParams probe;
-        HammingTcPlan tprobe;
-        make_params(0, nw, probe);
-        if (hamming_tc_plan(probe, tprobe) == (size_t)-1) return SNV_ERR_UNSUPPORTED;
-        if (tprobe.engine) {
-            // tensor-core engine: persistent CTAs (or CTA pairs) take (window, query tile [pair]) items round-robin,
-            // so a chunk should hold a whole number of items per SM (pair); ~24 chunks keep the pipeline's fill
-            // (first H2D) and drain (last D2H) short.  (Chunking device-resident searches to overlap the query
-            // expansion with the previous chunk's scan was measured: < 1 %, not worth the extra launches.)
-            const int64_t per_w = tprobe.engine == 4 ? ceil_div(qtiles, 2) : qtiles;
-            const int64_t units = tprobe.engine == 4 ? kNumSMs / 2 : kNumSMs;
-            int64_t a = units, b = per_w;
-            while (b) { const int64_t t = a % b; a = b; b = t; }
-            const int64_t unit = units / a;  // windows per chunk so that items per chunk is a multiple of the units
-            const int64_t target = 24;
-            int64_t cw = std::max<int64_t>(unit, nw / target / unit * unit);
-            if (cw * per_w < 2 * units) cw = ceil_div(2 * units, per_w);
-            chunk_w = (int)std::min<int64_t>(cw, nw);
-        } else {
-            chunk_w = (int)std::max<int64_t>(ceil_div(nw, 16), ceil_div((int64_t)kNumSMs * 16, qtiles));
-            if (chunk_w > nw) chunk_w = nw;
-        }
-    }
-    // chunk boundaries: uniform chunks of chunk_w windows; with many chunks the first and the last one are cut
-    // short (an eighth) so that the pipeline fills (first H2D + expansion) and drains (last scan + D2H) quickly
     std::vector<int> bounds;
-    bounds.push_back(0);
     {
-        const int nfull = (int)ceil_div(nw, chunk_w);
-        const int small = std::max(1, chunk_w / 8);
-        if (chunk_w < nw && nfull >= 8 && small < chunk_w) {
-            bounds.push_back(small);
-            int at = small;
-            while (nw - at > chunk_w + small) { at += chunk_w; bounds.push_back(at); }
-            if (nw - at > small) { at = nw - small; bounds.push_back(at); }
-        } else {
-            for (int at = chunk_w; at < nw; at += chunk_w) bounds.push_back(at);
-        }
-        bounds.push_back(nw);
+        HammingSearchParams probe;
+        make_params(0, nw, probe);
+        rc = hamming_chunk_bounds(probe, !q_dev || !out_dev, bounds);
+        if (rc) return rc;
     }
     const int nchunks = (int)bounds.size() - 1;
     size_t part_chunk = 0;  // partial-key bytes per chunk (row-split plans); every chunk gets its own slice

@@ -190,7 +190,7 @@ struct Item {
     int w, qt, split, t0, ntiles;
     int out_split;  // 1: this piece covers the whole panel and writes final results; > 1: partial keys [row][out_split][kt]
 };
-__device__ __forceinline__ Item decode_item(const TcParams& p, int item, int qt_mul = 1, int qt_add = 0)
+__host__ __device__ __forceinline__ Item decode_item(const TcParams& p, int item, int qt_mul = 1, int qt_add = 0)
 {
     Item it;
     if (p.tail_split > 1 && item >= p.items_a) {
@@ -1068,6 +1068,55 @@ size_t hamming_tc_plan(const HammingSearchParams& p, HammingTcPlan& plan)
     return total + 1024;
 }
 
+// The item bookkeeping of a launch (everything decode_item reads); returns the query rows covered by tail items.
+static int64_t fill_item_fields(const HammingSearchParams& p, const HammingTcPlan& plan, TcParams& tp)
+{
+    const bool pair = plan.engine == 4;
+    const int64_t rows = (int64_t)p.nw * p.nq;
+    tp.nw = p.nw; tp.nq = p.nq; tp.qtiles = pair ? (int)ceil_div(plan.qtiles, 2) : plan.qtiles;
+    tp.n = p.n;
+    tp.words = p.words; tp.kblocks = plan.kblocks;
+    tp.n_tiles = plan.n_tiles; tp.nsplit = plan.nsplit; tp.tiles_per_split = plan.tiles_per_split;
+    tp.items = p.nw * tp.qtiles * plan.nsplit;
+    tp.items_a = tp.items;
+    tp.tail_split = 0;
+    tp.tail_tiles = 0;
+    tp.tail_row0 = 0;
+    int64_t tail_rows = 0;
+    if (plan.tail_split > 1) {
+        tp.items_a = tp.items - plan.tail_items;
+        tp.tail_split = plan.tail_split;
+        tp.tail_tiles = plan.tail_tiles;
+        tp.items = tp.items_a + plan.tail_items * plan.tail_split;
+        const int64_t w_a = tp.items_a / tp.qtiles, qt_a = tp.items_a % tp.qtiles;
+        tp.tail_row0 = w_a * p.nq + qt_a * (pair ? 2 * BM : BM);
+        tail_rows = rows - tp.tail_row0;
+    }
+    return tail_rows;
+}
+
+// Host-side enumeration of the work items a launch with this plan would run, through the same decode_item the
+// kernel uses (tests/test_planner.py checks that they tile every (window, query tile, panel tile) exactly once).
+// out [cap][8] = (window, query tile, first panel tile, tiles, piece, pieces, partial-key row base, CTA slot).
+int64_t hamming_tc_debug_items(const HammingSearchParams& p, const HammingTcPlan& plan, int64_t* out, int64_t cap)
+{
+    if (!plan.engine) return 0;
+    TcParams tp{};
+    fill_item_fields(p, plan, tp);
+    const bool pair = plan.engine == 4;
+    const int ctas = pair ? std::min(tp.items, kNumSMs / 2) : std::min(tp.items, kNumSMs);
+    int64_t n = 0;
+    for (int item = 0; item < tp.items; ++item)
+        for (int r = 0; r < (pair ? 2 : 1); ++r, ++n) {
+            if (n >= cap) continue;
+            const Item it = decode_item(tp, item, pair ? 2 : 1, r);
+            const bool tail = tp.tail_split > 1 && item >= tp.items_a;
+            const int64_t v[8] = {it.w, it.qt, it.t0, it.ntiles, it.split, it.out_split, tail ? tp.tail_row0 : 0, item % ctas};
+            for (int j = 0; j < 8; ++j) out[n * 8 + j] = v[j];
+        }
+    return n;
+}
+
 int hamming_tc_launch(const HammingSearchParams& p, const HammingTcPlan& plan, void* ws, cudaStream_t stream)
 {
     if (p.nw <= 0 || p.nq <= 0) return SNV_OK;
@@ -1116,25 +1165,7 @@ int hamming_tc_launch(const HammingSearchParams& p, const HammingTcPlan& plan, v
     }
     TcParams tp{};
     const bool pair = plan.engine == 4;
-    tp.nw = p.nw; tp.nq = p.nq; tp.qtiles = pair ? (int)ceil_div(plan.qtiles, 2) : plan.qtiles;
-    tp.n = p.n;
-    tp.words = p.words; tp.kblocks = plan.kblocks;
-    tp.n_tiles = plan.n_tiles; tp.nsplit = plan.nsplit; tp.tiles_per_split = plan.tiles_per_split;
-    tp.items = p.nw * tp.qtiles * plan.nsplit;
-    tp.items_a = tp.items;
-    tp.tail_split = 0;
-    tp.tail_tiles = 0;
-    tp.tail_row0 = 0;
-    int64_t tail_rows = 0;
-    if (plan.tail_split > 1) {
-        tp.items_a = tp.items - plan.tail_items;
-        tp.tail_split = plan.tail_split;
-        tp.tail_tiles = plan.tail_tiles;
-        tp.items = tp.items_a + plan.tail_items * plan.tail_split;
-        const int64_t w_a = tp.items_a / tp.qtiles, qt_a = tp.items_a % tp.qtiles;
-        tp.tail_row0 = w_a * p.nq + qt_a * (pair ? 2 * BM : BM);
-        tail_rows = rows - tp.tail_row0;
-    }
+    const int64_t tail_rows = fill_item_fields(p, plan, tp);
     tp.idx_bits = plan.idx_bits; tp.k = p.k; tp.one = 1;
     tp.id_offset = p.id_offset;
     tp.q_bias = q_bias;

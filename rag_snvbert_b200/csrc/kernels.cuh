@@ -47,7 +47,8 @@ int hamming_launch(const HammingSearchParams& p, cudaStream_t stream);
 
 // Tensor-core engine for the same search (hamming_tc.cu): chosen per call by shape.
 struct HammingTcPlan {
-    int engine;  // 0 = popcount kernel (hamming_launch), 1 = tcgen05 with in-SM bit expansion, 2 = bring-up variant
+    int engine;  // 0 = popcount kernel (hamming_launch), 1 = tcgen05 fp8 with in-SM bit expansion, 2 = its bring-up variant,
+                 // 3 = tcgen05 fp4 (block-scaled), 4 = fp4 on CTA pairs
     int kt, kblocks, qtiles, n_tiles, nsplit, tiles_per_split, idx_bits;
     int tail_items, tail_split, tail_tiles;     // trailing items cut into row ranges so that the last round fills the machine
     int64_t off_bias, off_partial, off_panel;  // byte offsets inside the workspace
@@ -56,6 +57,8 @@ struct HammingTcPlan {
 // launch needs (0 when plan.engine == 0), or (size_t)-1 with the error set.
 size_t hamming_tc_plan(const HammingSearchParams& p, HammingTcPlan& plan);
 int hamming_tc_launch(const HammingSearchParams& p, const HammingTcPlan& plan, void* ws, cudaStream_t stream);
+// host only: the work items of that launch, out [cap][8]; returns how many there are (see hamming_tc.cu)
+int64_t hamming_tc_debug_items(const HammingSearchParams& p, const HammingTcPlan& plan, int64_t* out, int64_t cap);
 
 // ---------------------------------------------------------------- key merge / finalize
 // keys [nq_total][parts][kin] (uint64: hi = distance bits, lo = id, ~0 = empty) -> top k.
