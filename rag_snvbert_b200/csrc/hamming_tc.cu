@@ -73,9 +73,9 @@ constexpr int kAccStages = 2;
 constexpr int kTmemCols = 512;
 constexpr int kExpWarps = 4;
 constexpr int kExpThreads = kExpWarps * 32;
-// Epilogue shape by top-k width: k <= 8 runs 16 epilogue warps (4 per SM sub-partition: the selection is bound
-// by instruction latency, not throughput, so more warps hide it) on 64-column parts in 16-column groups; k <= 32
-// keeps 8 warps (register budget) on 128-column parts in 32-column groups.
+// Epilogue shape: 8 warps (2 per SM sub-partition) on 128-column parts of every tile, scored in 32-column groups.
+// (16 warps on 64-column parts - SNV_TC_EPI16, CTA-pair kernel at k <= 8 only - were measured slower: the kernel is
+// bound by issued instructions, more epilogue warps only add contention; profiles/r1_tc_breakdown_variants.txt.)
 template <int KT, bool PAIR = false>
 struct Epi {
     static constexpr int kWarps = (KT == 8 && PAIR && SNV_TC_EPI16) ? 16 : 8;

@@ -6,7 +6,7 @@ import torch
 from rag_snvbert_b200 import WindowedHammingIndex, _lib
 import bench
 
-W = int(os.environ.get("W", "296")); N, S, Q, k = 5008, 1030, 2000, 8
+W = int(os.environ.get("W", "296")); N, S, Q, k = (int(os.environ.get(n, d)) for n, d in (("N", 5008), ("S", 1030), ("Q", 2000), ("K", 8)))
 dev = torch.device("cuda", 0)
 panel = bench.gen_windows_device(torch, dev, 2000, W, N, S, 777)
 queries = bench.gen_windows_device(torch, dev, 5000, W, Q, S, 777)
@@ -26,4 +26,4 @@ torch.cuda.synchronize()
 kernel_ms = _lib.profile_last_ms()
 _lib.profile_enable(False)
 print(json.dumps({"lib": os.path.basename(_lib.so_path()), "env": {k: v for k, v in os.environ.items() if k.startswith("SNV_")},
-                  "W": W, "ms": ms, "kernel_ms": kernel_ms, "pairs_per_s": W * N * Q / ms * 1e3, "checksum": int(I.sum().item()), "dsum": int(D.sum().item())}))
+                  "W": W, "N": N, "Q": Q, "k": k, "ms": ms, "kernel_ms": kernel_ms, "pairs_per_s": W * N * Q / ms * 1e3, "checksum": int(I.sum().item()), "dsum": int(D.sum().item())}))
