@@ -381,13 +381,13 @@ def run_ours(a):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     sm_mhz = (clocks or {}).get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
     traffic = None
-    if engine in (1, 2, 3, 4):
+    if engine in (1, 2, 3, 4, 5):
         # tensor-core engine: the scan is a dense contraction (2 * pairs * sites FLOP, what faiss' sgemm path
         # computes) on tcgen05 with exact narrow-float operands.  Peak = the measured bf16 GEMM peak x 2 (fp8,
         # kind::f8f6f4) or x 4 (fp4, kind::mxf4): MEASURED_PEAKS.json has no fp8 / fp4 figure, the nominal
         # ratios are 2x and 4x.
         fp4 = engine >= 3
-        kname = "hamming_tc_kernel<K=8,%s>" % ({4: "fp4,cta-pair", 3: "fp4"}.get(engine, "fp8"))
+        kname = "hamming_tc_kernel<K=8,%s>" % ({5: "fp4,cta-pair,tmemA", 4: "fp4,cta-pair", 3: "fp4"}.get(engine, "fp8"))
         bf16 = float(peaks.get("bf16_tflops", 1590.0))
         mult = 4.0 if fp4 else 2.0
         peak = mult * bf16
@@ -452,7 +452,7 @@ def run_ours(a):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
         "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": dtype, "data": "synthetic",
-        "config": {"workload": workload_name(a), "windows_per_gpu": W, "engine": ["popcount", "tcgen05-fp8", "tcgen05-fp8-hbm", "tcgen05-fp4", "tcgen05-fp4-cta-pair"][engine], "parallelism": f"window-sharded x{world}, no collective",
+        "config": {"workload": workload_name(a), "windows_per_gpu": W, "engine": ["popcount", "tcgen05-fp8", "tcgen05-fp8-hbm", "tcgen05-fp4", "tcgen05-fp4-cta-pair", "tcgen05-fp4-cta-pair-tmemA"][engine], "parallelism": f"window-sharded x{world}, no collective",
                    "l2_policy": "inputs larger than L2 (packed panel 721 MB + queries 288 MB per GPU per step)"},
         "window_queries_per_s": value / N,
         "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
@@ -689,12 +689,12 @@ def run_cfg5(a):
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         scan_gbs = W * Q * (hi - lo) * 132 / (kern_ms * 1e-3) / 1e9
         engine = _lib.last_hamming_engine()
-        if engine in (1, 2, 3, 4):
+        if engine in (1, 2, 3, 4, 5):
             bf16 = float(peaks.get("bf16_tflops", 1590.0))
             mult = 4.0 if engine >= 3 else 2.0
             tf = 2.0 * W * Q * (hi - lo) * S / (kern_ms * 1e-3) / 1e12
             roofline = {"bound": "tensor", "achieved": tf, "peak": mult * bf16, "unit": "TFLOP/s", "frac": tf / (mult * bf16),
-                        "traffic": None, "kernel": "hamming_tc_kernel<K=32,%s>" % ({4: "fp4,cta-pair", 3: "fp4"}.get(engine, "fp8")), "kernel_ms": kern_ms,
+                        "traffic": None, "kernel": "hamming_tc_kernel<K=32,%s>" % ({5: "fp4,cta-pair,tmemA", 4: "fp4,cta-pair", 3: "fp4"}.get(engine, "fp8")), "kernel_ms": kern_ms,
                         "peak_source": "%g x measured bf16_tflops (%s rate)" % (mult, "fp4" if engine >= 3 else "fp8"),
                         "scan_equivalent": {"achieved": scan_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": scan_gbs / hbm_peak},
                         "note": "per-GPU local shard scan: algorithmic 2 x pairs x sites FLOP / kernel time"}
@@ -710,7 +710,7 @@ def run_cfg5(a):
             "vs_baseline": None, "dtype": dtype, "data": "synthetic",
             "config": {"workload": f"cfg5 biobank-scale: {W} of 500 windows x {N} ref haplotypes x {S} sites, {Q} queries/window, "
                                    f"k={k}, panel row-sharded over {world} GPU(s) + all-to-all of the per-shard top-k + on-device merge (result sharded by query)",
-                       "engine": ["popcount", "tcgen05-fp8", "tcgen05-fp8-hbm", "tcgen05-fp4", "tcgen05-fp4-cta-pair"][engine],
+                       "engine": ["popcount", "tcgen05-fp8", "tcgen05-fp8-hbm", "tcgen05-fp4", "tcgen05-fp4-cta-pair", "tcgen05-fp4-cta-pair-tmemA"][engine],
                        "rows_per_gpu": hi - lo, "l2_policy": "panel shard larger than L2"},
             "window_queries_per_s": value / N, "gpu_launches": int(launches),
             "roofline": roofline,

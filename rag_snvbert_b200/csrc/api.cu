@@ -478,8 +478,8 @@ static int hamming_chunk_bounds(const HammingSearchParams& p, bool host_io, std:
             // so a chunk should hold a whole number of items per SM (pair); ~24 chunks keep the pipeline's fill
             // (first H2D) and drain (last D2H) short.  (Chunking device-resident searches to overlap the query
             // expansion with the previous chunk's scan was measured: < 1 %, not worth the extra launches.)
-            const int64_t per_w = tprobe.engine == 4 ? ceil_div(qtiles, 2) : qtiles;
-            const int64_t units = tprobe.engine == 4 ? kNumSMs / 2 : kNumSMs;
+            const int64_t per_w = tprobe.engine >= 4 ? ceil_div(qtiles, 2) : qtiles;
+            const int64_t units = tprobe.engine >= 4 ? kNumSMs / 2 : kNumSMs;
             int64_t a = units, b = per_w;
             while (b) { const int64_t t = a % b; a = b; b = t; }
             const int64_t unit = units / a;  // windows per chunk so that items per chunk is a multiple of the units

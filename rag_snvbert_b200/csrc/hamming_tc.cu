@@ -106,21 +106,27 @@ constexpr size_t kListBytes16 = 64 * 1024; // 16 epilogue warps: 32 x 512 floats
 static_assert((Epi<8, true>::kParts - 1) * 8 * BM * 4 <= kListBytes && (Epi<32>::kParts - 1) * 32 * BM * 4 <= kListBytes,
               "the part-exchange buffer aliases the candidate slots");
 
-enum { MODE_FP8 = 0, MODE_FP8_HBM = 1, MODE_FP4 = 2, MODE_FP4_2CTA = 3 };
+enum { MODE_FP8 = 0, MODE_FP8_HBM = 1, MODE_FP4 = 2, MODE_FP4_2CTA = 3, MODE_FP4_2CTA_TA = 4 };
 
 // Three rings: the query operand comes from L2 (long latency: deep ring), the panel operand is made
 // in the SM (expander latency: 3 slots), raw packed k-blocks are small.
 template <int MODE>
 struct Cfg {
-    static constexpr bool kFp4 = MODE == MODE_FP4 || MODE == MODE_FP4_2CTA;
+    static constexpr bool kFp4 = MODE == MODE_FP4 || MODE == MODE_FP4_2CTA || MODE == MODE_FP4_2CTA_TA;
     // CTA pair (cta_group::2): two CTAs of a cluster hold 128 queries each (M = 256) and each expands HALF of every
     // panel tile; the pair's MMA reads both halves.  Halves the expander work and the B operand bytes per SM.
-    static constexpr bool kTwoCta = MODE == MODE_FP4_2CTA;
+    static constexpr bool kTwoCta = MODE == MODE_FP4_2CTA || MODE == MODE_FP4_2CTA_TA;
+    // Query operand in TENSOR MEMORY (bring-up, SNV_HAMMING_ENGINE=tc4x2ta): the 128-query tile of an item (up to 5
+    // k-blocks = 160 columns) is written to TMEM once per item by the epilogue warps and the MMAs take A from there,
+    // so there is no A ring, no per-tile TMA traffic for it and no shared-memory operand reads for A.
+    // TMEM: 2 x 160 accumulator columns | 160 operand columns | 32 columns of unit scales.
+    static constexpr bool kTmemA = MODE == MODE_FP4_2CTA_TA;
+    static constexpr int kMaxKbTmemA = 5;
     static constexpr bool kExpand = MODE != MODE_FP8_HBM;
-    static constexpr int BN = kFp4 ? 240 : 256;   // panel rows per tile = TMEM columns per accumulator stage
+    static constexpr int BN = kTmemA ? 160 : (kFp4 ? 240 : 256);   // panel rows per tile = TMEM columns per accumulator stage
     static constexpr int WPK = kFp4 ? 8 : 4;      // packed words per k-block
     static constexpr int WPM = kFp4 ? 2 : 1;      // packed words per MMA
-    static constexpr int kAStages = SNV_TC_ASTAGES;
+    static constexpr int kAStages = kTmemA ? 0 : SNV_TC_ASTAGES;
     static constexpr int kRawStages = SNV_TC_RAWSTAGES;
     static constexpr int kBRows = kTwoCta ? BN / 2 : BN;          // panel rows this CTA expands per tile
     static constexpr uint32_t kRawRow = WPK * 4;                // raw bytes per panel row and k-block
@@ -128,7 +134,9 @@ struct Cfg {
     static constexpr uint32_t kBSlot = kTwoCta ? kBBytes / 2 : kBBytes;  // 16 KB holds the pair kernel's 120 rows
     static constexpr uint32_t kRawBytes = kBRows * kRawRow;     // what one TMA box brings
     static constexpr uint32_t kBBox = BN * kRowBytes;           // fp8-hbm variant: one TMA box of operand rows
-    static constexpr uint32_t kSfCol = 2 * BN;                  // fp4: first TMEM column of the unit scales
+    static constexpr uint32_t kACol = 2 * BN;                   // TMEM-A mode: first TMEM column of the query operand
+    static constexpr uint32_t kSfCol = kTmemA ? 480 : 2 * BN;   // fp4: first TMEM column of the unit scales
+    static_assert(!kTmemA || kACol + 32 * kMaxKbTmemA <= kSfCol, "TMEM budget");
     static constexpr size_t kSmem = 1024 /*align slack*/ + (size_t)kAStages * kABytes + (size_t)kBStages * kBSlot +
                                     (size_t)kRawStages * kRawSlot + ((kTwoCta && SNV_TC_EPI16) ? kListBytes16 : kListBytes) + (kTwoCta ? 4 : 2) * BM * 4 /*thresholds*/ + 256 /*barriers*/;
     static_assert(kSmem <= 232448, "shared memory budget");
@@ -184,6 +192,7 @@ struct TcParams {
     float* D_f32;
     int64_t* I;
     uint64_t* partial;       // [nw * nq][nsplit][kt] when nsplit > 1
+    const uint8_t* q_ops;    // [nw * nq][kblocks * 128 B] query operand rows (read directly in the TMEM-A mode)
 };
 
 struct Item {
@@ -224,6 +233,27 @@ __device__ __forceinline__ void umma_mxf4_2cta(uint32_t tmem_d, uint64_t adesc, 
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
+        : "memory");
+}
+
+// A operand from tensor memory (row = lane, 8 packed E2M1 codes per 32-bit column, 8 columns per K = 64 MMA)
+__device__ __forceinline__ void umma_mxf4_2cta_ta(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
+                                                  uint32_t tmem_sfa, uint32_t tmem_sfb)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.block32 [%0], [%1], %2, %3, [%5], [%6], p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_st_32x32b_x16v(uint32_t taddr, const uint32_t (&v)[16])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
         : "memory");
 }
 
@@ -314,7 +344,7 @@ __device__ __forceinline__ void tmem_ld_wait_cols(uint32_t (&r)[N])
 }
 
 template <int KT, int MODE>
-__global__ void __launch_bounds__(threads_of<KT, MODE == MODE_FP4_2CTA>(), 1)
+__global__ void __launch_bounds__(threads_of<KT, Cfg<MODE>::kTwoCta>(), 1)
 hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_r, const TcParams p)
 {
     using C = Cfg<MODE>;
@@ -325,6 +355,7 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     constexpr int kAStages = C::kAStages;
     constexpr int kRawStages = C::kRawStages;
     constexpr bool TWO = C::kTwoCta;
+    constexpr bool TA = C::kTmemA;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     unsigned char* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);  // SWIZZLE_128B tiles: 1024-byte aligned
@@ -347,6 +378,7 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     uint64_t* tmem_full = raw_empty + kRawStages;   // [2] MMA -> epilogue
     uint64_t* tmem_empty = tmem_full + kAccStages;  // [2] epilogue -> MMA
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + kAccStages);
+    [[maybe_unused]] uint64_t* a_full = reinterpret_cast<uint64_t*>(tmem_ptr + 2);  // TMEM-A mode: epilogue warps -> MMA, once per item
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -378,6 +410,7 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             mbar_init(&tmem_full[s], 1);
             mbar_init(&tmem_empty[s], kPair * kEpiThreads);
         }
+        if constexpr (TA) mbar_init(a_full, kPair * E::kWarps);
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -406,8 +439,8 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 
     if (warp == 0) {
         // ================= TMA producer: query operand tiles =================
-        if (lane == 0) {
-            Ring<kAStages> ra;
+        if (!TA && lane == 0) {
+            Ring<(kAStages > 0 ? kAStages : 1)> ra;
             for (int item = item0; item < p.items; item += item_step) {
                 const Item it = decode_item(p, item, kQtMul, (int)cta_rank);
                 const int row_a = it.w * p.nq + it.qt * BM;
@@ -436,7 +469,7 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             // K-major SWIZZLE_128B descriptors: low word = (address >> 4) | LBO 1 << 16, high word constant
             // (SBO 1024 B, descriptor version 1, layout SWIZZLE_128B); one MMA per 32 operand bytes = per packed
             // word (fp8) or per two packed words (fp4)
-            const uint32_t a_lo0 = (smem_u32(a_tiles) >> 4) | 0x10000u;
+            const uint32_t a_lo0 = TA ? tmem_base + C::kACol : ((smem_u32(a_tiles) >> 4) | 0x10000u);  // TMEM-A: a column address
             const uint32_t b_lo0 = (smem_u32(b_tiles) >> 4) | 0x10000u;
             const int nm_tail = (p.words - WPK * (KB - 1) + C::WPM - 1) / C::WPM;
             const uint32_t sf_a = tmem_base + C::kSfCol, sf_b = tmem_base + C::kSfCol + 16u;
@@ -447,7 +480,8 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 #endif
                 const uint64_t adesc = kDescHi | (uint64_t)a_lo;
                 const uint64_t bdesc = kDescHi | (uint64_t)b_lo;
-                if constexpr (TWO) umma_mxf4_2cta(d_tmem, adesc, bdesc, idesc, acc, sf_a, sf_b);
+                if constexpr (TA) umma_mxf4_2cta_ta(d_tmem, a_lo, bdesc, idesc, acc, sf_a, sf_b);
+                else if constexpr (TWO) umma_mxf4_2cta(d_tmem, adesc, bdesc, idesc, acc, sf_a, sf_b);
                 else if constexpr (FP4) umma_mxf4(d_tmem, adesc, bdesc, idesc, acc, sf_a, sf_b);
                 else umma_f8(d_tmem, adesc, bdesc, idesc, acc);
             };
@@ -455,42 +489,52 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                 if constexpr (TWO) umma_commit_2cta(bar);
                 else umma_commit(bar);
             };
-            Ring<kAStages> ra;
+            Ring<(kAStages > 0 ? kAStages : 1)> ra;
             Ring<kBStages> rb;
             uint32_t tcount = 0;
+            [[maybe_unused]] uint32_t icount = 0;
+            // operand step between the 4 MMAs of a k-block: 32 bytes of the swizzled row (descriptor units of 16 B),
+            // or 8 TMEM columns
+            constexpr uint32_t kAStep = TA ? 8u : 2u;
             for (int item = item0; item < p.items; item += item_step) {
                 const Item it = decode_item(p, item, kQtMul, (int)cta_rank);
+                if constexpr (TA) {
+                    // both CTAs' epilogue warps have written this item's query tile to tensor memory
+                    mbar_wait(a_full, icount & 1u);
+                    ++icount;
+                    tcgen05_fence_after();
+                }
                 for (int t = 0; t < it.ntiles; ++t, ++tcount) {
                     const uint32_t as = tcount & 1u;
                     mbar_wait(&tmem_empty[as], ((tcount >> 1) & 1u) ^ 1u);
                     tcgen05_fence_after();
                     const uint32_t d_tmem = tmem_base + as * BN;
                     for (int kb = 0; kb < KB; ++kb) {
-                        mbar_wait(&full_a[ra.i], ra.phase);
+                        if constexpr (!TA) mbar_wait(&full_a[ra.i], ra.phase);
                         mbar_wait(&full_b[rb.i], rb.phase);
                         tcgen05_fence_after();
                         if (elect_one()) {
-                            const uint32_t a_lo = a_lo0 + (uint32_t)ra.i * (kABytes >> 4);
+                            const uint32_t a_lo = TA ? a_lo0 + (uint32_t)kb * 32u : a_lo0 + (uint32_t)ra.i * (kABytes >> 4);
                             const uint32_t b_lo = b_lo0 + (uint32_t)rb.i * (C::kBSlot >> 4);
                             if (kb != KB - 1) {
                                 mma(d_tmem, a_lo, b_lo, kb != 0 ? 1u : 0u);
-                                mma(d_tmem, a_lo + 2, b_lo + 2, 1u);
-                                mma(d_tmem, a_lo + 4, b_lo + 4, 1u);
-                                mma(d_tmem, a_lo + 6, b_lo + 6, 1u);
-                                commit(&empty_a[ra.i]);
+                                mma(d_tmem, a_lo + kAStep, b_lo + 2, 1u);
+                                mma(d_tmem, a_lo + 2 * kAStep, b_lo + 4, 1u);
+                                mma(d_tmem, a_lo + 3 * kAStep, b_lo + 6, 1u);
+                                if constexpr (!TA) commit(&empty_a[ra.i]);
                                 commit(&empty_b[rb.i]);
                             } else {
                                 mma(d_tmem, a_lo, b_lo, kb != 0 ? 1u : 0u);
-                                if (nm_tail > 1) mma(d_tmem, a_lo + 2, b_lo + 2, 1u);
-                                if (nm_tail > 2) mma(d_tmem, a_lo + 4, b_lo + 4, 1u);
-                                if (nm_tail > 3) mma(d_tmem, a_lo + 6, b_lo + 6, 1u);
-                                commit(&empty_a[ra.i]);
+                                if (nm_tail > 1) mma(d_tmem, a_lo + kAStep, b_lo + 2, 1u);
+                                if (nm_tail > 2) mma(d_tmem, a_lo + 2 * kAStep, b_lo + 4, 1u);
+                                if (nm_tail > 3) mma(d_tmem, a_lo + 3 * kAStep, b_lo + 6, 1u);
+                                if constexpr (!TA) commit(&empty_a[ra.i]);
                                 commit(&empty_b[rb.i]);
                                 commit(&tmem_full[as]);
                             }
                         }
                         __syncwarp();
-                        ra.next();
+                        if constexpr (!TA) ra.next();
                         rb.next();
                     }
                 }
@@ -642,6 +686,38 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         uint32_t tcount = 0;
         thrx[part * BM + row] = 3.0e38f;
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+        // TMEM-A mode: the epilogue warps write an item's query operand rows into tensor memory (thread = query row
+        // = TMEM lane; the column parts take alternate k-blocks: 8 x 16 B of the row -> 32 columns) and arrive, one
+        // lane per warp, on the leader's a_full barrier.
+        [[maybe_unused]] auto load_a = [&](int item_a) {
+            const Item nx = decode_item(p, item_a, kQtMul, (int)cta_rank);
+            const int qa = nx.qt * BM + row;
+            const bool act = qa < p.nq;
+            const uint4* src = reinterpret_cast<const uint4*>(p.q_ops + ((int64_t)nx.w * p.nq + (act ? qa : 0)) * (int64_t)(KB * kRowBytes));
+            const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + C::kACol;
+            for (int kb = part; kb < KB; kb += kParts) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t v[16];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const uint4 x = act ? __ldg(src + kb * 8 + h * 4 + c) : make_uint4(0u, 0u, 0u, 0u);
+                        v[4 * c] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w;
+                    }
+                    tmem_st_32x32b_x16v(ta + (uint32_t)(kb * 32 + h * 16), v);
+                }
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (TWO && !leader) mbar_arrive_cluster(a_full, 0u);
+                else mbar_arrive(a_full);
+            }
+        };
+        if constexpr (TA) {
+            if (item0 < p.items) load_a(item0);
+        }
         for (int item = item0; item < p.items; item += item_step) {
             const Item it = decode_item(p, item, kQtMul, (int)cta_rank);
             const int qi = it.qt * BM + row;
@@ -695,11 +771,22 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                 const int n0 = (it.t0 + t) * BN;
                 mbar_wait(&tmem_full[as], (tcount >> 1) & 1u);
                 tcgen05_fence_after();
-                int cols = (p.n - n0 < BN ? (int)(p.n - n0) : BN) - kPartCols * part;  // columns of this part in use
-                cols = cols < 0 ? 0 : (cols > kPartCols ? kPartCols : cols);
+                if constexpr (TA) {
+                    // the item's last accumulator is complete, so every MMA that reads its query tile has retired:
+                    // tensor memory can take the next item's tile while this tile is still being scored
+                    if (t == it.ntiles - 1 && item + item_step < p.items) load_a(item + item_step);
+                }
+                // columns [pstart, pstart + pwidth) of the tile belong to this part.  TMEM-A mode (160-column tiles):
+                // 96 + 64 columns, the wide side alternating from tile to tile so that both parts score whole
+                // 32-column groups and carry the same load over two tiles
+                const int c0 = TA ? ((tcount & 1u) ? 64 : 96) : kPartCols;
+                const int pstart = TA ? (part ? c0 : 0) : kPartCols * part;
+                const int pwidth = TA ? (part ? BN - c0 : c0) : kPartCols;
+                int cols = (p.n - n0 < BN ? (int)(p.n - n0) : BN) - pstart;  // columns of this part in use
+                cols = cols < 0 ? 0 : (cols > pwidth ? pwidth : cols);
                 const int nch = (cols + G - 1) / G;
-                const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + (uint32_t)(kPartCols * part);
-                const uint32_t col_base = (uint32_t)(t * BN + kPartCols * part);  // columns count from the split's first row
+                const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + (uint32_t)pstart;
+                const uint32_t col_base = (uint32_t)(t * BN + pstart);  // columns count from the split's first row
                 // exchange thresholds with the other column parts of this query (once per tile; stale is safe)
                 thrx[part * BM + row] = thr_mine;
                 thr_other = 3.0e38f;
@@ -957,14 +1044,19 @@ int launch_kernel(const CUtensorMap& map_q, const CUtensorMap& map_r, const TcPa
     return SNV_OK;
 }
 
-int mode_of_engine(int engine) { return engine == 4 ? MODE_FP4_2CTA : (engine == 3 ? MODE_FP4 : (engine == 2 ? MODE_FP8_HBM : MODE_FP8)); }
-int bn_of_engine(int engine) { return engine >= 3 ? Cfg<MODE_FP4>::BN : 256; }
+int mode_of_engine(int engine)
+{
+    return engine == 5 ? MODE_FP4_2CTA_TA : (engine == 4 ? MODE_FP4_2CTA : (engine == 3 ? MODE_FP4 : (engine == 2 ? MODE_FP8_HBM : MODE_FP8)));
+}
+int bn_of_engine(int engine) { return engine == 5 ? Cfg<MODE_FP4_2CTA_TA>::BN : (engine >= 3 ? Cfg<MODE_FP4>::BN : 256); }
 int wpk_of_engine(int engine) { return engine >= 3 ? Cfg<MODE_FP4>::WPK : 4; }
+bool pair_engine(int engine) { return engine >= 4; }  // items are query-tile PAIRS on SM pairs
 
 }  // namespace
 
 // 0 = popcount kernel, 1 = tensor cores fp8, 2 = fp8 with the panel pre-expanded in HBM (bring-up), 3 = tensor cores fp4,
-// 4 = fp4 on CTA pairs (cta_group::2)
+// 4 = fp4 on CTA pairs (cta_group::2), 5 = 4 with the query operand in tensor memory (bring-up: only when forced with
+// SNV_HAMMING_ENGINE=tc4x2ta, windows of at most 1280 sites; wider ones run engine 4)
 int hamming_engine_for(const HammingSearchParams& p)
 {
     int mode = -1;  // auto
@@ -974,10 +1066,12 @@ int hamming_engine_for(const HammingSearchParams& p)
         else if (!strcmp(e, "tc_hbm")) mode = 2;
         else if (!strcmp(e, "tc4")) mode = 3;
         else if (!strcmp(e, "tc4x2")) mode = 4;
+        else if (!strcmp(e, "tc4x2ta")) mode = 5;
     }
     const bool can = !p.work && p.n > 0 && p.nq > 0 && p.k >= 1 && p.k <= 32 && p.d < (1 << 12) &&
                      (int64_t)p.nw * p.nq < ((int64_t)1 << 31) && p.n < ((int64_t)1 << 31);
     if (!can || mode == 0) return 0;
+    if (mode == 5 && ceil_div(p.words, Cfg<MODE_FP4_2CTA_TA>::WPK) > Cfg<MODE_FP4_2CTA_TA>::kMaxKbTmemA) mode = 4;
     if (mode > 0) return mode;
     // auto: enough queries per window to fill a useful part of the 128-lane tile, and a panel worth a tile
     if (!(p.nq >= 32 && p.n >= 512)) return 0;
@@ -1004,8 +1098,9 @@ size_t hamming_tc_plan(const HammingSearchParams& p, HammingTcPlan& plan)
     // of the epilogue - and a split adds partial keys for the merge kernel.  The key's id field bounds the tiles
     // per item.
     // CTA-pair engine: an item is a PAIR of query tiles and runs on a pair of SMs
-    const int64_t units = plan.engine == 4 ? kNumSMs / 2 : kNumSMs;
-    const int64_t base = (int64_t)p.nw * (plan.engine == 4 ? ceil_div(plan.qtiles, 2) : plan.qtiles);
+    const bool pair = pair_engine(plan.engine);
+    const int64_t units = pair ? kNumSMs / 2 : kNumSMs;
+    const int64_t base = (int64_t)p.nw * (pair ? ceil_div(plan.qtiles, 2) : plan.qtiles);
     const int64_t min_split = ceil_div(plan.n_tiles, max_tiles_per_split);
     int64_t nsplit = min_split;
     {
@@ -1050,7 +1145,7 @@ size_t hamming_tc_plan(const HammingSearchParams& p, HammingTcPlan& plan)
             auto item_cost = [&](double tiles) { return tiles + 0.25 + ins * plan.kt * (1.0 + std::log(std::max(1.0, tiles * BN / plan.kt))); };
             const double now = (double)(R + 1) * item_cost((double)plan.n_tiles);
             const double then = (double)R * item_cost((double)plan.n_tiles) + item_cost((double)per) +
-                                3.5e-5 * (double)rem * (plan.engine == 4 ? 2 * BM : BM) * s2 * plan.kt;
+                                3.5e-5 * (double)rem * (pair ? 2 * BM : BM) * s2 * plan.kt;
             if (s2 >= 2 && then < 0.97 * now) {
                 plan.tail_items = (int)rem;
                 plan.tail_split = (int)s2;
@@ -1062,7 +1157,7 @@ size_t hamming_tc_plan(const HammingSearchParams& p, HammingTcPlan& plan)
     plan.off_bias = round_up(rows * plan.kblocks * kRowBytes, 256);
     plan.off_partial = plan.off_bias + round_up(rows * 4, 256);
     plan.off_panel = plan.off_partial + (plan.nsplit > 1 ? round_up(rows * plan.nsplit * plan.kt * 8, 256)
-                                                          : round_up((int64_t)plan.tail_items * (plan.engine == 4 ? 2 * BM : BM) * plan.tail_split * plan.kt * 8, 256));
+                                                          : round_up((int64_t)plan.tail_items * (pair ? 2 * BM : BM) * plan.tail_split * plan.kt * 8, 256));
     size_t total = plan.off_panel;
     if (plan.engine == 2) total += (size_t)p.nw * p.n * plan.kblocks * kRowBytes;
     return total + 1024;
@@ -1071,7 +1166,7 @@ size_t hamming_tc_plan(const HammingSearchParams& p, HammingTcPlan& plan)
 // The item bookkeeping of a launch (everything decode_item reads); returns the query rows covered by tail items.
 static int64_t fill_item_fields(const HammingSearchParams& p, const HammingTcPlan& plan, TcParams& tp)
 {
-    const bool pair = plan.engine == 4;
+    const bool pair = pair_engine(plan.engine);
     const int64_t rows = (int64_t)p.nw * p.nq;
     tp.nw = p.nw; tp.nq = p.nq; tp.qtiles = pair ? (int)ceil_div(plan.qtiles, 2) : plan.qtiles;
     tp.n = p.n;
@@ -1103,7 +1198,7 @@ int64_t hamming_tc_debug_items(const HammingSearchParams& p, const HammingTcPlan
     if (!plan.engine) return 0;
     TcParams tp{};
     fill_item_fields(p, plan, tp);
-    const bool pair = plan.engine == 4;
+    const bool pair = pair_engine(plan.engine);
     const int ctas = pair ? std::min(tp.items, kNumSMs / 2) : std::min(tp.items, kNumSMs);
     int64_t n = 0;
     for (int item = 0; item < tp.items; ++item)
@@ -1149,7 +1244,7 @@ int hamming_tc_launch(const HammingSearchParams& p, const HammingTcPlan& plan, v
         // raw packed panel [nw][n][stride] words: box = one k-block of words x one tile of rows of one window
         const cuuint64_t gdim[3] = {(cuuint64_t)p.stride, (cuuint64_t)p.n, (cuuint64_t)p.nw};
         const cuuint64_t gstride[2] = {(cuuint64_t)p.stride * 4, (cuuint64_t)p.panel_win_stride * 4};
-        const cuuint32_t box[3] = {(cuuint32_t)wpk_of_engine(plan.engine), (cuuint32_t)(plan.engine == 4 ? BN / 2 : BN), 1};
+        const cuuint32_t box[3] = {(cuuint32_t)wpk_of_engine(plan.engine), (cuuint32_t)(pair_engine(plan.engine) ? BN / 2 : BN), 1};
         int rc = encode_map(&map_r, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, p.panel, gdim, gstride, box, CU_TENSOR_MAP_SWIZZLE_NONE);
         if (rc) return rc;
     } else {
@@ -1164,17 +1259,19 @@ int hamming_tc_launch(const HammingSearchParams& p, const HammingTcPlan& plan, v
         if (rc) return rc;
     }
     TcParams tp{};
-    const bool pair = plan.engine == 4;
+    const bool pair = pair_engine(plan.engine);
     const int64_t tail_rows = fill_item_fields(p, plan, tp);
     tp.idx_bits = plan.idx_bits; tp.k = p.k; tp.one = 1;
     tp.id_offset = p.id_offset;
     tp.q_bias = q_bias;
     tp.D_i32 = p.D_i32; tp.D_f32 = p.D_f32; tp.I = p.I;
     tp.partial = partial;
+    tp.q_ops = q_ops;
     const int grid = pair ? 2 * std::min(tp.items, kNumSMs / 2) : std::min(tp.items, kNumSMs);
     int rc;
     const bool k8 = plan.kt == 8;
     switch (mode_of_engine(plan.engine)) {
+        case MODE_FP4_2CTA_TA: rc = k8 ? launch_kernel<8, MODE_FP4_2CTA_TA>(map_q, map_r, tp, grid, stream) : launch_kernel<32, MODE_FP4_2CTA_TA>(map_q, map_r, tp, grid, stream); break;
         case MODE_FP4_2CTA: rc = k8 ? launch_kernel<8, MODE_FP4_2CTA>(map_q, map_r, tp, grid, stream) : launch_kernel<32, MODE_FP4_2CTA>(map_q, map_r, tp, grid, stream); break;
         case MODE_FP4: rc = k8 ? launch_kernel<8, MODE_FP4>(map_q, map_r, tp, grid, stream) : launch_kernel<32, MODE_FP4>(map_q, map_r, tp, grid, stream); break;
         case MODE_FP8_HBM: rc = k8 ? launch_kernel<8, MODE_FP8_HBM>(map_q, map_r, tp, grid, stream) : launch_kernel<32, MODE_FP8_HBM>(map_q, map_r, tp, grid, stream); break;

@@ -38,12 +38,12 @@ def force_engine():
 
 
 def _bn(engine):
-    return 240 if engine >= 3 else 256
+    return 160 if engine == 5 else (240 if engine >= 3 else 256)
 
 
 def _check_cover(plan, items, nw, nq, n, k):
     eng = plan["engine"]
-    assert eng in (1, 2, 3, 4)
+    assert eng in (1, 2, 3, 4, 5)
     bn = _bn(eng)
     qtiles = -(-nq // BM)
     n_tiles = -(-n // bn)
@@ -58,7 +58,7 @@ def _check_cover(plan, items, nw, nq, n, k):
         assert 0 <= w < nw and nt >= 1 and 0 <= t0 and t0 + nt <= n_tiles
         assert 0 <= piece < npieces
         if qt >= qtiles:
-            assert eng == 4 and qt == qtiles and qtiles % 2 == 1  # the idle half of the last CTA pair
+            assert eng >= 4 and qt == qtiles and qtiles % 2 == 1  # the idle half of the last CTA pair
             continue
         cover[w, qt, t0 : t0 + nt] += 1
         key = (w, qt)
@@ -73,11 +73,11 @@ def _check_cover(plan, items, nw, nq, n, k):
         ids = sorted(p[0] for p in ps)
         assert ids == list(range(len(ps))) and all(p[1] == len(ps) for p in ps), (key, ps)
         assert len({p[2] for p in ps}) == 1
-    units = 74 if eng == 4 else 148
+    units = 74 if eng >= 4 else 148
     assert items[:, 7].max() < units
 
 
-@pytest.mark.parametrize("eng", ["tc", "tc4", "tc4x2"])
+@pytest.mark.parametrize("eng", ["tc", "tc4", "tc4x2", "tc4x2ta"])
 @pytest.mark.parametrize(
     "shape",
     [
@@ -96,7 +96,7 @@ def test_items_tile_the_search(L, force_engine, eng, shape):
     force_engine(eng)
     nw, nq, n, d, k = shape
     plan, items = L.debug_hamming_plan(nw, nq, n, d, k)
-    assert plan["engine"] == {"tc": 1, "tc4": 3, "tc4x2": 4}[eng]
+    assert plan["engine"] == {"tc": 1, "tc4": 3, "tc4x2": 4, "tc4x2ta": 5}[eng]
     _check_cover(plan, items, nw, nq, n, k)
 
 
@@ -104,7 +104,7 @@ def test_random_shapes(L, force_engine):
     rng = np.random.default_rng(2024)
     seen_split = seen_tail = 0
     for case in range(300):
-        force_engine(["tc", "tc4", "tc4x2"][case % 3])
+        force_engine(["tc", "tc4", "tc4x2", "tc4x2ta"][case % 4])
         nw = int(rng.integers(1, 200))
         nq = int(rng.integers(1, 1200))
         n = int(rng.choice([rng.integers(1, 600), rng.integers(600, 30000), rng.integers(30000, 400000)]))
@@ -142,6 +142,10 @@ def test_auto_engine_by_shape(L, force_engine):
     assert eng(1, 64, 5008, 1030, 33) == 0  # k > 32
     force_engine("popc")
     assert eng(1000, 2000, 5008, 1030, 8) == 0
+    # the TMEM-operand bring-up engine holds at most 5 k-blocks (1280 sites) of a query tile; wider windows run engine 4
+    force_engine("tc4x2ta")
+    assert eng(10, 2000, 5008, 1280, 8) == 5
+    assert eng(10, 2000, 5008, 1281, 8) == 4
 
 
 def test_bad_arguments(L):
@@ -183,8 +187,8 @@ def test_chunk_bounds_random(L, force_engine):
         sizes = np.diff(b)
         if plan["engine"] and len(sizes) >= 8:
             # full-size chunks hold a whole number of items per SM (pair)
-            per_w = -(-plan["qtiles"] // 2) if plan["engine"] == 4 else plan["qtiles"]
-            units = 74 if plan["engine"] == 4 else 148
+            per_w = -(-plan["qtiles"] // 2) if plan["engine"] >= 4 else plan["qtiles"]
+            units = 74 if plan["engine"] >= 4 else 148
             full = sizes[1:-2]
             assert (full == full[0]).all()
             assert (full[0] * per_w) % units == 0 or full[0] * per_w >= 2 * units

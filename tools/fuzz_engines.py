@@ -12,6 +12,8 @@ rng = np.random.default_rng(int(os.environ.get("SEED", "1234")))
 dev = torch.device("cuda", 0)
 n_cases = int(os.environ.get("CASES", "120"))
 bad = 0
+# ENGINES="tc4x2ta" (comma separated) checks other builds / bring-up engines against the popcount scan
+TC_ENGINES = tuple(e for e in os.environ.get("ENGINES", "tc,tc4,tc4x2").split(",") if e)
 for case in range(n_cases):
     W = int(rng.choice([1, 1, 2, 3, 5, 9]))
     N = int(rng.choice([1, 7, 100, 239, 240, 241, 479, 481, 1000, 2500, 5008, 12000]))
@@ -33,11 +35,11 @@ for case in range(n_cases):
     idx = WindowedHammingIndex(d, W, 0)
     idx.add(panel)
     out = {}
-    for eng in ("popc", "tc", "tc4", "tc4x2"):
+    for eng in ("popc",) + TC_ENGINES:
         os.environ["SNV_HAMMING_ENGINE"] = eng
         D, I = idx.search(q, k, observed=obs)
         out[eng] = (D.clone(), I.clone())
-    for eng in ("tc", "tc4", "tc4x2"):
+    for eng in TC_ENGINES:
         if not (torch.equal(out["popc"][0], out[eng][0]) and torch.equal(out["popc"][1], out[eng][1])):
             bad += 1
             print("MISMATCH", eng, dict(case=case, W=W, N=N, Q=Q, d=d, k=k, mode=str(mode), dens=dens), flush=True)
