@@ -15,7 +15,12 @@ from oracle import oracle as O
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["tc", "tc_hbm", "tc4", "tc4x2"])
+# tc4x2ta (query operand in tensor memory) is round-2 bring-up code: first parity run green
+# (profiles/r1_tmema_first_parity.txt), joins the matrix with SNV_TEST_TMEMA=1 until the full fuzz has passed on a B200
+_ENGINES = ["tc", "tc_hbm", "tc4", "tc4x2"] + (["tc4x2ta"] if os.environ.get("SNV_TEST_TMEMA") == "1" else [])
+
+
+@pytest.fixture(params=_ENGINES)
 def engine(request):
     old = os.environ.get("SNV_HAMMING_ENGINE")
     os.environ["SNV_HAMMING_ENGINE"] = request.param
