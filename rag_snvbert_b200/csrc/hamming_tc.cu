@@ -100,7 +100,12 @@ constexpr uint32_t kBBytes = 256 * kRowBytes;  // 32 KB slot (240 or 256 rows in
 #ifndef SNV_TC_RAWSTAGES
 #define SNV_TC_RAWSTAGES 4
 #endif
-constexpr int kBStages = SNV_TC_BSTAGES;
+#ifndef SNV_TC_TA_BSTAGES
+#define SNV_TC_TA_BSTAGES 6  // TMEM-A mode: the 64 KB of the query ring go to a deeper panel-operand ring
+#endif
+#ifndef SNV_TC_TA_RAWSTAGES
+#define SNV_TC_TA_RAWSTAGES 6
+#endif
 constexpr size_t kListBytes = 32 * 1024;  // one slot per (epilogue thread, column of a group): 32 x 256 floats
 constexpr size_t kListBytes16 = 64 * 1024; // 16 epilogue warps: 32 x 512 floats
 static_assert((Epi<8, true>::kParts - 1) * 8 * BM * 4 <= kListBytes && (Epi<32>::kParts - 1) * 32 * BM * 4 <= kListBytes,
@@ -127,7 +132,8 @@ struct Cfg {
     static constexpr int WPK = kFp4 ? 8 : 4;      // packed words per k-block
     static constexpr int WPM = kFp4 ? 2 : 1;      // packed words per MMA
     static constexpr int kAStages = kTmemA ? 0 : SNV_TC_ASTAGES;
-    static constexpr int kRawStages = SNV_TC_RAWSTAGES;
+    static constexpr int kBStages = kTmemA ? SNV_TC_TA_BSTAGES : SNV_TC_BSTAGES;
+    static constexpr int kRawStages = kTmemA ? SNV_TC_TA_RAWSTAGES : SNV_TC_RAWSTAGES;
     static constexpr int kBRows = kTwoCta ? BN / 2 : BN;          // panel rows this CTA expands per tile
     static constexpr uint32_t kRawRow = WPK * 4;                // raw bytes per panel row and k-block
     static constexpr uint32_t kRawSlot = kExpand ? (kTwoCta ? 128 : 256) * kRawRow : 0;
@@ -354,6 +360,7 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     constexpr int WPK = C::WPK;
     constexpr int kAStages = C::kAStages;
     constexpr int kRawStages = C::kRawStages;
+    constexpr int kBStages = C::kBStages;
     constexpr bool TWO = C::kTwoCta;
     constexpr bool TA = C::kTmemA;
     extern __shared__ unsigned char smem_raw[];
