@@ -106,6 +106,10 @@ constexpr uint32_t kBBytes = 256 * kRowBytes;  // 32 KB slot (240 or 256 rows in
 #ifndef SNV_TC_TA_RAWSTAGES
 #define SNV_TC_TA_RAWSTAGES 6
 #endif
+#ifndef SNV_TC_TA_STAGE_A
+#define SNV_TC_TA_STAGE_A 0  // 1: the next item's query rows are prefetched (cp.async) into shared memory while the current
+                             // item runs, so the hand-over at the item boundary reads shared memory, not L2
+#endif
 constexpr size_t kListBytes = 32 * 1024;  // one slot per (epilogue thread, column of a group): 32 x 256 floats
 constexpr size_t kListBytes16 = 64 * 1024; // 16 epilogue warps: 32 x 512 floats
 static_assert((Epi<8, true>::kParts - 1) * 8 * BM * 4 <= kListBytes && (Epi<32>::kParts - 1) * 32 * BM * 4 <= kListBytes,
@@ -132,7 +136,12 @@ struct Cfg {
     static constexpr int WPK = kFp4 ? 8 : 4;      // packed words per k-block
     static constexpr int WPM = kFp4 ? 2 : 1;      // packed words per MMA
     static constexpr int kAStages = kTmemA ? 0 : SNV_TC_ASTAGES;
-    static constexpr int kBStages = kTmemA ? SNV_TC_TA_BSTAGES : SNV_TC_BSTAGES;
+    static constexpr bool kStageA = kTmemA && SNV_TC_TA_STAGE_A;
+    static constexpr uint32_t kAStageRow = kMaxKbTmemA * kRowBytes + 16;   // staged query row (+16 B: spreads the banks)
+    static constexpr int kBStages = kTmemA ? (kStageA && SNV_TC_TA_BSTAGES > 4 ? 4 : SNV_TC_TA_BSTAGES) : SNV_TC_BSTAGES;
+    // bytes in front of the B ring: the query tile ring, or (TMEM-A mode) the staging rows of the next item's tile
+    static constexpr size_t kAOpBytes = kTmemA ? (kStageA ? (size_t)BM * kAStageRow : 0) : (size_t)kAStages * kABytes;
+    static_assert(kAOpBytes % 1024 == 0, "the B ring stays 1024-byte aligned");
     static constexpr int kRawStages = kTmemA ? SNV_TC_TA_RAWSTAGES : SNV_TC_RAWSTAGES;
     static constexpr int kBRows = kTwoCta ? BN / 2 : BN;          // panel rows this CTA expands per tile
     static constexpr uint32_t kRawRow = WPK * 4;                // raw bytes per panel row and k-block
@@ -143,8 +152,10 @@ struct Cfg {
     static constexpr uint32_t kACol = 2 * BN;                   // TMEM-A mode: first TMEM column of the query operand
     static constexpr uint32_t kSfCol = kTmemA ? 480 : 2 * BN;   // fp4: first TMEM column of the unit scales
     static_assert(!kTmemA || kACol + 32 * kMaxKbTmemA <= kSfCol, "TMEM budget");
-    static constexpr size_t kSmem = 1024 /*align slack*/ + (size_t)kAStages * kABytes + (size_t)kBStages * kBSlot +
-                                    (size_t)kRawStages * kRawSlot + ((kTwoCta && SNV_TC_EPI16) ? kListBytes16 : kListBytes) + (kTwoCta ? 4 : 2) * BM * 4 /*thresholds*/ + 256 /*barriers*/;
+    // mbarriers of the rings + TMEM stages, the TMEM base / runtime-one words and the a_full barrier
+    static constexpr size_t kBarBytes = ((size_t)(2 * (kAStages + kBStages + kRawStages + kAccStages)) * 8 + 16 + 255) / 256 * 256;
+    static constexpr size_t kSmem = 1024 /*align slack*/ + kAOpBytes + (size_t)kBStages * kBSlot +
+                                    (size_t)kRawStages * kRawSlot + ((kTwoCta && SNV_TC_EPI16) ? kListBytes16 : kListBytes) + (kTwoCta ? 4 : 2) * BM * 4 /*thresholds*/ + kBarBytes;
     static_assert(kSmem <= 232448, "shared memory budget");
 };
 
@@ -367,7 +378,7 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     const uint32_t raw_addr = smem_u32(smem_raw);
     unsigned char* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);  // SWIZZLE_128B tiles: 1024-byte aligned
     unsigned char* a_tiles = smem;
-    unsigned char* b_tiles = a_tiles + (size_t)kAStages * kABytes;
+    unsigned char* b_tiles = a_tiles + C::kAOpBytes;
     unsigned char* raws = b_tiles + (size_t)kBStages * C::kBSlot;
     uint32_t* lists = reinterpret_cast<uint32_t*>(raws + (size_t)kRawStages * C::kRawSlot);  // [group columns][epilogue threads]
     using E = Epi<KT, C::kTwoCta>;
@@ -722,11 +733,63 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                 else mbar_arrive(a_full);
             }
         };
+        // staged variant: stage_a() copies this thread's k-blocks of an item's row into shared memory asynchronously
+        // (the same thread reads them back, so cp.async.wait_group is all the ordering needed); load_a_staged() moves
+        // them on to tensor memory
+        [[maybe_unused]] auto stage_a = [&](int item_a) {
+            const uint32_t stage_row = smem_u32(a_tiles) + (uint32_t)row * C::kAStageRow;
+            const Item nx = decode_item(p, item_a, kQtMul, (int)cta_rank);
+            const int qa = nx.qt * BM + row;
+            const bool act = qa < p.nq;
+            const uint4* src = reinterpret_cast<const uint4*>(p.q_ops + ((int64_t)nx.w * p.nq + (act ? qa : 0)) * (int64_t)(KB * kRowBytes));
+#pragma unroll 1
+            for (int kb = part; kb < KB; kb += kParts) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint32_t dst = stage_row + (uint32_t)(kb * kRowBytes + c * 16);
+                    if (act) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + kb * 8 + c) : "memory");
+                    else asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        [[maybe_unused]] auto load_a_staged = [&]() {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            const uint32_t stage_row = smem_u32(a_tiles) + (uint32_t)row * C::kAStageRow;
+            const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + C::kACol;
+#pragma unroll 1
+            for (int kb = part; kb < KB; kb += kParts) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t v[16];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                     : "=r"(v[4 * c]), "=r"(v[4 * c + 1]), "=r"(v[4 * c + 2]), "=r"(v[4 * c + 3])
+                                     : "r"(stage_row + (uint32_t)(kb * kRowBytes + (h * 4 + c) * 16)));
+                    }
+                    tmem_st_32x32b_x16v(ta + (uint32_t)(kb * 32 + h * 16), v);
+                }
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (TWO && !leader) mbar_arrive_cluster(a_full, 0u);
+                else mbar_arrive(a_full);
+            }
+        };
         if constexpr (TA) {
-            if (item0 < p.items) load_a(item0);
+            if (item0 < p.items) {
+                if constexpr (C::kStageA) { stage_a(item0); load_a_staged(); }
+                else load_a(item0);
+            }
         }
         for (int item = item0; item < p.items; item += item_step) {
             const Item it = decode_item(p, item, kQtMul, (int)cta_rank);
+            if constexpr (C::kStageA) {
+                if (item + item_step < p.items) stage_a(item + item_step);  // lands while this item is scanned
+            }
             const int qi = it.qt * BM + row;
             const bool active = qi < p.nq;
             const int64_t q = (int64_t)it.w * p.nq + (active ? qi : 0);
@@ -781,7 +844,10 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                 if constexpr (TA) {
                     // the item's last accumulator is complete, so every MMA that reads its query tile has retired:
                     // tensor memory can take the next item's tile while this tile is still being scored
-                    if (t == it.ntiles - 1 && item + item_step < p.items) load_a(item + item_step);
+                    if (t == it.ntiles - 1 && item + item_step < p.items) {
+                        if constexpr (C::kStageA) load_a_staged();
+                        else load_a(item + item_step);
+                    }
                 }
                 // columns [pstart, pstart + pwidth) of the tile belong to this part.  TMEM-A mode (160-column tiles):
                 // 96 + 64 columns, the wide side alternating from tile to tile so that both parts score whole

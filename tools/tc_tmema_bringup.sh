@@ -28,5 +28,11 @@ for e in tc4x2 tc4x2ta; do
   echo "== $e cfg2 masked"; SNV_HAMMING_ENGINE=$e MASKED=1 W=296 timeout 60 python tools/time_hamming.py 2>&1 | tail -1
   echo "== $e cfg5 shard k=32"; SNV_HAMMING_ENGINE=$e W=8 N=25000 Q=10000 K=32 timeout 60 python tools/time_hamming.py 2>&1 | tail -1
 done
+# variants built by tools/build_tmema_variants.sh (if present): parity proxy = the checksums must equal the lines above
+for lib in tools/variants/libsnvknn_ta_*.so; do
+  [ -f "$lib" ] || continue
+  echo "== $(basename $lib) tc4x2ta cfg2"; SNVKNN_LIB=$PWD/$lib SNV_HAMMING_ENGINE=tc4x2ta W=296 timeout 60 python tools/time_hamming.py 2>&1 | tail -1
+  echo "== $(basename $lib) tc4x2ta cfg5 shard k=32"; SNVKNN_LIB=$PWD/$lib SNV_HAMMING_ENGINE=tc4x2ta W=8 N=25000 Q=10000 K=32 timeout 60 python tools/time_hamming.py 2>&1 | tail -1
+done
 } > gpurun_out/${TAG}_tmema.txt 2>&1
 cat gpurun_out/${TAG}_tmema.txt
