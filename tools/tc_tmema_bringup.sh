@@ -2,7 +2,8 @@
 # GPU bring-up of the TMEM-operand engine (SNV_HAMMING_ENGINE=tc4x2ta, hamming_tc_kernel<KT, MODE_FP4_2CTA_TA>):
 # 1. one tiny search under a timeout (a wrong barrier protocol would hang: never run it unguarded),
 # 2. parity against the popcount scan on random shapes, 3. timing next to the CTA-pair engine.
-# Not part of the test-suite until step 2 has passed on a B200.   Output: gpurun_out/${TAG}_tmema.txt
+# Not part of the test-suite until step 2 has passed on a B200.  Run tools/build_tmema_variants.sh (CPU) first to also
+# time the ring-depth / staged hand-over variants.   Output: gpurun_out/${TAG}_tmema.txt
 cd "$(dirname "$0")/.."
 TAG=${TAG:-r2}
 mkdir -p gpurun_out
