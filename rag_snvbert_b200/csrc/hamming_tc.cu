@@ -30,6 +30,13 @@
 // tile; slots are released and accumulators published with multicast tcgen05.commit, the peer's TMA completes on the
 // leader's barrier, the peer's expanders / epilogue arrive on the leader's barriers through mapa.
 //
+// Query operand in tensor memory (MODE_FP4_2CTA_TA, opt-in bring-up: SNV_HAMMING_ENGINE=tc4x2ta, <= 1280 sites): the
+// shared-memory port is what bounds the pair kernel (MMA operand reads + expander stores + TMA writes), and 38 % of
+// that traffic is the query tile, re-fetched and re-read for every panel tile.  Here the epilogue warps write an
+// item's query rows to TMEM once (tcgen05.st, thread = query row = lane, 8 codes per column) and the MMAs take A from
+// there (tcgen05.mma [d], [a], b-desc): no A ring, no A traffic.  TMEM = 2 x 160 accumulator columns + 160 operand
+// columns + 32 scale columns, so tiles are 160 panel rows wide.
+//
 // CTA (480 threads, one per SM, persistent over (window, query tile [pair], row split) items):
 //   warp 0       TMA producer of the query operand tile A [128 x 128 B] (SWIZZLE_128B)
 //   warp 1       TMEM allocator + MMA issuer (one elected lane): tcgen05.mma M128 / M256 into one of two accumulator stages
