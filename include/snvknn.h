@@ -232,6 +232,12 @@ int snv_last_hamming_engine(void);
 int snv_debug_hamming_plan(int n_windows, int nq, int64_t n, int d, int k, int32_t* plan_out, int64_t* items_out,
                            int64_t cap, int64_t* n_items);
 
+/* Host-only: the narrow-float operand codes the tensor-core engine derives from one packed word of a query (with its
+ * observed-site mask word) and of a panel row, computed by the same functions the kernels run.  fp4 != 0: E2M1, 16
+ * bytes each (2 codes per byte, 32 sites); fp4 == 0: E4M3, 32 bytes each (32 sites).  Byte i of q_codes multiplies
+ * byte i of panel_codes in the contraction; the sum over the word is popc((q ^ r) & m) - popc(q & m). */
+int snv_debug_tc_codes(int fp4, uint32_t q_word, uint32_t mask_word, uint32_t panel_word, uint8_t* q_codes, uint8_t* panel_codes);
+
 /* Host-only: the window-chunk boundaries snv_index_search would pipeline that search over (host_io != 0: queries or
  * results in host memory; 0: everything device resident = one chunk).  bounds_out[0 .. *n_bounds) = 0 < ... < n_windows. */
 int snv_debug_hamming_chunks(int n_windows, int nq, int64_t n, int d, int k, int host_io, int32_t* bounds_out, int cap,

@@ -56,6 +56,7 @@ SYMBOLS = {
     "snv_last_hamming_engine": (_i, []),
     "snv_debug_hamming_plan": (_i, [_i, _i, _i64, _i, _i, _vp, _vp, _i64, _vp]),
     "snv_debug_hamming_chunks": (_i, [_i, _i, _i64, _i, _i, _i, _vp, _i, _vp]),
+    "snv_debug_tc_codes": (_i, [_i, _u, _u, _u, _vp, _vp]),
 }
 
 _lib = None
@@ -141,6 +142,18 @@ def debug_hamming_plan(n_windows: int, nq: int, n: int, d: int, k: int, cap: int
     names = ["engine", "kt", "kblocks", "qtiles", "n_tiles", "nsplit", "tiles_per_split", "idx_bits", "tail_items",
              "tail_split", "tail_tiles", "workspace_kib"]
     return dict(zip(names, (int(v) for v in plan))), items[: cnt.value]
+
+
+def debug_tc_codes(fp4: bool, q_word: int, mask_word: int, panel_word: int):
+    """Operand codes of one packed word as the tensor-core kernels compute them (host only): (query codes, panel
+    codes) as uint8 arrays of 16 (fp4) or 32 (fp8) bytes."""
+    import numpy as np
+
+    n = 16 if fp4 else 32
+    a = np.zeros(n, np.uint8)
+    b = np.zeros(n, np.uint8)
+    check(lib().snv_debug_tc_codes(1 if fp4 else 0, q_word, mask_word, panel_word, a.ctypes.data, b.ctypes.data), "snv_debug_tc_codes")
+    return a, b
 
 
 def debug_hamming_chunks(n_windows: int, nq: int, n: int, d: int, k: int, host_io: bool = True):

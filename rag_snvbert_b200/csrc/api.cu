@@ -182,6 +182,13 @@ int snv_debug_hamming_plan(int n_windows, int nq, int64_t n, int d, int k, int32
     return SNV_OK;
 }
 
+int snv_debug_tc_codes(int fp4, uint32_t q_word, uint32_t mask_word, uint32_t panel_word, uint8_t* q_codes, uint8_t* panel_codes)
+{
+    if (!q_codes || !panel_codes) { set_error("snv_debug_tc_codes: null output"); return SNV_ERR_INVALID; }
+    hamming_tc_debug_codes(fp4, q_word, mask_word, panel_word, q_codes, panel_codes);
+    return SNV_OK;
+}
+
 int snv_debug_hamming_chunks(int n_windows, int nq, int64_t n, int d, int k, int host_io, int32_t* bounds_out, int cap,
                              int* n_bounds)
 {

@@ -171,14 +171,14 @@ struct Cfg {
 //   j (bit inside the byte):   0     1     2     3     4     5     6     7
 //   panel code              0x10  0x20  0x40  0x08  0x10  0x20  0x40  0x08   (2^-5 2^-3 2^1 2^-6 ...)
 //   query code              0x60  0x50  0x30  0x68  0x60  0x50  0x30  0x68   (32   8    0.5 64   ...)
-__device__ __forceinline__ void expand_panel_word_fp8(uint32_t w, uint4& c0, uint4& c1)
+__host__ __device__ __forceinline__ void expand_panel_word_fp8(uint32_t w, uint4& c0, uint4& c1)
 {
     const uint32_t lo = w << 4, hi = w >> 4;
     c0 = make_uint4(lo & 0x10101010u, lo & 0x20202020u, lo & 0x40404040u, w & 0x08080808u);
     c1 = make_uint4(w & 0x10101010u, w & 0x20202020u, w & 0x40404040u, hi & 0x08080808u);
 }
 
-__device__ __forceinline__ uint32_t query_code_fp8(int j)
+__host__ __device__ __forceinline__ uint32_t query_code_fp8(int j)
 {
     switch (j & 3) {
         case 0: return 0x60u;
@@ -192,12 +192,34 @@ __device__ __forceinline__ uint32_t query_code_fp8(int j)
 //   j (bit inside the nibble):  0    1    2    3 (moved to bit 2)
 //   panel code                  1    2    4    4        (0.5  1  2  2)
 //   query code                  4    2    1    1        (2    1  0.5 0.5), | 8 for allele 1
-__device__ __forceinline__ uint4 expand_panel_word_fp4(uint32_t w)
+__host__ __device__ __forceinline__ uint4 expand_panel_word_fp4(uint32_t w)
 {
     return make_uint4(w & 0x11111111u, w & 0x22222222u, w & 0x44444444u, (w >> 1) & 0x44444444u);
 }
 
-__device__ __forceinline__ uint32_t query_code_fp4(int j) { return j == 0 ? 4u : (j == 1 ? 2u : 1u); }
+__host__ __device__ __forceinline__ uint32_t query_code_fp4(int j) { return j == 0 ? 4u : (j == 1 ? 2u : 1u); }
+
+// One 16-byte chunk of a query operand row: fp4 - chunk <- one packed word (wq = q & m, wm = m), h unused;
+// fp8 - chunk pair (h = 0, 1) <- one packed word.  Code = magnitude where the site is observed, sign bit = allele 1.
+template <bool FP4>
+__host__ __device__ __forceinline__ uint4 expand_query_chunk(uint32_t wq, uint32_t wm, int h)
+{
+    uint32_t out[4];
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+        if constexpr (FP4) {
+            const uint32_t mb = (wm >> jj) & 0x11111111u;
+            const uint32_t sb = (wq >> jj) & 0x11111111u;
+            out[jj] = mb * query_code_fp4(jj) | sb * 8u;
+        } else {
+            const int j = 4 * h + jj;
+            const uint32_t mb = (wm >> j) & 0x01010101u;
+            const uint32_t sb = (wq >> j) & 0x01010101u;
+            out[jj] = mb * query_code_fp8(j) | sb * 0x80u;
+        }
+    }
+    return make_uint4(out[0], out[1], out[2], out[3]);
+}
 
 struct TcParams {
     int nw, nq, qtiles;      // qtiles: query tiles per window (tile PAIRS in the 2-CTA mode)
@@ -1029,21 +1051,7 @@ tc_expand_queries_kernel(const uint32_t* __restrict__ q, const uint32_t* __restr
             const int h = ch & 1;
             const uint32_t wm = observed(wi);
             const uint32_t wq = wi < words ? qr[wi] & wm : 0u;
-            uint32_t out[4];
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                if constexpr (FP4) {
-                    const uint32_t mb = (wm >> jj) & 0x11111111u;
-                    const uint32_t sb = (wq >> jj) & 0x11111111u;
-                    out[jj] = mb * query_code_fp4(jj) | sb * 8u;
-                } else {
-                    const int j = 4 * h + jj;
-                    const uint32_t mb = (wm >> j) & 0x01010101u;
-                    const uint32_t sb = (wq >> j) & 0x01010101u;
-                    out[jj] = mb * query_code_fp8(j) | sb * 0x80u;
-                }
-            }
-            out_row[ch] = make_uint4(out[0], out[1], out[2], out[3]);
+            out_row[ch] = expand_query_chunk<FP4>(wq, wm, h);
         }
     }
 }
@@ -1268,6 +1276,28 @@ static int64_t fill_item_fields(const HammingSearchParams& p, const HammingTcPla
         tail_rows = rows - tp.tail_row0;
     }
     return tail_rows;
+}
+
+// Host-side run of the operand code functions the kernels use (tests/test_tc_codes.py decodes the narrow floats and
+// checks that the contraction is the Hamming distance).  One packed word each of query, observed mask and panel row:
+// fp4: q_out / r_out 16 bytes (one chunk = 32 sites); fp8: 32 bytes (chunk pair).
+void hamming_tc_debug_codes(int fp4, uint32_t q, uint32_t m, uint32_t r, uint8_t* q_out, uint8_t* r_out)
+{
+    const uint32_t wq = q & m;
+    if (fp4) {
+        const uint4 a = expand_query_chunk<true>(wq, m, 0);
+        const uint4 b = expand_panel_word_fp4(r);
+        memcpy(q_out, &a, 16);
+        memcpy(r_out, &b, 16);
+    } else {
+        const uint4 a0 = expand_query_chunk<false>(wq, m, 0), a1 = expand_query_chunk<false>(wq, m, 1);
+        uint4 b0, b1;
+        expand_panel_word_fp8(r, b0, b1);
+        memcpy(q_out, &a0, 16);
+        memcpy(q_out + 16, &a1, 16);
+        memcpy(r_out, &b0, 16);
+        memcpy(r_out + 16, &b1, 16);
+    }
 }
 
 // Host-side enumeration of the work items a launch with this plan would run, through the same decode_item the

@@ -59,6 +59,8 @@ size_t hamming_tc_plan(const HammingSearchParams& p, HammingTcPlan& plan);
 int hamming_tc_launch(const HammingSearchParams& p, const HammingTcPlan& plan, void* ws, cudaStream_t stream);
 // host only: the work items of that launch, out [cap][8]; returns how many there are (see hamming_tc.cu)
 int64_t hamming_tc_debug_items(const HammingSearchParams& p, const HammingTcPlan& plan, int64_t* out, int64_t cap);
+// host only: operand codes of one packed word (query & mask -> A chunk, panel -> B chunk), fp4: 16 bytes, fp8: 32
+void hamming_tc_debug_codes(int fp4, uint32_t q, uint32_t m, uint32_t r, uint8_t* q_out, uint8_t* r_out);
 
 // ---------------------------------------------------------------- key merge / finalize
 // keys [nq_total][parts][kin] (uint64: hi = distance bits, lo = id, ~0 = empty) -> top k.
