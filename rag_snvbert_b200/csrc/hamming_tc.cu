@@ -205,7 +205,9 @@ template <bool FP4>
 __host__ __device__ __forceinline__ uint4 expand_query_chunk(uint32_t wq, uint32_t wm, int h)
 {
     uint32_t out[4];
+#ifdef __CUDA_ARCH__
 #pragma unroll
+#endif
     for (int jj = 0; jj < 4; ++jj) {
         if constexpr (FP4) {
             const uint32_t mb = (wm >> jj) & 0x11111111u;
@@ -357,7 +359,7 @@ __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, uint32_t v)
         ::"r"(taddr), "r"(v) : "memory");
 }
 
-__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16])
+[[maybe_unused]] __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16])
 {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
