@@ -17,4 +17,9 @@ build b3r4 -DSNV_TC_TA_BSTAGES=3 -DSNV_TC_TA_RAWSTAGES=4 &
 build b4r6 -DSNV_TC_TA_BSTAGES=4 -DSNV_TC_TA_RAWSTAGES=6 &
 build b8r8 -DSNV_TC_TA_BSTAGES=8 -DSNV_TC_TA_RAWSTAGES=8 &
 wait
+# diagnostic builds (wrong results by design): what is left without the epilogue / without the fold
+build noepi -DTC_DEBUG_NO_EPI &
+build nofold -DTC_DEBUG_NO_FOLD &
+build stagea_noepi -DSNV_TC_TA_STAGE_A=1 -DTC_DEBUG_NO_EPI &
+wait
 ls -la ../../tools/variants | grep ta_
