@@ -20,6 +20,8 @@ in a few lines of numpy — so what the fixtures pin is the REFERENCE-OWNED logi
   g4  V18 embedding search  EmbeddingRAGDataset.process_batch_retrieval
                             (embedding_rag_dataset.py:285-444) with the real BERTEmbedding:
                             torch.cdist + topk ids and the gathered rag_emb tensors
+  g5  observed-site search  expand_target_to_ref + build_partial_index_l2 (partial_faiss_intersect.py:46-111),
+                            see make_g5()
 """
 from __future__ import annotations
 
@@ -243,10 +245,82 @@ def main():
         dists_h1=topk_rec[0][0], I1=topk_rec[0][1], dists_h2=topk_rec[1][0], I2=topk_rec[1][1],
         rag_emb_h1=out["rag_emb_h1"].detach().numpy(), rag_emb_h2=out["rag_emb_h2"].detach().numpy(),
         k=np.array(k18))
+    make_g5()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")
 
 
+def make_g5():
+    """g5  observed-site search   expand_target_to_ref + build_partial_index_l2 of partial_faiss_intersect.py
+                                  (:46-80, :82-111), called per (window, target sample) as its main() does (:145-172).
+
+    build_partial_index_l2 lays the query out as [h1 sites.., h2 sites..] (:94) but the panel rows site-major
+    (s0h0, s0h1, s1h0, ..; :101) - a layout slip, so its literal output compares misaligned columns.  The fixture keeps
+    BOTH: `*_literal` = the function called exactly as main() calls it, and `*_aligned` = the same function given a
+    query whose [h1.., h2..] concatenation equals the site-major interleave (the evident intent, and what the engine
+    implements): everything else - valid-column selection from the mask, the per-sample panel slicing loop, the
+    index build and search - is the reference's own code in both."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("ref_pfi", os.path.join(REF, "partial_faiss_intersect.py"))
+    pfi = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(pfi)
+
+    rng = np.random.default_rng(55)
+    var_ref, s_ref, s_tgt, k = 260, 30, 5, 4
+    ref_pos = np.sort(rng.choice(np.arange(1000, 5000), var_ref, replace=False)).astype(np.int64)
+    # target: a subset of the ref sites (in order) plus a few positions the ref does not have
+    keep = np.sort(rng.choice(var_ref, 180, replace=False))
+    extra = np.setdiff1d(rng.choice(np.arange(1000, 5000), 40, replace=False), ref_pos)
+    tgt_pos = np.sort(np.concatenate([ref_pos[keep], extra])).astype(np.int64)
+    founders = (rng.random((6, var_ref)) < 0.35).astype(np.uint8)
+    ref_hap = founders[rng.integers(0, 6, 2 * s_ref)] ^ (rng.random((2 * s_ref, var_ref)) < 0.03)
+    ref_data = ref_hap.reshape(s_ref, 2, var_ref).transpose(2, 0, 1).astype(np.uint8).copy()        # [var_ref, S, 2]
+    tgt_full = founders[rng.integers(0, 6, 2 * s_tgt)] ^ (rng.random((2 * s_tgt, var_ref)) < 0.03)
+    tgt_full = tgt_full.reshape(s_tgt, 2, var_ref).transpose(2, 0, 1).astype(np.uint8)
+    pos_to_ref = {int(p): i for i, p in enumerate(ref_pos)}
+    tgt_data = np.zeros((tgt_pos.size, s_tgt, 2), np.uint8)
+    for t, p_ in enumerate(tgt_pos):
+        if int(p_) in pos_to_ref:
+            tgt_data[t] = tgt_full[pos_to_ref[int(p_)]]
+        else:
+            tgt_data[t] = rng.integers(0, 2, (s_tgt, 2))
+    expanded, missing_ref = pfi.expand_target_to_ref(ref_pos, tgt_data, tgt_pos)
+    missing = missing_ref.copy()  # the masks the searches below use (differs only where a window would have no site left)
+    windows = np.array([[0, 70], [70, 170], [170, 260], [40, 41]], np.int64)
+    I_lit = np.zeros((len(windows), s_tgt, k), np.int64)
+    D_lit = np.zeros((len(windows), s_tgt, k), np.float32)
+    I_al = np.zeros_like(I_lit)
+    D_al = np.zeros_like(D_lit)
+    for w, (a, b) in enumerate(windows):
+        ref_sub = np.transpose(ref_data[a:b], (1, 0, 2))  # (samp_ref, w_len, 2), :152-153
+        for s in range(s_tgt):
+            sub_tgt = expanded[a:b, s, :]
+            hap_1, hap_2 = sub_tgt[:, 0], sub_tgt[:, 1]
+            sub_mask = missing[a:b, s].copy()
+            if (sub_mask == 0).sum() == 0:
+                sub_mask[0] = 0  # keep at least one observed site: IndexFlatL2(0) is not a case main() survives
+                missing[a, s] = 0
+            kk = min(k, ref_sub.shape[0])
+            I, D, _, _ = pfi.build_partial_index_l2(hap_1, hap_2, sub_mask, ref_sub, top_k=kk)
+            I_lit[w, s], D_lit[w, s] = I, D
+            valid = np.where(sub_mask == 0)[0]
+            z = np.stack([hap_1[valid], hap_2[valid]], axis=1).reshape(-1)  # site-major interleave
+            h1p, h2p = hap_1.copy(), hap_2.copy()
+            h1p[valid], h2p[valid] = z[: valid.size], z[valid.size:]
+            I, D, _, _ = pfi.build_partial_index_l2(h1p, h2p, sub_mask, ref_sub, top_k=kk)
+            I_al[w, s], D_al[w, s] = I, D
+    np.savez_compressed(os.path.join(OUT, "g5_partial_intersect.npz"), ref_pos=ref_pos, tgt_pos=tgt_pos, tgt_data=tgt_data,
+                        ref_data=ref_data, expanded=expanded, missing_ref=missing_ref, missing=missing, windows=windows, k=np.array(k),
+                        I_literal=I_lit, D_literal=D_lit, I_aligned=I_al, D_aligned=D_al)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "g5":  # only the newest fixture (leaves g1-g4 untouched)
+        install_stubs()
+        sys.path.insert(0, REF)
+        os.chdir("/tmp")
+        make_g5()
+    else:
+        main()

@@ -113,3 +113,36 @@ def test_oracle_invariants():
     Dm, Im = O.merge_topk([d for d, _ in parts], [i + 125 * g for g, (_, i) in enumerate(parts)], 8, O.I32_MAX)
     np.testing.assert_array_equal(Im, Ie)
     np.testing.assert_array_equal(Dm, De)
+
+
+def test_g5_observed_site_search_matches_reference():
+    """partial_faiss_intersect.py: expand_target_to_ref (:46-80) and build_partial_index_l2 (:82-111) run by
+    tests/golden/make_golden.py; the product's host helper and the oracle's masked Hamming must reproduce them."""
+    from rag_snvbert_b200 import refdb
+
+    g = load("g5_partial_intersect.npz")
+    k = int(g["k"])
+    # product host code (numpy, no GPU involved) == the reference's own function
+    expanded, missing = refdb.expand_target_to_ref(g["ref_pos"], g["tgt_data"], g["tgt_pos"])
+    np.testing.assert_array_equal(expanded, g["expanded"])
+    np.testing.assert_array_equal(missing, g["missing_ref"])
+    rows_p = refdb.sample_rows(g["ref_data"], g["windows"])
+    rows_q = refdb.sample_rows(g["expanded"], g["windows"])
+    for w, (a, b) in enumerate(g["windows"]):
+        wl = b - a
+        panel = rows_p[w][:, : 2 * wl]
+        np.testing.assert_array_equal(panel, np.transpose(g["ref_data"][a:b], (1, 0, 2)).reshape(panel.shape[0], -1))
+        for s in range(rows_q.shape[1]):
+            observed = np.repeat(1 - g["missing"][a:b, s], 2)  # both haplotypes of a site share the sample's site mask
+            D, I = O.hamming_topk(panel, rows_q[w][s : s + 1, : 2 * wl], k, observed[None])
+            np.testing.assert_array_equal(I[0], g["I_aligned"][w, s])
+            np.testing.assert_array_equal(D[0].astype(np.float32), g["D_aligned"][w, s])
+            # the script's literal call pairs misaligned columns ([h1.., h2..] against s0h0, s0h1, ..): restated here only
+            # to show that the difference between `literal` and `aligned` is exactly that slip
+            valid = np.where(g["missing"][a:b, s] == 0)[0]
+            q_lit = np.concatenate([g["expanded"][a:b, s, 0][valid], g["expanded"][a:b, s, 1][valid]]).astype(np.int64)
+            p_lit = np.transpose(g["ref_data"][a:b], (1, 0, 2))[:, valid, :].reshape(panel.shape[0], -1).astype(np.int64)
+            d_lit = ((p_lit - q_lit[None]) ** 2).sum(1)
+            order = np.argsort(d_lit, kind="stable")[:k]
+            np.testing.assert_array_equal(order, g["I_literal"][w, s])
+            np.testing.assert_array_equal(d_lit[order].astype(np.float32), g["D_literal"][w, s])

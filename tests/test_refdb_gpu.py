@@ -107,3 +107,17 @@ def test_intersect_masks_on_device_match_host_and_drive_the_masked_search():
     Dh, Ih = index.search(q, 5, observed=obs_rows)
     np.testing.assert_array_equal(Id.cpu().numpy(), Ih)
     np.testing.assert_array_equal(Dd.cpu().numpy(), Dh)
+
+
+def test_partial_search_matches_the_reference_functions_golden():
+    """tests/golden/g5: (D, I) of the reference's own build_partial_index_l2 per (window, sample) on aligned columns
+    (partial_faiss_intersect.py:82-111, generated by tests/golden/make_golden.py) - windows of 70, 100, 90 and 1 site."""
+    import os
+
+    from rag_snvbert_b200 import refdb
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "g5_partial_intersect.npz"))
+    index = refdb.build_ref_db(g["ref_data"], g["windows"])
+    D, I = refdb.partial_search(index, g["expanded"], g["missing"], g["windows"], int(g["k"]))
+    np.testing.assert_array_equal(I, g["I_aligned"])
+    np.testing.assert_array_equal(D, g["D_aligned"])
