@@ -22,6 +22,7 @@ in a few lines of numpy — so what the fixtures pin is the REFERENCE-OWNED logi
                             torch.cdist + topk ids and the gathered rag_emb tensors
   g5  observed-site search  expand_target_to_ref + build_partial_index_l2 (partial_faiss_intersect.py:46-111),
                             see make_g5()
+  g6  offline DB workflow   build_ref_db_l2(args) + batch_test_faiss_l2(args) run whole, see make_g6()
 """
 from __future__ import annotations
 
@@ -246,6 +247,7 @@ def main():
         rag_emb_h1=out["rag_emb_h1"].detach().numpy(), rag_emb_h2=out["rag_emb_h2"].detach().numpy(),
         k=np.array(k18))
     make_g5()
+    make_g6()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")
@@ -316,11 +318,111 @@ def make_g5():
                         I_literal=I_lit, D_literal=D_lit, I_aligned=I_al, D_aligned=D_al)
 
 
+def make_g6():
+    """g6  offline DB workflow   build_ref_db_l2(args) (build_ref_db_l2.py:15-99) followed by batch_test_faiss_l2(args)
+                                  (batch_test_faiss_l2.py:48-136), both run WHOLE on synthetic files: a panel file and a
+                                  window csv read by the reference's PanelData / Window, genotypes served through an
+                                  h5py stub.  Pins the `window_{i}.npy` contents, the sample-row vector layout
+                                  (s0h0, s0h1, s1h0, ..) and the (D, I) of every window's batched search."""
+    import argparse
+    import importlib.util
+    import pickle
+    import shutil
+    import tempfile
+
+    rng = np.random.default_rng(66)
+    V, s_ref, s_tgt, k = 400, 36, 7, 5
+    founders = (rng.random((8, V)) < 0.3)
+    ref_gt = (founders[rng.integers(0, 8, 2 * s_ref)] ^ (rng.random((2 * s_ref, V)) < 0.02)).reshape(s_ref, 2, V).transpose(2, 0, 1)
+    tgt_gt = (founders[rng.integers(0, 8, 2 * s_tgt)] ^ (rng.random((2 * s_tgt, V)) < 0.02)).reshape(s_tgt, 2, V).transpose(2, 0, 1)
+    # multi-allelic codes > 0 are folded to 1 by the scripts (build_ref_db_l2.py:50, batch_test_faiss_l2.py:45)
+    ref_raw = ref_gt.astype(np.int8) * rng.integers(1, 3, ref_gt.shape).astype(np.int8)
+    tgt_raw = tgt_gt.astype(np.int8) * rng.integers(1, 3, tgt_gt.shape).astype(np.int8)
+    tgt_raw[3, 2] = ref_raw[3, 11]  # a planted near-copy is not needed: founders give ties already
+    pos = np.sort(rng.choice(np.arange(10_000, 90_000), V, replace=False)).astype(np.int64)
+    windows = np.array([[0, 130], [130, 250], [250, 400]], np.int64)
+
+    store = {}
+
+    class _Dataset:
+        def __init__(self, a):
+            self.a = a
+
+        def __getitem__(self, _):
+            return self.a.copy()
+
+    class _File:
+        def __init__(self, path, mode="r"):
+            self.d = store[str(path)]
+
+        def __getitem__(self, key):
+            return _Dataset(self.d[key])
+
+        def close(self):
+            pass
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+
+    sys.modules["h5py"].File = _File
+    faiss = sys.modules["faiss"]
+    faiss.write_index = lambda index, path: pickle.dump(index, open(path, "wb"))
+    faiss.read_index = lambda path: pickle.load(open(path, "rb"))
+
+    tmp = tempfile.mkdtemp(prefix="g6_")
+    try:
+        store[os.path.join(tmp, "ref.h5")] = {"calldata/GT": ref_raw, "variants/POS": pos}
+        store[os.path.join(tmp, "tgt.h5")] = {"calldata/GT": tgt_raw, "variants/POS": pos}
+        pops = ["AFR", "EUR", "EAS"]
+        with open(os.path.join(tmp, "ref.panel"), "w") as f:
+            f.write("sample\tpop\tsuper_pop\tgender\n")  # PanelData.from_file drops the header line (dataset.py:84-85)
+            for i in range(s_ref):
+                f.write(f"S{i}\tP{i % 5}\t{pops[i % 3]}\tmale\n")
+        with open(os.path.join(tmp, "win.csv"), "w") as f:
+            f.write("start,end\n" + "".join(f"{a},{b}\n" for a, b in windows))
+
+        def load(name):
+            spec = importlib.util.spec_from_file_location("ref_" + name, os.path.join(REF, name + ".py"))
+            m = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(m)
+            return m
+
+        db = os.path.join(tmp, "db")
+        load("build_ref_db_l2").build_ref_db_l2(argparse.Namespace(
+            ref_vcf=os.path.join(tmp, "ref.h5"), ref_panel=os.path.join(tmp, "ref.panel"),
+            window_csv=os.path.join(tmp, "win.csv"), output_dir=db))
+        rec = []
+        orig_search = _ShimIndexFlatL2.search
+
+        def rec_search(self, x, kk):
+            D, I = orig_search(self, x, kk)
+            rec.append((np.array(x), D, I))
+            return D, I
+
+        _ShimIndexFlatL2.search = rec_search
+        load("batch_test_faiss_l2").batch_test_faiss_l2(argparse.Namespace(
+            target_vcf=os.path.join(tmp, "tgt.h5"), window_csv=os.path.join(tmp, "win.csv"), ref_db=db, sample_idx=-1,
+            top_k=k, print_snippet=False, show_snp_len=10))
+        _ShimIndexFlatL2.search = orig_search
+        out = {"ref_raw": ref_raw, "tgt_raw": tgt_raw, "pos": pos, "windows": windows, "k": np.array(k)}
+        for w in range(len(windows)):
+            out[f"window_{w}"] = np.load(os.path.join(db, f"window_{w}.npy"))
+            out[f"pop_{w}"] = np.load(os.path.join(db, f"window_{w}_pop.npy"))
+            out[f"index_xb_{w}"] = pickle.load(open(os.path.join(db, f"window_{w}.faiss"), "rb")).xb
+            out[f"query_{w}"], out[f"D_{w}"], out[f"I_{w}"] = rec[w]
+        np.savez_compressed(os.path.join(OUT, "g6_ref_db_workflow.npz"), **out)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "g5":  # only the newest fixture (leaves g1-g4 untouched)
+    if len(sys.argv) > 1 and sys.argv[1] in ("g5", "g6"):  # only the newer fixtures (leaves g1-g4 untouched)
         install_stubs()
         sys.path.insert(0, REF)
         os.chdir("/tmp")
-        make_g5()
+        {"g5": make_g5, "g6": make_g6}[sys.argv[1]]()
     else:
         main()

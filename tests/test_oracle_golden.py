@@ -146,3 +146,26 @@ def test_g5_observed_site_search_matches_reference():
             order = np.argsort(d_lit, kind="stable")[:k]
             np.testing.assert_array_equal(order, g["I_literal"][w, s])
             np.testing.assert_array_equal(d_lit[order].astype(np.float32), g["D_literal"][w, s])
+
+
+def test_g6_offline_db_workflow_matches_reference():
+    """build_ref_db_l2.py + batch_test_faiss_l2.py run whole by tests/golden/make_golden.py: the sample-row vector layout
+    (product host helper), the window_{i}.npy contents and the per-window batched search results."""
+    from rag_snvbert_b200 import refdb
+
+    g = load("g6_ref_db_workflow.npz")
+    k = int(g["k"])
+    rows_p = refdb.sample_rows(g["ref_raw"], g["windows"])  # codes > 0 count as alt (build_ref_db_l2.py:50)
+    rows_q = refdb.sample_rows(g["tgt_raw"], g["windows"])
+    for w, (a, b) in enumerate(g["windows"]):
+        wl = b - a
+        np.testing.assert_array_equal(rows_p[w][:, : 2 * wl], g[f"index_xb_{w}"].astype(np.uint8))
+        assert (rows_p[w][:, 2 * wl:] == 0).all()
+        np.testing.assert_array_equal(rows_q[w][:, : 2 * wl], g[f"query_{w}"].astype(np.uint8))
+        np.testing.assert_array_equal(g[f"window_{w}"], np.transpose((g["ref_raw"][a:b] > 0), (1, 0, 2)).astype(np.int8))
+        D, I = O.hamming_topk(rows_p[w], rows_q[w], k)  # zero padding adds nothing
+        np.testing.assert_array_equal(I, g[f"I_{w}"])
+        np.testing.assert_array_equal(D.astype(np.float32), g[f"D_{w}"])
+        D2, I2 = O.l2_topk_f32_blas(g[f"index_xb_{w}"], g[f"query_{w}"], k)
+        np.testing.assert_array_equal(I2, g[f"I_{w}"])
+        np.testing.assert_array_equal(D2, g[f"D_{w}"])
