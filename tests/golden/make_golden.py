@@ -23,6 +23,7 @@ in a few lines of numpy — so what the fixtures pin is the REFERENCE-OWNED logi
   g5  observed-site search  expand_target_to_ref + build_partial_index_l2 (partial_faiss_intersect.py:46-111),
                             see make_g5()
   g6  offline DB workflow   build_ref_db_l2(args) + batch_test_faiss_l2(args) run whole, see make_g6()
+  g7  V18 inference search  EmbeddingRAGInferDataset.process_batch_retrieval (faiss flat index per window), see make_g7()
 """
 from __future__ import annotations
 
@@ -248,6 +249,7 @@ def main():
         k=np.array(k18))
     make_g5()
     make_g6()
+    make_g7()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")
@@ -418,11 +420,95 @@ def make_g6():
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+def make_g7():
+    """g7  V18 inference search   EmbeddingRAGInferDataset.process_batch_retrieval
+                                  (src/dataset/embedding_rag_infer_dataset.py:250-324) with the real BERTEmbedding: per
+                                  window group, faiss.IndexFlatL2(L*D).search of the flattened query embeddings against
+                                  the window's flattened masked-panel embeddings (built as :150-181 do), then the
+                                  unique-id re-embedding gather into rag_emb_h1 / rag_emb_h2.  Two windows, interleaved
+                                  batch: exercises the window grouping too."""
+    import torch
+
+    from src.dataset.embedding_rag_infer_dataset import EmbeddingRAGInferDataset
+    from src.dataset.vocab import WordVocab
+    from src.model.embedding.bert import BERTEmbedding
+
+    rng = np.random.default_rng(77)
+    torch.manual_seed(77)
+    vocab = WordVocab(["AFR", "EUR", "EAS"])
+    L, D, N, B, k = 80, 16, 40, 8, 2
+    emb = BERTEmbedding(vocab_size=len(vocab), embed_size=D, dropout=0.0, use_af=True)
+    emb.eval()
+    W = 2
+    ref_tokens_complete, ref_af, masks, flat_search, recs = [], [], [], [], []
+    for w in range(W):
+        hap = (rng.random((N, L - 2)) < 0.3).astype(np.int64)
+        tok = np.concatenate([np.full((N, 1), 2), np.where(hap == 0, 5, 6), np.full((N, 1), 3)], axis=1).astype(np.int64)
+        m = np.zeros(L, np.int64)
+        m[1:-1] = rng.random(L - 2) < 0.3
+        af = rng.random(L).astype(np.float32)
+        masked = tok.copy()
+        masked[:, m == 1] = vocab.mask_index
+        with torch.no_grad():
+            e = emb(torch.from_numpy(masked), af=torch.from_numpy(af).unsqueeze(0).expand(N, -1), pos=True)
+        ref_tokens_complete.append(tok)
+        ref_af.append(af)
+        masks.append(m)
+        flat_search.append(e.reshape(N, L * D).numpy().astype(np.float32))
+    indexes = []
+    for w in range(W):
+        ix = _ShimIndexFlatL2(L * D)   # :176-177
+        ix.add(flat_search[w])
+        indexes.append(ix)
+    win_of = [0, 1, 1, 0, 1, 0, 0, 1]
+    q_tok = np.zeros((2 * B, L), np.int64)
+    for i in range(2 * B):
+        w = win_of[i % B]
+        src = ref_tokens_complete[w][rng.integers(0, N)].copy()
+        flip = np.zeros(L, bool)
+        flip[1:-1] = rng.random(L - 2) < 0.05
+        src[flip] = np.where(src[flip] == 5, 6, 5)
+        src[masks[w] == 1] = vocab.mask_index
+        q_tok[i] = src
+    af_batch = np.stack([ref_af[w] for w in win_of])
+    fake = types.SimpleNamespace(embed_dim=D, ref_tokens_complete=ref_tokens_complete, ref_af_windows=ref_af,
+                                 load_index=lambda w: indexes[w])
+    orig_search = _ShimIndexFlatL2.search
+
+    def rec_search(self, x, k):
+        Dd, I = orig_search(self, x, k)
+        recs.append((np.array(x), Dd, I))
+        return Dd, I
+
+    _ShimIndexFlatL2.search = rec_search
+    batch = {"hap_1": torch.from_numpy(q_tok[:B]), "hap_2": torch.from_numpy(q_tok[B:]),
+             "af": torch.from_numpy(af_batch), "window_idx": torch.tensor(win_of)}
+    out = EmbeddingRAGInferDataset.process_batch_retrieval(fake, batch, emb, "cpu", k_retrieve=k)
+    _ShimIndexFlatL2.search = orig_search
+    # searches were issued per window group in first-appearance order (0 then 1), h1 then h2
+    groups = {w: [i for i, x in enumerate(win_of) if x == w] for w in (0, 1)}
+    g7 = {"k": np.array(k), "L": np.array(L), "D": np.array(D), "window_idx": np.array(win_of)}
+    r = 0
+    for w in (0, 1):
+        with torch.no_grad():
+            comp = emb(torch.from_numpy(ref_tokens_complete[w]),
+                       af=torch.from_numpy(ref_af[w]).unsqueeze(0).expand(N, -1), pos=True)
+        g7[f"ref_flat_{w}"] = flat_search[w]
+        g7[f"ref_complete_{w}"] = comp.numpy()
+        g7[f"members_{w}"] = np.array(groups[w])
+        for h in (1, 2):
+            g7[f"q{h}_flat_{w}"], g7[f"D{h}_{w}"], g7[f"I{h}_{w}"] = recs[r]
+            r += 1
+    g7["rag_emb_h1"] = out["rag_emb_h1"].numpy()
+    g7["rag_emb_h2"] = out["rag_emb_h2"].numpy()
+    np.savez_compressed(os.path.join(OUT, "g7_v18_infer.npz"), **g7)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] in ("g5", "g6"):  # only the newer fixtures (leaves g1-g4 untouched)
+    if len(sys.argv) > 1 and sys.argv[1] in ("g5", "g6", "g7"):  # only the newer fixtures (leaves g1-g4 untouched)
         install_stubs()
         sys.path.insert(0, REF)
         os.chdir("/tmp")
-        {"g5": make_g5, "g6": make_g6}[sys.argv[1]]()
+        {"g5": make_g5, "g6": make_g6, "g7": make_g7}[sys.argv[1]]()
     else:
         main()

@@ -169,3 +169,25 @@ def test_g6_offline_db_workflow_matches_reference():
         D2, I2 = O.l2_topk_f32_blas(g[f"index_xb_{w}"], g[f"query_{w}"], k)
         np.testing.assert_array_equal(I2, g[f"I_{w}"])
         np.testing.assert_array_equal(D2, g[f"D_{w}"])
+
+
+def test_g7_v18_inference_search_and_gather():
+    """EmbeddingRAGInferDataset.process_batch_retrieval (embedding_rag_infer_dataset.py:250-324): faiss flat L2 per
+    window group + unique-id gather, run by tests/golden/make_golden.py with the real BERTEmbedding."""
+    g = load("g7_v18_infer.npz")
+    k = int(g["k"])
+    for w in (0, 1):
+        ref = g[f"ref_flat_{w}"]
+        members = g[f"members_{w}"]
+        np.testing.assert_array_equal(members, np.where(g["window_idx"] == w)[0])  # the window grouping
+        for h in (1, 2):
+            q, Ig, Dg = g[f"q{h}_flat_{w}"], g[f"I{h}_{w}"], g[f"D{h}_{w}"]
+            d2 = O.l2_matrix_f64(ref, q)
+            tol = 1e-6 * ((q.astype(np.float64) ** 2).sum(1) + (ref.astype(np.float64) ** 2).sum(1).max())
+            D64, I64 = O.l2_topk_f64(ref, q, k)
+            O.assert_ids_match_within_tolerance(d2, I64, Ig, tol)
+            D32, I32 = O.l2_topk_f32_blas(ref, q, k)
+            O.assert_ids_match_within_tolerance(d2, I32, Ig, tol)
+            np.testing.assert_allclose(Dg, np.take_along_axis(d2, Ig, 1), rtol=0, atol=float(tol.max()) * 4)
+            rows = O.gather_rows(g[f"ref_complete_{w}"].reshape(ref.shape[0], -1), Ig)
+            np.testing.assert_array_equal(rows.reshape((len(members), k) + g["rag_emb_h1"].shape[2:]), g[f"rag_emb_h{h}"][members])
