@@ -141,32 +141,6 @@ def test_golden_g2_v17_collate_through_faiss_compat():
     np.testing.assert_array_equal(np.concatenate(h2), g["rag_seg_h2"])
 
 
-def test_golden_g7_v18_inference_search_and_gather():
-    """tests/golden/g7: the reference's EmbeddingRAGInferDataset.process_batch_retrieval (faiss.IndexFlatL2(L*D) per
-    window, embedding_rag_infer_dataset.py:250-324): ids within the stated tolerance, gathered rows exact."""
-    import rag_snvbert_b200.faiss_compat as faiss
-
-    g = np.load(os.path.join(G, "g7_v18_infer.npz"))
-    k = int(g["k"])
-    for w in (0, 1):
-        ref = np.ascontiguousarray(g[f"ref_flat_{w}"])
-        index = faiss.IndexFlatL2(ref.shape[1])  # :176-177
-        index.add(ref)
-        comp = np.ascontiguousarray(g[f"ref_complete_{w}"].reshape(ref.shape[0], -1))
-        cidx = _l2(comp.shape[1])
-        cidx.add(comp)
-        members = g[f"members_{w}"]
-        for h in (1, 2):
-            q = np.ascontiguousarray(g[f"q{h}_flat_{w}"])
-            D, I = index.search(q, k)  # :283-285
-            d64 = O.l2_matrix_f64(ref, q)
-            tol = 1e-5 * ((q.astype(np.float64) ** 2).sum(1) + (ref.astype(np.float64) ** 2).sum(1).max())
-            O.assert_ids_match_within_tolerance(d64, I, g[f"I{h}_{w}"], 2 * tol)
-            np.testing.assert_allclose(D, np.take_along_axis(d64, I, 1), rtol=0, atol=float(tol.max()))
-            rows = cidx.gather_rows(np.ascontiguousarray(g[f"I{h}_{w}"]))
-            np.testing.assert_array_equal(rows.reshape((len(members), k) + g["rag_emb_h1"].shape[2:]), g[f"rag_emb_h{h}"][members])
-
-
 def test_golden_g4_v18_embedding_search_and_gather():
     g = np.load(os.path.join(G, "g4_v18_embedding.npz"))
     k = int(g["k"])

@@ -107,50 +107,3 @@ def test_intersect_masks_on_device_match_host_and_drive_the_masked_search():
     Dh, Ih = index.search(q, 5, observed=obs_rows)
     np.testing.assert_array_equal(Id.cpu().numpy(), Ih)
     np.testing.assert_array_equal(Dd.cpu().numpy(), Dh)
-
-
-def test_partial_search_matches_the_reference_functions_golden():
-    """tests/golden/g5: (D, I) of the reference's own build_partial_index_l2 per (window, sample) on aligned columns
-    (partial_faiss_intersect.py:82-111, generated by tests/golden/make_golden.py) - windows of 70, 100, 90 and 1 site."""
-    import os
-
-    from rag_snvbert_b200 import refdb
-
-    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "g5_partial_intersect.npz"))
-    index = refdb.build_ref_db(g["ref_data"], g["windows"])
-    D, I = refdb.partial_search(index, g["expanded"], g["missing"], g["windows"], int(g["k"]))
-    np.testing.assert_array_equal(I, g["I_aligned"])
-    np.testing.assert_array_equal(D, g["D_aligned"])
-
-
-def test_offline_db_workflow_matches_the_reference_scripts_golden(tmp_path):
-    """tests/golden/g6: build_ref_db_l2.py and batch_test_faiss_l2.py run whole (tests/golden/make_golden.py).  The
-    window_{i}.npy files the reference wrote are read back by load_ref_db, the batched search must return the scripts'
-    (D, I); the scripts' literal calls (IndexFlatL2(dims).add / write_index / read_index / search) go through
-    faiss_compat with the same result."""
-    import os
-
-    import rag_snvbert_b200.faiss_compat as faiss
-    from rag_snvbert_b200 import refdb
-
-    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "g6_ref_db_workflow.npz"))
-    k, win = int(g["k"]), g["windows"]
-    for w in range(len(win)):
-        np.save(tmp_path / f"window_{w}.npy", g[f"window_{w}"])
-    index = refdb.load_ref_db(str(tmp_path), len(win))
-    D, I = refdb.batch_search(index, g["tgt_raw"], win, k)
-    built = refdb.build_ref_db(g["ref_raw"], win)
-    D2, I2 = refdb.batch_search(built, g["tgt_raw"], win, k)
-    for w in range(len(win)):
-        np.testing.assert_array_equal(I[w], g[f"I_{w}"])
-        np.testing.assert_array_equal(D[w], g[f"D_{w}"])
-        np.testing.assert_array_equal(I2[w], g[f"I_{w}"])
-        np.testing.assert_array_equal(D2[w], g[f"D_{w}"])
-        # build_ref_db_l2.py:86-93 and batch_test_faiss_l2.py:94,110, call for call
-        flat = faiss.IndexFlatL2(g[f"index_xb_{w}"].shape[1])
-        flat.add(g[f"index_xb_{w}"])
-        faiss.write_index(flat, str(tmp_path / f"window_{w}.faiss"))
-        again = faiss.read_index(str(tmp_path / f"window_{w}.faiss"))
-        Df, If = again.search(g[f"query_{w}"], k)
-        np.testing.assert_array_equal(If, g[f"I_{w}"])
-        np.testing.assert_array_equal(Df, g[f"D_{w}"])
