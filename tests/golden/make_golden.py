@@ -24,6 +24,7 @@ in a few lines of numpy — so what the fixtures pin is the REFERENCE-OWNED logi
                             see make_g5()
   g6  offline DB workflow   build_ref_db_l2(args) + batch_test_faiss_l2(args) run whole, see make_g6()
   g7  V18 inference search  EmbeddingRAGInferDataset.process_batch_retrieval (faiss flat index per window), see make_g7()
+  g8  intersect workflow    build_ref_db_intersect(args) + test_faiss_intersect(args) in both distance modes, see make_g8()
 """
 from __future__ import annotations
 
@@ -250,6 +251,7 @@ def main():
     make_g5()
     make_g6()
     make_g7()
+    make_g8()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")
@@ -504,11 +506,137 @@ def make_g7():
     np.savez_compressed(os.path.join(OUT, "g7_v18_infer.npz"), **g7)
 
 
+class _ShimIndexBinaryFlat:
+    """faiss.IndexBinaryFlat in numpy: Hamming distance between np.packbits codes, int32 D, (distance, id) order."""
+
+    def __init__(self, d_bits):
+        self.d = int(d_bits)
+        self.codes = np.zeros((0, (self.d + 7) // 8), np.uint8)
+
+    @property
+    def ntotal(self):
+        return self.codes.shape[0]
+
+    def add(self, x):
+        x = np.ascontiguousarray(x, dtype=np.uint8)
+        assert x.ndim == 2 and x.shape[1] == self.codes.shape[1]
+        self.codes = np.concatenate([self.codes, x])
+
+    def search(self, x, k):
+        x = np.ascontiguousarray(x, dtype=np.uint8)
+        dist = np.unpackbits(x[:, None, :] ^ self.codes[None, :, :], axis=2).sum(2).astype(np.int32)
+        order = np.argsort(dist, axis=1, kind="stable")[:, :k]
+        return np.take_along_axis(dist, order, 1), order.astype(np.int64)
+
+
+def make_g8():
+    """g8  intersect workflow    build_ref_db_intersect(args) (build_ref_db_intersect.py:14-81) followed by
+                                  test_faiss_intersect(args) (test_faiss_intersect.py:57-203) in BOTH distance modes
+                                  ('l2': IndexFlatL2 on the shared sites; 'binary': bitpack_2d_array + IndexBinaryFlat),
+                                  run whole on synthetic files.  The target carries the reference's variant list except
+                                  that a quarter of its positions differ, so every window's intersection is partial
+                                  (the script slices the target with the same index window as the reference).
+                                  Pins window_{i}_pos.npy, the per-window shared-site sets and both modes' (D, I)."""
+    import argparse
+    import importlib.util
+    import shutil
+    import tempfile
+
+    rng = np.random.default_rng(88)
+    V, s_ref, s_tgt, k = 360, 40, 6, 4
+    founders = (rng.random((8, V)) < 0.3)
+    ref_gt = (founders[rng.integers(0, 8, 2 * s_ref)] ^ (rng.random((2 * s_ref, V)) < 0.02)).reshape(s_ref, 2, V).transpose(2, 0, 1).astype(np.int8)
+    tgt_gt = (founders[rng.integers(0, 8, 2 * s_tgt)] ^ (rng.random((2 * s_tgt, V)) < 0.02)).reshape(s_tgt, 2, V).transpose(2, 0, 1).astype(np.int8)
+    ref_pos = (1000 + 5 * np.arange(V) + rng.integers(0, 2, V)).astype(np.int64)     # gaps >= 4
+    tgt_pos = ref_pos.copy()
+    moved = rng.random(V) < 0.25
+    tgt_pos[moved] += 2                                                                # never equals another ref position
+    windows = np.array([[0, 100], [100, 232], [232, 360]], np.int64)                   # 2 * shared sites happens to vary mod 8
+    store = {}
+
+    class _Dataset:
+        def __init__(self, a):
+            self.a = a
+
+        def __getitem__(self, _):
+            return self.a.copy()
+
+    class _File:
+        def __init__(self, path, mode="r"):
+            self.d = store[str(path)]
+
+        def __getitem__(self, key):
+            return _Dataset(self.d[key])
+
+        def close(self):
+            pass
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+
+    sys.modules["h5py"].File = _File
+    sys.modules["faiss"].IndexBinaryFlat = _ShimIndexBinaryFlat
+    tmp = tempfile.mkdtemp(prefix="g8_")
+    try:
+        store[os.path.join(tmp, "ref.h5")] = {"calldata/GT": ref_gt, "variants/POS": ref_pos}
+        store[os.path.join(tmp, "tgt.h5")] = {"calldata/GT": tgt_gt, "variants/POS": tgt_pos}
+        with open(os.path.join(tmp, "ref.panel"), "w") as f:
+            f.write("sample\tpop\tsuper_pop\tgender\n")
+            for i in range(s_ref):
+                f.write(f"S{i}\tP{i % 5}\t{['AFR', 'EUR', 'EAS'][i % 3]}\tmale\n")
+        with open(os.path.join(tmp, "win.csv"), "w") as f:
+            f.write("start,end\n" + "".join(f"{a},{b}\n" for a, b in windows))
+
+        def load(name):
+            spec = importlib.util.spec_from_file_location("ref_" + name, os.path.join(REF, name + ".py"))
+            m = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(m)
+            return m
+
+        db = os.path.join(tmp, "db")
+        load("build_ref_db_intersect").build_ref_db_intersect(argparse.Namespace(
+            ref_vcf=os.path.join(tmp, "ref.h5"), ref_panel=os.path.join(tmp, "ref.panel"),
+            window_csv=os.path.join(tmp, "win.csv"), output_dir=db))
+        tfi = load("test_faiss_intersect")
+        out = {"ref_gt": ref_gt, "tgt_gt": tgt_gt, "ref_pos": ref_pos, "tgt_pos": tgt_pos, "windows": windows, "k": np.array(k)}
+        for mode, shim in (("l2", _ShimIndexFlatL2), ("binary", _ShimIndexBinaryFlat)):
+            rec = []
+            orig_add, orig_search = shim.add, shim.search
+
+            def rec_add(self, x, _o=orig_add):
+                rec.append(["add", np.array(x)])
+                return _o(self, x)
+
+            def rec_search(self, x, kk, _o=orig_search):
+                D, I = _o(self, x, kk)
+                rec.append(["search", np.array(x), D, I])
+                return D, I
+
+            shim.add, shim.search = rec_add, rec_search
+            tfi.test_faiss_intersect(argparse.Namespace(
+                target_vcf=os.path.join(tmp, "tgt.h5"), ref_db=db, window_csv=os.path.join(tmp, "win.csv"),
+                distance_mode=mode, top_k=k, sample_idx=-1, show_snps=False, show_snp_len=10))
+            shim.add, shim.search = orig_add, orig_search
+            assert len(rec) == 2 * len(windows)
+            for w in range(len(windows)):
+                out[f"{mode}_added_{w}"] = rec[2 * w][1]
+                out[f"{mode}_query_{w}"], out[f"{mode}_D_{w}"], out[f"{mode}_I_{w}"] = rec[2 * w + 1][1:]
+        for w in range(len(windows)):
+            out[f"window_{w}"] = np.load(os.path.join(db, f"window_{w}.npy"))
+            out[f"window_pos_{w}"] = np.load(os.path.join(db, f"window_{w}_pos.npy"))
+        np.savez_compressed(os.path.join(OUT, "g8_intersect_workflow.npz"), **out)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] in ("g5", "g6", "g7"):  # only the newer fixtures (leaves g1-g4 untouched)
+    if len(sys.argv) > 1 and sys.argv[1] in ("g5", "g6", "g7", "g8"):  # only the newer fixtures (leaves g1-g4 untouched)
         install_stubs()
         sys.path.insert(0, REF)
         os.chdir("/tmp")
-        {"g5": make_g5, "g6": make_g6, "g7": make_g7}[sys.argv[1]]()
+        {"g5": make_g5, "g6": make_g6, "g7": make_g7, "g8": make_g8}[sys.argv[1]]()
     else:
         main()

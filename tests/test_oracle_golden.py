@@ -191,3 +191,31 @@ def test_g7_v18_inference_search_and_gather():
             np.testing.assert_allclose(Dg, np.take_along_axis(d2, Ig, 1), rtol=0, atol=float(tol.max()) * 4)
             rows = O.gather_rows(g[f"ref_complete_{w}"].reshape(ref.shape[0], -1), Ig)
             np.testing.assert_array_equal(rows.reshape((len(members), k) + g["rag_emb_h1"].shape[2:]), g[f"rag_emb_h{h}"][members])
+
+
+def test_g8_intersect_workflow_matches_reference():
+    """build_ref_db_intersect.py + test_faiss_intersect.py (both distance modes) run whole by tests/golden/make_golden.py:
+    the shared-site selection (product host helpers), the np.packbits codes and both modes' (D, I)."""
+    from rag_snvbert_b200 import refdb
+
+    g = load("g8_intersect_workflow.npz")
+    k, win = int(g["k"]), g["windows"]
+    obs = refdb.intersect_windows(g["ref_pos"], g["tgt_pos"], win)            # [W, Lmax] per site
+    expanded, missing = refdb.expand_target_to_ref(g["ref_pos"], g["tgt_gt"], g["tgt_pos"])
+    rows_p = refdb.sample_rows(g["ref_gt"], win)
+    rows_q = refdb.sample_rows(expanded, win)
+    for w, (a, b) in enumerate(win):
+        wl = b - a
+        np.testing.assert_array_equal(g[f"window_pos_{w}"], g["ref_pos"][a:b])
+        np.testing.assert_array_equal(obs[w, :wl], 1 - missing[a:b, 0])       # the two host helpers agree on the shared sites
+        cols = np.repeat(obs[w, :wl], 2).astype(bool)                          # both haplotypes of a shared site
+        np.testing.assert_array_equal(rows_p[w][:, : 2 * wl][:, cols], g[f"l2_added_{w}"].astype(np.uint8))
+        np.testing.assert_array_equal(rows_q[w][:, : 2 * wl][:, cols], g[f"l2_query_{w}"].astype(np.uint8))
+        np.testing.assert_array_equal(O.packbits_msb(g[f"l2_added_{w}"].astype(np.uint8)), g[f"binary_added_{w}"])
+        np.testing.assert_array_equal(O.packbits_msb(g[f"l2_query_{w}"].astype(np.uint8)), g[f"binary_query_{w}"])
+        observed = np.zeros(rows_p.shape[2], np.uint8)
+        observed[: 2 * wl] = cols
+        D, I = O.hamming_topk(rows_p[w], rows_q[w], k, observed)
+        for mode in ("l2", "binary"):
+            np.testing.assert_array_equal(I, g[f"{mode}_I_{w}"])
+            np.testing.assert_array_equal(D.astype(g[f"{mode}_D_{w}"].dtype), g[f"{mode}_D_{w}"])
