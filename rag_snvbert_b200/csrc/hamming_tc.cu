@@ -722,6 +722,7 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     } else {
         // ================= epilogue: thread = query row (TMEM lane), kParts warps per lane quarter =================
         constexpr int kParts = E::kParts, kPartCols = E::kPartCols, G = E::kGroup;
+        static_assert(!TA || kParts == 2, "the TMEM-A tile split (96 + 64 columns) is written for two column parts");
         constexpr uint32_t kSlotStride = E::kSlotStride;
         const int quarter = warp & 3;                   // TMEM lanes [32 * quarter, +32)
         const int part = (warp - kFirstEpiWarp) >> 2;   // columns [kPartCols * part, +kPartCols) of every tile
