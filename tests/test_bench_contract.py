@@ -57,3 +57,16 @@ def test_product_arm_needs_a_gpu():
     assert r.returncode != 0
     assert "no CUDA device" in (r.stderr + r.stdout)
     assert _json_lines(r.stdout) == []
+
+
+def test_reference_arm_under_torchrun_two_ranks():
+    """the driver's own launch line for N > 1: rank 0 alone measures and prints, the other rank exits 0"""
+    e = dict(os.environ)
+    e.pop("SNV_HAMMING_ENGINE", None)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29631", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+           "--warmup", "0", "--cpu-seconds", "2", "--windows", "20"]
+    r = subprocess.run(cmd, cwd=ROOT, env=e, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = _json_lines(r.stdout)
+    assert len(lines) == 1 and lines[0]["impl"] == "reference" and lines[0]["n_gpus"] == 2 and lines[0]["value"] > 0
