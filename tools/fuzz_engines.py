@@ -14,9 +14,13 @@ n_cases = int(os.environ.get("CASES", "120"))
 bad = 0
 # ENGINES="tc4x2ta" (comma separated) checks other builds / bring-up engines against the popcount scan
 TC_ENGINES = tuple(e for e in os.environ.get("ENGINES", "tc,tc4,tc4x2").split(",") if e)
+# panel sizes around the tile widths (240 / 256 rows; 160 for the TMEM-operand engine)
+N_CHOICES = [1, 7, 100, 239, 240, 241, 479, 481, 1000, 2500, 5008, 12000]
+if "tc4x2ta" in TC_ENGINES:
+    N_CHOICES += [159, 160, 161, 319, 321, 800]
 for case in range(n_cases):
     W = int(rng.choice([1, 1, 2, 3, 5, 9]))
-    N = int(rng.choice([1, 7, 100, 239, 240, 241, 479, 481, 1000, 2500, 5008, 12000]))
+    N = int(rng.choice(N_CHOICES))
     Q = int(rng.choice([1, 2, 31, 33, 127, 128, 129, 255, 257, 600]))
     d = int(rng.choice([5, 64, 255, 256, 257, 511, 513, 1024, 1030, 1057, 2049, 3000]))
     k = int(rng.choice([1, 2, 5, 8, 9, 17, 32]))
