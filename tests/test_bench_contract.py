@@ -70,3 +70,12 @@ def test_reference_arm_under_torchrun_two_ranks():
     assert r.returncode == 0, r.stderr[-2000:]
     lines = _json_lines(r.stdout)
     assert len(lines) == 1 and lines[0]["impl"] == "reference" and lines[0]["n_gpus"] == 2 and lines[0]["value"] > 0
+
+
+def test_reference_arm_cfg5_runs_on_the_host():
+    """cfg 5 (200k-row panel, k = 32): the CPU arm sub-samples the queries of a window and needs no GPU"""
+    r = _run(["--workload", "cfg5", "--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-seconds", "2", "--refs", "20000"])
+    assert r.returncode == 0, r.stderr[-2000:]
+    (d,) = _json_lines(r.stdout)
+    assert d["impl"] == "reference" and "k=32" in d["metric"] and d["scaling"] == "strong" and d["value"] > 0
+    assert "cfg5" in d["config"]["workload"] and "20000 ref" in d["config"]["workload"]
