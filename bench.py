@@ -181,6 +181,14 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- CPU arm
+def host_threads() -> int:
+    """Cores this process may run on (not OMP_NUM_THREADS: torchrun sets that to 1 for every rank)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_reference_sample(a, seconds):
     """The reference's CPU algorithm for this path (faiss IndexBinaryFlat-style popcount scan +
     per-query heap, restated in oracle/snv_oracle.c: 'port'; faiss itself is absent from the
@@ -189,7 +197,9 @@ def cpu_reference_sample(a, seconds):
     from oracle import oracle as O
     from oracle import cbind
 
-    threads = cbind.max_threads()
+    # explicit thread count: torch.distributed.run exports OMP_NUM_THREADS=1 to every rank, which must not
+    # handicap the baseline (the arm runs on rank 0 alone and may use every core the process is allowed on)
+    threads = host_threads()
     s = (a.sites + 31) // 32
     stride = -(-s // 4) * 4
     # the sample is made of whole windows (a smaller slice under-reports the rate and the sample comes out short),
@@ -203,9 +213,9 @@ def cpu_reference_sample(a, seconds):
         rate = rng.uniform(0.1, 0.9, size=(nq0, 1))
         M = O.pack_bits_u32((rng.random((nq0, a.sites)) >= rate).astype(np.uint8), stride)[None]
     # calibrate on one window, then size the sample for ~`seconds`
-    cbind.hamming_topk_packed(P, Qfull[:, :nq0], a.k, None if M is None else M[:, :nq0], words=s)
+    cbind.hamming_topk_packed(P, Qfull[:, :nq0], a.k, None if M is None else M[:, :nq0], words=s, n_threads=threads)
     t0 = time.perf_counter()
-    cbind.hamming_topk_packed(P, Qfull[:, :nq0], a.k, None if M is None else M[:, :nq0], words=s)
+    cbind.hamming_topk_packed(P, Qfull[:, :nq0], a.k, None if M is None else M[:, :nq0], words=s, n_threads=threads)
     dt0 = max(time.perf_counter() - t0, 1e-6)
     rate0 = nq0 * a.refs / dt0
     n_win = int(max(1, min(a.windows, seconds * rate0 / (nq0 * a.refs))))
@@ -213,7 +223,7 @@ def cpu_reference_sample(a, seconds):
     Qn = np.ascontiguousarray(np.broadcast_to(Qfull, (n_win,) + Qfull.shape[1:]))
     Mn = None if M is None else np.ascontiguousarray(np.broadcast_to(M, (n_win,) + M.shape[1:]))
     t0 = time.perf_counter()
-    cbind.hamming_topk_packed(Pn, Qn, a.k, Mn, words=s)
+    cbind.hamming_topk_packed(Pn, Qn, a.k, Mn, words=s, n_threads=threads)
     dt = time.perf_counter() - t0
     val = n_win * nq0 * a.refs / dt
     sample = (f"{n_win} of {a.windows} windows x {nq0}" + ("" if nq0 == a.queries else f" of {a.queries}") +
@@ -474,11 +484,18 @@ def cfg4_cpu(a, refs, q):
     """faiss's BLAS path restated with numpy/OpenBLAS (oracle.l2_topk_f32_blas), all host threads."""
     from oracle import oracle as O
 
-    O.l2_topk_f32_blas(refs[:512], q[:256], a.k)
-    t0 = time.perf_counter()
-    O.l2_topk_f32_blas(refs, q, a.k)
-    dt = time.perf_counter() - t0
-    threads = len(os.sched_getaffinity(0))
+    threads = host_threads()
+    try:  # BLAS pools also obey torchrun's OMP_NUM_THREADS=1: set the pool size explicitly
+        from threadpoolctl import threadpool_limits
+        ctx = threadpool_limits(limits=threads)
+    except Exception:
+        import contextlib
+        ctx = contextlib.nullcontext()
+    with ctx:
+        O.l2_topk_f32_blas(refs[:512], q[:256], a.k)
+        t0 = time.perf_counter()
+        O.l2_topk_f32_blas(refs, q, a.k)
+        dt = time.perf_counter() - t0
     sample = (f"full step: {q.shape[0]} queries x {refs.shape[0]} refs x dim {refs.shape[1]}, k={a.k}, numpy/BLAS "
               f"|x|^2+|y|^2-2xy restatement of faiss (oracle.l2_topk_f32_blas), {threads} host threads, {dt:.2f} s")
     return q.shape[0] * refs.shape[0] / dt, threads, sample, dt

@@ -70,6 +70,10 @@ def test_reference_arm_under_torchrun_two_ranks():
     assert r.returncode == 0, r.stderr[-2000:]
     lines = _json_lines(r.stdout)
     assert len(lines) == 1 and lines[0]["impl"] == "reference" and lines[0]["n_gpus"] == 2 and lines[0]["value"] > 0
+    # torchrun exports OMP_NUM_THREADS=1 to its ranks: the baseline must still use every core the process may run on
+    cores = len(os.sched_getaffinity(0))
+    assert lines[0]["cpu_baseline"]["cores"] == cores
+    assert f"{cores} OpenMP threads" in lines[0]["cpu_baseline"]["sample"]
 
 
 def test_reference_arm_cfg5_runs_on_the_host():
