@@ -88,8 +88,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
 
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
+#ifdef TC_DEBUG_SPIN_WAIT
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+#else
     while (!mbar_try_wait(bar, parity)) {
     }
+#endif
 }
 
 // For waits that are normally long and not latency critical (a producer running ahead of its

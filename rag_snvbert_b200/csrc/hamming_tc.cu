@@ -64,6 +64,21 @@
 #ifndef SNV_TC_EPI16
 #define SNV_TC_EPI16 0  // 1: 16 epilogue warps for k <= 8 in the CTA-pair kernel (measured slower on B200: 1.98 vs 1.76 ms per 296 windows)
 #endif
+#ifndef SNV_TC_LIST_EPI
+#define SNV_TC_LIST_EPI 1  // fp4 engines: candidate-list epilogue (column index carried by the accumulator, folds deferred to tile ends)
+#endif
+#ifndef SNV_TC_LIST_CAP
+#define SNV_TC_LIST_CAP 32  // pending entries (column pairs) a thread can hold (x 8 B x epilogue threads of shared memory)
+#endif
+#ifndef SNV_TC_FOLD_AT
+#define SNV_TC_FOLD_AT 16   // fold inside a tile when some lane holds this many entries (<= SNV_TC_LIST_CAP - 16)
+#endif
+#ifndef SNV_TC_DEFER_PUBLISH
+#define SNV_TC_DEFER_PUBLISH 1  // expanders publish a B slot one k-block late (its stores drain behind the next block's loads)
+#endif
+#ifndef SNV_TC_WARP_ARRIVE
+#define SNV_TC_WARP_ARRIVE 1  // epilogue warps release an accumulator stage with one arrival per warp (0: one per thread)
+#endif
 #ifndef SNV_TC_DEFAULT_ENGINE
 #define SNV_TC_DEFAULT_ENGINE 4  // what "auto" picks for tensor-core shapes: 1 = fp8, 3 = fp4, 4 = fp4 on CTA pairs
 #endif
@@ -121,6 +136,7 @@ constexpr size_t kListBytes = 32 * 1024;  // one slot per (epilogue thread, colu
 constexpr size_t kListBytes16 = 64 * 1024; // 16 epilogue warps: 32 x 512 floats
 static_assert((Epi<8, true>::kParts - 1) * 8 * BM * 4 <= kListBytes && (Epi<32>::kParts - 1) * 32 * BM * 4 <= kListBytes,
               "the part-exchange buffer aliases the candidate slots");
+static_assert((size_t)SNV_TC_LIST_CAP * 2048 >= (size_t)32 * BM * 4, "the part-exchange buffer aliases the candidate lists");
 
 enum { MODE_FP8 = 0, MODE_FP8_HBM = 1, MODE_FP4 = 2, MODE_FP4_2CTA = 3, MODE_FP4_2CTA_TA = 4 };
 
@@ -139,6 +155,15 @@ struct Cfg {
     static constexpr bool kTmemA = MODE == MODE_FP4_2CTA_TA;
     static constexpr int kMaxKbTmemA = 5;
     static constexpr bool kExpand = MODE != MODE_FP8_HBM;
+    // Candidate-list epilogue (fp4 engines).  One extra MMA per tile adds (panel row within the tile) / 256 to every
+    // accumulator - operand codes 1.0 on the query side, a constant per-row code block on the panel side, block scale
+    // 2^-8 - so a candidate's value carries its own column: the scan is compare + predicated append to a per-thread
+    // list, and the lists are folded into the sorted top-k once per tile part (or when a list fills) instead of after
+    // every 32 columns.
+    static constexpr bool kListEpi = kFp4 && kTwoCta && SNV_TC_LIST_EPI;  // (the single-CTA kernel has no shared memory left for lists)
+    static constexpr int kListCap = SNV_TC_LIST_CAP;
+    static constexpr int kFoldAt = SNV_TC_FOLD_AT;
+    static_assert(!kListEpi || kFoldAt + 16 <= kListCap, "a 32-column group (16 pairs) must always fit behind the fold mark");
     static constexpr int BN = kTmemA ? 160 : (kFp4 ? 240 : 256);   // panel rows per tile = TMEM columns per accumulator stage
     static constexpr int WPK = kFp4 ? 8 : 4;      // packed words per k-block
     static constexpr int WPM = kFp4 ? 2 : 1;      // packed words per MMA
@@ -161,8 +186,11 @@ struct Cfg {
     static_assert(!kTmemA || kACol + 32 * kMaxKbTmemA <= kSfCol, "TMEM budget");
     // mbarriers of the rings + TMEM stages, the TMEM base / runtime-one words and the a_full barrier
     static constexpr size_t kBarBytes = ((size_t)(2 * (kAStages + kBStages + kRawStages + kAccStages)) * 8 + 16 + 255) / 256 * 256;
+    // candidate slots / lists of the epilogue threads (8 warps; 16 with SNV_TC_EPI16 in the pair kernels at k <= 8)
+    static constexpr size_t kSlotBytes = kListEpi ? (size_t)kListCap * 8 * ((kTwoCta && SNV_TC_EPI16) ? 512 : 256)
+                                                  : ((kTwoCta && SNV_TC_EPI16) ? kListBytes16 : kListBytes);
     static constexpr size_t kSmem = 1024 /*align slack*/ + kAOpBytes + (size_t)kBStages * kBSlot +
-                                    (size_t)kRawStages * kRawSlot + ((kTwoCta && SNV_TC_EPI16) ? kListBytes16 : kListBytes) + (kTwoCta ? 4 : 2) * BM * 4 /*thresholds*/ + kBarBytes;
+                                    (size_t)kRawStages * kRawSlot + kSlotBytes + (kTwoCta ? 4 : 2) * BM * 4 /*thresholds*/ + kBarBytes;
     static_assert(kSmem <= 232448, "shared memory budget");
 };
 
@@ -234,6 +262,7 @@ struct TcParams {
     int items_a, tail_split, tail_tiles;
     int64_t tail_row0;       // first query row of the tail items (their partial keys are indexed from it)
     int idx_bits, k, one;
+    int idx_slot;            // list epilogue: MMA slot (32 operand bytes) of the column-index block, = ceil(words / 2); else -1
     int64_t id_offset;
     const int32_t* q_bias;   // [nw * nq] popc(q & m)
     int32_t* D_i32;
@@ -415,7 +444,7 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     using E = Epi<KT, C::kTwoCta>;
     constexpr int kEpiThreads = E::kThreads;
     uint32_t* xchg = lists;                                                                 // [parts - 1][KT][128], after the slots are folded
-    constexpr size_t kSlots = (KT == 8 && C::kTwoCta && SNV_TC_EPI16) ? kListBytes16 : kListBytes;
+    constexpr size_t kSlots = C::kSlotBytes;
     volatile float* thrx = reinterpret_cast<float*>(lists + kSlots / 4);               // [parts][128 queries] published thresholds
     uint64_t* bars = reinterpret_cast<uint64_t*>(lists + kSlots / 4 + (C::kTwoCta ? 4 : 2) * BM);
     uint64_t* full_a = bars;                        // [kAStages]   TMA -> MMA
@@ -457,7 +486,7 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         }
         for (int s = 0; s < kAccStages; ++s) {
             mbar_init(&tmem_full[s], 1);
-            mbar_init(&tmem_empty[s], kPair * kEpiThreads);
+            mbar_init(&tmem_empty[s], kPair * ((SNV_TC_WARP_ARRIVE || C::kListEpi) ? E::kWarps : kEpiThreads));
         }
         if constexpr (TA) mbar_init(a_full, kPair * E::kWarps);
         fence_barrier_init();
@@ -475,8 +504,13 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     if constexpr (FP4) {
         // unit block scales (UE8M0 0x7F = 2^0) in the 32 TMEM columns behind the accumulators, all 128 lanes
         if (warp >= kFirstExpWarp && warp < kFirstExpWarp + 4) {
+            // columns [0, 8) and [16, 32): 2^0 (A / B scales of the packed-site MMAs); [8, 16): 2^-8 (UE8M0 0x77), the A
+            // scale of the column-index MMA of the list epilogue
             const uint32_t t = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + C::kSfCol;
-            tmem_st_32x32b_x16(t, 0x7F7F7F7Fu);
+            uint32_t sfv[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) sfv[i] = (C::kListEpi && i >= 8) ? 0x77777777u : 0x7F7F7F7Fu;
+            tmem_st_32x32b_x16v(t, sfv);
             tmem_st_32x32b_x16(t + 16u, 0x7F7F7F7Fu);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         }
@@ -520,10 +554,13 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             // word (fp8) or per two packed words (fp4)
             const uint32_t a_lo0 = TA ? tmem_base + C::kACol : ((smem_u32(a_tiles) >> 4) | 0x10000u);  // TMEM-A: a column address
             const uint32_t b_lo0 = (smem_u32(b_tiles) >> 4) | 0x10000u;
+            // MMAs of the last k-block over packed sites (list epilogue: 0..3, followed by the column-index MMA)
             const int nm_tail = (p.words - WPK * (KB - 1) + C::WPM - 1) / C::WPM;
-            const uint32_t sf_a = tmem_base + C::kSfCol, sf_b = tmem_base + C::kSfCol + 16u;
-            (void)sf_a; (void)sf_b;
-            auto mma = [&](uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t acc) {
+            const uint32_t sf_a0 = tmem_base + C::kSfCol, sf_b = tmem_base + C::kSfCol + 16u;
+            (void)sf_a0; (void)sf_b;
+            auto mma = [&](uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t acc, uint32_t sf_a_off = 0u) {
+                const uint32_t sf_a = sf_a0 + sf_a_off;
+                (void)sf_a;
 #ifdef TC_DEBUG_NO_MMA
                 return;
 #endif
@@ -535,6 +572,11 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                 else umma_f8(d_tmem, adesc, bdesc, idesc, acc);
             };
             auto commit = [&](uint64_t* bar) {
+#ifdef TC_DEBUG_PLAIN_COMMIT
+                mbar_arrive(bar);
+                if constexpr (TWO) mbar_arrive_cluster(bar, 1u);
+                return;
+#endif
                 if constexpr (TWO) umma_commit_2cta(bar);
                 else umma_commit(bar);
             };
@@ -573,10 +615,19 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                                 if constexpr (!TA) commit(&empty_a[ra.i]);
                                 commit(&empty_b[rb.i]);
                             } else {
-                                mma(d_tmem, a_lo, b_lo, kb != 0 ? 1u : 0u);
-                                if (nm_tail > 1) mma(d_tmem, a_lo + kAStep, b_lo + 2, 1u);
-                                if (nm_tail > 2) mma(d_tmem, a_lo + 2 * kAStep, b_lo + 4, 1u);
-                                if (nm_tail > 3) mma(d_tmem, a_lo + 3 * kAStep, b_lo + 6, 1u);
+                                if constexpr (C::kListEpi) {
+                                    // packed-site MMAs of the last k-block, then the column-index MMA (A scale 2^-8)
+                                    uint32_t acc = kb != 0 ? 1u : 0u;
+                                    if (nm_tail > 0) { mma(d_tmem, a_lo, b_lo, acc); acc = 1u; }
+                                    if (nm_tail > 1) mma(d_tmem, a_lo + kAStep, b_lo + 2, 1u);
+                                    if (nm_tail > 2) mma(d_tmem, a_lo + 2 * kAStep, b_lo + 4, 1u);
+                                    mma(d_tmem, a_lo + (uint32_t)nm_tail * kAStep, b_lo + 2u * (uint32_t)nm_tail, acc, 8u);
+                                } else {
+                                    mma(d_tmem, a_lo, b_lo, kb != 0 ? 1u : 0u);
+                                    if (nm_tail > 1) mma(d_tmem, a_lo + kAStep, b_lo + 2, 1u);
+                                    if (nm_tail > 2) mma(d_tmem, a_lo + 2 * kAStep, b_lo + 4, 1u);
+                                    if (nm_tail > 3) mma(d_tmem, a_lo + 3 * kAStep, b_lo + 6, 1u);
+                                }
                                 if constexpr (!TA) commit(&empty_a[ra.i]);
                                 commit(&empty_b[rb.i]);
                                 commit(&tmem_full[as]);
@@ -601,8 +652,12 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                     for (int kb = 0; kb < KB; ++kb) {
                         if constexpr (EXPAND) {
                             mbar_wait_relaxed(&raw_empty[rr.i], rr.phase ^ 1u);
+#ifdef TC_DEBUG_NO_RAW
+                            mbar_arrive(&raw_full[rr.i]);
+#else
                             mbar_arrive_expect_tx(&raw_full[rr.i], C::kRawBytes);
                             tma_load_3d(raws + (size_t)rr.i * C::kRawSlot, &map_r, kb * WPK, n0, it.w, &raw_full[rr.i]);
+#endif
                             rr.next();
                         } else {
                             mbar_wait_relaxed(&empty_b[rb.i], rb.phase ^ 1u);
@@ -634,6 +689,38 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             int pending = -1;  // B slot whose stores still need the proxy fence + arrive (deferred by one k-block)
             const int tail_words = p.words - WPK * (KB - 1);  // packed words of the last k-block that an MMA reads
             const int tail_chunks = FP4 ? ((tail_words + 1) & ~1) : 2 * tail_words;  // 16-byte chunks to write there
+            // list epilogue: the 32 operand bytes behind the last packed words hold the row's column-index code block:
+            // 64 E2M1 values that sum to c = the row's position in the tile (c / 6 sixes, then the remainder as 0, 1, 2,
+            // 3, 4 or 4 + 1); the query side holds 1.0 there and the MMA's A scale is 2^-8, so the accumulator gets c / 256
+            [[maybe_unused]] uint4 ic0[2], ic1[2];      // chunk pair of row et (and et + kHalfRows)
+            [[maybe_unused]] uint32_t ioff0 = 0u, ioff1 = 0u;
+            if constexpr (C::kListEpi) {
+                const int ich = 2 * p.idx_slot - 8 * (KB - 1);  // first of the two chunks, inside the last k-block
+                ioff0 = (uint32_t)(et * kRowBytes + ((ich ^ sw) << 4));
+                ioff1 = (uint32_t)(et * kRowBytes + (((ich + 1) ^ sw) << 4));
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const int c = (int)cta_rank * C::kBRows + et + r * kHalfRows;
+                    const int n6 = c / 6, rem = c - 6 * n6;
+                    uint32_t wds[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        uint32_t wv = 0u;
+#pragma unroll
+                        for (int nb = 0; nb < 8; ++nb) {
+                            const int e = 8 * i + nb;
+                            uint32_t code = 0u;
+                            if (e < n6) code = 7u;                                            // 6.0
+                            else if (e == n6) code = rem == 0 ? 0u : (rem == 1 ? 2u : (rem == 2 ? 4u : (rem == 3 ? 5u : 6u)));  // 0 1 2 3 4(4)
+                            else if (e == n6 + 1 && rem == 5) code = 2u;                      // + 1.0
+                            wv |= code << (4 * nb);
+                        }
+                        wds[i] = wv;
+                    }
+                    ic0[r] = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+                    ic1[r] = make_uint4(wds[4], wds[5], wds[6], wds[7]);
+                }
+            }
             auto lds128 = [](uint32_t addr) {
                 uint4 v;
                 asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
@@ -690,24 +777,40 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                         if (pending >= 0) {
                             // the previous k-block's stores have had time to drain: make them visible to the
                             // tensor core (async proxy) and publish the slot
+#ifndef TC_DEBUG_NO_FENCE
                             fence_proxy_async();
+#endif
                             __syncwarp();
                             publish(pending);
                         }
                         mbar_wait(&empty_b[rb.i], rb.phase ^ 1u);
                         if (act) {
                             const uint32_t dst = b_base + (uint32_t)rb.i * C::kBSlot;
-                            if (kb != KB - 1 || tail_chunks == 8) {
+                            if (kb != KB - 1 || (!C::kListEpi && tail_chunks == 8)) {
                                 expand_row(w0, dst, 8);
                                 if constexpr (kTwoRows) expand_row(w1, dst + kHalfRows * kRowBytes, 8);
                             } else {
                                 expand_row(w0, dst, tail_chunks);
                                 if constexpr (kTwoRows) expand_row(w1, dst + kHalfRows * kRowBytes, tail_chunks);
+                                if constexpr (C::kListEpi) {
+                                    sts128(dst + ioff0, ic0[0]);
+                                    sts128(dst + ioff1, ic1[0]);
+                                    if constexpr (kTwoRows) {
+                                        sts128(dst + kHalfRows * kRowBytes + ioff0, ic0[1]);
+                                        sts128(dst + kHalfRows * kRowBytes + ioff1, ic1[1]);
+                                    }
+                                }
                             }
                         }
                         __syncwarp();  // every lane has consumed its raw words
                         if (lane == 0) mbar_arrive(&raw_empty[rr.i]);
+#if SNV_TC_DEFER_PUBLISH
                         pending = rb.i;
+#else
+                        fence_proxy_async();
+                        __syncwarp();
+                        publish(rb.i);
+#endif
                         rr.next();
                         rb.next();
                     }
@@ -868,6 +971,120 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                     refresh_thr();
                 }
             };
+            // ---- candidate-list epilogue (fp4 CTA-pair engines): every accumulator arrives as  a + c / 256  (a = distance -
+            // bias, c = its column in the tile, added by the column-index MMA), so a candidate is self-describing.  The
+            // scan takes the columns in pairs: one minimum, one compare, and - predicated - one 8-byte store of the pair
+            // to the thread's list plus a count bump; the lists are folded into the sorted top-k once per tile part,
+            // after the accumulator stage has gone back to the MMA warp, or earlier when some lane holds kFoldAt
+            // entries.  a < thr  <=>  a + c / 256 < thr  for integer a, thr and c < 256; the threshold only ever
+            // decreases, so a stale one admits extra candidates but never loses one, and the fold re-checks every
+            // member of a pair against the current k-th best key.
+            [[maybe_unused]] constexpr uint32_t kLStride = (uint32_t)kEpiThreads * 8u;  // bytes between a thread's entries
+            [[maybe_unused]] const uint32_t list_base = smem_u32(lists) + (uint32_t)et * 8u;
+            [[maybe_unused]] uint32_t lcnt = 0u;
+            [[maybe_unused]] auto fold_list = [&](uint32_t tile_col0) {
+                const uint32_t mx = __reduce_max_sync(0xffffffffu, lcnt);
+                if (mx == 0u) return;
+                auto key_of_v = [&](float v) {
+                    // 256 a + c as an integer (|.| < 2^19): the low mantissa bits of v * 256 + 1.5 * 2^23; +inf (a column
+                    // past the panel end) gives a key above every real one
+                    const int32_t iv = (int32_t)__float_as_uint(fmaf(v, 256.0f, 12582912.0f)) - 0x4B400000;
+                    const uint32_t key = ((uint32_t)((iv >> 8) + qb) << idx_bits) + tile_col0 + (uint32_t)(iv & 255);
+                    return v < 3.0e38f ? key : kSent32;
+                };
+#pragma unroll 1
+                for (uint32_t i = 0; i < mx; ++i) {
+                    if (i < lcnt) {
+                        float v1, v2;
+                        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v1), "=f"(v2) : "r"(list_base + i * kLStride));
+                        const uint32_t key1 = key_of_v(v1), key2 = key_of_v(v2);
+                        if (key1 < best[KT - 1]) topk_insert<KT, uint32_t>(best, key1);
+                        if (key2 < best[KT - 1]) topk_insert<KT, uint32_t>(best, key2);
+                    }
+                }
+                lcnt = 0u;
+                refresh_thr();
+            };
+            if constexpr (C::kListEpi) {
+                for (int t = 0; t < it.ntiles; ++t, ++tcount) {
+                    const uint32_t as = tcount & 1u;
+                    const int n0 = (it.t0 + t) * BN;
+                    mbar_wait(&tmem_full[as], (tcount >> 1) & 1u);
+                    tcgen05_fence_after();
+                    if constexpr (TA) {
+                        if (t == it.ntiles - 1 && item + item_step < p.items) {
+                            if constexpr (C::kStageA) load_a_staged();
+                            else load_a(item + item_step);
+                        }
+                    }
+                    const int c0 = TA ? ((tcount & 1u) ? 64 : 96) : kPartCols;
+                    const int pstart = TA ? (part ? c0 : 0) : kPartCols * part;
+                    const int pwidth = TA ? (part ? BN - c0 : c0) : kPartCols;
+                    int cols = (p.n - n0 < BN ? (int)(p.n - n0) : BN) - pstart;  // columns of this part in use
+                    cols = cols < 0 ? 0 : (cols > pwidth ? pwidth : cols);
+                    const int nch = (cols + G - 1) / G;
+                    const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + (uint32_t)pstart;
+                    const uint32_t tile_col0 = (uint32_t)(t * BN);  // columns count from the split's first row
+                    thrx[part * BM + row] = thr_mine;
+                    thr_other = 3.0e38f;
+#pragma unroll
+                    for (int o = 1; o < kParts; ++o) thr_other = fminf(thr_other, thrx[((part + o) % kParts) * BM + row] + 1.0f);
+                    thr = fminf(thr_mine, thr_other);
+                    uint32_t accA[G], accB[G];
+                    auto scan = [&](uint32_t (&acc)[G], int u) {
+                        if (G * u + G > cols) {
+#pragma unroll
+                            for (int j = 0; j < G; ++j)
+                                if (G * u + j >= cols) acc[j] = 0x7F800000u;  // past the panel end (+inf): never a candidate
+                        }
+#ifdef TC_DEBUG_NO_EPI
+                        return;
+#endif
+                        static_for<G / 2>([&](auto jc) {
+                            constexpr int j = 2 * decltype(jc)::value;
+                            const float a0 = __uint_as_float(acc[j]), a1 = __uint_as_float(acc[j + 1]);
+                            if (fminf(a0, a1) < thr) {
+                                asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(list_base + lcnt * kLStride), "f"(a0), "f"(a1) : "memory");
+                                lcnt += 1u;
+                            }
+                        });
+                        // keep every list behind the fold mark, so that the next group always fits
+                        if (u + 1 < nch && __any_sync(0xffffffffu, lcnt >= (uint32_t)C::kFoldAt)) fold_list(tile_col0);
+                    };
+                    if (nch > 0) tmem_ld_cols<G>(tbase, accA);
+                    if (nch > 0) {
+                        tmem_ld_wait_cols<G>(accA);
+                        if (nch > 1) tmem_ld_cols<G>(tbase + (uint32_t)G, accB);
+                        scan(accA, 0);
+                    }
+                    if (nch > 1) {
+                        tmem_ld_wait_cols<G>(accB);
+                        if (nch > 2) tmem_ld_cols<G>(tbase + (uint32_t)(2 * G), accA);
+                        scan(accB, 1);
+                    }
+                    if (nch > 2) {
+                        tmem_ld_wait_cols<G>(accA);
+                        if (nch > 3) tmem_ld_cols<G>(tbase + (uint32_t)(3 * G), accB);
+                        scan(accA, 2);
+                    }
+                    if (nch > 3) {
+                        tmem_ld_wait_cols<G>(accB);
+                        scan(accB, 3);
+                    }
+                    // the accumulator stage goes back to the MMA warp before the fold (which works from shared memory)
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (TWO && !leader) mbar_arrive_cluster(&tmem_empty[as], 0u);
+                        else mbar_arrive(&tmem_empty[as]);
+                    }
+#ifndef TC_DEBUG_NO_FOLD
+                    fold_list(tile_col0);
+#else
+                    lcnt = 0u;
+#endif
+                }
+            } else
             for (int t = 0; t < it.ntiles; ++t, ++tcount) {
                 const uint32_t as = tcount & 1u;
                 const int n0 = (it.t0 + t) * BN;
@@ -937,7 +1154,13 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                     fold((m4[0] | m4[1]) | (m4[2] | m4[3]), col0);
 #endif
                 };
+#ifdef TC_DEBUG_NO_EPI_LD
+                if (tbase == 0xffffffffu)
+#endif
                 if (nch > 0) tmem_ld_cols<G>(tbase, accA);
+#ifdef TC_DEBUG_NO_EPI_LD
+                if (tbase == 0xffffffffu) {
+#endif
                 if (nch > 0) {
                     tmem_ld_wait_cols<G>(accA);
                     if (nch > 1) tmem_ld_cols<G>(tbase + (uint32_t)G, accB);
@@ -957,9 +1180,21 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                     tmem_ld_wait_cols<G>(accB);
                     process(accB, 3);
                 }
+#ifdef TC_DEBUG_NO_EPI_LD
+                }
+#endif
                 tcgen05_fence_before();
+#if SNV_TC_WARP_ARRIVE
+                // one arrival per warp: a remote (peer -> leader) arrival per thread costs the pair ~2 k clocks per tile
+                __syncwarp();
+                if (lane == 0) {
+                    if (TWO && !leader) mbar_arrive_cluster(&tmem_empty[as], 0u);
+                    else mbar_arrive(&tmem_empty[as]);
+                }
+#else
                 if (TWO && !leader) mbar_arrive_cluster(&tmem_empty[as], 0u);
                 else mbar_arrive(&tmem_empty[as]);
+#endif
             }
             // ---- merge the parts of each query through shared memory, then write the result
             thrx[part * BM + row] = 3.0e38f;  // reset for the next item (ordered by the barriers below)
@@ -1026,7 +1261,7 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 template <bool FP4>
 __global__ void __launch_bounds__(128)
 tc_expand_queries_kernel(const uint32_t* __restrict__ q, const uint32_t* __restrict__ mask, int64_t mask_win_stride,
-                         int64_t mask_q_stride, int nq, int64_t rows, int stride, int words, int d, int kblocks,
+                         int64_t mask_q_stride, int nq, int64_t rows, int stride, int words, int d, int kblocks, int idx_chunk,
                          uint8_t* __restrict__ ops, int32_t* __restrict__ bias)
 {
     const int lane = threadIdx.x & 31;
@@ -1054,7 +1289,10 @@ tc_expand_queries_kernel(const uint32_t* __restrict__ q, const uint32_t* __restr
             const int h = ch & 1;
             const uint32_t wm = observed(wi);
             const uint32_t wq = wi < words ? qr[wi] & wm : 0u;
-            out_row[ch] = expand_query_chunk<FP4>(wq, wm, h);
+            uint4 v = expand_query_chunk<FP4>(wq, wm, h);
+            // list epilogue: 1.0 (E2M1 code 2) in the 64 positions of the column-index MMA
+            if (FP4 && (ch == idx_chunk || ch == idx_chunk + 1)) v = make_uint4(0x22222222u, 0x22222222u, 0x22222222u, 0x22222222u);
+            out_row[ch] = v;
         }
     }
 }
@@ -1139,6 +1377,14 @@ int mode_of_engine(int engine)
 {
     return engine == 5 ? MODE_FP4_2CTA_TA : (engine == 4 ? MODE_FP4_2CTA : (engine == 3 ? MODE_FP4 : (engine == 2 ? MODE_FP8_HBM : MODE_FP8)));
 }
+bool list_epi_engine(int engine) { return engine >= 4 && Cfg<MODE_FP4_2CTA>::kListEpi; }
+int idx_slot_of(int words) { return (words + 1) / 2; }  // MMA slot of the column-index block: right behind the packed words
+// k-blocks (128 operand bytes per row) of an engine's operand rows
+int kblocks_of_engine(int engine, int words)
+{
+    if (list_epi_engine(engine)) return (int)ceil_div(idx_slot_of(words) + 1, 4);
+    return (int)ceil_div(words, engine >= 3 ? Cfg<MODE_FP4>::WPK : 4);
+}
 int bn_of_engine(int engine) { return engine == 5 ? Cfg<MODE_FP4_2CTA_TA>::BN : (engine >= 3 ? Cfg<MODE_FP4>::BN : 256); }
 int wpk_of_engine(int engine) { return engine >= 3 ? Cfg<MODE_FP4>::WPK : 4; }
 bool pair_engine(int engine) { return engine >= 4; }  // items are query-tile PAIRS on SM pairs
@@ -1162,7 +1408,7 @@ int hamming_engine_for(const HammingSearchParams& p)
     const bool can = !p.work && p.n > 0 && p.nq > 0 && p.k >= 1 && p.k <= 32 && p.d < (1 << 12) &&
                      (int64_t)p.nw * p.nq < ((int64_t)1 << 31) && p.n < ((int64_t)1 << 31);
     if (!can || mode == 0) return 0;
-    if (mode == 5 && ceil_div(p.words, Cfg<MODE_FP4_2CTA_TA>::WPK) > Cfg<MODE_FP4_2CTA_TA>::kMaxKbTmemA) mode = 4;
+    if (mode == 5 && kblocks_of_engine(5, p.words) > Cfg<MODE_FP4_2CTA_TA>::kMaxKbTmemA) mode = 4;
     if (mode > 0) return mode;
     // auto: enough queries per window to fill a useful part of the 128-lane tile, and a panel worth a tile
     if (!(p.nq >= 32 && p.n >= 512)) return 0;
@@ -1177,7 +1423,7 @@ size_t hamming_tc_plan(const HammingSearchParams& p, HammingTcPlan& plan)
     if (!plan.engine) return 0;
     const int BN = bn_of_engine(plan.engine);
     plan.kt = p.k <= 8 ? 8 : 32;
-    plan.kblocks = (int)ceil_div(p.words, wpk_of_engine(plan.engine));
+    plan.kblocks = kblocks_of_engine(plan.engine, p.words);
     plan.qtiles = (int)ceil_div(p.nq, BM);
     plan.n_tiles = (int)ceil_div(p.n, BN);
     plan.idx_bits = 32 - bit_length64((int64_t)p.d + 1);
@@ -1339,10 +1585,11 @@ int hamming_tc_launch(const HammingSearchParams& p, const HammingTcPlan& plan, v
         const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(rows, 4), (int64_t)kNumSMs * 64);  // 4 warps = 4 rows per block
         if (plan.engine >= 3)
             tc_expand_queries_kernel<true><<<grid, 128, 0, stream>>>(p.q, p.mask, p.mask_win_stride, p.mask_q_stride, p.nq, rows, p.stride,
-                                                                    p.words, p.d, plan.kblocks, q_ops, q_bias);
+                                                                    p.words, p.d, plan.kblocks, list_epi_engine(plan.engine) ? 2 * idx_slot_of(p.words) : -2,
+                                                                    q_ops, q_bias);
         else
             tc_expand_queries_kernel<false><<<grid, 128, 0, stream>>>(p.q, p.mask, p.mask_win_stride, p.mask_q_stride, p.nq, rows, p.stride,
-                                                                     p.words, p.d, plan.kblocks, q_ops, q_bias);
+                                                                     p.words, p.d, plan.kblocks, -2, q_ops, q_bias);
         SNV_LAUNCH_CHECK();
     }
     CUtensorMap map_q, map_r;
@@ -1375,6 +1622,7 @@ int hamming_tc_launch(const HammingSearchParams& p, const HammingTcPlan& plan, v
     const bool pair = pair_engine(plan.engine);
     const int64_t tail_rows = fill_item_fields(p, plan, tp);
     tp.idx_bits = plan.idx_bits; tp.k = p.k; tp.one = 1;
+    tp.idx_slot = list_epi_engine(plan.engine) ? idx_slot_of(p.words) : -1;
     tp.id_offset = p.id_offset;
     tp.q_bias = q_bias;
     tp.D_i32 = p.D_i32; tp.D_f32 = p.D_f32; tp.I = p.I;

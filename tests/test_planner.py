@@ -142,10 +142,11 @@ def test_auto_engine_by_shape(L, force_engine):
     assert eng(1, 64, 5008, 1030, 33) == 0  # k > 32
     force_engine("popc")
     assert eng(1000, 2000, 5008, 1030, 8) == 0
-    # the TMEM-operand bring-up engine holds at most 5 k-blocks (1280 sites) of a query tile; wider windows run engine 4
+    # the TMEM-operand engine holds at most 5 k-blocks of a query tile (20 MMA slots of 64 sites, one of them the
+    # column-index block of the list epilogue: 1216 sites); wider windows run engine 4
     force_engine("tc4x2ta")
-    assert eng(10, 2000, 5008, 1280, 8) == 5
-    assert eng(10, 2000, 5008, 1281, 8) == 4
+    assert eng(10, 2000, 5008, 1216, 8) == 5
+    assert eng(10, 2000, 5008, 1217, 8) == 4
 
 
 def test_bad_arguments(L):

@@ -1,9 +1,11 @@
 #!/bin/bash
-# ncu capture of the tensor-core Hamming kernel (one GPU; plain run first)
+# ncu --set full capture (with source counters) of the tensor-core Hamming kernel, one GPU; the same command runs without ncu first.
+# ENGINE=tc4x2|tc4x2ta|...  W=windows  TAG=output prefix (gpurun_out/${TAG}_tc_full.ncu-rep)
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-export SNV_HAMMING_ENGINE=${ENGINE:-tc} W=${W:-148}
-python tools/time_hamming.py > gpurun_out/r2_tc_plain.log 2>&1 &&
+T=${TAG:-r2}
+export SNV_HAMMING_ENGINE=${ENGINE:-tc4x2} W=${W:-148}
+python tools/time_hamming.py > gpurun_out/${T}_tc_plain.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:hamming_tc_kernel -s 3 -c 1 -f \
-    -o gpurun_out/r2_tc_full python tools/time_hamming.py > gpurun_out/r2_tc_ncu.log 2>&1
-cat gpurun_out/r2_tc_plain.log; tail -5 gpurun_out/r2_tc_ncu.log
+    -o gpurun_out/${T}_tc_full python tools/time_hamming.py > gpurun_out/${T}_tc_ncu.log 2>&1
+echo rc=$?; cat gpurun_out/${T}_tc_plain.log | cut -c1-300; tail -3 gpurun_out/${T}_tc_ncu.log
