@@ -134,6 +134,16 @@ int snv_index_search(snv_index* idx, int w0, int nw, const void* q, int64_t nq, 
                      float* D_f32, int64_t* I, unsigned flags, void* stream);
 
 /*
+ * The same search with COMPACT results for host-buffer callers of the offline sweeps (batch_test_faiss_l2.py:109-111
+ * keeps every window's (D, I)): D uint16 [nw][nq][k], I int32 [nw][nq][k] - 6 instead of 12 bytes per neighbour
+ * over PCIe, identical values (ids are row numbers inside the window: no id_offset; padding: I = -1, D = 0xFFFF).
+ * HAMMING indexes with ntotal < 2^31 and d < 65535; anything else -> SNV_ERR_UNSUPPORTED.
+ */
+int snv_index_search_compact(snv_index* idx, int w0, int nw, const void* q, int64_t nq, int q_dtype,
+                             const void* mask, int mask_mode, int k, uint16_t* D_u16, int32_t* I_i32,
+                             unsigned flags, void* stream);
+
+/*
  * Ragged per-window batches: a training / inference batch regrouped by window_idx before the
  * search (src/dataset/rag_train_dataset.py:239-281, src/dataset/embedding_rag_dataset.py:318-321,
  * src/dataset/sampler.py:58-119).  q is [nq_total][row] in caller order, window_ids (HOST int32

@@ -42,6 +42,7 @@ SYMBOLS = {
     "snv_index_reset": (_i, [_vp]),
     "snv_index_add": (_i, [_vp, _vp, _i64, _i, _u, _vp]),
     "snv_index_search": (_i, [_vp, _i, _i, _vp, _i64, _i, _vp, _i, _i, _i64, _vp, _vp, _vp, _u, _vp]),
+    "snv_index_search_compact": (_i, [_vp, _i, _i, _vp, _i64, _i, _vp, _i, _i, _vp, _vp, _u, _vp]),
     "snv_index_search_grouped": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _i, _vp, _vp, _vp, _u, _vp]),
     "snv_index_gather_tokens_grouped": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _i, _vp, _u, _vp]),
     "snv_index_gather_tokens": (_i, [_vp, _i, _i, _vp, _i64, _i, _vp, _i, _vp, _u, _vp]),

@@ -14,14 +14,25 @@ static thread_local std::string t_error;
 long long g_launch_count = 0;
 void set_error(const std::string& msg) { t_error = msg; }
 
-int g_last_hamming_engine = -1;
-static bool g_prof_on = false;
-static cudaEvent_t g_prof_e0 = nullptr, g_prof_e1 = nullptr;
-static bool g_prof_valid = false;
+// Measurement hooks are per calling thread (searches on distinct streams from distinct threads do not share them).
+// The events belong to the device that is current when they are first used.
+thread_local int g_last_hamming_engine = -1;
+static thread_local bool g_prof_on = false;
+static thread_local cudaEvent_t g_prof_e0 = nullptr, g_prof_e1 = nullptr;
+static thread_local int g_prof_dev = -1;
+static thread_local bool g_prof_valid = false;
 void profile_begin(cudaStream_t stream)
 {
     if (!g_prof_on) return;
-    if (!g_prof_e0) { cudaEventCreate(&g_prof_e0); cudaEventCreate(&g_prof_e1); }
+    int dev = -1;
+    cudaGetDevice(&dev);
+    if (g_prof_e0 && dev != g_prof_dev) {  // the search moved to another device: events are per device
+        cudaEventDestroy(g_prof_e0);
+        cudaEventDestroy(g_prof_e1);
+        g_prof_e0 = g_prof_e1 = nullptr;
+        g_prof_valid = false;
+    }
+    if (!g_prof_e0) { cudaEventCreate(&g_prof_e0); cudaEventCreate(&g_prof_e1); g_prof_dev = dev; }
     cudaEventRecord(g_prof_e0, stream);
 }
 void profile_end(cudaStream_t stream)
@@ -314,22 +325,41 @@ int snv_index_reset(snv_index* idx)
 }
 
 // re-layout [W][cap][row] -> [W][new_cap][row]
-static int grow_array(void** arr, size_t row_bytes, int W, int64_t ntotal, int64_t old_cap, int64_t new_cap,
-                      cudaStream_t stream)
+// Re-lays out up to three [W][cap][row] arrays for a larger capacity, all or nothing: every new array is allocated before
+// anything is copied or freed, so a failed allocation leaves the index exactly as it was (pointers and cap unchanged).
+struct GrowSpec {
+    void** arr;
+    size_t row_bytes;
+};
+static int grow_arrays(const GrowSpec* specs, int n_specs, int W, int64_t ntotal, int64_t old_cap, int64_t new_cap,
+                       cudaStream_t stream)
 {
-    void* np = nullptr;
-    cudaError_t e = cudaMalloc(&np, (size_t)W * new_cap * row_bytes);
+    void* fresh[3] = {nullptr, nullptr, nullptr};
+    for (int i = 0; i < n_specs; ++i) {
+        cudaError_t e = cudaMalloc(&fresh[i], (size_t)W * new_cap * specs[i].row_bytes);
+        if (e != cudaSuccess) {
+            for (int j = 0; j < i; ++j) cudaFree(fresh[j]);
+            set_error(std::string("cudaMalloc(panel): ") + cudaGetErrorString(e));
+            return SNV_ERR_NOMEM;
+        }
+    }
+    cudaError_t e = cudaSuccess;
+    if (ntotal > 0) {
+        for (int i = 0; i < n_specs && e == cudaSuccess; ++i)
+            if (*specs[i].arr)
+                e = cudaMemcpy2DAsync(fresh[i], (size_t)new_cap * specs[i].row_bytes, *specs[i].arr, (size_t)old_cap * specs[i].row_bytes,
+                                      (size_t)ntotal * specs[i].row_bytes, W, cudaMemcpyDeviceToDevice, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    }
     if (e != cudaSuccess) {
-        set_error(std::string("cudaMalloc(panel): ") + cudaGetErrorString(e));
-        return SNV_ERR_NOMEM;
+        for (int i = 0; i < n_specs; ++i) cudaFree(fresh[i]);
+        set_error(std::string("index growth copy: ") + cudaGetErrorString(e));
+        return SNV_ERR_CUDA;
     }
-    if (*arr && ntotal > 0) {
-        SNV_CUDA_CHECK(cudaMemcpy2DAsync(np, (size_t)new_cap * row_bytes, *arr, (size_t)old_cap * row_bytes,
-                                         (size_t)ntotal * row_bytes, W, cudaMemcpyDeviceToDevice, stream));
-        SNV_CUDA_CHECK(cudaStreamSynchronize(stream));
+    for (int i = 0; i < n_specs; ++i) {
+        if (*specs[i].arr) cudaFree(*specs[i].arr);
+        *specs[i].arr = fresh[i];
     }
-    if (*arr) cudaFree(*arr);
-    *arr = np;
     return SNV_OK;
 }
 
@@ -362,16 +392,13 @@ int snv_index_add(snv_index* idx, const void* x, int64_t n, int dtype, unsigned 
         int64_t new_cap = std::max<int64_t>(need, idx->cap + idx->cap / 2);
         int rc;
         if (hamming) {
-            rc = grow_array((void**)&idx->panel, (size_t)idx->stride * 4, W, idx->ntotal, idx->cap, new_cap, stream);
-            if (rc) return rc;
+            const GrowSpec g[1] = {{(void**)&idx->panel, (size_t)idx->stride * 4}};
+            rc = grow_arrays(g, 1, W, idx->ntotal, idx->cap, new_cap, stream);
         } else {
-            rc = grow_array((void**)&idx->rows, (size_t)idx->d * 4, W, idx->ntotal, idx->cap, new_cap, stream);
-            if (rc) return rc;
-            rc = grow_array((void**)&idx->ops, (size_t)idx->kp * 4, W, idx->ntotal, idx->cap, new_cap, stream);
-            if (rc) return rc;
-            rc = grow_array((void**)&idx->norms, 4, W, idx->ntotal, idx->cap, new_cap, stream);
-            if (rc) return rc;
+            const GrowSpec g[3] = {{(void**)&idx->rows, (size_t)idx->d * 4}, {(void**)&idx->ops, (size_t)idx->kp * 4}, {(void**)&idx->norms, 4}};
+            rc = grow_arrays(g, 3, W, idx->ntotal, idx->cap, new_cap, stream);
         }
+        if (rc) return rc;
         idx->cap = new_cap;
     }
 
@@ -519,10 +546,14 @@ static int hamming_chunk_bounds(const HammingSearchParams& p, bool host_io, std:
     return SNV_OK;
 }
 
+// c_D16 / c_I32 non-null: compact results (snv_index_search_compact) - the scan writes (int32, int64) rows into the
+// index's workspace, a narrowing kernel turns each chunk into (uint16, int32) rows, and only those travel.
 static int search_hamming(snv_index* idx, int w0, int nw, const void* q, int64_t nq, int q_dtype,
                           const void* mask, int mask_mode, int k, int64_t id_offset, int32_t* D_i32,
-                          float* D_f32, int64_t* I, unsigned flags, cudaStream_t stream)
+                          float* D_f32, int64_t* I, unsigned flags, cudaStream_t stream, uint16_t* c_D16 = nullptr,
+                          int32_t* c_I32 = nullptr)
 {
+    const bool compact = c_I32 != nullptr;
     const bool q_dev = flags & SNV_Q_ON_DEVICE;
     const bool out_dev = flags & SNV_OUT_ON_DEVICE;
     const bool invert = flags & SNV_MASK_IS_MISSING;
@@ -549,7 +580,11 @@ static int search_hamming(snv_index* idx, int w0, int nw, const void* q, int64_t
         if (!q_dev) { rc = idx->ws_min.reserve((size_t)mrows_total * in_row); if (rc) return rc; }
         if (m_needs_pack) { rc = idx->ws_mask.reserve((size_t)mrows_total * row_b); if (rc) return rc; }
     }
-    if (!out_dev) {
+    if (compact) {
+        rc = idx->ws_di.reserve((size_t)nqt * k * 4); if (rc) return rc;
+        rc = idx->ws_i.reserve((size_t)nqt * k * 8); if (rc) return rc;
+        if (!out_dev) { rc = idx->ws_df.reserve((size_t)nqt * k * 6); if (rc) return rc; }  // uint16 rows, then int32 rows
+    } else if (!out_dev) {
         if (D_i32) { rc = idx->ws_di.reserve((size_t)nqt * k * 4); if (rc) return rc; }
         if (D_f32) { rc = idx->ws_df.reserve((size_t)nqt * k * 4); if (rc) return rc; }
         rc = idx->ws_i.reserve((size_t)nqt * k * 8);
@@ -648,7 +683,11 @@ static int search_hamming(snv_index* idx, int w0, int nw, const void* q, int64_t
             p.mask_q_stride = mask_mode == SNV_MASK_PER_WINDOW ? 0 : idx->stride;
         }
         const int64_t o0 = r0 * k;
-        if (out_dev) {
+        if (compact) {
+            p.D_i32 = (int32_t*)idx->ws_di.p + o0;
+            p.D_f32 = nullptr;
+            p.I = (int64_t*)idx->ws_i.p + o0;
+        } else if (out_dev) {
             p.D_i32 = D_i32 ? D_i32 + o0 : nullptr;
             p.D_f32 = D_f32 ? D_f32 + o0 : nullptr;
             p.I = I + o0;
@@ -673,7 +712,17 @@ static int search_hamming(snv_index* idx, int w0, int nw, const void* q, int64_t
             rc = hamming_launch(p, cs);
             if (rc) return rc;
         }
-        if (!out_dev) {
+        if (compact) {
+            const size_t cnt = (size_t)rows * k;
+            uint16_t* d16 = out_dev ? c_D16 + o0 : (uint16_t*)idx->ws_df.p + o0;
+            int32_t* i32 = out_dev ? c_I32 + o0 : (int32_t*)((uint16_t*)idx->ws_df.p + (size_t)nqt * k) + o0;
+            rc = narrow_results_launch(p.D_i32, p.I, (int64_t)cnt, d16, i32, cs);
+            if (rc) return rc;
+            if (!out_dev) {
+                SNV_CUDA_CHECK(cudaMemcpyAsync(c_D16 + o0, d16, cnt * 2, cudaMemcpyDeviceToHost, cs));
+                SNV_CUDA_CHECK(cudaMemcpyAsync(c_I32 + o0, i32, cnt * 4, cudaMemcpyDeviceToHost, cs));
+            }
+        } else if (!out_dev) {
             const size_t cnt = (size_t)rows * k;
             if (D_i32) SNV_CUDA_CHECK(cudaMemcpyAsync(D_i32 + o0, p.D_i32, cnt * 4, cudaMemcpyDeviceToHost, cs));
             if (D_f32) SNV_CUDA_CHECK(cudaMemcpyAsync(D_f32 + o0, p.D_f32, cnt * 4, cudaMemcpyDeviceToHost, cs));
@@ -904,6 +953,23 @@ int snv_index_search(snv_index* idx, int w0, int nw, const void* q, int64_t nq, 
     if (mask_mode != SNV_MASK_NONE) { set_error("snv_index_search: masks apply to HAMMING indexes only"); return SNV_ERR_INVALID; }
     if (D_i32) { set_error("snv_index_search: D_i32 applies to HAMMING indexes only"); return SNV_ERR_INVALID; }
     return search_l2(idx, w0, nw, q, nq, k, id_offset, D_f32, I, flags, stream);
+}
+
+int snv_index_search_compact(snv_index* idx, int w0, int nw, const void* q, int64_t nq, int q_dtype, const void* mask,
+                             int mask_mode, int k, uint16_t* D_u16, int32_t* I_i32, unsigned flags, void* stream_)
+{
+    if (!idx || idx->kind != SNV_KIND_HAMMING) { set_error("snv_index_search_compact: needs a HAMMING index"); return SNV_ERR_INVALID; }
+    if (w0 < 0 || nw < 0 || w0 + nw > idx->n_windows) { set_error("snv_index_search_compact: window range out of bounds"); return SNV_ERR_INVALID; }
+    if (nq < 0 || nq > 0x7fffffff) { set_error("snv_index_search_compact: bad nq"); return SNV_ERR_INVALID; }
+    if (k < 1) { set_error("snv_index_search_compact: k must be >= 1"); return SNV_ERR_INVALID; }
+    if (idx->ntotal > 0x7fffffffLL || idx->d >= 65535) { set_error("snv_index_search_compact: ids or distances do not fit the compact types"); return SNV_ERR_UNSUPPORTED; }
+    if (nw == 0 || nq == 0) return SNV_OK;
+    if (!q || !D_u16 || !I_i32) { set_error("snv_index_search_compact: q, D and I must not be null"); return SNV_ERR_INVALID; }
+    if (mask_mode < SNV_MASK_NONE || mask_mode > SNV_MASK_PER_QUERY) { set_error("snv_index_search_compact: bad mask_mode"); return SNV_ERR_INVALID; }
+    DeviceGuard g(idx->device);
+    if (!g.ok) { set_error("snv_index_search_compact: cudaSetDevice failed"); return SNV_ERR_CUDA; }
+    return search_hamming(idx, w0, nw, q, nq, q_dtype, mask, mask_mode, k, 0, nullptr, nullptr, nullptr, flags, (cudaStream_t)stream_,
+                          D_u16, I_i32);
 }
 
 int snv_index_search_grouped(snv_index* idx, const void* q, const int32_t* window_ids, int64_t nq_total,

@@ -123,14 +123,10 @@ constexpr uint32_t kBBytes = 256 * kRowBytes;  // 32 KB slot (240 or 256 rows in
 #define SNV_TC_RAWSTAGES 4
 #endif
 #ifndef SNV_TC_TA_BSTAGES
-#define SNV_TC_TA_BSTAGES 6  // TMEM-A mode: the 64 KB of the query ring go to a deeper panel-operand ring
+#define SNV_TC_TA_BSTAGES 2  // TMEM-A mode: B slots hold a whole tile (all k-blocks of the CTA's 80 rows, 50 KB each)
 #endif
 #ifndef SNV_TC_TA_RAWSTAGES
-#define SNV_TC_TA_RAWSTAGES 6
-#endif
-#ifndef SNV_TC_TA_STAGE_A
-#define SNV_TC_TA_STAGE_A 0  // 1: the next item's query rows are prefetched (cp.async) into shared memory while the current
-                             // item runs, so the hand-over at the item boundary reads shared memory, not L2
+#define SNV_TC_TA_RAWSTAGES 3  // TMEM-A mode: raw slots hold the packed rows of a whole tile (80 rows x row stride)
 #endif
 constexpr size_t kListBytes = 32 * 1024;  // one slot per (epilogue thread, column of a group): 32 x 256 floats
 constexpr size_t kListBytes16 = 64 * 1024; // 16 epilogue warps: 32 x 512 floats
@@ -168,18 +164,22 @@ struct Cfg {
     static constexpr int WPK = kFp4 ? 8 : 4;      // packed words per k-block
     static constexpr int WPM = kFp4 ? 2 : 1;      // packed words per MMA
     static constexpr int kAStages = kTmemA ? 0 : SNV_TC_ASTAGES;
-    static constexpr bool kStageA = kTmemA && SNV_TC_TA_STAGE_A;
-    static constexpr uint32_t kAStageRow = kMaxKbTmemA * kRowBytes + 16;   // staged query row (+16 B: spreads the banks)
-    static constexpr int kBStages = kTmemA ? (kStageA && SNV_TC_TA_BSTAGES > 4 ? 4 : SNV_TC_TA_BSTAGES) : SNV_TC_BSTAGES;
-    // bytes in front of the B ring: the query tile ring, or (TMEM-A mode) the staging rows of the next item's tile
-    static constexpr size_t kAOpBytes = kTmemA ? (kStageA ? (size_t)BM * kAStageRow : 0) : (size_t)kAStages * kABytes;
+    static constexpr int kBStages = kTmemA ? SNV_TC_TA_BSTAGES : SNV_TC_BSTAGES;
+    // bytes in front of the B ring: the query tile ring (none in the TMEM-A mode)
+    static constexpr size_t kAOpBytes = (size_t)kAStages * kABytes;
     static_assert(kAOpBytes % 1024 == 0, "the B ring stays 1024-byte aligned");
     static constexpr int kRawStages = kTmemA ? SNV_TC_TA_RAWSTAGES : SNV_TC_RAWSTAGES;
     static constexpr int kBRows = kTwoCta ? BN / 2 : BN;          // panel rows this CTA expands per tile
     static constexpr uint32_t kRawRow = WPK * 4;                // raw bytes per panel row and k-block
-    static constexpr uint32_t kRawSlot = kExpand ? (kTwoCta ? 128 : 256) * kRawRow : 0;
-    static constexpr uint32_t kBSlot = kTwoCta ? kBBytes / 2 : kBBytes;  // 16 KB holds the pair kernel's 120 rows
-    static constexpr uint32_t kRawBytes = kBRows * kRawRow;     // what one TMA box brings
+    // TMEM-A mode works per TILE, not per k-block: one raw TMA box brings the 80 packed rows whole (row stride <= 48
+    // words), the expanders fill one B slot = kMaxKbTmemA sub-tiles of [80 rows x 128 B] (SWIZZLE_128B each), the MMA
+    // warp issues every MMA of the tile behind one barrier wait
+    static constexpr int kMaxStrideTmemA = 48;
+    static constexpr uint32_t kBSub = (uint32_t)kBRows * kRowBytes;   // one k-block sub-tile of a per-tile B slot
+    static_assert(!kTmemA || kBSub % 1024 == 0, "sub-tiles stay swizzle-atom aligned");
+    static constexpr uint32_t kRawSlot = !kExpand ? 0 : (kTmemA ? (uint32_t)(kBRows * kMaxStrideTmemA * 4 + 1024) : (kTwoCta ? 128 : 256) * kRawRow);
+    static constexpr uint32_t kBSlot = kTmemA ? kMaxKbTmemA * kBSub : (kTwoCta ? kBBytes / 2 : kBBytes);  // 16 KB holds the pair kernel's 120 rows
+    static constexpr uint32_t kRawBytes = kBRows * kRawRow;     // what one TMA box brings (TMEM-A mode: rows x stride, a runtime value)
     static constexpr uint32_t kBBox = BN * kRowBytes;           // fp8-hbm variant: one TMA box of operand rows
     static constexpr uint32_t kACol = 2 * BN;                   // TMEM-A mode: first TMEM column of the query operand
     static constexpr uint32_t kSfCol = kTmemA ? 480 : 2 * BN;   // fp4: first TMEM column of the unit scales
@@ -189,8 +189,10 @@ struct Cfg {
     // candidate slots / lists of the epilogue threads (8 warps; 16 with SNV_TC_EPI16 in the pair kernels at k <= 8)
     static constexpr size_t kSlotBytes = kListEpi ? (size_t)kListCap * 8 * ((kTwoCta && SNV_TC_EPI16) ? 512 : 256)
                                                   : ((kTwoCta && SNV_TC_EPI16) ? kListBytes16 : kListBytes);
+    static constexpr size_t kQbBytes = kTmemA ? 2 * 2 * BM * 4 + (size_t)kBRows * 32 : 0;  // TMEM-A mode: partial query biases
+                                                                    // [item parity][part][row], then the column-index codes [row][32 B]
     static constexpr size_t kSmem = 1024 /*align slack*/ + kAOpBytes + (size_t)kBStages * kBSlot +
-                                    (size_t)kRawStages * kRawSlot + kSlotBytes + (kTwoCta ? 4 : 2) * BM * 4 /*thresholds*/ + kBarBytes;
+                                    (size_t)kRawStages * kRawSlot + kSlotBytes + (kTwoCta ? 4 : 2) * BM * 4 /*thresholds*/ + kQbBytes + kBarBytes;
     static_assert(kSmem <= 232448, "shared memory budget");
 };
 
@@ -269,7 +271,12 @@ struct TcParams {
     float* D_f32;
     int64_t* I;
     uint64_t* partial;       // [nw * nq][nsplit][kt] when nsplit > 1
-    const uint8_t* q_ops;    // [nw * nq][kblocks * 128 B] query operand rows (read directly in the TMEM-A mode)
+    const uint8_t* q_ops;    // [nw * nq][kblocks * 128 B] query operand rows (smem-A engines)
+    // TMEM-A mode: the epilogue warps build the query operand from the packed rows themselves
+    const uint32_t* q;       // [nw][nq][stride] packed queries
+    const uint32_t* mask;    // nullptr or observed-site rows
+    int64_t mask_win_stride, mask_q_stride;
+    int stride, d;
 };
 
 struct Item {
@@ -332,6 +339,22 @@ __device__ __forceinline__ void tmem_st_32x32b_x16v(uint32_t taddr, const uint32
         ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
           "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
         : "memory");
+}
+
+// Column-index code block of panel row c of a tile (list epilogue): 64 E2M1 values that sum to c - c / 6 sixes (code 7),
+// then the remainder as 0, 1, 2, 3, 4 or 4 + 1 - against 1.0 on the query side and an A scale of 2^-8.
+__device__ __forceinline__ void index_code_words(int c, uint32_t (&wds)[8])
+{
+    const int n6 = c / 6, rem = c - 6 * n6;
+    const uint32_t rcode = rem == 0 ? 0u : (rem == 1 ? 2u : (rem == 2 ? 4u : (rem == 3 ? 5u : 6u)));   // 0 1 2 3 4 (4)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int full = n6 - 8 * i;                                  // nibbles of this word below position n6
+        uint32_t wv = full >= 8 ? 0x77777777u : (full > 0 ? 0x77777777u & ((1u << (4 * full)) - 1u) : 0u);   // 6.0 each
+        if (full >= 0 && full < 8) wv |= rcode << (4 * full);                              // the remainder at position n6
+        if (rem == 5 && full + 1 >= 0 && full + 1 < 8) wv |= 2u << (4 * (full + 1));       // + 1.0 at position n6 + 1
+        wds[i] = wv;
+    }
 }
 
 // compile-time unrolled loop: f(std::integral_constant<int, 0>{}), ..., f(std::integral_constant<int, N - 1>{})
@@ -446,7 +469,8 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     uint32_t* xchg = lists;                                                                 // [parts - 1][KT][128], after the slots are folded
     constexpr size_t kSlots = C::kSlotBytes;
     volatile float* thrx = reinterpret_cast<float*>(lists + kSlots / 4);               // [parts][128 queries] published thresholds
-    uint64_t* bars = reinterpret_cast<uint64_t*>(lists + kSlots / 4 + (C::kTwoCta ? 4 : 2) * BM);
+    [[maybe_unused]] volatile int32_t* qbx = reinterpret_cast<int32_t*>(lists + kSlots / 4 + (C::kTwoCta ? 4 : 2) * BM);  // TMEM-A: [2][2][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(lists + kSlots / 4 + (C::kTwoCta ? 4 : 2) * BM + C::kQbBytes / 4);
     uint64_t* full_a = bars;                        // [kAStages]   TMA -> MMA
     uint64_t* empty_a = full_a + kAStages;          // [kAStages]   MMA -> TMA
     uint64_t* full_b = empty_a + kAStages;          // [kBStages]   expanders (or TMA) -> MMA
@@ -470,7 +494,7 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     constexpr uint32_t kPair = TWO ? 2u : 1u;
 
     if (warp == 0 && lane == 0) {
-        prefetch_tensormap(&map_q);
+        if constexpr (!TA) prefetch_tensormap(&map_q);
         prefetch_tensormap(&map_r);
         for (int s = 0; s < kAStages; ++s) {
             mbar_init(&full_a[s], 1);
@@ -587,14 +611,37 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             // operand step between the 4 MMAs of a k-block: 32 bytes of the swizzled row (descriptor units of 16 B),
             // or 8 TMEM columns
             constexpr uint32_t kAStep = TA ? 8u : 2u;
-            for (int item = item0; item < p.items; item += item_step) {
-                const Item it = decode_item(p, item, kQtMul, (int)cta_rank);
-                if constexpr (TA) {
+            if constexpr (TA) {
+                // per-tile pipeline: one wait for the tile's operand slot, every MMA of the tile, two commits
+                const int nslots = p.idx_slot + 1;  // MMA slots of 64 sites; the last one is the column-index block
+                for (int item = item0; item < p.items; item += item_step) {
+                    const Item it = decode_item(p, item, kQtMul, (int)cta_rank);
                     // both CTAs' epilogue warps have written this item's query tile to tensor memory
                     mbar_wait(a_full, icount & 1u);
                     ++icount;
                     tcgen05_fence_after();
+                    for (int t = 0; t < it.ntiles; ++t, ++tcount) {
+                        const uint32_t as = tcount & 1u;
+                        mbar_wait(&tmem_empty[as], ((tcount >> 1) & 1u) ^ 1u);
+                        mbar_wait(&full_b[rb.i], rb.phase);
+                        tcgen05_fence_after();
+                        if (elect_one()) {
+                            const uint32_t d_tmem = tmem_base + as * BN;
+                            const uint32_t b_lo = b_lo0 + (uint32_t)rb.i * (C::kBSlot >> 4);
+                            for (int sl = 0; sl < nslots - 1; ++sl)
+                                mma(d_tmem, a_lo0 + 8u * (uint32_t)sl, b_lo + (uint32_t)(sl >> 2) * (C::kBSub >> 4) + 2u * (uint32_t)(sl & 3), sl ? 1u : 0u);
+                            const int sl = nslots - 1;
+                            mma(d_tmem, a_lo0 + 8u * (uint32_t)sl, b_lo + (uint32_t)(sl >> 2) * (C::kBSub >> 4) + 2u * (uint32_t)(sl & 3), 1u, 8u);
+                            commit(&empty_b[rb.i]);
+                            commit(&tmem_full[as]);
+                        }
+                        __syncwarp();
+                        rb.next();
+                    }
                 }
+            } else
+            for (int item = item0; item < p.items; item += item_step) {
+                const Item it = decode_item(p, item, kQtMul, (int)cta_rank);
                 for (int t = 0; t < it.ntiles; ++t, ++tcount) {
                     const uint32_t as = tcount & 1u;
                     mbar_wait(&tmem_empty[as], ((tcount >> 1) & 1u) ^ 1u);
@@ -649,6 +696,13 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                 const Item it = decode_item(p, item, kQtMul, (int)cta_rank);
                 for (int t = 0; t < it.ntiles; ++t) {
                     const int n0 = (it.t0 + t) * BN + (int)cta_rank * C::kBRows;  // this CTA's rows of the tile
+                    if constexpr (TA) {
+                        // the CTA's 80 packed rows of the tile, whole (box = row stride x 80 rows)
+                        mbar_wait_relaxed(&raw_empty[rr.i], rr.phase ^ 1u);
+                        mbar_arrive_expect_tx(&raw_full[rr.i], (uint32_t)(C::kBRows * p.stride * 4));
+                        tma_load_3d(raws + (size_t)rr.i * C::kRawSlot, &map_r, 0, n0, it.w, &raw_full[rr.i]);
+                        rr.next();
+                    } else
                     for (int kb = 0; kb < KB; ++kb) {
                         if constexpr (EXPAND) {
                             mbar_wait_relaxed(&raw_empty[rr.i], rr.phase ^ 1u);
@@ -700,23 +754,8 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                 ioff1 = (uint32_t)(et * kRowBytes + (((ich + 1) ^ sw) << 4));
 #pragma unroll
                 for (int r = 0; r < 2; ++r) {
-                    const int c = (int)cta_rank * C::kBRows + et + r * kHalfRows;
-                    const int n6 = c / 6, rem = c - 6 * n6;
                     uint32_t wds[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        uint32_t wv = 0u;
-#pragma unroll
-                        for (int nb = 0; nb < 8; ++nb) {
-                            const int e = 8 * i + nb;
-                            uint32_t code = 0u;
-                            if (e < n6) code = 7u;                                            // 6.0
-                            else if (e == n6) code = rem == 0 ? 0u : (rem == 1 ? 2u : (rem == 2 ? 4u : (rem == 3 ? 5u : 6u)));  // 0 1 2 3 4(4)
-                            else if (e == n6 + 1 && rem == 5) code = 2u;                      // + 1.0
-                            wv |= code << (4 * nb);
-                        }
-                        wds[i] = wv;
-                    }
+                    index_code_words((int)cta_rank * C::kBRows + et + r * kHalfRows, wds);
                     ic0[r] = make_uint4(wds[0], wds[1], wds[2], wds[3]);
                     ic1[r] = make_uint4(wds[4], wds[5], wds[6], wds[7]);
                 }
@@ -760,6 +799,61 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                     else mbar_arrive(&full_b[slot]);
                 }
             };
+            if constexpr (TA) {
+                // Per tile: 80 rows x nhalves half-k-blocks (4 packed words -> 4 operand chunks) spread over the 128
+                // expander threads; unit u = (half h = u / 80, row = u % 80).  The last half holds the tail words, a zero
+                // chunk up to the slot boundary and the row's column-index code.
+                const int nslots = p.idx_slot + 1;
+                const int nhalves = (nslots + 1) >> 1;
+                const int units = nhalves * C::kBRows;
+                const int ich = 2 * p.idx_slot;          // chunk (= packed word position) of the index block
+                const uint32_t rstride = (uint32_t)p.stride * 4u;
+                // the rows' column-index codes, once: table [row][32 B] in shared memory (thread = row), visible to the four
+                // expander warps after their own named barrier
+                const uint32_t idx_tab = smem_u32(const_cast<int32_t*>(qbx)) + 2u * 2u * BM * 4u;
+                if (act) {
+                    sts128(idx_tab + (uint32_t)et * 32u, ic0[0]);
+                    sts128(idx_tab + (uint32_t)et * 32u + 16u, ic1[0]);
+                }
+                asm volatile("bar.sync 2, %0;" ::"n"(kExpThreads) : "memory");
+                for (int item = item0; item < p.items; item += item_step) {
+                    const Item it = decode_item(p, item, kQtMul, (int)cta_rank);
+                    for (int t = 0; t < it.ntiles; ++t) {
+                        mbar_wait(&raw_full[rr.i], rr.phase);
+                        mbar_wait(&empty_b[rb.i], rb.phase ^ 1u);
+                        const uint32_t src0 = smem_u32(raws) + (uint32_t)rr.i * C::kRawSlot;
+                        const uint32_t dst0 = b_base + (uint32_t)rb.i * C::kBSlot;
+#pragma unroll 2
+                        for (int u = et; u < units; u += kExpThreads) {
+                            const int h = u / C::kBRows, r = u - h * C::kBRows;
+                            const int word0 = 4 * h;
+                            const uint4 wv = lds128(src0 + (uint32_t)r * rstride + (uint32_t)h * 16u);
+                            const uint32_t dst = dst0 + (uint32_t)(h >> 1) * C::kBSub + (uint32_t)r * kRowBytes;
+                            const uint32_t sw2 = (uint32_t)(r & 7), cb = (uint32_t)(h & 1) * 4u;
+                            const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+                            if (word0 + 4 <= p.words) {
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) sts128(dst + (((cb + i) ^ sw2) << 4), expand_panel_word_fp4(ww[i]));
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const int wi = word0 + i;
+                                    const uint32_t a = dst + (((cb + i) ^ sw2) << 4);
+                                    if (wi < ich) sts128(a, expand_panel_word_fp4(wi < p.words ? ww[i] : 0u));
+                                    else if (wi == ich) sts128(a, lds128(idx_tab + (uint32_t)r * 32u));
+                                    else if (wi == ich + 1) sts128(a, lds128(idx_tab + (uint32_t)r * 32u + 16u));
+                                }
+                            }
+                        }
+                        fence_proxy_async();
+                        __syncwarp();
+                        publish(rb.i);
+                        if (lane == 0) mbar_arrive(&raw_empty[rr.i]);
+                        rr.next();
+                        rb.next();
+                    }
+                }
+            } else
             for (int item = item0; item < p.items; item += item_step) {
                 const Item it = decode_item(p, item, kQtMul, (int)cta_rank);
                 for (int t = 0; t < it.ntiles; ++t) {
@@ -816,7 +910,7 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                     }
                 }
             }
-            if (pending >= 0) {
+            if (!TA && pending >= 0) {
                 fence_proxy_async();
                 __syncwarp();
                 publish(pending);
@@ -839,27 +933,47 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         uint32_t tcount = 0;
         thrx[part * BM + row] = 3.0e38f;
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-        // TMEM-A mode: the epilogue warps write an item's query operand rows into tensor memory (thread = query row
-        // = TMEM lane; the column parts take alternate k-blocks: 8 x 16 B of the row -> 32 columns) and arrive, one
-        // lane per warp, on the leader's a_full barrier.
-        [[maybe_unused]] auto load_a = [&](int item_a) {
+        // TMEM-A mode: the epilogue warps build an item's query operand in tensor memory straight from the PACKED query
+        // rows (thread = query row = TMEM lane): 4 packed words (+ observed-site mask words) -> 4 operand chunks = 16
+        // columns per tcgen05.st; the two column parts take alternate word quads, each adds up its share of the bias
+        // popc(q & m) and leaves it in shared memory for the item's start.  One lane per warp then arrives on the
+        // leader's a_full barrier.  No expansion kernel, no 640-byte operand rows in HBM.
+        [[maybe_unused]] auto load_a = [&](int item_a, int slot) {
             const Item nx = decode_item(p, item_a, kQtMul, (int)cta_rank);
             const int qa = nx.qt * BM + row;
             const bool act = qa < p.nq;
-            const uint4* src = reinterpret_cast<const uint4*>(p.q_ops + ((int64_t)nx.w * p.nq + (act ? qa : 0)) * (int64_t)(KB * kRowBytes));
+            const int64_t qrow = (int64_t)nx.w * p.nq + (act ? qa : 0);
+            const uint4* qsrc = reinterpret_cast<const uint4*>(p.q + qrow * p.stride);
+            const uint4* msrc = p.mask ? reinterpret_cast<const uint4*>(p.mask + (int64_t)nx.w * p.mask_win_stride + (int64_t)(act ? qa : 0) * p.mask_q_stride)
+                                       : nullptr;
             const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + C::kACol;
-            for (int kb = part; kb < KB; kb += kParts) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    uint32_t v[16];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const uint4 x = act ? __ldg(src + kb * 8 + h * 4 + c) : make_uint4(0u, 0u, 0u, 0u);
-                        v[4 * c] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w;
-                    }
-                    tmem_st_32x32b_x16v(ta + (uint32_t)(kb * 32 + h * 16), v);
+            const int nquads = (2 * (p.idx_slot + 1) + 3) >> 2;   // word quads that hold operand chunks (index block included)
+            const int ich = 2 * p.idx_slot;
+            int32_t bias = 0;
+#pragma unroll 1
+            for (int qd = part; qd < nquads; qd += kParts) {
+                const int w0 = 4 * qd;
+                uint4 qv = make_uint4(0u, 0u, 0u, 0u), mv = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+                if (act && w0 < p.stride) {
+                    qv = __ldg(qsrc + qd);
+                    if (msrc) mv = __ldg(msrc + qd);
                 }
+                const uint32_t qw[4] = {qv.x, qv.y, qv.z, qv.w}, mw[4] = {mv.x, mv.y, mv.z, mv.w};
+                uint32_t v[16];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int w = w0 + i, lo = 32 * w;
+                    // observed-site bits of packed word w: sites < d, restricted by the mask row; 0 past the row end
+                    uint32_t m = (w < p.words && act) ? (lo + 32 <= p.d ? 0xFFFFFFFFu : (1u << (p.d - lo)) - 1u) & mw[i] : 0u;
+                    const uint32_t wq = qw[i] & m;
+                    bias += __popc(wq);
+                    uint4 x = expand_query_chunk<true>(wq, m, 0);
+                    if (w == ich || w == ich + 1) x = make_uint4(0x22222222u, 0x22222222u, 0x22222222u, 0x22222222u);  // 1.0 x 64: index MMA
+                    v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
+                }
+                tmem_st_32x32b_x16v(ta + (uint32_t)(16 * qd), v);
             }
+            qbx[(slot * kParts + part) * BM + row] = bias;
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tcgen05_fence_before();
             __syncwarp();
@@ -868,67 +982,25 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                 else mbar_arrive(a_full);
             }
         };
-        // staged variant: stage_a() copies this thread's k-blocks of an item's row into shared memory asynchronously
-        // (the same thread reads them back, so cp.async.wait_group is all the ordering needed); load_a_staged() moves
-        // them on to tensor memory
-        [[maybe_unused]] auto stage_a = [&](int item_a) {
-            const uint32_t stage_row = smem_u32(a_tiles) + (uint32_t)row * C::kAStageRow;
-            const Item nx = decode_item(p, item_a, kQtMul, (int)cta_rank);
-            const int qa = nx.qt * BM + row;
-            const bool act = qa < p.nq;
-            const uint4* src = reinterpret_cast<const uint4*>(p.q_ops + ((int64_t)nx.w * p.nq + (act ? qa : 0)) * (int64_t)(KB * kRowBytes));
-#pragma unroll 1
-            for (int kb = part; kb < KB; kb += kParts) {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const uint32_t dst = stage_row + (uint32_t)(kb * kRowBytes + c * 16);
-                    if (act) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + kb * 8 + c) : "memory");
-                    else asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
-                }
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        };
-        [[maybe_unused]] auto load_a_staged = [&]() {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            const uint32_t stage_row = smem_u32(a_tiles) + (uint32_t)row * C::kAStageRow;
-            const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + C::kACol;
-#pragma unroll 1
-            for (int kb = part; kb < KB; kb += kParts) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    uint32_t v[16];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                                     : "=r"(v[4 * c]), "=r"(v[4 * c + 1]), "=r"(v[4 * c + 2]), "=r"(v[4 * c + 3])
-                                     : "r"(stage_row + (uint32_t)(kb * kRowBytes + (h * 4 + c) * 16)));
-                    }
-                    tmem_st_32x32b_x16v(ta + (uint32_t)(kb * 32 + h * 16), v);
-                }
-            }
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                if (TWO && !leader) mbar_arrive_cluster(a_full, 0u);
-                else mbar_arrive(a_full);
-            }
-        };
+        [[maybe_unused]] uint32_t icount = 0;
         if constexpr (TA) {
-            if (item0 < p.items) {
-                if constexpr (C::kStageA) { stage_a(item0); load_a_staged(); }
-                else load_a(item0);
-            }
+            if (item0 < p.items) load_a(item0, 0);
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // the partial biases of the first item are visible
         }
         for (int item = item0; item < p.items; item += item_step) {
             const Item it = decode_item(p, item, kQtMul, (int)cta_rank);
-            if constexpr (C::kStageA) {
-                if (item + item_step < p.items) stage_a(item + item_step);  // lands while this item is scanned
-            }
             const int qi = it.qt * BM + row;
             const bool active = qi < p.nq;
             const int64_t q = (int64_t)it.w * p.nq + (active ? qi : 0);
-            const int32_t qb = active ? p.q_bias[q] : 0;
+            int32_t qb;
+            if constexpr (TA) {
+                // popc(q & m): the two parts' shares, written when the tile was built (ordered by the item-end barriers)
+                const int sl = (int)(icount & 1u);
+                qb = qbx[(sl * kParts) * BM + row] + qbx[(sl * kParts + 1) * BM + row];
+                ++icount;
+            } else {
+                qb = active ? p.q_bias[q] : 0;
+            }
             uint32_t best[KT];
 #pragma unroll
             for (int i = 0; i < KT; ++i) best[i] = kSent32;
@@ -992,14 +1064,19 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                     const uint32_t key = ((uint32_t)((iv >> 8) + qb) << idx_bits) + tile_col0 + (uint32_t)(iv & 255);
                     return v < 3.0e38f ? key : kSent32;
                 };
+                // two entries (four keys) per round, loads predicated, and - at k <= 8 - the inserts unguarded: inserting
+                // a key that is not below the k-th best (or the empty sentinel) leaves the list unchanged, so the round
+                // is straight-line code instead of four warp-divergent branches
 #pragma unroll 1
-                for (uint32_t i = 0; i < mx; ++i) {
-                    if (i < lcnt) {
-                        float v1, v2;
-                        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v1), "=f"(v2) : "r"(list_base + i * kLStride));
-                        const uint32_t key1 = key_of_v(v1), key2 = key_of_v(v2);
-                        if (key1 < best[KT - 1]) topk_insert<KT, uint32_t>(best, key1);
-                        if (key2 < best[KT - 1]) topk_insert<KT, uint32_t>(best, key2);
+                for (uint32_t i = 0; i < mx; i += 2) {
+                    float v[4] = {3.0e38f, 3.0e38f, 3.0e38f, 3.0e38f};
+                    if (i < lcnt) asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v[0]), "=f"(v[1]) : "r"(list_base + i * kLStride));
+                    if (i + 1u < lcnt) asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v[2]), "=f"(v[3]) : "r"(list_base + (i + 1u) * kLStride));
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const uint32_t key = key_of_v(v[e]);
+                        if constexpr (KT <= 8) topk_insert<KT, uint32_t>(best, key);
+                        else if (key < best[KT - 1]) topk_insert<KT, uint32_t>(best, key);
                     }
                 }
                 lcnt = 0u;
@@ -1012,10 +1089,7 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                     mbar_wait(&tmem_full[as], (tcount >> 1) & 1u);
                     tcgen05_fence_after();
                     if constexpr (TA) {
-                        if (t == it.ntiles - 1 && item + item_step < p.items) {
-                            if constexpr (C::kStageA) load_a_staged();
-                            else load_a(item + item_step);
-                        }
+                        if (t == it.ntiles - 1 && item + item_step < p.items) load_a(item + item_step, (int)(icount & 1u));
                     }
                     const int c0 = TA ? ((tcount & 1u) ? 64 : 96) : kPartCols;
                     const int pstart = TA ? (part ? c0 : 0) : kPartCols * part;
@@ -1093,10 +1167,7 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                 if constexpr (TA) {
                     // the item's last accumulator is complete, so every MMA that reads its query tile has retired:
                     // tensor memory can take the next item's tile while this tile is still being scored
-                    if (t == it.ntiles - 1 && item + item_step < p.items) {
-                        if constexpr (C::kStageA) load_a_staged();
-                        else load_a(item + item_step);
-                    }
+                    if (t == it.ntiles - 1 && item + item_step < p.items) load_a(item + item_step, (int)(icount & 1u));
                 }
                 // columns [pstart, pstart + pwidth) of the tile belong to this part.  TMEM-A mode (160-column tiles):
                 // 96 + 64 columns, the wide side alternating from tile to tile so that both parts score whole
@@ -1344,11 +1415,8 @@ template <int KT, int MODE>
 int launch_kernel(const CUtensorMap& map_q, const CUtensorMap& map_r, const TcParams& tp, int grid, cudaStream_t stream)
 {
     constexpr size_t smem = Cfg<MODE>::kSmem;
-    static bool attr = false;
-    if (!attr) {
-        SNV_CUDA_CHECK(cudaFuncSetAttribute(hamming_tc_kernel<KT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
-    }
+    // the dynamic shared-memory opt-in is per device / context: set on every launch, never cached process-wide
+    SNV_CUDA_CHECK(cudaFuncSetAttribute(hamming_tc_kernel<KT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     profile_begin(stream);
     if constexpr (Cfg<MODE>::kTwoCta) {
         // CTA pairs: a cluster of two CTAs on the two SMs of a TPC
@@ -1408,7 +1476,7 @@ int hamming_engine_for(const HammingSearchParams& p)
     const bool can = !p.work && p.n > 0 && p.nq > 0 && p.k >= 1 && p.k <= 32 && p.d < (1 << 12) &&
                      (int64_t)p.nw * p.nq < ((int64_t)1 << 31) && p.n < ((int64_t)1 << 31);
     if (!can || mode == 0) return 0;
-    if (mode == 5 && kblocks_of_engine(5, p.words) > Cfg<MODE_FP4_2CTA_TA>::kMaxKbTmemA) mode = 4;
+    if (mode == 5 && (kblocks_of_engine(5, p.words) > Cfg<MODE_FP4_2CTA_TA>::kMaxKbTmemA || p.stride > Cfg<MODE_FP4_2CTA_TA>::kMaxStrideTmemA)) mode = 4;
     if (mode > 0) return mode;
     // auto: enough queries per window to fill a useful part of the 128-lane tile, and a panel worth a tile
     if (!(p.nq >= 32 && p.n >= 512)) return 0;
@@ -1581,7 +1649,8 @@ int hamming_tc_launch(const HammingSearchParams& p, const HammingTcPlan& plan, v
     uint8_t* panel_ops = q_ops + plan.off_panel;
     const int kbytes = plan.kblocks * kRowBytes;
     const int BN = bn_of_engine(plan.engine);
-    {
+    const bool tmem_a = mode_of_engine(plan.engine) == MODE_FP4_2CTA_TA;  // builds its query operand in the scan kernel
+    if (!tmem_a) {
         const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(rows, 4), (int64_t)kNumSMs * 64);  // 4 warps = 4 rows per block
         if (plan.engine >= 3)
             tc_expand_queries_kernel<true><<<grid, 128, 0, stream>>>(p.q, p.mask, p.mask_win_stride, p.mask_q_stride, p.nq, rows, p.stride,
@@ -1593,7 +1662,8 @@ int hamming_tc_launch(const HammingSearchParams& p, const HammingTcPlan& plan, v
         SNV_LAUNCH_CHECK();
     }
     CUtensorMap map_q, map_r;
-    {
+    memset(&map_q, 0, sizeof(map_q));
+    if (!tmem_a) {
         const cuuint64_t gdim[2] = {(cuuint64_t)kbytes, (cuuint64_t)rows};
         const cuuint64_t gstride[1] = {(cuuint64_t)kbytes};
         const cuuint32_t box[2] = {kRowBytes, BM};
@@ -1604,7 +1674,8 @@ int hamming_tc_launch(const HammingSearchParams& p, const HammingTcPlan& plan, v
         // raw packed panel [nw][n][stride] words: box = one k-block of words x one tile of rows of one window
         const cuuint64_t gdim[3] = {(cuuint64_t)p.stride, (cuuint64_t)p.n, (cuuint64_t)p.nw};
         const cuuint64_t gstride[2] = {(cuuint64_t)p.stride * 4, (cuuint64_t)p.panel_win_stride * 4};
-        const cuuint32_t box[3] = {(cuuint32_t)wpk_of_engine(plan.engine), (cuuint32_t)(pair_engine(plan.engine) ? BN / 2 : BN), 1};
+        // (TMEM-A mode: whole packed rows, one box per tile)
+        const cuuint32_t box[3] = {(cuuint32_t)(tmem_a ? p.stride : wpk_of_engine(plan.engine)), (cuuint32_t)(pair_engine(plan.engine) ? BN / 2 : BN), 1};
         int rc = encode_map(&map_r, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, p.panel, gdim, gstride, box, CU_TENSOR_MAP_SWIZZLE_NONE);
         if (rc) return rc;
     } else {
@@ -1628,6 +1699,8 @@ int hamming_tc_launch(const HammingSearchParams& p, const HammingTcPlan& plan, v
     tp.D_i32 = p.D_i32; tp.D_f32 = p.D_f32; tp.I = p.I;
     tp.partial = partial;
     tp.q_ops = q_ops;
+    tp.q = p.q; tp.mask = p.mask; tp.mask_win_stride = p.mask_win_stride; tp.mask_q_stride = p.mask_q_stride;
+    tp.stride = p.stride; tp.d = p.d;
     const int grid = pair ? 2 * std::min(tp.items, kNumSMs / 2) : std::min(tp.items, kNumSMs);
     int rc;
     const bool k8 = plan.kt == 8;

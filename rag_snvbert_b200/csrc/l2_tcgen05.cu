@@ -560,11 +560,8 @@ int l2_launch(const L2SearchParams& p, cudaStream_t stream)
         ps.dot = reinterpret_cast<float*>(p.partial);
         uint64_t* keys = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(p.partial) + round_up((size_t)p.nq * p.dot_ld * 4, 256));
         SNV_CUDA_CHECK(cudaMemsetAsync(ps.dot, 0, (size_t)p.nq * p.dot_ld * 4, stream));
-        static bool attr_sk = false;
-        if (!attr_sk) {
-            SNV_CUDA_CHECK(cudaFuncSetAttribute(l2_topk_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-            attr_sk = true;
-        }
+        // (the opt-in is per device / context: set on every launch, never cached process-wide)
+        SNV_CUDA_CHECK(cudaFuncSetAttribute(l2_topk_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
         const int64_t n_tiles = ceil_div(p.n, BN);
         const unsigned grid_sk = (unsigned)(m_tiles * n_tiles * p.ksplit);
         profile_begin(stream);
@@ -579,11 +576,9 @@ int l2_launch(const L2SearchParams& p, cudaStream_t stream)
         return merge_keys_launch(keys, 1, (int)p.n, p.nq, p.k, p.id_offset, true, nullptr, p.D_f32, p.I, stream);
     }
     const unsigned grid = p.pair ? (unsigned)(2 * ceil_div(m_tiles, 2) * p.nsplit) : (unsigned)(m_tiles * p.nsplit);
-    auto launch = [&](auto kern, bool& attr_done) -> int {
-        if (!attr_done) {
-            SNV_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-            attr_done = true;
-        }
+    auto launch = [&](auto kern) -> int {
+        // the dynamic shared-memory opt-in is per device / context: set on every launch, never cached process-wide
+        SNV_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
         profile_begin(stream);
         if (p.pair) {
             cudaLaunchConfig_t cfg = {};
@@ -605,9 +600,8 @@ int l2_launch(const L2SearchParams& p, cudaStream_t stream)
         profile_end(stream);
         return SNV_OK;
     };
-    static bool attr8 = false, attr32 = false, attr8p = false, attr32p = false;
-    if (p.kt == 8) rc = p.pair ? launch(l2_topk_kernel<8, false, true>, attr8p) : launch(l2_topk_kernel<8, false, false>, attr8);
-    else rc = p.pair ? launch(l2_topk_kernel<32, false, true>, attr32p) : launch(l2_topk_kernel<32, false, false>, attr32);
+    if (p.kt == 8) rc = p.pair ? launch(l2_topk_kernel<8, false, true>) : launch(l2_topk_kernel<8, false, false>);
+    else rc = p.pair ? launch(l2_topk_kernel<32, false, true>) : launch(l2_topk_kernel<32, false, false>);
     if (rc) return rc;
     SNV_LAUNCH_CHECK();
     return merge_keys_launch(p.partial, p.nsplit * 2, p.kt, p.nq, p.k, p.id_offset, true, nullptr, p.D_f32, p.I, stream);

@@ -549,4 +549,28 @@ int intersect_masks_launch(const int64_t* ref_pos, int64_t n_ref, const int64_t*
     return SNV_OK;
 }
 
+// ---- compact result rows: (int32 distance, int64 id) -> (uint16 distance, int32 id) ------------------------------
+// Host-buffer searches move 12 bytes per neighbour back over PCIe; ids below 2^31 and Hamming distances below 65535
+// fit 6.  Missing entries (id -1, distance INT32_MAX) become (-1, 0xFFFF).
+__global__ void __launch_bounds__(256)
+narrow_results_kernel(const int32_t* __restrict__ D, const int64_t* __restrict__ I, int64_t n, uint16_t* __restrict__ D16,
+                      int32_t* __restrict__ I32)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t id = I[i];
+        const int32_t d = D[i];
+        I32[i] = (int32_t)id;
+        D16[i] = id < 0 ? (uint16_t)0xFFFF : (uint16_t)d;
+    }
+}
+
+int narrow_results_launch(const int32_t* D, const int64_t* I, int64_t n, uint16_t* D16, int32_t* I32, cudaStream_t stream)
+{
+    if (n <= 0) return SNV_OK;
+    const int grid = (int)std::min<int64_t>(ceil_div(n, 256), (int64_t)kNumSMs * 8);
+    narrow_results_kernel<<<grid, 256, 0, stream>>>(D, I, n, D16, I32);
+    SNV_LAUNCH_CHECK();
+    return SNV_OK;
+}
+
 }  // namespace snv

@@ -223,6 +223,66 @@ class WindowedHammingIndex(_IndexBase):
             return D[0], I[0]
         return D, I
 
+    def search_compact(self, q, k: int, observed=None, missing=None, w0: int = 0, out=None):
+        """search() with compact results: (D uint16 [nw, nq, k], I int32 [nw, nq, k]) - the same distances and row ids in
+        half the bytes (6 instead of 12 per neighbour), for host-buffer sweeps whose cost is the PCIe return trip
+        (batch_test_faiss_l2.py:109-111 keeps every window's D, I).  Padding: I = -1, D = 0xFFFF.  `out=(D, I)`:
+        caller-owned (e.g. pinned) buffers of those dtypes."""
+        if int(k) < 1:
+            raise ValueError("k must be >= 1")
+        a = _Arg(q)
+        squeeze = len(a.shape) == 2
+        if squeeze:
+            nw, nq = 1, a.shape[0]
+        elif len(a.shape) == 3:
+            nw, nq = a.shape[0], a.shape[1]
+        else:
+            raise ValueError(f"search_compact: expected a 2-D or 3-D query array, got shape {a.shape}")
+        dt, a = _hamming_dtype(a, self.d, self.stride, "search_compact")
+        flags = L.Q_ON_DEVICE | L.OUT_ON_DEVICE if a.on_device else 0
+        m_ptr, m_mode = None, L.MASK_NONE
+        if observed is not None and missing is not None:
+            raise ValueError("search_compact: give observed= or missing=, not both")
+        mk = observed if observed is not None else missing
+        if mk is not None:
+            m = _Arg(mk)
+            if m.on_device != a.on_device:
+                raise ValueError("search_compact: queries and mask must live in the same memory (both numpy or both CUDA)")
+            if tuple(m.shape) == tuple(a.shape):
+                m_mode = L.MASK_PER_QUERY
+            elif tuple(m.shape) == tuple(a.shape[:-2] + a.shape[-1:]):
+                m_mode = L.MASK_PER_WINDOW
+            else:
+                raise ValueError(f"search_compact: mask shape {m.shape} matches neither the queries nor one row per window")
+            mdt, m = _hamming_dtype(m, self.d, self.stride, "search_compact(mask)")
+            if mdt != dt:
+                raise ValueError("search_compact: mask and queries must use the same dtype")
+            m_ptr = m.ptr
+            if missing is not None:
+                flags |= L.MASK_IS_MISSING
+        shape = (nw, nq, int(k))
+        if out is not None:
+            Do, Io = _Arg(out[0]), _Arg(out[1])
+            if (Do.on_device != a.on_device or Io.on_device != a.on_device or Do.np_dtype not in (np.dtype(np.uint16), np.dtype(np.int16))
+                    or Io.np_dtype != np.dtype(np.int32) or int(np.prod(Do.shape)) != int(np.prod(shape))
+                    or int(np.prod(Io.shape)) != int(np.prod(shape)) or Do.arr is not out[0] or Io.arr is not out[1]):
+                raise ValueError("search_compact: out=(D, I) must be contiguous uint16 / int32 arrays of the result size, "
+                                 "in the same memory as the queries")
+            D, Dp, I, Ip = out[0].reshape(shape), Do.ptr, out[1].reshape(shape), Io.ptr
+        else:
+            if a.on_device:
+                D = torch.empty(shape, dtype=torch.int16, device=f"cuda:{self.device}")  # uint16 bit patterns
+                Dp = D.data_ptr()
+            else:
+                D = np.empty(shape, dtype=np.uint16)
+                Dp = D.ctypes.data
+            I, Ip = self._alloc_out(a.on_device, shape, np.int32)
+        L.check(self._lib.snv_index_search_compact(self._h, int(w0), nw, a.ptr, nq, dt, m_ptr, m_mode, int(k), Dp, Ip, flags,
+                                                   _current_stream(self.device)), "snv_index_search_compact")
+        if squeeze:
+            return D[0], I[0]
+        return D, I
+
     def search_grouped(self, q, window_ids, k: int, observed=None, missing=None, dist_dtype=np.int32):
         """Ragged per-window batch (a training batch regrouped by window_idx,
         src/dataset/rag_train_dataset.py:239-281): q [nq_total, d] in caller order, window_ids

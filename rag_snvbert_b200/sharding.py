@@ -94,3 +94,130 @@ def search_window_sharded(search_fn: Callable, n_windows: int, world: int, rank:
     No collective: callers that need every window on every rank gather the results themselves."""
     lo, hi = shard_range(n_windows, world, rank)
     return lo, hi, (search_fn(lo, hi) if hi > lo else None)
+
+
+class RowShardedSearch:
+    """Row-sharded exact k-NN over a multi-window index, pipelined: the panel rows of every window are split over the
+    ranks (this rank holds rows [row_lo, row_lo + ntotal)); the merged result comes back sharded by QUERY - rank r
+    gets queries shard_range(nq, G, r) of every window, D / I [nw, nq_r, k] - which is what a data-parallel consumer
+    wants and moves 1/G of the bytes an all-gather would.
+
+    Per call the windows are cut into `chunks` groups.  For each group: local scan with global ids on the caller's
+    stream; then, on a side stream, ONE all_to_all_single of the packed candidates (one int64 key = distance << 40 | id
+    per neighbour instead of separate int32 / int64 arrays: 8 instead of 12 bytes on the wire, one collective
+    instead of two) and the on-device k-way merge - overlapping the next group's scan.  The result equals the
+    unsharded search by construction of the (distance, id) total order.
+
+    `search_fn(queries [nw_c, nq, ..], k, w0) -> (D, I) [nw_c, nq, k]` (ids global) and `merge_fn(D [G, n, k], I [G, n, k], k)`
+    are injectable so that the plumbing runs on CPU tensors over gloo in the tests; by default they are the CUDA
+    index's search (`index.search(q, k, w0=w0, id_offset=row_lo)`) and `topk_merge`."""
+
+    _ID_BITS = 40
+
+    def __init__(self, index, row_lo: int, world: Optional[int] = None, group=None, merge_fn: Optional[Callable] = None,
+                 search_fn: Optional[Callable] = None, chunks: Optional[int] = None):
+        import torch.distributed as dist
+
+        self.index = index
+        self.row_lo = int(row_lo)
+        self.group = group
+        self.world = int(world) if world is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
+        self.rank = dist.get_rank(group) if (self.world > 1 and dist.is_initialized()) else 0
+        if merge_fn is None:
+            from .index import topk_merge as merge_fn  # noqa: PLC0415
+        self.merge_fn = merge_fn
+        self.search_fn = search_fn or (lambda q, k, w0: index.search(q, k, w0=w0, id_offset=self.row_lo))
+        self.chunks = chunks
+        self._side = None
+        self._last = ""
+
+    def describe(self) -> str:
+        return self._last or "not run yet"
+
+    @classmethod
+    def pack_keys(cls, D, I):
+        """(D int32 >= 0, I int64 global id or -1) -> one int64 key per neighbour; missing entries -> the largest key"""
+        import torch
+
+        key = (D.to(torch.int64) << cls._ID_BITS) | (I & ((1 << cls._ID_BITS) - 1))
+        return torch.where(I < 0, torch.full_like(key, torch.iinfo(torch.int64).max), key)
+
+    @classmethod
+    def unpack_keys(cls, key):
+        import torch
+
+        missing = key == torch.iinfo(torch.int64).max
+        D = torch.where(missing, torch.full_like(key, 0x7FFFFFFF), key >> cls._ID_BITS).to(torch.int32)
+        I = torch.where(missing, torch.full_like(key, -1), key & ((1 << cls._ID_BITS) - 1))
+        return D, I
+
+    def search(self, queries, k: int):
+        """queries [nw, nq, ..] (the same on every rank) -> (q_lo, q_hi, D [nw, q_hi - q_lo, k], I [..]): this rank's
+        queries of every window, merged over all row shards."""
+        import torch
+        import torch.distributed as dist
+
+        nw, nq = int(queries.shape[0]), int(queries.shape[1])
+        G = self.world
+        if G == 1:
+            D, I = self.search_fn(queries, k, 0)
+            self._last = "single shard: no exchange"
+            return 0, nq, D, I
+        cuts = [shard_range(nq, G, r) for r in range(G)]
+        q_lo, q_hi = cuts[self.rank]
+        even = nq % G == 0
+        n_chunks = self.chunks if self.chunks else (2 if nw >= 4 else 1)
+        n_chunks = max(1, min(int(n_chunks), nw))
+        bounds = [shard_range(nw, n_chunks, c) for c in range(n_chunks)]
+        on_gpu = queries.is_cuda
+        outD = outI = None
+        main = side = None
+        if on_gpu:
+            main = torch.cuda.current_stream(queries.device)
+            if self._side is None:
+                self._side = torch.cuda.Stream(queries.device)
+            side = self._side
+            side.wait_stream(main)
+        for (w0, w1) in bounds:
+            D, I = self.search_fn(queries[w0:w1], k, w0)
+            wc = w1 - w0
+            if outD is None:
+                outD = torch.empty((nw, q_hi - q_lo, k), dtype=D.dtype, device=D.device)
+                outI = torch.empty((nw, q_hi - q_lo, k), dtype=torch.int64, device=D.device)
+
+            def exchange_and_merge(D=D, I=I, w0=w0, w1=w1, wc=wc):
+                packed = D.dtype == torch.int32
+                parts = [self.pack_keys(D, I)] if packed else [D, I]
+                got = []
+                for t in parts:
+                    if even:
+                        qg = nq // G
+                        send = t.reshape(wc, G, qg, k).permute(1, 0, 2, 3).contiguous()   # [dest][window][query][k]
+                        recv = torch.empty_like(send)
+                        dist.all_to_all_single(recv, send, group=self.group)
+                        got.append(recv.reshape(G, wc * qg, k))
+                    else:
+                        send = torch.cat([t[:, a:b].reshape(-1, k) for a, b in cuts], dim=0)
+                        recv = torch.empty((G * wc * (q_hi - q_lo), k), dtype=t.dtype, device=t.device)
+                        dist.all_to_all_single(recv, send, output_split_sizes=[wc * (q_hi - q_lo)] * G,
+                                               input_split_sizes=[wc * (b - a) for a, b in cuts], group=self.group)
+                        got.append(recv.reshape(G, wc * (q_hi - q_lo), k))
+                Dg, Ig = self.unpack_keys(got[0]) if packed else (got[0], got[1])
+                Dm, Im = self.merge_fn(Dg.contiguous(), Ig.contiguous(), k)
+                outD[w0:w1] = Dm.reshape(wc, q_hi - q_lo, k)
+                outI[w0:w1] = Im.reshape(wc, q_hi - q_lo, k)
+
+            if on_gpu:
+                ev = main.record_event()
+                with torch.cuda.stream(side):
+                    side.wait_event(ev)
+                    exchange_and_merge()
+                D.record_stream(side)
+                I.record_stream(side)
+            else:
+                exchange_and_merge()
+        if on_gpu:
+            main.wait_stream(side)
+        self._last = (f"{n_chunks} window group(s) per call; per group one all_to_all_single of packed int64 (distance << 40 | id) keys "
+                      f"({nq // G if even else q_hi - q_lo} queries x k from each of {G} ranks) + k-way merge on a side stream, overlapping the next group's scan")
+        return q_lo, q_hi, outD, outI

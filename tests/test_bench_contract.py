@@ -33,7 +33,7 @@ def test_reference_arm_line():
     assert d["impl"] == "reference" and d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 1
     assert d["metric"].startswith("ref-haplotypes scanned/s") and d["unit"] == "ref-haplotypes/s"
     assert d["value"] > 0 and d["ms_per_step"] > 0
-    assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None
+    assert d["higher_is_better"] is True and d["scaling"] == "strong" and d["vs_baseline"] is None  # the job's windows, as BASELINE words it
     assert d["data"] == "synthetic" and "workload" in d["config"] and "model" not in d["config"]
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["unit"] == d["unit"] and cb["sample"]

@@ -480,3 +480,55 @@ def test_topk_merge_arbitrary_order_and_padding(parts, kin, kout, dt):
         exp_i[: len(order)] = i[order]
         np.testing.assert_array_equal(Im[q], exp_i)
         np.testing.assert_array_equal(Dm[q], exp_d)
+
+
+@pytest.mark.parametrize("shape", [(3, 700, 300, 1030, 8), (10, 5008, 260, 1030, 8), (1, 40, 9, 77, 5), (2, 3, 4, 33, 8)])
+@pytest.mark.parametrize("where", ["host", "device"])
+def test_compact_results_equal_the_wide_ones(shape, where):
+    """search_compact: (uint16 D, int32 I) must carry exactly the values of (int32 D, int64 I), padding included
+    (k > rows), from host buffers (pipelined chunks) and from device tensors, with and without masks."""
+    import torch
+
+    W, N, Q, d, k = shape
+    rng = np.random.default_rng(sum(shape))
+    panel = (rng.random((W, N, d)) < 0.4).astype(np.uint8)
+    q = (rng.random((W, Q, d)) < 0.4).astype(np.uint8)
+    obs = (rng.random((W, Q, d)) < 0.7).astype(np.uint8)
+    idx = _idx(d, W)
+    idx.add(panel)
+    for m in (None, obs):
+        if where == "host":
+            D, I = idx.search(q, k, observed=m)
+            Dc, Ic = idx.search_compact(q, k, observed=m)
+            assert Dc.dtype == np.uint16 and Ic.dtype == np.int32
+        else:
+            qd = torch.from_numpy(q).cuda()
+            md = None if m is None else torch.from_numpy(m).cuda()
+            D, I = idx.search(qd, k, observed=md)
+            Dc, Ic = idx.search_compact(qd, k, observed=md)
+            D, I = D.cpu().numpy(), I.cpu().numpy()
+            Dc, Ic = Dc.cpu().numpy().view(np.uint16), Ic.cpu().numpy()
+        np.testing.assert_array_equal(Ic.astype(np.int64), I)
+        np.testing.assert_array_equal(np.where(I < 0, 0x7FFFFFFF, Dc.astype(np.int32)), D)
+        if k > N:
+            assert (Ic[..., N:] == -1).all() and (Dc[..., N:] == 0xFFFF).all()
+
+
+def test_row_sharded_search_object_single_rank_and_key_packing():
+    """RowShardedSearch on one rank is the plain search; pack/unpack of the exchange keys on the device"""
+    import torch
+
+    from rag_snvbert_b200.sharding import RowShardedSearch
+
+    rng = np.random.default_rng(5)
+    panel = (rng.random((2, 600, 200)) < 0.4).astype(np.uint8)
+    q = torch.from_numpy((rng.random((2, 50, 200)) < 0.4).astype(np.uint8)).cuda()
+    idx = _idx(200, 2)
+    idx.add(panel)
+    s = RowShardedSearch(idx, 1000, world=1)
+    lo, hi, D, I = s.search(q, 8)
+    D0, I0 = idx.search(q, 8, id_offset=1000)
+    assert (lo, hi) == (0, 50) and torch.equal(D, D0) and torch.equal(I, I0)
+    key = RowShardedSearch.pack_keys(D, I)
+    D2, I2 = RowShardedSearch.unpack_keys(key)
+    assert torch.equal(D2, D) and torch.equal(I2, I)

@@ -83,3 +83,60 @@ def test_world2_row_and_window_sharding():
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
     assert dict(out) == {0: (True, True), 1: (True, True)}
+
+
+def test_key_packing_roundtrip():
+    from rag_snvbert_b200.sharding import RowShardedSearch
+
+    D = torch.tensor([[0, 5, 1030, 0x7FFFFFFF]], dtype=torch.int32)
+    I = torch.tensor([[0, 199999, (1 << 40) - 1, -1]], dtype=torch.int64)
+    key = RowShardedSearch.pack_keys(D, I)
+    assert bool((key[0, :3][1:] > key[0, :3][:-1]).all()) and int(key[0, 3]) == torch.iinfo(torch.int64).max
+    D2, I2 = RowShardedSearch.unpack_keys(key)
+    assert torch.equal(D2, D) and torch.equal(I2, I)
+
+
+def _worker_pipelined(rank, world, port, out):
+    from rag_snvbert_b200.sharding import RowShardedSearch
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ok = True
+        for (W, N, S, Q, k, chunks) in [(5, 900, 200, 40, 8, 2), (3, 700, 130, 37, 5, 3), (1, 300, 64, 16, 32, None)]:
+            panels = [O.hapgen(100 + w, N, S) for w in range(W)]
+            q = np.stack([O.hapgen(200 + w, Q, S, founder_seed=100 + w) for w in range(W)])
+            lo, hi = shard_range(N, world, rank)
+
+            def search_fn(queries, kk, w0, lo=lo, hi=hi, panels=panels):
+                Ds, Is = [], []
+                for j in range(queries.shape[0]):
+                    D, I = O.hamming_topk(panels[w0 + j][lo:hi], queries[j].numpy(), kk)
+                    Ds.append(D)
+                    Is.append(np.where(I >= 0, I + lo, -1))
+                return torch.from_numpy(np.stack(Ds)), torch.from_numpy(np.stack(Is))
+
+            def merge_fn(Dp, Ip, kk):
+                D, I = O.merge_topk(list(Dp.numpy()), list(Ip.numpy()), kk, O.I32_MAX)
+                return torch.from_numpy(D), torch.from_numpy(I)
+
+            s = RowShardedSearch(None, lo, world=world, merge_fn=merge_fn, search_fn=search_fn, chunks=chunks)
+            qlo, qhi, D, I = s.search(torch.from_numpy(q), k)
+            ok = ok and (qlo, qhi) == shard_range(Q, world, rank) and tuple(D.shape) == (W, qhi - qlo, k)
+            for w in range(W):
+                De, Ie = O.hamming_topk(panels[w], q[w], k)
+                ok = ok and bool((I[w].numpy() == Ie[qlo:qhi]).all() and (D[w].numpy() == De[qlo:qhi]).all())
+            ok = ok and "all_to_all_single" in s.describe()
+        out[rank] = ok
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_pipelined_row_sharded_search():
+    """RowShardedSearch (window groups, packed-key all_to_all_single, merged result sharded by query) == unsharded"""
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_pipelined, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert dict(out) == {0: True, 1: True}
