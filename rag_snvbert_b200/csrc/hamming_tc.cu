@@ -80,7 +80,7 @@
 #define SNV_TC_WARP_ARRIVE 1  // epilogue warps release an accumulator stage with one arrival per warp (0: one per thread)
 #endif
 #ifndef SNV_TC_DEFAULT_ENGINE
-#define SNV_TC_DEFAULT_ENGINE 4  // what "auto" picks for tensor-core shapes: 1 = fp8, 3 = fp4, 4 = fp4 on CTA pairs
+#define SNV_TC_DEFAULT_ENGINE 5  // what "auto" picks for tensor-core shapes: 1 = fp8, 3 = fp4, 4 = fp4 on CTA pairs, 5 = 4 with the query operand in tensor memory
 #endif
 
 namespace snv {
@@ -823,25 +823,39 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                         mbar_wait(&empty_b[rb.i], rb.phase ^ 1u);
                         const uint32_t src0 = smem_u32(raws) + (uint32_t)rr.i * C::kRawSlot;
                         const uint32_t dst0 = b_base + (uint32_t)rb.i * C::kBSlot;
-#pragma unroll 2
-                        for (int u = et; u < units; u += kExpThreads) {
-                            const int h = u / C::kBRows, r = u - h * C::kBRows;
-                            const int word0 = 4 * h;
-                            const uint4 wv = lds128(src0 + (uint32_t)r * rstride + (uint32_t)h * 16u);
-                            const uint32_t dst = dst0 + (uint32_t)(h >> 1) * C::kBSub + (uint32_t)r * kRowBytes;
-                            const uint32_t sw2 = (uint32_t)(r & 7), cb = (uint32_t)(h & 1) * 4u;
-                            const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
-                            if (word0 + 4 <= p.words) {
+                        // every raw load of the tile first (up to 7 units per thread), then the expansion: the loads'
+                        // latencies overlap instead of adding up
+                        constexpr int kMaxUnits = (2 * C::kMaxKbTmemA * C::kBRows + kExpThreads - 1) / kExpThreads;
+                        uint4 wv[kMaxUnits];
 #pragma unroll
-                                for (int i = 0; i < 4; ++i) sts128(dst + (((cb + i) ^ sw2) << 4), expand_panel_word_fp4(ww[i]));
-                            } else {
+                        for (int i = 0; i < kMaxUnits; ++i) {
+                            const int u = et + i * kExpThreads;
+                            if (u < units) {
+                                const int h = u / C::kBRows, r = u - h * C::kBRows;
+                                wv[i] = lds128(src0 + (uint32_t)r * rstride + (uint32_t)h * 16u);
+                            }
+                        }
 #pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    const int wi = word0 + i;
-                                    const uint32_t a = dst + (((cb + i) ^ sw2) << 4);
-                                    if (wi < ich) sts128(a, expand_panel_word_fp4(wi < p.words ? ww[i] : 0u));
-                                    else if (wi == ich) sts128(a, lds128(idx_tab + (uint32_t)r * 32u));
-                                    else if (wi == ich + 1) sts128(a, lds128(idx_tab + (uint32_t)r * 32u + 16u));
+                        for (int i = 0; i < kMaxUnits; ++i) {
+                            const int u = et + i * kExpThreads;
+                            if (u < units) {
+                                const int h = u / C::kBRows, r = u - h * C::kBRows;
+                                const int word0 = 4 * h;
+                                const uint32_t dst = dst0 + (uint32_t)(h >> 1) * C::kBSub + (uint32_t)r * kRowBytes;
+                                const uint32_t sw2 = (uint32_t)(r & 7), cb = (uint32_t)(h & 1) * 4u;
+                                const uint32_t ww[4] = {wv[i].x, wv[i].y, wv[i].z, wv[i].w};
+                                if (word0 + 4 <= p.words) {
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) sts128(dst + (((cb + j) ^ sw2) << 4), expand_panel_word_fp4(ww[j]));
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        const int wi = word0 + j;
+                                        const uint32_t a = dst + (((cb + j) ^ sw2) << 4);
+                                        if (wi < ich) sts128(a, expand_panel_word_fp4(wi < p.words ? ww[j] : 0u));
+                                        else if (wi == ich) sts128(a, lds128(idx_tab + (uint32_t)r * 32u));
+                                        else if (wi == ich + 1) sts128(a, lds128(idx_tab + (uint32_t)r * 32u + 16u));
+                                    }
                                 }
                             }
                         }
@@ -1064,19 +1078,26 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                     const uint32_t key = ((uint32_t)((iv >> 8) + qb) << idx_bits) + tile_col0 + (uint32_t)(iv & 255);
                     return v < 3.0e38f ? key : kSent32;
                 };
-                // two entries (four keys) per round, loads predicated, and - at k <= 8 - the inserts unguarded: inserting
-                // a key that is not below the k-th best (or the empty sentinel) leaves the list unchanged, so the round
-                // is straight-line code instead of four warp-divergent branches
+                // Two entries per round, loads predicated.  Of an entry's two values the smaller one is what qualified the
+                // pair: it is inserted unguarded at k <= 8 (inserting a key that is not below the k-th best, or the empty
+                // sentinel, leaves the list unchanged: straight-line code); the larger one is a candidate only if it is
+                // below the threshold the scan used as well, which is rare, so its insert sits behind a branch the warp
+                // seldom takes.  Values order like their keys: v = a + c / 256.
 #pragma unroll 1
                 for (uint32_t i = 0; i < mx; i += 2) {
                     float v[4] = {3.0e38f, 3.0e38f, 3.0e38f, 3.0e38f};
                     if (i < lcnt) asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v[0]), "=f"(v[1]) : "r"(list_base + i * kLStride));
                     if (i + 1u < lcnt) asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v[2]), "=f"(v[3]) : "r"(list_base + (i + 1u) * kLStride));
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const uint32_t key = key_of_v(v[e]);
-                        if constexpr (KT <= 8) topk_insert<KT, uint32_t>(best, key);
-                        else if (key < best[KT - 1]) topk_insert<KT, uint32_t>(best, key);
+                    for (int e = 0; e < 4; e += 2) {
+                        const float lo = fminf(v[e], v[e + 1]), hi = fmaxf(v[e], v[e + 1]);
+                        const uint32_t klo = key_of_v(lo);
+                        if constexpr (KT <= 8) topk_insert<KT, uint32_t>(best, klo);
+                        else if (klo < best[KT - 1]) topk_insert<KT, uint32_t>(best, klo);
+                        if (hi < thr) {
+                            const uint32_t khi = key_of_v(hi);
+                            if (khi < best[KT - 1]) topk_insert<KT, uint32_t>(best, khi);
+                        }
                     }
                 }
                 lcnt = 0u;
@@ -1480,8 +1501,12 @@ int hamming_engine_for(const HammingSearchParams& p)
     if (mode > 0) return mode;
     // auto: enough queries per window to fill a useful part of the 128-lane tile, and a panel worth a tile
     if (!(p.nq >= 32 && p.n >= 512)) return 0;
-    // CTA pairs need two query tiles per window to keep both SMs of a pair busy
-    return (SNV_TC_DEFAULT_ENGINE == 4 && p.nq <= BM) ? 3 : SNV_TC_DEFAULT_ENGINE;
+    // CTA pairs need two query tiles per window to keep both SMs of a pair busy; windows of at most 1216 sites
+    // (5 k-blocks of operand incl. the column-index block) keep the query operand in tensor memory (engine 5)
+    if (SNV_TC_DEFAULT_ENGINE >= 4 && p.nq <= BM) return 3;
+    if (SNV_TC_DEFAULT_ENGINE == 5 && (kblocks_of_engine(5, p.words) > Cfg<MODE_FP4_2CTA_TA>::kMaxKbTmemA || p.stride > Cfg<MODE_FP4_2CTA_TA>::kMaxStrideTmemA))
+        return 4;
+    return SNV_TC_DEFAULT_ENGINE;
 }
 
 size_t hamming_tc_plan(const HammingSearchParams& p, HammingTcPlan& plan)
@@ -1559,8 +1584,10 @@ size_t hamming_tc_plan(const HammingSearchParams& p, HammingTcPlan& plan)
         }
     }
     const int64_t rows = (int64_t)p.nw * p.nq;
-    plan.off_bias = round_up(rows * plan.kblocks * kRowBytes, 256);
-    plan.off_partial = plan.off_bias + round_up(rows * 4, 256);
+    // (engine 5 builds its query operand in the scan kernel: no operand rows, no biases in the workspace)
+    const bool ws_ops = mode_of_engine(plan.engine) != MODE_FP4_2CTA_TA;
+    plan.off_bias = ws_ops ? round_up(rows * plan.kblocks * kRowBytes, 256) : 0;
+    plan.off_partial = plan.off_bias + (ws_ops ? round_up(rows * 4, 256) : 0);
     plan.off_panel = plan.off_partial + (plan.nsplit > 1 ? round_up(rows * plan.nsplit * plan.kt * 8, 256)
                                                           : round_up((int64_t)plan.tail_items * (pair ? 2 * BM : BM) * plan.tail_split * plan.kt * 8, 256));
     size_t total = plan.off_panel;

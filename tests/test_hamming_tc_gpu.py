@@ -15,9 +15,8 @@ from oracle import oracle as O
 pytestmark = pytest.mark.gpu
 
 
-# tc4x2ta (query operand in tensor memory) is round-2 bring-up code: first parity run green
-# (profiles/r1_tmema_first_parity.txt), joins the matrix with SNV_TEST_TMEMA=1 until the full fuzz has passed on a B200
-_ENGINES = ["tc", "tc_hbm", "tc4", "tc4x2"] + (["tc4x2ta"] if os.environ.get("SNV_TEST_TMEMA") == "1" else [])
+# tc4x2ta (query operand in tensor memory, the default for windows of up to 1216 sites) fuzzed clean on B200 in round 2
+_ENGINES = ["tc", "tc_hbm", "tc4", "tc4x2", "tc4x2ta"]
 
 
 @pytest.fixture(params=_ENGINES)
@@ -194,7 +193,7 @@ def test_auto_engine_choice_by_shape():
         idx = WindowedHammingIndex(1030, 1)
         idx.add(panel)
         idx.search((rng.random((1, 300, 1030)) < 0.3).astype(np.uint8), 8)
-        assert _lib.last_hamming_engine() == 4
+        assert _lib.last_hamming_engine() == 5  # CTA pairs, query operand in tensor memory (<= 1216 sites)
         idx.search((rng.random((1, 100, 1030)) < 0.3).astype(np.uint8), 8)
         assert _lib.last_hamming_engine() == 3
         idx.search((rng.random((1, 2, 1030)) < 0.3).astype(np.uint8), 8)

@@ -121,20 +121,24 @@ def test_cfg_shapes_pick_expected_plans(L, force_engine):
     """the plans the committed measurements were taken with"""
     force_engine(None)
     plan, items = L.debug_hamming_plan(1000, 2000, 5008, 1030, 8)
-    assert plan["engine"] == 4 and plan["nsplit"] == 1 and plan["kblocks"] == 5 and plan["n_tiles"] == 21
+    assert plan["engine"] == 5 and plan["nsplit"] == 1 and plan["kblocks"] == 5 and plan["n_tiles"] == 32
     # a chunk of cfg 2 as api.cu cuts it: items a multiple of the 74 SM pairs -> no splits at all
     plan, items = L.debug_hamming_plan(37, 2000, 5008, 1030, 8)
     assert plan["nsplit"] == 1 and plan["tail_split"] == 0 and len(items) == 2 * 37 * 8
-    # cfg 5 step: 8 windows x 40 tile pairs = 320 items = 4 rounds + 24 -> the 24 trailing items are cut in 3
+    # cfg 5 step on one GPU (k = 32)
     plan, items = L.debug_hamming_plan(8, 10000, 200000, 1030, 32)
-    assert plan["engine"] == 4 and plan["kt"] == 32 and plan["nsplit"] == 1
+    assert plan["engine"] == 5 and plan["kt"] == 32
+    # its 8-GPU row shard: 8 windows x 40 tile pairs = 320 items = 4 rounds + 24 -> the 24 trailing items are cut in 3
+    plan, items = L.debug_hamming_plan(8, 10000, 25000, 1030, 32)
+    assert plan["engine"] == 5 and plan["kt"] == 32 and plan["nsplit"] == 1
     assert plan["tail_items"] == 24 and plan["tail_split"] == 3
 
 
 def test_auto_engine_by_shape(L, force_engine):
     force_engine(None)
     eng = lambda *a: L.debug_hamming_plan(*a)[0]["engine"]
-    assert eng(1, 300, 2000, 1030, 8) == 4
+    assert eng(1, 300, 2000, 1030, 8) == 5
+    assert eng(1, 300, 2000, 1500, 8) == 4  # wider than the tensor-memory operand budget: shared-memory query ring
     assert eng(1, 100, 2000, 1030, 8) == 3  # one query tile: nothing for the second CTA of a pair
     assert eng(1, 2, 5008, 1030, 8) == 0  # the reference's training-time call: popcount scan
     assert eng(1, 64, 600, 5000, 8) == 0  # d >= 4096
@@ -175,7 +179,7 @@ def test_chunk_bounds_cfg2(L, force_engine):
 def test_chunk_bounds_random(L, force_engine):
     rng = np.random.default_rng(7)
     for case in range(300):
-        force_engine([None, "popc", "tc4", "tc4x2", "tc"][case % 5])
+        force_engine([None, "popc", "tc4", "tc4x2", "tc", "tc4x2ta"][case % 6])
         nw = int(rng.integers(1, 3000))
         nq = int(rng.integers(1, 5000))
         n = int(rng.integers(1, 20000))

@@ -13,7 +13,7 @@ dev = torch.device("cuda", 0)
 n_cases = int(os.environ.get("CASES", "120"))
 bad = 0
 # ENGINES="tc4x2ta" (comma separated) checks other builds / bring-up engines against the popcount scan
-TC_ENGINES = tuple(e for e in os.environ.get("ENGINES", "tc,tc4,tc4x2").split(",") if e)
+TC_ENGINES = tuple(e for e in os.environ.get("ENGINES", "tc,tc4,tc4x2,tc4x2ta").split(",") if e)
 # panel sizes around the tile widths (240 / 256 rows; 160 for the TMEM-operand engine)
 N_CHOICES = [1, 7, 100, 239, 240, 241, 479, 481, 1000, 2500, 5008, 12000]
 if "tc4x2ta" in TC_ENGINES:
