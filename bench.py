@@ -718,6 +718,8 @@ def bench_cfg1(ctx, a, steps, warmup, want_cpu):
 
     panel, q = cfg1_inputs(a)
     k = a.k
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()  # the library allocates with cudaMalloc: give back what torch cached for the earlier workloads
 
     def step():
         index = faiss.IndexFlatL2(a.sites)

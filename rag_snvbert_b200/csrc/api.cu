@@ -583,7 +583,7 @@ static int search_hamming(snv_index* idx, int w0, int nw, const void* q, int64_t
     if (compact) {
         rc = idx->ws_di.reserve((size_t)nqt * k * 4); if (rc) return rc;
         rc = idx->ws_i.reserve((size_t)nqt * k * 8); if (rc) return rc;
-        if (!out_dev) { rc = idx->ws_df.reserve((size_t)nqt * k * 6); if (rc) return rc; }  // uint16 rows, then int32 rows
+        if (!out_dev) { rc = idx->ws_df.reserve((size_t)nqt * k * 6); if (rc) return rc; }  // int32 rows, then uint16 rows
     } else if (!out_dev) {
         if (D_i32) { rc = idx->ws_di.reserve((size_t)nqt * k * 4); if (rc) return rc; }
         if (D_f32) { rc = idx->ws_df.reserve((size_t)nqt * k * 4); if (rc) return rc; }
@@ -714,8 +714,9 @@ static int search_hamming(snv_index* idx, int w0, int nw, const void* q, int64_t
         }
         if (compact) {
             const size_t cnt = (size_t)rows * k;
-            uint16_t* d16 = out_dev ? c_D16 + o0 : (uint16_t*)idx->ws_df.p + o0;
-            int32_t* i32 = out_dev ? c_I32 + o0 : (int32_t*)((uint16_t*)idx->ws_df.p + (size_t)nqt * k) + o0;
+            // staging: the int32 rows first, the uint16 rows behind them (keeps both naturally aligned)
+            int32_t* i32 = out_dev ? c_I32 + o0 : (int32_t*)idx->ws_df.p + o0;
+            uint16_t* d16 = out_dev ? c_D16 + o0 : (uint16_t*)((int32_t*)idx->ws_df.p + (size_t)nqt * k) + o0;
             rc = narrow_results_launch(p.D_i32, p.I, (int64_t)cnt, d16, i32, cs);
             if (rc) return rc;
             if (!out_dev) {
