@@ -77,6 +77,9 @@ typedef enum snv_mask_mode {
  * of embedding vectors (position / allele-frequency terms) so that |q|^2 + |r|^2 - 2 q.r does not
  * cancel catastrophically.  Not for integer-valued rows (it would make their products inexact). */
 #define SNV_L2_CENTER 0x10
+/* OR-ed into l2_mode: decide SNV_L2_CENTER on the first add() - on when the rows hold anything but small integers
+ * (embeddings), off for integer-valued rows (tokens, 0/1 genotypes).  The Python classes default to this. */
+#define SNV_L2_CENTER_AUTO 0x20
 
 typedef struct snv_index snv_index;
 

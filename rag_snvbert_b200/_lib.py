@@ -21,6 +21,7 @@ MASK_NONE, MASK_PER_WINDOW, MASK_PER_QUERY = 0, 1, 2
 Q_ON_DEVICE, OUT_ON_DEVICE, MASK_IS_MISSING, X_ON_DEVICE = 0x1, 0x2, 0x4, 0x8
 L2_TF32, L2_TF32X3 = 0, 1
 L2_CENTER = 0x10
+L2_CENTER_AUTO = 0x20
 
 _c = ctypes
 _vp, _i, _i64, _u = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_uint

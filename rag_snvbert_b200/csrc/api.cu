@@ -262,7 +262,7 @@ int snv_index_create(int kind, int64_t d, int n_windows, int device, int l2_mode
     if (d <= 0) { set_error("snv_index_create: d must be positive"); return SNV_ERR_INVALID; }
     if (n_windows < 1) { set_error("snv_index_create: n_windows must be >= 1"); return SNV_ERR_INVALID; }
     if (kind == SNV_KIND_L2 && (l2_mode & 0xF) != SNV_L2_TF32 && (l2_mode & 0xF) != SNV_L2_TF32X3) { set_error("snv_index_create: bad l2_mode"); return SNV_ERR_INVALID; }
-    if (kind == SNV_KIND_L2 && (l2_mode & ~0x1F)) { set_error("snv_index_create: bad l2_mode flags"); return SNV_ERR_INVALID; }
+    if (kind == SNV_KIND_L2 && (l2_mode & ~0x3F)) { set_error("snv_index_create: bad l2_mode flags"); return SNV_ERR_INVALID; }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
@@ -321,6 +321,7 @@ int snv_index_reset(snv_index* idx)
     if (!idx) { set_error("snv_index_reset: null index"); return SNV_ERR_INVALID; }
     idx->ntotal = 0;
     if (idx->mean) { cudaFree(idx->mean); idx->mean = nullptr; }
+    if (idx->l2_mode & SNV_L2_CENTER_AUTO) idx->l2_mode &= ~SNV_L2_CENTER;  // decided again on the next first add
     return SNV_OK;
 }
 
@@ -431,7 +432,22 @@ int snv_index_add(snv_index* idx, const void* x, int64_t n, int dtype, unsigned 
             const size_t rb = (size_t)idx->d * 4;
             SNV_CUDA_CHECK(cudaMemcpy2DAsync(idx->rows + idx->ntotal * idx->d, (size_t)idx->cap * rb, xd,
                                              (size_t)n * rb, (size_t)n * rb, W, cudaMemcpyDeviceToDevice, stream));
+            if ((idx->l2_mode & SNV_L2_CENTER_AUTO) && idx->ntotal == 0 && !(idx->l2_mode & SNV_L2_CENTER)) {
+                // decide once, on the first rows: integer-valued vectors (tokens, genotypes) stay as they are - their
+                // products are exact - anything else is centred on its column means (one 4-byte read back)
+                int rc = idx->ws_misc.reserve(16);
+                if (rc) return rc;
+                int one = 1, integral = 1;
+                SNV_CUDA_CHECK(cudaMemcpyAsync(idx->ws_misc.p, &one, 4, cudaMemcpyHostToDevice, stream));
+                rc = l2_integral_check_launch((const float*)xd, (int64_t)W * n * idx->d, (int*)idx->ws_misc.p, stream);
+                if (rc) return rc;
+                SNV_CUDA_CHECK(cudaMemcpyAsync(&integral, idx->ws_misc.p, 4, cudaMemcpyDeviceToHost, stream));
+                SNV_CUDA_CHECK(cudaStreamSynchronize(stream));
+                if (!integral) idx->l2_mode |= SNV_L2_CENTER;
+            }
             const bool center = idx->l2_mode & SNV_L2_CENTER;
+            const int pchunks = l2_prep_chunks(idx->d);
+            if (pchunks > 1) { int rc = idx->ws_qnorm.reserve((size_t)n * pchunks * 4); if (rc) return rc; }
             if (center && !idx->mean) {
                 if (cudaMalloc(&idx->mean, (size_t)W * idx->d * 4) != cudaSuccess) { set_error("cudaMalloc(mean)"); return SNV_ERR_NOMEM; }
                 for (int w = 0; w < W; ++w) {
@@ -442,7 +458,7 @@ int snv_index_add(snv_index* idx, const void* x, int64_t n, int dtype, unsigned 
             for (int w = 0; w < W; ++w) {
                 int rc = l2_prep_launch((const float*)xd + (size_t)w * n * idx->d, center ? idx->mean + (size_t)w * idx->d : nullptr, n, idx->d, idx->l2_mode, false,
                                         idx->kp, idx->ops + ((size_t)w * idx->cap + idx->ntotal) * idx->kp,
-                                        idx->norms + (size_t)w * idx->cap + idx->ntotal, stream);
+                                        idx->norms + (size_t)w * idx->cap + idx->ntotal, pchunks > 1 ? (float*)idx->ws_qnorm.p : nullptr, stream);
                 if (rc) return rc;
             }
         }
@@ -877,7 +893,8 @@ static int search_l2(snv_index* idx, int w0, int nw, const void* q, int64_t nq, 
     }
     rc = idx->ws_qops.reserve((size_t)nqt * idx->kp * 4);
     if (rc) return rc;
-    rc = idx->ws_qnorm.reserve((size_t)nqt * 4);
+    const int pchunks = l2_prep_chunks(idx->d);
+    rc = idx->ws_qnorm.reserve((size_t)nqt * 4 * (pchunks > 1 ? 1 + pchunks : 1));
     if (rc) return rc;
     {
         const bool center = (idx->l2_mode & SNV_L2_CENTER) && idx->mean;
@@ -885,7 +902,8 @@ static int search_l2(snv_index* idx, int w0, int nw, const void* q, int64_t nq, 
             const int64_t rows = center ? nq : nqt;
             rc = l2_prep_launch(qd + (size_t)w * nq * idx->d, center ? idx->mean + (size_t)(w0 + w) * idx->d : nullptr, rows,
                                 idx->d, idx->l2_mode, true, idx->kp, (float*)idx->ws_qops.p + (size_t)w * nq * idx->kp,
-                                (float*)idx->ws_qnorm.p + (size_t)w * nq, stream);
+                                (float*)idx->ws_qnorm.p + (size_t)w * nq,
+                                pchunks > 1 ? (float*)idx->ws_qnorm.p + nqt + (size_t)w * nq * pchunks : nullptr, stream);
             if (rc) return rc;
         }
     }

@@ -122,8 +122,14 @@ size_t l2_plan(L2SearchParams& p);
 int l2_launch(const L2SearchParams& p, cudaStream_t stream);
 // fp32 rows [rows][d] -> operand rows [rows][kp] (mode TF32: x | 0-pad; TF32X3 with
 // is_query: hi|lo|hi, panel: hi|hi|lo) and squared norms.
+// norm_parts: scratch [rows][l2_prep_chunks(d)] floats, needed when l2_prep_chunks(d) > 1 (|x|^2 is then summed from
+// per-chunk partial sums in a fixed order: deterministic)
 int l2_prep_launch(const float* x, const float* mean, int64_t rows, int64_t d, int mode, bool is_query, int kp,
-                   float* ops, float* norms, cudaStream_t stream);
+                   float* ops, float* norms, float* norm_parts, cudaStream_t stream);
+int l2_prep_chunks(int64_t d);
+// 1 when every value of x [count] is integral and |x| <= 2^11 (token / genotype vectors: products exact in tf32), else 0;
+// flag is a device int the kernel ANDs into (initialise to 1)
+int l2_integral_check_launch(const float* x, int64_t count, int* flag, cudaStream_t stream);
 // column means of x [rows][d] (centering; squared L2 is translation invariant)
 int l2_colmean_launch(const float* x, int64_t rows, int64_t d, float* mean, cudaStream_t stream);
 int l2_operand_depth(int64_t d, int mode);

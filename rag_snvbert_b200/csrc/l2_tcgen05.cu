@@ -85,8 +85,9 @@ l2_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     const int n_tiles_total = (int)((p.n + BN - 1) / BN);
     // fused mode: CTA = (query tile, contiguous range of panel tiles), full depth.
     // split-K mode (skinny problems, e.g. 48 x 2008 x 197,760): CTA = (query tile, ONE panel tile,
-    // a range of k-blocks); partial dot products are reduced with fp32 atomics (round-to-nearest,
-    // and the truncating tensor-core accumulation chains stay short), selection runs afterwards.
+    // a range of k-blocks); every CTA stores its partial dot products into its own slice and the
+    // selection pass adds the slices in a fixed order (round-to-nearest, deterministic; the truncating
+    // tensor-core accumulation chains stay short).
     int split, mt, t0, my_tiles, kb0, num_kb;
     if constexpr (SPLITK) {
         int b = blockIdx.x;
@@ -224,10 +225,13 @@ l2_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ci * 32), acc);
                 tmem_ld_wait(acc);
                 if (q < p.nq) {
-                    float* dst = p.dot + q * p.dot_ld + n0 + ci * 32;
+                    // this CTA's own slice dot[k-split][q][n0 ..]: plain stores, summed in a fixed order afterwards
+                    // (deterministic, unlike fp32 atomics; pad columns of the last tile are written too and never read)
+                    float4* dst = reinterpret_cast<float4*>(p.dot + ((int64_t)(kb0 / p.kb_per_split) * p.nq + q) * p.dot_ld + n0 + ci * 32);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (ci * 32 + j < ncols) atomicAdd(dst + j, __uint_as_float(acc[j]));
+                    for (int j = 0; j < 8; ++j)
+                        dst[j] = make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]), __uint_as_float(acc[4 * j + 2]),
+                                             __uint_as_float(acc[4 * j + 3]));
                 }
             }
             tcgen05_fence_before();
@@ -350,13 +354,15 @@ l2_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 
 // ---- split-K selection input: dot products -> ordered keys ----------------------------------
 __global__ void __launch_bounds__(256)
-l2_keys_kernel(const float* __restrict__ dot, int64_t dot_ld, const float* __restrict__ q_norm,
+l2_keys_kernel(const float* __restrict__ dot, int64_t dot_ld, int ksplit, const float* __restrict__ q_norm,
                const float* __restrict__ ref_norm, int64_t nq, int64_t n, uint64_t* __restrict__ keys)
 {
     const int64_t total = nq * n;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t q = i / n, c = i % n;
-        float d = fmaf(-2.f, dot[q * dot_ld + c], q_norm[q] + ref_norm[c]);
+        float dotv = 0.f;
+        for (int ks = 0; ks < ksplit; ++ks) dotv += dot[((int64_t)ks * nq + q) * dot_ld + c];  // fixed order
+        float d = fmaf(-2.f, dotv, q_norm[q] + ref_norm[c]);
         d = d < 0.f ? 0.f : d;
         keys[i] = ((uint64_t)__float_as_uint(d) << 32) | (uint64_t)(uint32_t)c;
     }
@@ -387,7 +393,8 @@ l2_scale_kernel(float* __restrict__ v, int64_t d, float scale)
 constexpr int kPrepChunk = 2048;
 __global__ void __launch_bounds__(256)
 l2_prep_kernel(const float* __restrict__ x, const float* __restrict__ mean, int64_t rows, int64_t d, int mode,
-               bool is_query, int kp, int chunks_per_row, float* __restrict__ ops, float* __restrict__ norms)
+               bool is_query, int kp, int chunks_per_row, float* __restrict__ ops, float* __restrict__ norms,
+               float* __restrict__ norm_parts)
 {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -423,9 +430,33 @@ l2_prep_kernel(const float* __restrict__ x, const float* __restrict__ mean, int6
         for (int s2 = 16; s2 > 0; s2 >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s2);
         if (lane == 0) {
             if (chunks_per_row == 1) norms[r] = acc;
-            else atomicAdd(&norms[r], acc);
+            else norm_parts[r * chunks_per_row + item % chunks_per_row] = acc;  // summed in order by l2_norm_reduce_kernel
         }
     }
+}
+
+// Are all values integral and small (tokens, genotypes)?  Their tf32 products are exact, so centering would only hurt;
+// anything else (embeddings) gets the column means subtracted by default.  flag &= 0 on the first offender.
+__global__ void __launch_bounds__(256)
+l2_integral_check_kernel(const float* __restrict__ x, int64_t count, int* __restrict__ flag)
+{
+    bool ok = true;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = x[i];
+        ok = ok && (v == rintf(v)) && fabsf(v) <= 2048.f;
+    }
+    if (!__all_sync(0xffffffffu, ok) && (threadIdx.x & 31) == 0) atomicAnd(flag, 0);
+}
+
+// |x|^2 of long rows: the per-chunk partial sums added in a fixed order (double accumulation), one thread per row
+__global__ void __launch_bounds__(128)
+l2_norm_reduce_kernel(const float* __restrict__ parts, int64_t rows, int chunks, float* __restrict__ norms)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    double acc = 0.0;
+    for (int c = 0; c < chunks; ++c) acc += (double)parts[r * chunks + c];
+    norms[r] = (float)acc;
 }
 
 // ---- host: tensor maps ---------------------------------------------------------------------
@@ -458,16 +489,31 @@ int l2_operand_depth(int64_t d, int mode)
     return (int)round_up(k, BK);
 }
 
+int l2_prep_chunks(int64_t d) { return (int)ceil_div(d, kPrepChunk); }
+
 int l2_prep_launch(const float* x, const float* mean, int64_t rows, int64_t d, int mode, bool is_query, int kp,
-                   float* ops, float* norms, cudaStream_t stream)
+                   float* ops, float* norms, float* norm_parts, cudaStream_t stream)
 {
     if (rows <= 0) return SNV_OK;
     const int block = 256;
-    const int chunks = (int)ceil_div(d, kPrepChunk);
-    if (chunks > 1) SNV_CUDA_CHECK(cudaMemsetAsync(norms, 0, (size_t)rows * 4, stream));
+    const int chunks = l2_prep_chunks(d);
+    if (chunks > 1 && !norm_parts) { set_error("l2_prep: rows deeper than one chunk need the partial-norm scratch"); return SNV_ERR_INVALID; }
     int64_t grid = ceil_div(rows * chunks, block / 32);
     if (grid > (int64_t)kNumSMs * 16) grid = (int64_t)kNumSMs * 16;
-    l2_prep_kernel<<<(unsigned)grid, block, 0, stream>>>(x, mean, rows, d, mode & 0xF, is_query, kp, chunks, ops, norms);
+    l2_prep_kernel<<<(unsigned)grid, block, 0, stream>>>(x, mean, rows, d, mode & 0xF, is_query, kp, chunks, ops, norms, norm_parts);
+    SNV_LAUNCH_CHECK();
+    if (chunks > 1) {
+        l2_norm_reduce_kernel<<<(unsigned)ceil_div(rows, 128), 128, 0, stream>>>(norm_parts, rows, chunks, norms);
+        SNV_LAUNCH_CHECK();
+    }
+    return SNV_OK;
+}
+
+int l2_integral_check_launch(const float* x, int64_t count, int* flag, cudaStream_t stream)
+{
+    if (count <= 0) return SNV_OK;
+    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(count, 256 * 8), (int64_t)kNumSMs * 16);
+    l2_integral_check_kernel<<<grid, 256, 0, stream>>>(x, count, flag);
     SNV_LAUNCH_CHECK();
     return SNV_OK;
 }
@@ -533,8 +579,8 @@ size_t l2_plan(L2SearchParams& p)
             p.ksplit = (int)ceil_div(total_kb, p.kb_per_split);
             p.dot_ld = round_up(p.n, 32);
             p.pair = false;  // split-K runs on single CTAs
-            // workspace: dot [nq][dot_ld] fp32, then keys [nq][n] u64
-            return (size_t)p.nq * p.dot_ld * 4 + (size_t)p.nq * p.n * 8 + 256;
+            // workspace: dot [ksplit][nq][dot_ld] fp32 (one slice per k-split), then keys [nq][n] u64
+            return (size_t)round_up((int64_t)p.ksplit * p.nq * p.dot_ld * 4, 256) + (size_t)p.nq * p.n * 8 + 256;
         }
     }
     return (size_t)p.nq * p.nsplit * 2 * p.kt * sizeof(uint64_t);  // two epilogue warps per row
@@ -558,8 +604,7 @@ int l2_launch(const L2SearchParams& p, cudaStream_t stream)
         // split-K: zero the dot matrix, accumulate partial products, then select
         L2SearchParams ps = p;
         ps.dot = reinterpret_cast<float*>(p.partial);
-        uint64_t* keys = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(p.partial) + round_up((size_t)p.nq * p.dot_ld * 4, 256));
-        SNV_CUDA_CHECK(cudaMemsetAsync(ps.dot, 0, (size_t)p.nq * p.dot_ld * 4, stream));
+        uint64_t* keys = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(p.partial) + round_up((int64_t)p.ksplit * p.nq * p.dot_ld * 4, 256));
         // (the opt-in is per device / context: set on every launch, never cached process-wide)
         SNV_CUDA_CHECK(cudaFuncSetAttribute(l2_topk_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
         const int64_t n_tiles = ceil_div(p.n, BN);
@@ -570,7 +615,7 @@ int l2_launch(const L2SearchParams& p, cudaStream_t stream)
         SNV_LAUNCH_CHECK();
         const int64_t total = p.nq * p.n;
         const unsigned gk = (unsigned)std::min<int64_t>(ceil_div(total, 256), (int64_t)kNumSMs * 16);
-        l2_keys_kernel<<<gk, 256, 0, stream>>>(ps.dot, p.dot_ld, p.q_norm, p.ref_norm, p.nq, p.n, keys);
+        l2_keys_kernel<<<gk, 256, 0, stream>>>(ps.dot, p.dot_ld, p.ksplit, p.q_norm, p.ref_norm, p.nq, p.n, keys);
         SNV_LAUNCH_CHECK();
         if (p.n > 0x7fffffff) { set_error("L2 split-K: panel too large"); return SNV_ERR_UNSUPPORTED; }
         return merge_keys_launch(keys, 1, (int)p.n, p.nq, p.k, p.id_offset, true, nullptr, p.D_f32, p.I, stream);

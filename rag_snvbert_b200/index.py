@@ -377,17 +377,20 @@ class WindowedL2Index(_IndexBase):
     kind = L.KIND_L2
 
     def __init__(self, d: int, n_windows: int = 1, device: Optional[int] = None, precision: str = "tf32x3",
-                 center: bool = False):
+                 center: Optional[bool] = None):
         """center=True subtracts the column means of the first rows added from panel and queries
-        (squared L2 is translation invariant): use it for embedding vectors, which share a large
-        position / allele-frequency component; leave it off for integer-valued rows (tokens,
-        genotypes), whose products are exact as they are."""
+        (squared L2 is translation invariant): embedding vectors share a large position /
+        allele-frequency component, and without it |q|^2 + |r|^2 - 2 q.r cancels badly at depths like
+        the reference's L*D = 197,760.  Integer-valued rows (tokens, genotypes) are exact as they are
+        and must not be centred.  center=None (default) decides on the first add(): centred unless
+        every value is a small integer."""
         modes = {"tf32": L.L2_TF32, "tf32x3": L.L2_TF32X3}
         if precision not in modes:
             raise ValueError("precision must be 'tf32' or 'tf32x3'")
-        super().__init__(d, n_windows, device, modes[precision] | (L.L2_CENTER if center else 0))
+        flag = L.L2_CENTER_AUTO if center is None else (L.L2_CENTER if center else 0)
+        super().__init__(d, n_windows, device, modes[precision] | flag)
         self.precision = precision
-        self.center = bool(center)
+        self.center = center
 
     def add(self, x) -> None:
         a = _Arg(x)

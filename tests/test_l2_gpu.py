@@ -316,3 +316,56 @@ def test_indexflatl2_binary_fast_path_equals_float_kernel():
     fast.add(np.full((1, 1030), 0.25, dtype=np.float32))
     fast.search(q, 8)
     assert fast.last_search_path == "l2"
+
+
+def test_reference_real_depth_v18_shape_default_mode():
+    """The reference's REAL inference / training retrieval shape (embedding_rag_infer_dataset.py:173-181,281-285;
+    embedding_rag_dataset.py:392-402): N = 2008 reference haplotypes, 48 queries, vectors of L*D = 1030*192 = 197,760
+    floats, built like BERTEmbedding output (token + position/AF components shared by all rows).  DEFAULT index
+    settings (tf32x3, centring decided automatically) must meet the stated 1e-5 (|q|^2 + |r|^2) against float64,
+    return the float64 nearest neighbour except inside that tolerance, be bit-reproducible run to run (split-K
+    reduces in a fixed order) and agree with the reference's own GPU path, a warmed torch.cdist + topk."""
+    import torch
+
+    from rag_snvbert_b200 import WindowedL2Index
+
+    L, Dm, N, nq, k = 1030, 192, 2008, 48, 1
+    dev = "cuda"
+    g = torch.Generator(device=dev)
+    g.manual_seed(0)
+    T = torch.randn(7, Dm, device=dev, generator=g)
+    P = torch.randn(L, Dm, device=dev, generator=g)
+    founders = torch.rand(16, L, device=dev, generator=g) < 0.25
+    mask = torch.rand(L, device=dev, generator=g) < 0.3
+
+    def embed(n):
+        h = founders[torch.randint(0, 16, (n,), device=dev, generator=g)].clone()
+        h ^= torch.rand(n, L, device=dev, generator=g) < 0.02
+        tok = torch.where(h, 6, 5)
+        tok[:, mask] = 4
+        return (T[tok] + P[None]).reshape(n, L * Dm).contiguous()
+
+    refs, q = embed(N), embed(nq)
+    # float64 reference in column blocks (the full double copies would be 3.2 GB + ...: fine, but blocks keep it light)
+    d64 = torch.zeros((nq, N), dtype=torch.float64, device=dev)
+    for c0 in range(0, L * Dm, 16384):
+        a, b = q[:, c0:c0 + 16384].double(), refs[:, c0:c0 + 16384].double()
+        d64 += (a * a).sum(1)[:, None] + (b * b).sum(1)[None, :] - 2.0 * (a @ b.T)
+    idx = WindowedL2Index(L * Dm, 1, 0)          # defaults: tf32x3, centring decided on the first add
+    idx.add(refs)
+    D1, I1 = idx.search(q, k)
+    D2, I2 = idx.search(q, k)
+    assert torch.equal(D1, D2) and torch.equal(I1, I2), "split-K search is not reproducible"
+    scale = ((q.double() ** 2).sum(1) + (refs.double() ** 2).sum(1).max())
+    tol = 1e-5 * scale
+    got = torch.gather(d64, 1, I1)
+    err = (D1.double() - got).abs()
+    assert bool((err <= tol[:, None]).all()), f"max |dD| {float(err.max())} vs tol {float(tol.min())}"
+    best = d64.min(1).values
+    assert bool(((got[:, 0] - best) <= 2 * tol).all()), "a returned neighbour is outside the tolerance of the float64 nearest"
+    # the reference's GPU path on the same tensors (warmed): same neighbours except inside the tolerance
+    for _ in range(2):
+        It = torch.cdist(q, refs, p=2).topk(k, dim=1, largest=False).indices
+    agree = (It == I1)
+    gap = (torch.gather(d64, 1, It) - got).abs()
+    assert bool((agree | (gap <= 2 * tol[:, None])).all())
