@@ -450,8 +450,10 @@ int snv_index_add(snv_index* idx, const void* x, int64_t n, int dtype, unsigned 
             if (pchunks > 1) { int rc = idx->ws_qnorm.reserve((size_t)n * pchunks * 4); if (rc) return rc; }
             if (center && !idx->mean) {
                 if (cudaMalloc(&idx->mean, (size_t)W * idx->d * 4) != cudaSuccess) { set_error("cudaMalloc(mean)"); return SNV_ERR_NOMEM; }
+                { int rc = idx->ws_partial.reserve(l2_colmean_scratch_bytes(n, idx->d)); if (rc) return rc; }
                 for (int w = 0; w < W; ++w) {
-                    int rc = l2_colmean_launch((const float*)xd + (size_t)w * n * idx->d, n, idx->d, idx->mean + (size_t)w * idx->d, stream);
+                    int rc = l2_colmean_launch((const float*)xd + (size_t)w * n * idx->d, n, idx->d, idx->mean + (size_t)w * idx->d,
+                                               (float*)idx->ws_partial.p, stream);
                     if (rc) return rc;
                 }
             }

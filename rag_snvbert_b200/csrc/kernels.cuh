@@ -131,7 +131,9 @@ int l2_prep_chunks(int64_t d);
 // flag is a device int the kernel ANDs into (initialise to 1)
 int l2_integral_check_launch(const float* x, int64_t count, int* flag, cudaStream_t stream);
 // column means of x [rows][d] (centering; squared L2 is translation invariant)
-int l2_colmean_launch(const float* x, int64_t rows, int64_t d, float* mean, cudaStream_t stream);
+// (scratch: l2_colmean_scratch_bytes(rows, d) bytes of device memory; the result is deterministic)
+int l2_colmean_launch(const float* x, int64_t rows, int64_t d, float* mean, float* scratch, cudaStream_t stream);
+size_t l2_colmean_scratch_bytes(int64_t rows, int64_t d);
 int l2_operand_depth(int64_t d, int mode);
 
 }  // namespace snv

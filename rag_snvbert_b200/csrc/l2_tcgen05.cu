@@ -369,23 +369,30 @@ l2_keys_kernel(const float* __restrict__ dot, int64_t dot_ld, int ksplit, const 
 }
 
 // ---- centering: column means of the first rows added (L2 is translation invariant) ------------
+// Deterministic: every (column, block of rows) partial sum is produced by one thread in row order, and the partials of a
+// column are added in block order (double accumulation) by one thread - no atomics, so two indexes built from the same
+// rows centre identically, bit for bit.
+constexpr int kMeanRowsPerBlock = 256;
 __global__ void __launch_bounds__(256)
-l2_colsum_kernel(const float* __restrict__ x, int64_t rows, int64_t d, int rows_per_block, float* __restrict__ sums)
+l2_colsum_kernel(const float* __restrict__ x, int64_t rows, int64_t d, float* __restrict__ parts)
 {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= d) return;
-    const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
-    const int64_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+    const int64_t r0 = (int64_t)blockIdx.y * kMeanRowsPerBlock;
+    const int64_t r1 = r0 + kMeanRowsPerBlock < rows ? r0 + kMeanRowsPerBlock : rows;
     float acc = 0.f;
     for (int64_t r = r0; r < r1; ++r) acc += x[r * d + c];
-    atomicAdd(&sums[c], acc);
+    parts[(int64_t)blockIdx.y * d + c] = acc;
 }
 
 __global__ void __launch_bounds__(256)
-l2_scale_kernel(float* __restrict__ v, int64_t d, float scale)
+l2_colmean_reduce_kernel(const float* __restrict__ parts, int64_t nblocks, int64_t d, double inv_rows, float* __restrict__ mean)
 {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < d) v[c] *= scale;
+    if (c >= d) return;
+    double acc = 0.0;
+    for (int64_t b = 0; b < nblocks; ++b) acc += (double)parts[b * d + c];
+    mean[c] = (float)(acc * inv_rows);
 }
 
 // ---- operand preparation: one warp per (row, 2048-column chunk) ------------------------------
@@ -518,16 +525,20 @@ int l2_integral_check_launch(const float* x, int64_t count, int* flag, cudaStrea
     return SNV_OK;
 }
 
-int l2_colmean_launch(const float* x, int64_t rows, int64_t d, float* mean, cudaStream_t stream)
+size_t l2_colmean_scratch_bytes(int64_t rows, int64_t d) { return (size_t)ceil_div(std::max<int64_t>(rows, 1), kMeanRowsPerBlock) * (size_t)d * 4; }
+
+int l2_colmean_launch(const float* x, int64_t rows, int64_t d, float* mean, float* scratch, cudaStream_t stream)
 {
-    SNV_CUDA_CHECK(cudaMemsetAsync(mean, 0, (size_t)d * 4, stream));
-    if (rows <= 0) return SNV_OK;
+    if (rows <= 0) {
+        SNV_CUDA_CHECK(cudaMemsetAsync(mean, 0, (size_t)d * 4, stream));
+        return SNV_OK;
+    }
     const int block = 256;
-    const int rpb = 64;
-    dim3 grid((unsigned)ceil_div(d, block), (unsigned)ceil_div(rows, rpb));
-    l2_colsum_kernel<<<grid, block, 0, stream>>>(x, rows, d, rpb, mean);
+    const int64_t nblocks = ceil_div(rows, kMeanRowsPerBlock);
+    dim3 grid((unsigned)ceil_div(d, block), (unsigned)nblocks);
+    l2_colsum_kernel<<<grid, block, 0, stream>>>(x, rows, d, scratch);
     SNV_LAUNCH_CHECK();
-    l2_scale_kernel<<<(unsigned)ceil_div(d, block), block, 0, stream>>>(mean, d, 1.0f / (float)rows);
+    l2_colmean_reduce_kernel<<<(unsigned)ceil_div(d, block), block, 0, stream>>>(scratch, nblocks, d, 1.0 / (double)rows, mean);
     SNV_LAUNCH_CHECK();
     return SNV_OK;
 }
@@ -574,6 +585,10 @@ size_t l2_plan(L2SearchParams& p)
         int64_t ks = ceil_div(2 * kNumSMs, ctas);
         const int64_t max_ks = total_kb / 16;  // at least 16 k-blocks (64 MMAs) per CTA
         if (ks > max_ks) ks = max_ks;
+        // Short accumulation chains: the tensor core adds into its fp32 accumulator by truncation (~1 ulp of the running
+        // sum per MMA step), so a k-split never runs more than 128 k-blocks (512 MMA steps); the slices are then added in
+        // fp32 round-to-nearest.  At the reference's depth (197,760 x 3 operand columns) that is 145 slices.
+        if (ks >= 2 && ceil_div(total_kb, ks) > 128) ks = ceil_div(total_kb, 128);
         if (ks >= 2) {
             p.kb_per_split = (int)ceil_div(total_kb, ks);
             p.ksplit = (int)ceil_div(total_kb, p.kb_per_split);
