@@ -791,7 +791,7 @@ def bench_cfg5(ctx, a, steps, warmup, want_cpu):
     index = WindowedHammingIndex(S, W, ctx.local)
     index.add(panel)
     del panel
-    searcher = RowShardedSearch(index, lo, world=ctx.world)
+    searcher = RowShardedSearch(index, lo, world=ctx.world, chunks=int(os.environ.get("SNV_CFG5_CHUNKS", "0")) or None)
 
     def step():
         return searcher.search(queries, k)

@@ -201,6 +201,19 @@ int snv_topk_merge(int device, const int32_t* D_i32, const float* D_f32, const i
                    int64_t nq, int k_in, int k_out, int32_t* Do_i32, float* Do_f32, int64_t* Io,
                    void* stream);
 
+/*
+ * The exchange step of a row-sharded search (one rank per GPU; the collective itself is the caller's, e.g.
+ * torch.distributed.all_to_all_single over NCCL).  snv_exchange_pack turns this rank's results D / I [nw][nq][k]
+ * (global ids) into int64 keys (distance << 40 | id; missing -> INT64_MAX) laid out [parts][nw][nq / parts][k], i.e.
+ * grouped by the rank that owns each query, so that one all-to-all delivers [parts][n][k] (n = nw * nq / parts rows,
+ * one sorted list per source rank); snv_exchange_merge reduces that to the k_out best per row, Do_i32 / Io [n][k_out].
+ * All pointers are DEVICE pointers; ids must be < 2^40, nq % parts == 0, k_out <= 32.
+ */
+int snv_exchange_pack(int device, const int32_t* D_i32, const int64_t* I, int nw, int64_t nq, int k, int parts,
+                      int64_t* keys, void* stream);
+int snv_exchange_merge(int device, const int64_t* keys, int parts, int64_t n, int k_in, int k_out, int32_t* Do_i32,
+                       int64_t* Io, void* stream);
+
 /* device-side pack helper: rows in `dtype` (U8 / F32 / PACKED_U8 / I64_TOKENS) ->
  * packed uint32 [rows][snv_packed_stride(d)] (device pointers; all on `stream`).
  * For I64_TOKENS `out_observed` (nullable) receives the observed-site plane (token in {5,6}). */

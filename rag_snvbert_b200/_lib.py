@@ -50,6 +50,8 @@ SYMBOLS = {
     "snv_index_gather_rows": (_i, [_vp, _i, _i, _vp, _i64, _i, _vp, _u, _vp]),
     "snv_index_export": (_i, [_vp, _i, _vp]),
     "snv_topk_merge": (_i, [_i, _vp, _vp, _vp, _i, _i64, _i, _i, _vp, _vp, _vp, _vp]),
+    "snv_exchange_pack": (_i, [_i, _vp, _vp, _i, _i64, _i, _i, _vp, _vp]),
+    "snv_exchange_merge": (_i, [_i, _vp, _i, _i64, _i, _i, _vp, _vp, _vp]),
     "snv_pack_rows": (_i, [_i, _vp, _i64, _i64, _i, _i, _vp, _vp, _vp]),
     "snv_intersect_masks": (_i, [_i, _vp, _i64, _vp, _i64, _vp, _i, _i64, _i, _vp, _vp]),
     "snv_launch_count": (_i64, []),

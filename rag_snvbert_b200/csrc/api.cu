@@ -1164,6 +1164,24 @@ int snv_topk_merge(int device, const int32_t* D_i32, const float* D_f32, const i
     return merge_results_launch(D_i32, D_f32, I, parts, nq, k_in, k_out, Do_i32, Do_f32, Io, (cudaStream_t)stream_);
 }
 
+int snv_exchange_pack(int device, const int32_t* D_i32, const int64_t* I, int nw, int64_t nq, int k, int parts, int64_t* keys,
+                      void* stream)
+{
+    if (!D_i32 || !I || !keys || nw < 0 || nq < 0 || k < 1) { set_error("snv_exchange_pack: bad arguments"); return SNV_ERR_INVALID; }
+    DeviceGuard g(device);
+    if (!g.ok) { set_error("snv_exchange_pack: cudaSetDevice failed"); return SNV_ERR_CUDA; }
+    return exchange_pack_launch(D_i32, I, nw, nq, k, parts, keys, (cudaStream_t)stream);
+}
+
+int snv_exchange_merge(int device, const int64_t* keys, int parts, int64_t n, int k_in, int k_out, int32_t* Do_i32, int64_t* Io,
+                       void* stream)
+{
+    if (!keys || !Do_i32 || !Io || parts < 1 || n < 0 || k_in < 1) { set_error("snv_exchange_merge: bad arguments"); return SNV_ERR_INVALID; }
+    DeviceGuard g(device);
+    if (!g.ok) { set_error("snv_exchange_merge: cudaSetDevice failed"); return SNV_ERR_CUDA; }
+    return exchange_merge_launch(keys, parts, n, k_in, k_out, Do_i32, Io, (cudaStream_t)stream);
+}
+
 int snv_intersect_masks(int device, const int64_t* ref_pos, int64_t n_ref, const int64_t* tgt_pos, int64_t n_tgt,
                         const int64_t* window_info, int n_windows, int64_t d, int ploidy, uint32_t* out, void* stream_)
 {

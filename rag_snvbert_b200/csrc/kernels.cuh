@@ -76,6 +76,10 @@ int merge_results_launch(const int32_t* D_i32, const float* D_f32, const int64_t
 // (int32 D, int64 I) -> (uint16 D, int32 I): the compact wire format of host-buffer searches
 int narrow_results_launch(const int32_t* D, const int64_t* I, int64_t n, uint16_t* D16, int32_t* I32, cudaStream_t stream);
 
+// row-sharded panel: per-rank (D, I) -> destination-major int64 exchange keys; received keys -> merged (D, I)
+int exchange_pack_launch(const int32_t* D, const int64_t* I, int nw, int64_t nq, int k, int parts, int64_t* keys, cudaStream_t stream);
+int exchange_merge_launch(const int64_t* keys, int parts, int64_t n, int kin, int kout, int32_t* Do, int64_t* Io, cudaStream_t stream);
+
 // ---------------------------------------------------------------- pack
 int pack_launch(const void* x, int64_t rows, int64_t d, int dtype, bool invert, int stride,
                 uint32_t* out, uint32_t* out_observed, cudaStream_t stream);

@@ -573,4 +573,85 @@ int narrow_results_launch(const int32_t* D, const int64_t* I, int64_t n, uint16_
     return SNV_OK;
 }
 
+// ---- row-sharded panel: exchange keys ------------------------------------------------------------------------------
+// One int64 key per neighbour, distance << 40 | global id (missing -> INT64_MAX), laid out destination-major so that ONE
+// all_to_all_single moves every rank's candidates for the queries another rank owns: 8 instead of 12 bytes on the wire,
+// one collective instead of two, one pack launch instead of a chain of elementwise kernels.
+constexpr int kXchgIdBits = 40;
+__global__ void __launch_bounds__(256)
+exchange_pack_kernel(const int32_t* __restrict__ D, const int64_t* __restrict__ I, int nw, int64_t nq, int k, int parts,
+                     int64_t* __restrict__ keys)
+{
+    const int64_t qg = nq / parts;
+    const int64_t total = (int64_t)nw * nq * k;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int j = (int)(i % k);
+        const int64_t row = i / k;
+        const int64_t q = row % nq, w = row / nq;
+        const int64_t g = q / qg;
+        const int64_t id = I[i];
+        const int64_t key = id < 0 ? 0x7FFFFFFFFFFFFFFFLL : (((int64_t)D[i] << kXchgIdBits) | (id & ((1LL << kXchgIdBits) - 1)));
+        keys[(((g * nw + w) * qg) + (q - g * qg)) * k + j] = key;
+    }
+}
+
+// keys [parts][n][kin] (what the all-to-all delivered: one sorted list per source rank and row) -> the k_out best per row,
+// unpacked to (int32 distance, int64 id).  One warp per row: every lane keeps the best of its share, then k_out rounds of
+// warp-minimum + pop.  Keys are unique (they embed the id), INT64_MAX = empty.
+template <int KT>
+__global__ void __launch_bounds__(256)
+exchange_merge_kernel(const int64_t* __restrict__ keys, int parts, int64_t n, int kin, int kout, int32_t* __restrict__ Do,
+                      int64_t* __restrict__ Io)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= n) return;  // warp-uniform
+    constexpr uint64_t kEmpty = 0x7FFFFFFFFFFFFFFFull;
+    uint64_t best[KT];
+#pragma unroll
+    for (int i = 0; i < KT; ++i) best[i] = kSent64;
+    const int total = parts * kin;
+    for (int t = lane; t < total; t += 32) {
+        const int part = t / kin, j = t - part * kin;
+        const uint64_t key = (uint64_t)keys[((int64_t)part * n + row) * kin + j];
+        if (key < kEmpty && key < best[KT - 1]) topk_insert<KT, uint64_t>(best, key);
+    }
+    for (int i = 0; i < kout; ++i) {
+        const uint64_t m = warp_min_u64(best[0]);
+        const unsigned owners = __ballot_sync(0xffffffffu, best[0] == m);
+        if (m != kSent64 && lane == __ffs(owners) - 1) {
+#pragma unroll
+            for (int j = 0; j < KT - 1; ++j) best[j] = best[j + 1];
+            best[KT - 1] = kSent64;
+        }
+        if (lane == 0) {
+            const bool empty = m == kSent64;
+            Do[row * kout + i] = empty ? 0x7FFFFFFF : (int32_t)(m >> kXchgIdBits);
+            Io[row * kout + i] = empty ? -1 : (int64_t)(m & ((1ull << kXchgIdBits) - 1));
+        }
+    }
+}
+
+int exchange_pack_launch(const int32_t* D, const int64_t* I, int nw, int64_t nq, int k, int parts, int64_t* keys, cudaStream_t stream)
+{
+    const int64_t total = (int64_t)nw * nq * k;
+    if (total <= 0) return SNV_OK;
+    if (parts < 1 || nq % parts != 0) { set_error("exchange_pack: the queries of a window must split evenly over the ranks"); return SNV_ERR_INVALID; }
+    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(total, 256), (int64_t)kNumSMs * 16);
+    exchange_pack_kernel<<<grid, 256, 0, stream>>>(D, I, nw, nq, k, parts, keys);
+    SNV_LAUNCH_CHECK();
+    return SNV_OK;
+}
+
+int exchange_merge_launch(const int64_t* keys, int parts, int64_t n, int kin, int kout, int32_t* Do, int64_t* Io, cudaStream_t stream)
+{
+    if (n <= 0) return SNV_OK;
+    if (kout < 1 || kout > 32) { set_error("exchange_merge: k_out must be in [1, 32]"); return SNV_ERR_UNSUPPORTED; }
+    const unsigned grid = (unsigned)ceil_div(n, 256 / 32);
+    if (kout <= 8) exchange_merge_kernel<8><<<grid, 256, 0, stream>>>(keys, parts, n, kin, kout, Do, Io);
+    else exchange_merge_kernel<32><<<grid, 256, 0, stream>>>(keys, parts, n, kin, kout, Do, Io);
+    SNV_LAUNCH_CHECK();
+    return SNV_OK;
+}
+
 }  // namespace snv

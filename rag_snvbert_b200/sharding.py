@@ -123,6 +123,7 @@ class RowShardedSearch:
         self.group = group
         self.world = int(world) if world is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
         self.rank = dist.get_rank(group) if (self.world > 1 and dist.is_initialized()) else 0
+        self._native = merge_fn is None
         if merge_fn is None:
             from .index import topk_merge as merge_fn  # noqa: PLC0415
         self.merge_fn = merge_fn
@@ -166,7 +167,9 @@ class RowShardedSearch:
         cuts = [shard_range(nq, G, r) for r in range(G)]
         q_lo, q_hi = cuts[self.rank]
         even = nq % G == 0
-        n_chunks = self.chunks if self.chunks else (2 if nw >= 4 else 1)
+        # window groups: pipelining pays once a group still fills the machine for several rounds (small groups lose more to
+        # the scan's tail than the overlap wins)
+        n_chunks = self.chunks if self.chunks else (2 if nw >= 16 else 1)
         n_chunks = max(1, min(int(n_chunks), nw))
         bounds = [shard_range(nw, n_chunks, c) for c in range(n_chunks)]
         on_gpu = queries.is_cuda
@@ -186,6 +189,21 @@ class RowShardedSearch:
                 outI = torch.empty((nw, q_hi - q_lo, k), dtype=torch.int64, device=D.device)
 
             def exchange_and_merge(D=D, I=I, w0=w0, w1=w1, wc=wc):
+                if on_gpu and even and D.dtype == torch.int32 and self._native:
+                    # CUDA fast path: one pack kernel, one collective, one merge kernel writing the result slice
+                    from . import _lib as L
+                    from .index import _current_stream
+
+                    qg = nq // G
+                    dev = D.device.index
+                    send = torch.empty((G, wc, qg, k), dtype=torch.int64, device=D.device)
+                    L.check(L.lib().snv_exchange_pack(dev, D.data_ptr(), I.data_ptr(), wc, nq, int(k), G, send.data_ptr(),
+                                                      _current_stream(dev)), "snv_exchange_pack")
+                    recv = torch.empty_like(send)
+                    dist.all_to_all_single(recv, send, group=self.group)
+                    L.check(L.lib().snv_exchange_merge(dev, recv.data_ptr(), G, wc * qg, int(k), int(k), outD[w0:w1].data_ptr(),
+                                                       outI[w0:w1].data_ptr(), _current_stream(dev)), "snv_exchange_merge")
+                    return
                 packed = D.dtype == torch.int32
                 parts = [self.pack_keys(D, I)] if packed else [D, I]
                 got = []

@@ -532,3 +532,35 @@ def test_row_sharded_search_object_single_rank_and_key_packing():
     key = RowShardedSearch.pack_keys(D, I)
     D2, I2 = RowShardedSearch.unpack_keys(key)
     assert torch.equal(D2, D) and torch.equal(I2, I)
+
+
+def test_exchange_pack_and_merge_kernels_match_torch_reference():
+    """snv_exchange_pack / snv_exchange_merge (the row-sharded exchange on the device) against the torch statement of the
+    same steps: destination-major int64 keys, then the k best of [parts] sorted lists per row, padding included."""
+    import torch
+
+    from rag_snvbert_b200 import _lib as L
+    from rag_snvbert_b200.sharding import RowShardedSearch
+
+    g = torch.Generator(device="cuda")
+    g.manual_seed(3)
+    for (nw, nq, k, G) in [(3, 40, 8, 4), (2, 64, 32, 8), (1, 6, 5, 2)]:
+        D = torch.randint(0, 1031, (nw, nq, k), device="cuda", generator=g, dtype=torch.int32).sort(dim=2).values
+        I = torch.randint(0, 200000, (nw, nq, k), device="cuda", generator=g, dtype=torch.int64)
+        I[:, :, -1] = torch.where(torch.rand((nw, nq), device="cuda", generator=g) < 0.2, -1, I[:, :, -1])
+        D[:, :, -1] = torch.where(I[:, :, -1] < 0, 0x7FFFFFFF, D[:, :, -1])
+        keys = torch.empty((G, nw, nq // G, k), dtype=torch.int64, device="cuda")
+        L.check(L.lib().snv_exchange_pack(0, D.data_ptr(), I.data_ptr(), nw, nq, k, G, keys.data_ptr(), 0), "pack")
+        torch.cuda.synchronize()
+        ref = RowShardedSearch.pack_keys(D, I).reshape(nw, G, nq // G, k).permute(1, 0, 2, 3).contiguous()
+        assert torch.equal(keys, ref)
+        # merge: treat the G destination blocks as G source ranks' lists for n rows
+        n = nw * (nq // G)
+        lists = keys.reshape(G, n, k).sort(dim=2).values.contiguous()
+        Do = torch.empty((n, k), dtype=torch.int32, device="cuda")
+        Io = torch.empty((n, k), dtype=torch.int64, device="cuda")
+        L.check(L.lib().snv_exchange_merge(0, lists.data_ptr(), G, n, k, k, Do.data_ptr(), Io.data_ptr(), 0), "merge")
+        torch.cuda.synchronize()
+        allk = lists.permute(1, 0, 2).reshape(n, G * k).sort(dim=1).values[:, :k]
+        De, Ie = RowShardedSearch.unpack_keys(allk)
+        assert torch.equal(Do, De) and torch.equal(Io, Ie)
