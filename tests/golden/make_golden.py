@@ -25,6 +25,8 @@ in a few lines of numpy — so what the fixtures pin is the REFERENCE-OWNED logi
   g6  offline DB workflow   build_ref_db_l2(args) + batch_test_faiss_l2(args) run whole, see make_g6()
   g7  V18 inference search  EmbeddingRAGInferDataset.process_batch_retrieval (faiss flat index per window), see make_g7()
   g8  intersect workflow    build_ref_db_intersect(args) + test_faiss_intersect(args) in both distance modes, see make_g8()
+  g9  V18 training retrieval EmbeddingRAGDataset.process_batch_retrieval over a batch that interleaves two windows, with
+                            the GRADIENTS of a loss on rag_emb_h1 / rag_emb_h2 w.r.t. every embedding parameter, see make_g9()
 """
 from __future__ import annotations
 
@@ -252,6 +254,7 @@ def main():
     make_g6()
     make_g7()
     make_g8()
+    make_g9()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")
@@ -632,11 +635,81 @@ def make_g8():
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+def make_g9():
+    """g9  V18 training retrieval   the real EmbeddingRAGDataset.process_batch_retrieval (embedding_rag_dataset.py:285-444)
+                                    + the real BERTEmbedding (src/model/embedding/bert.py) in TRAIN mode (dropout 0) on a
+                                    batch whose samples alternate between two windows (so the JIT cache is rebuilt
+                                    mid-batch, :334-377), k = 2.  Pins the outputs rag_emb_h1 / rag_emb_h2 [B, k, L, D]
+                                    AND the gradients of  sum(rag_emb_h1 * W1) + sum(rag_emb_h2 * W2)  w.r.t. every
+                                    parameter of the embedding layer - the re-encode-with-grad path (:406-438)."""
+    import torch
+
+    from src.dataset.vocab import WordVocab
+    from src.dataset.embedding_rag_dataset import EmbeddingRAGDataset
+    from src.model.embedding.bert import BERTEmbedding
+
+    rng = np.random.default_rng(20261019)
+    torch.manual_seed(11)
+    vocab = WordVocab(["AFR", "EUR", "EAS"])
+    L, D, N, B, k = 64, 16, 40, 8, 2
+    emb = BERTEmbedding(vocab_size=len(vocab), embed_size=D, dropout=0.0, use_af=True)
+    emb.train()
+    W = 2
+    ref_tokens, ref_af, masks = [], [], []
+    for w in range(W):
+        hap = (rng.random((N, L - 2)) < 0.35).astype(np.int64)
+        ref_tokens.append(np.concatenate([np.full((N, 1), 2), np.where(hap == 0, 5, 6), np.full((N, 1), 3)], axis=1).astype(np.int64))
+        ref_af.append(rng.random(L).astype(np.float32))
+        m = np.zeros(L, np.int64)
+        m[1:-1] = rng.random(L - 2) < 0.3
+        masks.append(m)
+    window_idx = [0, 1, 0, 1, 1, 0, 0, 1]
+
+    def queries():
+        rows = []
+        for w in window_idx:
+            src = ref_tokens[w][rng.integers(0, N)].copy()
+            flip = rng.random(L) < 0.06
+            flip[0] = flip[-1] = False
+            src[flip] = 11 - src[flip]  # 5 <-> 6
+            src[masks[w] == 1] = vocab.mask_index
+            rows.append(src)
+        return np.stack(rows)
+
+    h1, h2 = queries(), queries()
+    af = np.stack([ref_af[w] for w in window_idx]).astype(np.float32)
+    fake = types.SimpleNamespace(
+        embed_dim=D, jit_cache_win_idx=-1, jit_ref_emb_search=None, jit_ref_tokens_raw=None, jit_ref_af_raw=None,
+        ref_tokens_complete=ref_tokens, ref_af_windows=ref_af, window_masks=masks, vocab=vocab)
+    fake._apply_mask_to_tokens_gpu = lambda t, m: EmbeddingRAGDataset._apply_mask_to_tokens_gpu(fake, t, m)
+    batch = {"hap_1": torch.from_numpy(h1), "hap_2": torch.from_numpy(h2), "af": torch.from_numpy(af), "window_idx": list(window_idx)}
+    out = EmbeddingRAGDataset.process_batch_retrieval(fake, batch, emb, "cpu", k)
+    W1 = torch.from_numpy(rng.standard_normal((B, k, L, D)).astype(np.float32))
+    W2 = torch.from_numpy(rng.standard_normal((B, k, L, D)).astype(np.float32))
+    loss = (out["rag_emb_h1"] * W1).sum() + (out["rag_emb_h2"] * W2).sum()
+    emb.zero_grad()
+    loss.backward()
+    rec = {"L": np.array(L), "D": np.array(D), "N": np.array(N), "k": np.array(k), "mask_index": np.array(vocab.mask_index),
+           "vocab_size": np.array(len(vocab)), "window_idx": np.array(window_idx), "hap_1": h1, "hap_2": h2, "af": af,
+           "rag_emb_h1": out["rag_emb_h1"].detach().numpy(), "rag_emb_h2": out["rag_emb_h2"].detach().numpy(),
+           "W1": W1.numpy(), "W2": W2.numpy(), "loss": np.array(float(loss))}
+    for w in range(W):
+        rec[f"ref_tokens_{w}"] = ref_tokens[w]
+        rec[f"ref_af_{w}"] = ref_af[w]
+        rec[f"mask_{w}"] = masks[w]
+    for name, t in emb.state_dict().items():
+        rec["state/" + name] = t.detach().numpy()
+    for name, prm in emb.named_parameters():
+        rec["grad/" + name] = (prm.grad if prm.grad is not None else torch.zeros_like(prm)).numpy()
+    np.savez_compressed(os.path.join(OUT, "g9_v18_train_grad.npz"), **rec)
+    print("g9: loss", float(loss), "params", [n for n, _ in emb.named_parameters()])
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] in ("g5", "g6", "g7", "g8"):  # only the newer fixtures (leaves g1-g4 untouched)
+    if len(sys.argv) > 1 and sys.argv[1] in ("g5", "g6", "g7", "g8", "g9"):  # only the newer fixtures (leaves g1-g4 untouched)
         install_stubs()
         sys.path.insert(0, REF)
         os.chdir("/tmp")
-        {"g5": make_g5, "g6": make_g6, "g7": make_g7, "g8": make_g8}[sys.argv[1]]()
+        {"g5": make_g5, "g6": make_g6, "g7": make_g7, "g8": make_g8, "g9": make_g9}[sys.argv[1]]()
     else:
         main()
