@@ -4,7 +4,7 @@ outputs rag_emb_h1 / rag_emb_h2 [B, k, L, D] and the gradients of a loss on them
 import numpy as np
 import pytest
 
-from tests.test_oracle_golden import _g9_check, _g9_setup
+from g9_helpers import _g9_check, _g9_setup
 
 pytestmark = pytest.mark.gpu
 
