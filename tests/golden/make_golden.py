@@ -656,22 +656,29 @@ def make_g9():
     emb.train()
     W = 2
     ref_tokens, ref_af, masks = [], [], []
+    # Tie-free by construction (float32 cdist and any other exact engine must then agree on the ids): reference rows come
+    # in pairs, row 2i+1 = row 2i with 5 observed sites flipped; a query is a row 2i with 2 OTHER observed sites flipped, so
+    # its nearest rows are 2i (2 mismatches) and 2i+1 (7), every other row being ~20 away
     for w in range(W):
-        hap = (rng.random((N, L - 2)) < 0.35).astype(np.int64)
-        ref_tokens.append(np.concatenate([np.full((N, 1), 2), np.where(hap == 0, 5, 6), np.full((N, 1), 3)], axis=1).astype(np.int64))
-        ref_af.append(rng.random(L).astype(np.float32))
         m = np.zeros(L, np.int64)
         m[1:-1] = rng.random(L - 2) < 0.3
         masks.append(m)
+        obs = np.flatnonzero(m[1:-1] == 0)
+        hap = (rng.random((N, L - 2)) < 0.35).astype(np.int64)
+        for i in range(0, N, 2):
+            hap[i + 1] = hap[i]
+            hap[i + 1, rng.choice(obs, 5, replace=False)] ^= 1
+        ref_tokens.append(np.concatenate([np.full((N, 1), 2), np.where(hap == 0, 5, 6), np.full((N, 1), 3)], axis=1).astype(np.int64))
+        ref_af.append(rng.random(L).astype(np.float32))
     window_idx = [0, 1, 0, 1, 1, 0, 0, 1]
 
     def queries():
         rows = []
         for w in window_idx:
-            src = ref_tokens[w][rng.integers(0, N)].copy()
-            flip = rng.random(L) < 0.06
-            flip[0] = flip[-1] = False
-            src[flip] = 11 - src[flip]  # 5 <-> 6
+            src = ref_tokens[w][2 * rng.integers(0, N // 2)].copy()
+            obs = np.flatnonzero(masks[w][1:-1] == 0) + 1
+            pos = rng.choice(obs, 2, replace=False)
+            src[pos] = 11 - src[pos]  # 5 <-> 6
             src[masks[w] == 1] = vocab.mask_index
             rows.append(src)
         return np.stack(rows)
