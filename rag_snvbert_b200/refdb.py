@@ -59,6 +59,96 @@ def load_ref_db(ref_db_dir: str, n_windows: int, device: Optional[int] = None) -
     return index
 
 
+def load_ref_db_meta(ref_db_dir: str, n_windows: int):
+    """The side files of the reference DB directory: `window_{i}_pos.npy` (site positions of the window, written by
+    build_ref_db_intersect.py:73-74) and `window_{i}_pop.npy` (population label per reference sample,
+    build_ref_db_l2.py:80-83 / build_ref_db_intersect.py:75).  Returns (pos, pop): pos = list of int64 arrays or None
+    when the directory has no position files (the L2 builder does not write them); pop = array of labels (the same for
+    every window: it is the panel's sample list) or None."""
+    pos, pop = [], None
+    for w in range(n_windows):
+        pp = os.path.join(ref_db_dir, f"window_{w}_pos.npy")
+        if not os.path.exists(pp):
+            pos = None
+            break
+        pos.append(np.load(pp).astype(np.int64))
+    lp = os.path.join(ref_db_dir, "window_0_pop.npy")
+    if os.path.exists(lp):
+        pop = np.load(lp, allow_pickle=True)
+    return pos, pop
+
+
+# ---- bit-packed panel container ------------------------------------------------------------------------------
+# The .npy cubes cost 1 byte per allele (and the .faiss files 4): a 5,008-sample x 1,030-site window is 10.3 MB as
+# window_{i}.npy, 41 MB as window_{i}.faiss and 0.36 MB packed.  `save_packed_db` writes the index's own device layout
+# (uint32 words, site s -> word s / 32, bit s % 32, row stride snv_packed_stride(d)) for ALL windows into one file, so a
+# later run adds it with a straight copy - no 0/1 expansion, no re-packing.  Layout (little endian):
+#   magic "SNVP" | version u32 = 1 | n_windows u32 | rows i64 | d i64 | stride u32 | has_pos u8 | has_pop u8 | pad u16 |
+#   n_sites i32 [n_windows] | panel u32 [n_windows][rows][stride] |
+#   (has_pos) per window: count i64, positions i64 [count] | (has_pop) npy-serialised label array
+_PACKED_MAGIC = b"SNVP"
+
+
+def save_packed_db(path: str, index: WindowedHammingIndex, n_sites=None, positions=None, pop=None) -> None:
+    """index -> one packed container file.  n_sites: real site count per window (default d), positions / pop as returned
+    by load_ref_db_meta."""
+    import io
+    import struct
+
+    W, n, d, stride = index.n_windows, index.ntotal, index.d, index.stride
+    ns = np.full(W, d, np.int32) if n_sites is None else np.ascontiguousarray(np.asarray(n_sites, dtype=np.int32))
+    if ns.shape != (W,):
+        raise ValueError("n_sites must have one entry per window")
+    with open(path, "wb") as f:
+        f.write(_PACKED_MAGIC)
+        f.write(struct.pack("<IIqqIBBH", 1, W, n, d, stride, 1 if positions is not None else 0, 1 if pop is not None else 0, 0))
+        f.write(ns.astype("<i4").tobytes())
+        for w in range(W):
+            f.write(index.export_packed(w).astype("<u4").tobytes())
+        if positions is not None:
+            if len(positions) != W:
+                raise ValueError("positions must have one array per window")
+            for pw in positions:
+                pw = np.ascontiguousarray(np.asarray(pw, dtype="<i8"))
+                f.write(struct.pack("<q", pw.size))
+                f.write(pw.tobytes())
+        if pop is not None:
+            buf = io.BytesIO()
+            np.save(buf, np.asarray(pop).astype(str), allow_pickle=False)
+            f.write(buf.getvalue())
+
+
+def load_packed_db(path: str, device: Optional[int] = None):
+    """-> (index, n_sites int32 [W], positions list | None, pop array | None).  The panel is added as packed rows: the
+    bytes of the file go to the device as they are."""
+    import io
+    import struct
+
+    with open(path, "rb") as f:
+        if f.read(4) != _PACKED_MAGIC:
+            raise ValueError(f"{path}: not a packed reference DB (bad magic)")
+        ver, W, n, d, stride, has_pos, has_pop, _ = struct.unpack("<IIqqIBBH", f.read(4 + 4 + 8 + 8 + 4 + 1 + 1 + 2))
+        if ver != 1:
+            raise ValueError(f"{path}: unsupported container version {ver}")
+        ns = np.frombuffer(f.read(4 * W), dtype="<i4").astype(np.int32)
+        index = WindowedHammingIndex(int(d), int(W), device)
+        if stride != index.stride:
+            raise ValueError(f"{path}: row stride {stride} does not match this library's {index.stride} for d = {d}")
+        panel = np.frombuffer(f.read(4 * W * n * stride), dtype="<u4")
+        if panel.size != W * n * stride:
+            raise ValueError(f"{path}: truncated panel")
+        if n:
+            index.add(panel.reshape(W, n, stride))
+        positions = None
+        if has_pos:
+            positions = []
+            for _w in range(W):
+                (cnt,) = struct.unpack("<q", f.read(8))
+                positions.append(np.frombuffer(f.read(8 * cnt), dtype="<i8").astype(np.int64))
+        pop = np.load(io.BytesIO(f.read()), allow_pickle=False) if has_pop else None
+    return index, ns, positions, pop
+
+
 def batch_search(index: WindowedHammingIndex, target_gt: np.ndarray, window_info: np.ndarray, top_k: int,
                  samples=None) -> Tuple[np.ndarray, np.ndarray]:
     """batch_test_faiss_l2.py:80-110 for every window at once -> D float32 [W, nq, k], I int64."""

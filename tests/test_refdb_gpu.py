@@ -107,3 +107,40 @@ def test_intersect_masks_on_device_match_host_and_drive_the_masked_search():
     Dh, Ih = index.search(q, 5, observed=obs_rows)
     np.testing.assert_array_equal(Id.cpu().numpy(), Ih)
     np.testing.assert_array_equal(Dd.cpu().numpy(), Dh)
+
+
+def test_packed_container_and_side_files_roundtrip(tmp_path):
+    """the reference DB directory's side files (window_{i}_pos.npy, window_{i}_pop.npy: build_ref_db_intersect.py:73-75,
+    build_ref_db_l2.py:80-83) and the bit-packed one-file container: same search results as the index it was saved from"""
+    from rag_snvbert_b200 import refdb
+
+    rng, ref, tgt, win = _data(9)
+    V = ref.shape[0]
+    ref_pos = np.sort(rng.choice(10 * V, V, replace=False))
+    pop_labels = np.array(["AFR", "EUR", "EAS"])[rng.integers(0, 3, ref.shape[1])]
+    for w, (a, b) in enumerate(win):
+        np.save(tmp_path / f"window_{w}.npy", np.transpose(ref[a:b], (1, 0, 2)))
+        np.save(tmp_path / f"window_{w}_pos.npy", ref_pos[a:b])
+        np.save(tmp_path / f"window_{w}_pop.npy", pop_labels)
+    index = refdb.load_ref_db(str(tmp_path), len(win))
+    pos, pop = refdb.load_ref_db_meta(str(tmp_path), len(win))
+    assert len(pos) == len(win) and all(np.array_equal(p, ref_pos[a:b]) for p, (a, b) in zip(pos, win))
+    assert np.array_equal(pop.astype(str), pop_labels)
+    n_sites = 2 * (win[:, 1] - win[:, 0])
+    path = str(tmp_path / "panel.snvp")
+    refdb.save_packed_db(path, index, n_sites=n_sites, positions=pos, pop=pop)
+    raw = sum((tmp_path / f"window_{w}.npy").stat().st_size for w in range(len(win)))
+    assert (tmp_path / "panel.snvp").stat().st_size < raw / 4   # 1 bit instead of 1 byte per allele (+ positions)
+    again, ns2, pos2, pop2 = refdb.load_packed_db(path)
+    assert again.ntotal == index.ntotal and again.d == index.d and np.array_equal(ns2, n_sites)
+    assert all(np.array_equal(a, b) for a, b in zip(pos, pos2)) and np.array_equal(pop2, pop_labels)
+    D, I = refdb.batch_search(index, tgt, win, 5)
+    D2, I2 = refdb.batch_search(again, tgt, win, 5)
+    np.testing.assert_array_equal(I2, I)
+    np.testing.assert_array_equal(D2, D)
+    # a directory written by build_ref_db_l2 has no position files
+    (tmp_path / "l2").mkdir()
+    np.save(tmp_path / "l2" / "window_0.npy", np.transpose(ref[0:10], (1, 0, 2)))
+    np.save(tmp_path / "l2" / "window_0_pop.npy", pop_labels)
+    pos3, pop3 = refdb.load_ref_db_meta(str(tmp_path / "l2"), 1)
+    assert pos3 is None and np.array_equal(pop3.astype(str), pop_labels)
