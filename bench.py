@@ -794,10 +794,13 @@ def bench_cfg5(ctx, a, steps, warmup, want_cpu):
     searcher = RowShardedSearch(index, lo, world=ctx.world, chunks=int(os.environ.get("SNV_CFG5_CHUNKS", "0")) or None)
 
     def step():
-        return searcher.search(queries, k)
+        # sync=False: the exchange + merge of this batch stay on the side stream and overlap the next batch's scan; the
+        # timed region ends with searcher.wait() + a device synchronisation, so every batch is complete inside it
+        return searcher.search(queries, k, sync=False)
 
     for _ in range(max(warmup, 3)):
         q_lo, q_hi, D, I = step()
+    searcher.wait()
     ctx.barrier()
     sampler = ClockSampler(ctx.local)
     if ctx.rank == 0:
@@ -809,6 +812,7 @@ def bench_cfg5(ctx, a, steps, warmup, want_cpu):
     e0.record()
     for _ in range(steps):
         q_lo, q_hi, D, I = step()
+    searcher.wait()
     e1.record()
     ctx.barrier()
     kern_ms = _lib.profile_last_ms()

@@ -936,6 +936,7 @@ static int search_l2(snv_index* idx, int w0, int nw, const void* q, int64_t nq, 
         p.id_offset = id_offset;
         p.D_f32 = Dd + (size_t)w * nq * k;
         p.I = Id + (size_t)w * nq * k;
+        p.one = 1;
         const size_t part = l2_plan(p);
         if (part == (size_t)-1) return SNV_ERR_UNSUPPORTED;
         rc = idx->ws_partial.reserve(part ? part : 16);

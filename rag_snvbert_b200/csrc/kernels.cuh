@@ -121,6 +121,7 @@ struct L2SearchParams {
     int64_t dot_ld;
     int ksplit, kb_per_split;
     bool pair;  // CTA pairs (cta_group::2): two query tiles per cluster, each CTA streams half of every panel tile
+    int one;    // 1 as a runtime value (keeps the epilogue's mask adds on the FMA pipe)
 };
 size_t l2_plan(L2SearchParams& p);
 int l2_launch(const L2SearchParams& p, cudaStream_t stream);

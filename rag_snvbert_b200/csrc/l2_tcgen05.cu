@@ -31,6 +31,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -54,11 +55,24 @@ constexpr int kThreads = 64 + kEpiThreads;
 constexpr uint32_t kABytes = BM * BK * 4;   // 16 KB
 constexpr uint32_t kBBytes = BN * BK * 4;   // 32 KB
 constexpr uint32_t kStageBytes = kABytes + kBBytes;
+#ifndef SNV_L2_SLOT_EPI
+#define SNV_L2_SLOT_EPI 1  // epilogue: per-column slots + 32-column masks (0: the round-1 per-thread candidate lists)
+#endif
 constexpr int kListCap = 24;   // per-thread candidate list (epilogue): folded when > 8 are pending, checked every 16 columns
 constexpr size_t kListBytes = (size_t)kListCap * kEpiThreads * 8;
 constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + 2 * BN * 4 /*rn*/ + kListBytes + 256 /*barriers*/;
 
 using namespace tc;
+
+// f(std::integral_constant<int, 0>{}) ... f(std::integral_constant<int, 31>{}): compile-time column index
+template <int I = 0, typename F>
+__device__ __forceinline__ void static_for32(F&& f)
+{
+    if constexpr (I < 32) {
+        f(std::integral_constant<int, I>{});
+        static_for32<I + 1>(f);
+    }
+}
 
 template <int KT, bool SPLITK, bool PAIR = false>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -247,6 +261,60 @@ l2_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         uint64_t best[KT];
 #pragma unroll
         for (int i = 0; i < KT; ++i) best[i] = kSent64;
+#if SNV_L2_SLOT_EPI
+        // Selection (slot + mask, the scheme of the tensor-core Hamming kernel's first generation): per column ONE fused
+        // multiply-add  d' = |r|^2 - 2 q.r  and ONE compare against  thr - |q|^2  (so |q|^2 never enters the per-column
+        // work), then - predicated - a store of d' into the column's own slot and a bit in a 32-column mask (four partial
+        // masks; the bit is a multiply-add by a runtime 1: FMA pipe).  After each 32-column chunk the lanes pop their
+        // mask bits in lockstep, two per round, and only then clamp, build the 64-bit key (float bits, id) and insert
+        // into the sorted register top-k.  The compare threshold carries a few ulp of slack: the key compare decides.
+        float* my_slot = reinterpret_cast<float*>(lists) + et;  // column j of the chunk at my_slot[j * kEpiThreads]
+        float thr = 3.4028234663852886e38f, thrq = 3.4028234663852886e38f;
+        const uint32_t one = (uint32_t)p.one;
+        auto refresh = [&]() {
+            thr = best[KT - 1] == kSent64 ? 3.4028234663852886e38f : __uint_as_float((uint32_t)(best[KT - 1] >> 32));
+            const float t = thr - qn;
+            thrq = best[KT - 1] == kSent64 ? 3.4028234663852886e38f : t + fabsf(t) * 9.5367431640625e-7f + 1e-30f;  // + 2^-20 relative
+        };
+        auto fold = [&](uint32_t mask, int col0) {
+            if (__any_sync(0xffffffffu, mask != 0u)) {
+                do {
+                    if (mask != 0u) {
+                        const int j1 = __ffs((int)mask) - 1;
+                        mask &= mask - 1u;
+                        const bool two = mask != 0u;
+                        const int j2 = two ? __ffs((int)mask) - 1 : j1;
+                        mask &= mask - 1u;
+                        const float d1 = fmaxf(my_slot[j1 * kEpiThreads] + qn, 0.f);   // tiny negative round-off clamps to 0 like faiss
+                        const float d2 = fmaxf(my_slot[j2 * kEpiThreads] + qn, 0.f);
+                        const uint64_t key1 = ((uint64_t)__float_as_uint(d1) << 32) | (uint64_t)(uint32_t)(col0 + j1);
+                        const uint64_t key2 = two ? ((uint64_t)__float_as_uint(d2) << 32) | (uint64_t)(uint32_t)(col0 + j2) : kSent64;
+                        if (key1 < best[KT - 1]) topk_insert<KT, uint64_t>(best, key1);
+                        if (key2 < best[KT - 1]) topk_insert<KT, uint64_t>(best, key2);
+                    }
+                } while (__any_sync(0xffffffffu, mask != 0u));
+                refresh();
+            }
+        };
+        auto process = [&](uint32_t (&acc)[32], const float* rn, int c0, int n0) {
+            uint32_t m4[4] = {0u, 0u, 0u, 0u};
+            const uint32_t slot0 = smem_u32(my_slot);
+            const float4* rn4 = reinterpret_cast<const float4*>(rn + c0);
+            float4 v = rn4[0];
+            static_for32([&](auto jc) {
+                constexpr int j = decltype(jc)::value;
+                const float r = (j & 3) == 0 ? v.x : ((j & 3) == 1 ? v.y : ((j & 3) == 2 ? v.z : v.w));
+                const float dp = fmaf(-2.f, __uint_as_float(acc[j]), r);
+                if constexpr ((j & 3) == 3 && j < 31) v = rn4[(j + 1) >> 2];
+                if (dp < thrq) {
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(slot0 + (uint32_t)(j * kEpiThreads * 4)), "f"(dp) : "memory");
+                    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(m4[j & 3]) : "r"(one), "n"(1u << j));
+                }
+            });
+            fold((m4[0] | m4[1]) | (m4[2] | m4[3]), n0 + c0);
+        };
+        auto fold_final = [&]() {};
+#else
         // Selection: candidates that beat the (possibly stale, hence looser) threshold are appended
         // to a per-thread list in shared memory; lists are folded into the sorted register top-k
         // only when some lane has more than 8 pending — all lanes insert in lockstep, instead of
@@ -292,6 +360,8 @@ l2_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             score16(acc, bias, n0 + c0);
             score16(acc + 16, bias + 16, n0 + c0 + 16);
         };
+        auto fold_final = [&]() { fold(); };
+#endif
         // |r|^2 of the first tile (1 per thread; +inf past the panel end so those columns never
         // pass the threshold); later tiles are prefetched one tile ahead
         float rn_next = (t0 * BN + et < p.n) ? p.ref_norm[t0 * BN + et] : __int_as_float(0x7f800000);
@@ -333,7 +403,7 @@ l2_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             if (PAIR && !leader) mbar_arrive_cluster(&tmem_empty[as], 0u);
             else mbar_arrive(&tmem_empty[as]);
         }
-        fold();
+        fold_final();
         if (active) {
             uint64_t* out = p.partial + (((int64_t)q * p.nsplit + split) * 2 + half) * KT;
 #pragma unroll

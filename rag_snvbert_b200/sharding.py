@@ -130,6 +130,7 @@ class RowShardedSearch:
         self.search_fn = search_fn or (lambda q, k, w0: index.search(q, k, w0=w0, id_offset=self.row_lo))
         self.chunks = chunks
         self._side = None
+        self._pending = None
         self._last = ""
 
     def describe(self) -> str:
@@ -152,9 +153,21 @@ class RowShardedSearch:
         I = torch.where(missing, torch.full_like(key, -1), key & ((1 << cls._ID_BITS) - 1))
         return D, I
 
-    def search(self, queries, k: int):
+    def wait(self) -> None:
+        """Make the caller's current stream wait for the exchange + merge of the last `search(..., sync=False)`."""
+        import torch
+
+        if self._pending is not None:
+            torch.cuda.current_stream(self._pending[1]).wait_event(self._pending[0])
+            self._pending = None
+
+    def search(self, queries, k: int, sync: bool = True):
         """queries [nw, nq, ..] (the same on every rank) -> (q_lo, q_hi, D [nw, q_hi - q_lo, k], I [..]): this rank's
-        queries of every window, merged over all row shards."""
+        queries of every window, merged over all row shards.
+
+        sync=False (CUDA): the exchange + merge stay on the side stream and the call returns without making the caller's
+        stream wait for them, so the NEXT batch's scan overlaps this batch's NVLink exchange (software pipelining across
+        batches).  The returned D / I must not be read before `wait()` (or any later `search(..., sync=True)`)."""
         import torch
         import torch.distributed as dist
 
@@ -235,7 +248,13 @@ class RowShardedSearch:
             else:
                 exchange_and_merge()
         if on_gpu:
-            main.wait_stream(side)
+            if sync:
+                main.wait_stream(side)
+                self._pending = None
+            else:
+                self._pending = (side.record_event(), queries.device)
+                outD.record_stream(main)
+                outI.record_stream(main)
         self._last = (f"{n_chunks} window group(s) per call; per group one all_to_all_single of packed int64 (distance << 40 | id) keys "
                       f"({nq // G if even else q_hi - q_lo} queries x k from each of {G} ranks) + k-way merge on a side stream, overlapping the next group's scan")
         return q_lo, q_hi, outD, outI
