@@ -46,7 +46,6 @@ constexpr int BM = 128;        // queries per CTA tile (TMEM lanes)
 constexpr int BN = 256;        // panel rows per MMA tile (TMEM columns per accumulator stage)
 constexpr int BK = 32;         // fp32 elements per k-block = one 128-byte swizzle row
 constexpr int UMMA_K = 8;      // tf32: 32 bytes per MMA
-constexpr int kStages = 3;
 constexpr int kAccStages = 2;
 constexpr int kTmemCols = kAccStages * BN;  // 512
 constexpr int kEpiWarps = 8;    // two per TMEM lane quarter, alternating 32-column chunks
@@ -55,12 +54,25 @@ constexpr int kThreads = 64 + kEpiThreads;
 constexpr uint32_t kABytes = BM * BK * 4;   // 16 KB
 constexpr uint32_t kBBytes = BN * BK * 4;   // 32 KB
 constexpr uint32_t kStageBytes = kABytes + kBBytes;
+// Ring geometry per mode.  The k-loop is bound by bytes in flight (ring depth x stage bytes against the L2 latency), not
+// by L2 bandwidth: single CTAs hold 3 stages of 48 KB; a CTA of a pair loads only half of every panel tile (32 KB per
+// stage), so the same shared memory holds 5 k-blocks in flight.
+template <bool PAIR>
+struct Ring2 {
+    static constexpr int kStages = PAIR ? 5 : 3;
+    static constexpr uint32_t kStageBytes = PAIR ? kABytes + kBBytes / 2 : kABytes + kBBytes;
+};
 #ifndef SNV_L2_SLOT_EPI
 #define SNV_L2_SLOT_EPI 1  // epilogue: per-column slots + 32-column masks (0: the round-1 per-thread candidate lists)
 #endif
 constexpr int kListCap = 24;   // per-thread candidate list (epilogue): folded when > 8 are pending, checked every 16 columns
-constexpr size_t kListBytes = (size_t)kListCap * kEpiThreads * 8;
-constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + 2 * BN * 4 /*rn*/ + kListBytes + 256 /*barriers*/;
+constexpr size_t kListBytes = SNV_L2_SLOT_EPI ? (size_t)32 * kEpiThreads * 4 : (size_t)kListCap * kEpiThreads * 8;
+template <bool PAIR>
+constexpr size_t smem_bytes()
+{
+    return 1024 /*align slack*/ + (size_t)Ring2<PAIR>::kStages * Ring2<PAIR>::kStageBytes + 2 * BN * 4 /*rn*/ + kListBytes + 256 /*barriers*/;
+}
+static_assert(smem_bytes<false>() <= 232448 && smem_bytes<true>() <= 232448, "shared memory budget");
 
 using namespace tc;
 
@@ -83,6 +95,8 @@ l2_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     // 1024-byte alignment for SWIZZLE_128B tiles
     const uint32_t raw_addr = smem_u32(smem_raw);
     unsigned char* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+    constexpr int kStages = Ring2<PAIR>::kStages;
+    constexpr uint32_t kStageBytes = Ring2<PAIR>::kStageBytes;
     unsigned char* tiles = smem;
     float* rn_s = reinterpret_cast<float*>(smem + (size_t)kStages * kStageBytes);  // [2][BN]
     uint64_t* lists = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * kStageBytes + 2 * BN * 4);  // [kListCap][128]
@@ -626,10 +640,11 @@ size_t l2_plan(L2SearchParams& p)
     p.kt = p.k <= 8 ? 8 : 32;
     const int64_t n_tiles = p.n > 0 ? ceil_div(p.n, BN) : 0;
     const int64_t m_tiles = ceil_div(p.nq, BM);
-    // CTA pairs (cta_group::2; SNV_L2_PAIR=1, needs two query tiles): each CTA of a pair streams only half of every
-    // panel tile.  Measured on B200: no gain (cfg 4: 59.4 us either way; 8192 x 50000 x 256 tf32x3: 875 vs 885 us, where
-    // the single-CTA kernel already runs at 86 % of the tf32 rate), so the single-CTA kernel stays the default.
-    p.pair = false;
+    // CTA pairs (cta_group::2, needs two query tiles): each CTA of a pair streams only half of every panel tile, so its
+    // ring holds 5 k-blocks in flight instead of 3 in the same shared memory.  Round 1 measured the pair kernel with the
+    // single-CTA ring geometry (3 stages) and found no gain; with 5 stages cfg 4 runs 59.6 vs 65.9 us (tensor pipe 70 %
+    // of active cycles), so pairs are the default wherever a window has two query tiles.
+    p.pair = m_tiles >= 2;   // SNV_L2_PAIR=0 forces single CTAs
     if (const char* e = getenv("SNV_L2_PAIR")) p.pair = m_tiles >= 2 && atoi(e) != 0;
     const int64_t m_items = p.pair ? ceil_div(m_tiles, 2) : m_tiles;
     const int64_t units = p.pair ? kNumSMs / 2 : kNumSMs;
@@ -691,11 +706,11 @@ int l2_launch(const L2SearchParams& p, cudaStream_t stream)
         ps.dot = reinterpret_cast<float*>(p.partial);
         uint64_t* keys = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(p.partial) + round_up((int64_t)p.ksplit * p.nq * p.dot_ld * 4, 256));
         // (the opt-in is per device / context: set on every launch, never cached process-wide)
-        SNV_CUDA_CHECK(cudaFuncSetAttribute(l2_topk_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+        SNV_CUDA_CHECK(cudaFuncSetAttribute(l2_topk_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<false>()));
         const int64_t n_tiles = ceil_div(p.n, BN);
         const unsigned grid_sk = (unsigned)(m_tiles * n_tiles * p.ksplit);
         profile_begin(stream);
-        l2_topk_kernel<8, true><<<grid_sk, kThreads, kSmemBytes, stream>>>(map_q, map_r, ps);
+        l2_topk_kernel<8, true><<<grid_sk, kThreads, smem_bytes<false>(), stream>>>(map_q, map_r, ps);
         profile_end(stream);
         SNV_LAUNCH_CHECK();
         const int64_t total = p.nq * p.n;
@@ -707,6 +722,7 @@ int l2_launch(const L2SearchParams& p, cudaStream_t stream)
     }
     const unsigned grid = p.pair ? (unsigned)(2 * ceil_div(m_tiles, 2) * p.nsplit) : (unsigned)(m_tiles * p.nsplit);
     auto launch = [&](auto kern) -> int {
+        const size_t kSmemBytes = p.pair ? smem_bytes<true>() : smem_bytes<false>();
         // the dynamic shared-memory opt-in is per device / context: set on every launch, never cached process-wide
         SNV_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
         profile_begin(stream);
