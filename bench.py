@@ -544,12 +544,14 @@ def bench_windows(ctx, a, scaling, steps, warmup, want_e2e=True, want_clocks=Tru
         def pinned(shape, dt):
             return torch.empty(shape, dtype=dt, pin_memory=True)
 
-        hq = pinned((Wr, Q, stride), torch.int32)
-        hq.copy_(queries)
+        # host rows in the dense packed layout (33 words = 132 bytes per 1030-site row; the device re-strides to 36)
+        words = (S + 31) // 32
+        hq = pinned((Wr, Q, words), torch.int32)
+        hq.copy_(queries[:, :, :words])
         hm = None
         if masks is not None:
-            hm = pinned((Wr, Q, stride), torch.int32)
-            hm.copy_(masks)
+            hm = pinned((Wr, Q, words), torch.int32)
+            hm.copy_(masks[:, :, :words])
         hq_np, hm_np = hq.numpy(), (None if hm is None else hm.numpy())
         hD = pinned((Wr, Q, k), torch.int32).numpy()   # caller-owned pinned result buffers
         hI = pinned((Wr, Q, k), torch.int64).numpy()
@@ -565,7 +567,7 @@ def bench_windows(ctx, a, scaling, steps, warmup, want_e2e=True, want_clocks=Tru
         d2h = Dh.nbytes + Ih.nbytes
         e2e = {"value": pairs_job / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": dt * 1e3, "host_copy_gbs_per_rank": (h2d + d2h) / dt / 1e9,
-               "api": "WindowedHammingIndex.search(pinned numpy packed uint32 [W,Q,stride], out=pinned (D int32, I int64)); "
+               "api": "WindowedHammingIndex.search(pinned numpy dense packed uint32 [W,Q,33], out=pinned (D int32, I int64)); "
                       "window chunks pipelined over 3 streams inside libsnvknn (H2D | scan | D2H); bytes are per rank"}
         assert np.array_equal(Ih, I.cpu().numpy()) and np.array_equal(Dh, D.cpu().numpy()), "host/device result mismatch"
         # compact wire format: int32 ids + uint16 distances (ids < panel rows, distances <= sites), same results

@@ -53,7 +53,9 @@ typedef enum snv_dtype {
     SNV_DT_F32 = 1,        /* HAMMING: non-zero = alt allele; L2: the vector  [rows][d]       */
     SNV_DT_PACKED_U32 = 2, /* native packed rows            [rows][snv_packed_stride(d)]      */
     SNV_DT_PACKED_U8 = 3,  /* np.packbits rows (faiss binary codes) [rows][(d+7)/8] bytes     */
-    SNV_DT_I64_TOKENS = 4  /* model tokens (5/6 alleles, 4 = MASK, 0/2/3 specials) [rows][d]  */
+    SNV_DT_I64_TOKENS = 4, /* model tokens (5/6 alleles, 4 = MASK, 0/2/3 specials) [rows][d]  */
+    SNV_DT_PACKED_U32_DENSE = 5 /* packed rows WITHOUT stride padding [rows][snv_packed_words(d)]: the wire format of
+                                 * host-buffer sweeps (132 instead of 144 bytes per 1030-site row); re-strided on the device */
 } snv_dtype;
 
 typedef enum snv_mask_mode {

@@ -16,7 +16,7 @@ _CSRC = os.path.join(_PKG, "csrc")
 # enums of include/snvknn.h
 SNV_OK = 0
 KIND_HAMMING, KIND_L2 = 0, 1
-DT_U8, DT_F32, DT_PACKED_U32, DT_PACKED_U8, DT_I64_TOKENS = 0, 1, 2, 3, 4
+DT_U8, DT_F32, DT_PACKED_U32, DT_PACKED_U8, DT_I64_TOKENS, DT_PACKED_U32_DENSE = 0, 1, 2, 3, 4, 5
 MASK_NONE, MASK_PER_WINDOW, MASK_PER_QUERY = 0, 1, 2
 Q_ON_DEVICE, OUT_ON_DEVICE, MASK_IS_MISSING, X_ON_DEVICE = 0x1, 0x2, 0x4, 0x8
 L2_TF32, L2_TF32X3 = 0, 1

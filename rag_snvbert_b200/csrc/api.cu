@@ -96,6 +96,7 @@ size_t dtype_row_bytes(int dtype, int64_t d, int stride)
         case SNV_DT_PACKED_U32: return (size_t)stride * 4;
         case SNV_DT_PACKED_U8: return (size_t)((d + 7) / 8);
         case SNV_DT_I64_TOKENS: return (size_t)d * 8;
+        case SNV_DT_PACKED_U32_DENSE: return (size_t)((d + 31) / 32) * 4;
         default: return 0;
     }
 }
@@ -372,7 +373,7 @@ int snv_index_add(snv_index* idx, const void* x, int64_t n, int dtype, unsigned 
     if (!x) { set_error("snv_index_add: x is null"); return SNV_ERR_INVALID; }
     const bool hamming = idx->kind == SNV_KIND_HAMMING;
     if (hamming) {
-        if (dtype != SNV_DT_U8 && dtype != SNV_DT_F32 && dtype != SNV_DT_PACKED_U32 &&
+        if (dtype != SNV_DT_U8 && dtype != SNV_DT_F32 && dtype != SNV_DT_PACKED_U32 && dtype != SNV_DT_PACKED_U32_DENSE &&
             dtype != SNV_DT_PACKED_U8 && dtype != SNV_DT_I64_TOKENS) {
             set_error("snv_index_add: bad dtype for a HAMMING index");
             return SNV_ERR_INVALID;

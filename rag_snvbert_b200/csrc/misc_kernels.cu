@@ -468,6 +468,25 @@ int merge_results_launch(const int32_t* D_i32, const float* D_f32, const int64_t
     return SNV_OK;
 }
 
+// dense packed rows [rows][words] -> strided packed rows [rows][stride] (pad words zero; optional complement over the d sites)
+__global__ void __launch_bounds__(256)
+restride_words_kernel(const uint32_t* __restrict__ x, int64_t rows, int words, int stride, int64_t d, bool invert,
+                      uint32_t* __restrict__ out)
+{
+    const int64_t total = rows * stride;
+    for (int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; item < total; item += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = item / stride;
+        const int w = (int)(item % stride);
+        uint32_t v = w < words ? x[r * words + w] : 0u;
+        if (invert) {
+            const int64_t lo = (int64_t)w * 32;
+            const uint32_t valid = lo + 32 <= d ? 0xFFFFFFFFu : (lo < d ? (1u << (d - lo)) - 1u : 0u);
+            v = ~v & valid;
+        }
+        out[item] = v;
+    }
+}
+
 int pack_launch(const void* x, int64_t rows, int64_t d, int dtype, bool invert, int stride,
                 uint32_t* out, uint32_t* out_observed, cudaStream_t stream)
 {
@@ -488,6 +507,14 @@ int pack_launch(const void* x, int64_t rows, int64_t d, int dtype, bool invert, 
         case SNV_DT_PACKED_U8: {
             const int g2 = (int)std::min<int64_t>(ceil_div(rows * stride, block), (int64_t)kNumSMs * 16);
             pack_bytes_kernel<<<g2, block, 0, stream>>>((const uint8_t*)x, rows, ceil_div(d, 8), stride, out);
+            break;
+        }
+        case SNV_DT_PACKED_U32_DENSE: {
+            // dense packed rows (words uint32 each) -> strided rows: the byte re-pack with 4 * words bytes per row is
+            // exactly a little-endian word copy with zero padding; `invert` (masks given as MISSING sites) flips the
+            // observed bits afterwards
+            const int g2 = (int)std::min<int64_t>(ceil_div(rows * stride, block), (int64_t)kNumSMs * 16);
+            restride_words_kernel<<<g2, block, 0, stream>>>((const uint32_t*)x, rows, words, stride, d, invert, out);
             break;
         }
         default:

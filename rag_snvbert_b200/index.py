@@ -66,9 +66,12 @@ def _hamming_dtype(a: _Arg, d: int, stride: int, what: str, codes: bool = False)
             raise ValueError(f"{what}: binary codes must be uint8 [.., {(d + 7) // 8}]")
         return L.DT_PACKED_U8, a
     if dt in (np.dtype(np.uint32), np.dtype(np.int32)):
-        if last != stride:
-            raise ValueError(f"{what}: packed rows must have {stride} uint32 words (snv_packed_stride({d})), got {last}")
-        return L.DT_PACKED_U32, a
+        words = (d + 31) // 32
+        if last == stride:
+            return L.DT_PACKED_U32, a
+        if last == words:  # dense rows without the stride padding: the compact wire format (re-strided on the device)
+            return L.DT_PACKED_U32_DENSE, a
+        raise ValueError(f"{what}: packed rows must have {stride} uint32 words (snv_packed_stride({d})) or, dense, {words}; got {last}")
     if last != d:
         raise ValueError(f"{what}: last dimension must be d={d}, got {last}")
     if dt == np.dtype(np.float32):

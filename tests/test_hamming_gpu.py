@@ -564,3 +564,41 @@ def test_exchange_pack_and_merge_kernels_match_torch_reference():
         allk = lists.permute(1, 0, 2).reshape(n, G * k).sort(dim=1).values[:, :k]
         De, Ie = RowShardedSearch.unpack_keys(allk)
         assert torch.equal(Do, De) and torch.equal(Io, Ie)
+
+
+@pytest.mark.parametrize("d", [1030, 100, 1024, 33])
+def test_dense_packed_rows_equal_strided_rows(d):
+    """SNV_DT_PACKED_U32_DENSE: packed rows without the stride padding (the 132-byte wire format) for add, queries and
+    masks (observed and missing) give exactly the results of the strided rows, from host and from device buffers"""
+    import torch
+
+    from rag_snvbert_b200 import _lib
+
+    rng = np.random.default_rng(d)
+    W, N, Q, k = 2, 600, 70, 8
+    stride, words = _lib.packed_stride(d), _lib.packed_words(d)
+    panel = (rng.random((W, N, d)) < 0.4).astype(np.uint8)
+    q = (rng.random((W, Q, d)) < 0.4).astype(np.uint8)
+    miss = (rng.random((W, Q, d)) < 0.3).astype(np.uint8)
+    pk = lambda x: O.pack_bits_u32(x.reshape(-1, d), stride).reshape(x.shape[:-1] + (stride,))  # noqa: E731
+    idx = _idx(d, W)
+    idx.add(panel)
+    D0, I0 = idx.search(q, k, missing=miss)
+    D1, I1 = idx.search(q, k)
+    qd, md = np.ascontiguousarray(pk(q)[..., :words]), np.ascontiguousarray(pk(miss)[..., :words])
+    if words == stride:
+        return  # no padding for this d: the dense and the strided layouts coincide
+    for conv in (lambda x: x, lambda x: torch.from_numpy(x.view(np.int32)).cuda()):
+        D, I = idx.search(conv(qd), k, missing=conv(md))
+        D, I = (D.cpu().numpy(), I.cpu().numpy()) if hasattr(D, "cpu") else (D, I)
+        np.testing.assert_array_equal(I, I0)
+        np.testing.assert_array_equal(D, D0)
+        D, I = idx.search(conv(qd), k)
+        D, I = (D.cpu().numpy(), I.cpu().numpy()) if hasattr(D, "cpu") else (D, I)
+        np.testing.assert_array_equal(I, I1)
+        np.testing.assert_array_equal(D, D1)
+    idx2 = _idx(d, W)
+    idx2.add(np.ascontiguousarray(pk(panel)[..., :words]))   # dense rows into add()
+    D, I = idx2.search(q, k)
+    np.testing.assert_array_equal(I, I1)
+    np.testing.assert_array_equal(D, D1)
