@@ -536,7 +536,8 @@ static int hamming_chunk_bounds(const HammingSearchParams& p, bool host_io, std:
             int64_t a = units, b = per_w;
             while (b) { const int64_t t = a % b; a = b; b = t; }
             const int64_t unit = units / a;  // windows per chunk so that items per chunk is a multiple of the units
-            const int64_t target = 24;
+            int64_t target = 24;
+            if (const char* e = getenv("SNV_PIPE_CHUNKS")) target = std::max(1, atoi(e));  // tuning override
             int64_t cw = std::max<int64_t>(unit, nw / target / unit * unit);
             if (cw * per_w < 2 * units) cw = ceil_div(2 * units, per_w);
             chunk_w = (int)std::min<int64_t>(cw, nw);

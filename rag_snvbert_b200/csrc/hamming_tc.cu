@@ -98,19 +98,25 @@ constexpr int kExpThreads = kExpWarps * 32;
 // Epilogue shape: 8 warps (2 per SM sub-partition) on 128-column parts of every tile, scored in 32-column groups.
 // (16 warps on 64-column parts - SNV_TC_EPI16, CTA-pair kernel at k <= 8 only - were measured slower: the kernel is
 // bound by issued instructions, more epilogue warps only add contention; profiles/r1_tc_breakdown_variants.txt.)
-template <int KT, bool PAIR = false>
+enum { MODE_FP8 = 0, MODE_FP8_HBM = 1, MODE_FP4 = 2, MODE_FP4_2CTA = 3, MODE_FP4_2CTA_TA = 4 };
+#ifndef SNV_TC_TA_EPI12
+#define SNV_TC_TA_EPI12 0  // TMEM-A engine at k <= 8: 12 epilogue warps (three column parts per lane quarter) instead of 8
+#endif
+template <int KT, int MODE>
 struct Epi {
-    static constexpr int kWarps = (KT == 8 && PAIR && SNV_TC_EPI16) ? 16 : 8;
+    static constexpr bool kPairMode = MODE == MODE_FP4_2CTA || MODE == MODE_FP4_2CTA_TA;
+    static constexpr int kWarps = (MODE == MODE_FP4_2CTA_TA && KT == 8 && SNV_TC_TA_EPI12) ? 12
+                                  : ((KT == 8 && kPairMode && SNV_TC_EPI16) ? 16 : 8);
     static constexpr int kThreads = kWarps * 32;
     static constexpr int kParts = kWarps / 4;          // warps per TMEM lane quarter = column parts of a tile
-    static constexpr int kPartCols = 256 / kParts;     // 64 or 128
+    static constexpr int kPartCols = 256 / (kParts == 3 ? 4 : kParts);     // 64 or 128 (smem-A engines)
     static constexpr int kGroup = 32;                  // columns scored between two folds
     static constexpr uint32_t kSlotStride = kThreads * 4;  // bytes between the candidate slots of consecutive columns
 };
 constexpr int kFirstExpWarp = 3;
 constexpr int kFirstEpiWarp = kFirstExpWarp + kExpWarps;  // 7
-template <int KT, bool PAIR>
-constexpr int threads_of() { return 32 * (kFirstEpiWarp + Epi<KT, PAIR>::kWarps); }  // 736 or 480
+template <int KT, int MODE>
+constexpr int threads_of() { return 32 * (kFirstEpiWarp + Epi<KT, MODE>::kWarps); }  // 480 (608 / 736 with more epilogue warps)
 constexpr uint32_t kABytes = BM * kRowBytes;   // 16 KB
 constexpr uint32_t kBBytes = 256 * kRowBytes;  // 32 KB slot (240 or 256 rows in use)
 #ifndef SNV_TC_BSTAGES
@@ -130,11 +136,10 @@ constexpr uint32_t kBBytes = 256 * kRowBytes;  // 32 KB slot (240 or 256 rows in
 #endif
 constexpr size_t kListBytes = 32 * 1024;  // one slot per (epilogue thread, column of a group): 32 x 256 floats
 constexpr size_t kListBytes16 = 64 * 1024; // 16 epilogue warps: 32 x 512 floats
-static_assert((Epi<8, true>::kParts - 1) * 8 * BM * 4 <= kListBytes && (Epi<32>::kParts - 1) * 32 * BM * 4 <= kListBytes,
+static_assert((Epi<8, MODE_FP4_2CTA>::kParts - 1) * 8 * BM * 4 <= kListBytes && (Epi<32, MODE_FP8>::kParts - 1) * 32 * BM * 4 <= kListBytes,
               "the part-exchange buffer aliases the candidate slots");
-static_assert((size_t)SNV_TC_LIST_CAP * 2048 >= (size_t)32 * BM * 4, "the part-exchange buffer aliases the candidate lists");
-
-enum { MODE_FP8 = 0, MODE_FP8_HBM = 1, MODE_FP4 = 2, MODE_FP4_2CTA = 3, MODE_FP4_2CTA_TA = 4 };
+static_assert((size_t)SNV_TC_LIST_CAP * 2048 >= (size_t)32 * BM * 4 && (size_t)24 * 8 * 384 >= (size_t)2 * 8 * BM * 4,
+              "the part-exchange buffer aliases the candidate lists");
 
 // Three rings: the query operand comes from L2 (long latency: deep ring), the panel operand is made
 // in the SM (expander latency: 3 slots), raw packed k-blocks are small.
@@ -157,8 +162,10 @@ struct Cfg {
     // list, and the lists are folded into the sorted top-k once per tile part (or when a list fills) instead of after
     // every 32 columns.
     static constexpr bool kListEpi = kFp4 && kTwoCta && SNV_TC_LIST_EPI;  // (the single-CTA kernel has no shared memory left for lists)
-    static constexpr int kListCap = SNV_TC_LIST_CAP;
-    static constexpr int kFoldAt = SNV_TC_FOLD_AT;
+    static constexpr bool kEpi12 = MODE == MODE_FP4_2CTA_TA && SNV_TC_TA_EPI12;   // (k <= 8 kernels; sizes below cover both)
+    static constexpr int kListCap = kEpi12 ? 24 : SNV_TC_LIST_CAP;
+    static constexpr int kFoldAt = kEpi12 ? 8 : SNV_TC_FOLD_AT;
+    static constexpr int kPartsMax = kEpi12 ? 3 : 2;
     static_assert(!kListEpi || kFoldAt + 16 <= kListCap, "a 32-column group (16 pairs) must always fit behind the fold mark");
     static constexpr int BN = kTmemA ? 160 : (kFp4 ? 240 : 256);   // panel rows per tile = TMEM columns per accumulator stage
     static constexpr int WPK = kFp4 ? 8 : 4;      // packed words per k-block
@@ -168,7 +175,7 @@ struct Cfg {
     // bytes in front of the B ring: the query tile ring (none in the TMEM-A mode)
     static constexpr size_t kAOpBytes = (size_t)kAStages * kABytes;
     static_assert(kAOpBytes % 1024 == 0, "the B ring stays 1024-byte aligned");
-    static constexpr int kRawStages = kTmemA ? SNV_TC_TA_RAWSTAGES : SNV_TC_RAWSTAGES;
+    static constexpr int kRawStages = kTmemA ? ((MODE == MODE_FP4_2CTA_TA && SNV_TC_TA_EPI12) ? 2 : SNV_TC_TA_RAWSTAGES) : SNV_TC_RAWSTAGES;
     static constexpr int kBRows = kTwoCta ? BN / 2 : BN;          // panel rows this CTA expands per tile
     static constexpr uint32_t kRawRow = WPK * 4;                // raw bytes per panel row and k-block
     // TMEM-A mode works per TILE, not per k-block: one raw TMA box brings the 80 packed rows whole (row stride <= 48
@@ -187,9 +194,9 @@ struct Cfg {
     // mbarriers of the rings + TMEM stages, the TMEM base / runtime-one words and the a_full barrier
     static constexpr size_t kBarBytes = ((size_t)(2 * (kAStages + kBStages + kRawStages + kAccStages)) * 8 + 16 + 255) / 256 * 256;
     // candidate slots / lists of the epilogue threads (8 warps; 16 with SNV_TC_EPI16 in the pair kernels at k <= 8)
-    static constexpr size_t kSlotBytes = kListEpi ? (size_t)kListCap * 8 * ((kTwoCta && SNV_TC_EPI16) ? 512 : 256)
+    static constexpr size_t kSlotBytes = kListEpi ? (size_t)kListCap * 8 * (kEpi12 ? 384 : ((kTwoCta && SNV_TC_EPI16) ? 512 : 256))
                                                   : ((kTwoCta && SNV_TC_EPI16) ? kListBytes16 : kListBytes);
-    static constexpr size_t kQbBytes = kTmemA ? 2 * 2 * BM * 4 + (size_t)kBRows * 32 : 0;  // TMEM-A mode: partial query biases
+    static constexpr size_t kQbBytes = kTmemA ? 2 * kPartsMax * BM * 4 + (size_t)kBRows * 32 : 0;  // TMEM-A mode: partial query biases
                                                                     // [item parity][part][row], then the column-index codes [row][32 B]
     static constexpr size_t kSmem = 1024 /*align slack*/ + kAOpBytes + (size_t)kBStages * kBSlot +
                                     (size_t)kRawStages * kRawSlot + kSlotBytes + (kTwoCta ? 4 : 2) * BM * 4 /*thresholds*/ + kQbBytes + kBarBytes;
@@ -444,7 +451,7 @@ __device__ __forceinline__ void tmem_ld_wait_cols(uint32_t (&r)[N])
 }
 
 template <int KT, int MODE>
-__global__ void __launch_bounds__(threads_of<KT, Cfg<MODE>::kTwoCta>(), 1)
+__global__ void __launch_bounds__(threads_of<KT, MODE>(), 1)
 hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_r, const TcParams p)
 {
     using C = Cfg<MODE>;
@@ -464,7 +471,7 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     unsigned char* b_tiles = a_tiles + C::kAOpBytes;
     unsigned char* raws = b_tiles + (size_t)kBStages * C::kBSlot;
     uint32_t* lists = reinterpret_cast<uint32_t*>(raws + (size_t)kRawStages * C::kRawSlot);  // [group columns][epilogue threads]
-    using E = Epi<KT, C::kTwoCta>;
+    using E = Epi<KT, MODE>;
     constexpr int kEpiThreads = E::kThreads;
     uint32_t* xchg = lists;                                                                 // [parts - 1][KT][128], after the slots are folded
     constexpr size_t kSlots = C::kSlotBytes;
@@ -810,7 +817,7 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                 const uint32_t rstride = (uint32_t)p.stride * 4u;
                 // the rows' column-index codes, once: table [row][32 B] in shared memory (thread = row), visible to the four
                 // expander warps after their own named barrier
-                const uint32_t idx_tab = smem_u32(const_cast<int32_t*>(qbx)) + 2u * 2u * BM * 4u;
+                const uint32_t idx_tab = smem_u32(const_cast<int32_t*>(qbx)) + 2u * (uint32_t)C::kPartsMax * BM * 4u;
                 if (act) {
                     sts128(idx_tab + (uint32_t)et * 32u, ic0[0]);
                     sts128(idx_tab + (uint32_t)et * 32u + 16u, ic1[0]);
@@ -933,7 +940,7 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     } else {
         // ================= epilogue: thread = query row (TMEM lane), kParts warps per lane quarter =================
         constexpr int kParts = E::kParts, kPartCols = E::kPartCols, G = E::kGroup;
-        static_assert(!TA || kParts == 2, "the TMEM-A tile split (96 + 64 columns) is written for two column parts");
+        static_assert(!TA || kParts == 2 || kParts == 3, "the TMEM-A tile split is written for two (96 + 64) or three (64 + 64 + 32) column parts");
         constexpr uint32_t kSlotStride = E::kSlotStride;
         const int quarter = warp & 3;                   // TMEM lanes [32 * quarter, +32)
         const int part = (warp - kFirstEpiWarp) >> 2;   // columns [kPartCols * part, +kPartCols) of every tile
@@ -987,7 +994,7 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                 }
                 tmem_st_32x32b_x16v(ta + (uint32_t)(16 * qd), v);
             }
-            qbx[(slot * kParts + part) * BM + row] = bias;
+            qbx[(slot * C::kPartsMax + part) * BM + row] = bias;
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tcgen05_fence_before();
             __syncwarp();
@@ -1010,7 +1017,9 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             if constexpr (TA) {
                 // popc(q & m): the two parts' shares, written when the tile was built (ordered by the item-end barriers)
                 const int sl = (int)(icount & 1u);
-                qb = qbx[(sl * kParts) * BM + row] + qbx[(sl * kParts + 1) * BM + row];
+                qb = 0;
+#pragma unroll
+                for (int pp = 0; pp < kParts; ++pp) qb += qbx[(sl * C::kPartsMax + pp) * BM + row];
                 ++icount;
             } else {
                 qb = active ? p.q_bias[q] : 0;
@@ -1112,9 +1121,22 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                     if constexpr (TA) {
                         if (t == it.ntiles - 1 && item + item_step < p.items) load_a(item + item_step, (int)(icount & 1u));
                     }
-                    const int c0 = TA ? ((tcount & 1u) ? 64 : 96) : kPartCols;
-                    const int pstart = TA ? (part ? c0 : 0) : kPartCols * part;
-                    const int pwidth = TA ? (part ? BN - c0 : c0) : kPartCols;
+                    // columns [pstart, pstart + pwidth) of the tile belong to this part.  160-column tiles: two parts take
+                    // 96 + 64 columns, three parts 64 + 64 + 32, the assignment rotating from tile to tile so that every part
+                    // scores whole 32-column groups and carries the same load over two (three) tiles
+                    int pstart, pwidth;
+                    if constexpr (!TA) {
+                        pstart = kPartCols * part;
+                        pwidth = kPartCols;
+                    } else if constexpr (kParts == 3) {
+                        const int slot3 = (part + (int)(tcount % 3u)) % 3;
+                        pstart = 64 * slot3;
+                        pwidth = slot3 == 2 ? BN - 128 : 64;
+                    } else {
+                        const int c0 = (tcount & 1u) ? 64 : 96;
+                        pstart = part ? c0 : 0;
+                        pwidth = part ? BN - c0 : c0;
+                    }
                     int cols = (p.n - n0 < BN ? (int)(p.n - n0) : BN) - pstart;  // columns of this part in use
                     cols = cols < 0 ? 0 : (cols > pwidth ? pwidth : cols);
                     const int nch = (cols + G - 1) / G;
@@ -1443,7 +1465,7 @@ int launch_kernel(const CUtensorMap& map_q, const CUtensorMap& map_r, const TcPa
         // CTA pairs: a cluster of two CTAs on the two SMs of a TPC
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)grid);
-        cfg.blockDim = dim3((unsigned)threads_of<KT, true>());
+        cfg.blockDim = dim3((unsigned)threads_of<KT, MODE>());
         cfg.dynamicSmemBytes = smem;
         cfg.stream = stream;
         cudaLaunchAttribute at[1];
@@ -1455,7 +1477,7 @@ int launch_kernel(const CUtensorMap& map_q, const CUtensorMap& map_r, const TcPa
         cfg.numAttrs = 1;
         SNV_CUDA_CHECK(cudaLaunchKernelEx(&cfg, hamming_tc_kernel<KT, MODE>, map_q, map_r, tp));
     } else {
-        hamming_tc_kernel<KT, MODE><<<grid, threads_of<KT, false>(), smem, stream>>>(map_q, map_r, tp);
+        hamming_tc_kernel<KT, MODE><<<grid, threads_of<KT, MODE>(), smem, stream>>>(map_q, map_r, tp);
     }
     profile_end(stream);
     SNV_LAUNCH_CHECK();
