@@ -130,8 +130,10 @@ int snv_index_add(snv_index* idx, const void* x, int64_t n, int dtype, unsigned 
  * D_i32 (HAMMING only) and/or D_f32 (squared L2 == Hamming for 0/1 rows); either D pointer may
  * be NULL.  Results are in the canonical order (distance ascending, id ascending), ties at
  * the k-boundary keep the lowest ids.  Padding: D_i32 = INT32_MAX, D_f32 = FLT_MAX.
- * LIMIT: k <= 32 (the running top-k lives in registers); larger k -> SNV_ERR_UNSUPPORTED.  faiss takes any k; every
- * call site of the reference asks for k <= 5 (src/train.py:105, src/infer.py:66, --top_k default 5).
+ * LIMIT of this entry point: k <= 32 (the running top-k lives in registers); larger k -> SNV_ERR_UNSUPPORTED.  faiss
+ * takes any k (every call site of the reference asks for k <= 5: src/train.py:105, src/infer.py:66, --top_k default 5);
+ * the Python classes serve k > 32 exactly through a block path built on this call: the panel re-added as windows of
+ * 32 rows, one k = 32 search returning every distance of every block, then a top-k over the (distance, id) keys.
  *
  * HAMMING only: `mask` (same dtype family as q: U8/F32/PACKED_U32) restricts the distance to
  * observed sites, popc((q ^ r) & m) — partial_faiss_intersect.py:82-111.

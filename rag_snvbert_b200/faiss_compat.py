@@ -35,15 +35,7 @@ def _is_binary(x) -> bool:
     return bool(np.logical_or(x == 0, x == 1).all())
 
 
-MAX_K = 32  # neighbours per query the kernels select in registers (include/snvknn.h); the reference uses k <= 5
-
-
-def _check_k(k: int) -> None:
-    """faiss accepts any k; this engine keeps the running top-k in registers and stops at 32 - more than every call site of
-    the reference asks for (k = 1 / 3 / 5: train_with_val_optimized.py:64, src/train.py:105, src/infer.py:66; --top_k of the
-    offline scripts defaults to 5).  Fail up front with a plain message instead of deep inside the library."""
-    if int(k) > MAX_K:
-        raise ValueError(f"k = {k}: this engine returns at most {MAX_K} neighbours per query (documented limit, include/snvknn.h)")
+MAX_K = 32  # neighbours the kernels select in registers; larger k (faiss takes any) goes through the block path of index.py
 
 
 class IndexFlatL2:
@@ -86,11 +78,10 @@ class IndexFlatL2:
     def search(self, x, k: int):
         x = _check_matrix(x, self.d, np.float32, "search")
         assert k > 0
-        _check_k(k)
         # worth it only when the scan outweighs the 0/1 check and the packing of the queries
         # (BASELINE cfg 1, 1000 x 5008 x 1030, is faster on the float kernel: 0.40 vs 0.75 ms from numpy)
         big = float(x.shape[0]) * self.ntotal * self.d >= self.binary_min_work
-        if self._binary and self._shadow is not None and big and int(k) <= 32 and _is_binary(x):
+        if self._binary and self._shadow is not None and big and int(k) <= MAX_K and _is_binary(x):
             self.last_search_path = "hamming"
             return self._shadow.search(x, int(k), dist_dtype=np.float32)
         self.last_search_path = "l2"
@@ -131,7 +122,6 @@ class IndexBinaryFlat:
     def search(self, x, k: int):
         x = _check_matrix(x, self.code_size, np.uint8, "search")
         assert k > 0
-        _check_k(k)
         return self._impl.search(x, int(k), codes=True)
 
     def reset(self) -> None:

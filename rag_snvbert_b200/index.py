@@ -28,6 +28,9 @@ except Exception:  # pragma: no cover
     torch = None
 
 
+MAX_K = 32  # neighbours the kernels select in registers; larger k takes the block path (_search_large_k)
+
+
 def _is_torch(x) -> bool:
     return torch is not None and isinstance(x, torch.Tensor)
 
@@ -172,6 +175,10 @@ class WindowedHammingIndex(_IndexBase):
         arrays, so the device-to-host copies of a host-buffer call overlap the scan)."""
         if int(k) < 1:
             raise ValueError("k must be >= 1")
+        if int(k) > MAX_K:
+            if out is not None or codes:
+                raise ValueError(f"search: k > {MAX_K} takes the block path, which allocates its own results (no out=, no codes=)")
+            return self._search_large_k(q, int(k), observed, missing, int(w0), int(id_offset), dist_dtype)
         a = _Arg(q)
         squeeze = len(a.shape) == 2
         if squeeze:
@@ -224,6 +231,83 @@ class WindowedHammingIndex(_IndexBase):
                                            _current_stream(self.device)), "snv_index_search")
         if squeeze:
             return D[0], I[0]
+        return D, I
+
+    # ---- k > 32 (faiss accepts any k; the kernels select at most 32 neighbours in registers)
+    def _packed_on_device(self, x, what):
+        """any accepted row dtype (numpy or CUDA tensor) -> packed int32 CUDA tensor [..., stride]"""
+        a = _Arg(x)
+        t = a.arr if a.on_device else torch.from_numpy(np.ascontiguousarray(a.arr)).to(f"cuda:{self.device}")
+        dt, a2 = _hamming_dtype(_Arg(t), self.d, self.stride, what)
+        t = a2.arr
+        if dt == L.DT_PACKED_U32:
+            return t.view(torch.int32) if t.dtype != torch.int32 else t
+        if dt == L.DT_PACKED_U32_DENSE:
+            pad = torch.zeros(t.shape[:-1] + (self.stride - t.shape[-1],), dtype=t.dtype, device=t.device)
+            return torch.cat([t, pad], dim=-1).view(torch.int32)
+        flat = pack_rows(t.reshape(-1, t.shape[-1]), self.d)
+        return flat.reshape(t.shape[:-1] + (self.stride,))
+
+    def _search_large_k(self, q, k, observed, missing, w0, id_offset, dist_dtype):
+        """Exact top-k for k > 32 by the BLOCK path: the window's panel is re-added as ntotal / 32 windows of 32 rows, one
+        launch searches every block with k = 32 - which returns ALL of a block's distances - and the k best of the
+        (distance, id) keys are selected with one torch.topk.  Same total order, same padding as the in-kernel path; far
+        slower per pair (every query meets every 32-row block as its own tiny window), which is acceptable for the rare
+        large k (the reference asks for k <= 5)."""
+        if torch is None or not torch.cuda.is_available():
+            raise RuntimeError("search with k > 32 needs torch with CUDA")
+        was_numpy = not _Arg(q).on_device
+        qp = self._packed_on_device(q, "search")
+        qdim = qp.dim()
+        squeeze = qdim == 2
+        if squeeze:
+            qp = qp.unsqueeze(0)
+        nw, nq = int(qp.shape[0]), int(qp.shape[1])
+        mk = observed if observed is not None else missing
+        if observed is not None and missing is not None:
+            raise ValueError("search: give observed= or missing=, not both")
+        mp = None
+        if mk is not None:
+            mp = self._packed_on_device(mk, "search(mask)")
+            if mp.dim() == qdim:                      # one mask row per query
+                mp = mp.unsqueeze(0) if squeeze else mp
+            elif mp.dim() == qdim - 1:                # one mask row per window
+                mp = mp.reshape(nw, 1, self.stride).expand(nw, nq, self.stride)
+            else:
+                raise ValueError("search: mask shape matches neither the queries nor one row per window")
+            mp = mp.contiguous()
+        n, B = self.ntotal, MAX_K
+        nb = max(1, -(-n // B))
+        dev = qp.device
+        Ds, Is = [], []
+        for w in range(nw):
+            rows = torch.from_numpy(self.export_packed(w0 + w).view(np.int32)).to(dev)        # [n, stride]
+            pad = torch.zeros((nb * B - n, self.stride), dtype=torch.int32, device=dev)
+            blocks = WindowedHammingIndex(self.d, nb, self.device)
+            blocks.add(torch.cat([rows, pad]).reshape(nb, B, self.stride))
+            qrep = qp[w].unsqueeze(0).expand(nb, nq, self.stride).contiguous()
+            kw = {}
+            if mp is not None:
+                kw["observed" if observed is not None else "missing"] = mp[w].unsqueeze(0).expand(nb, nq, self.stride).contiguous()
+            Db, Ib = blocks.search(qrep, B, **kw)                                             # [nb, nq, 32]: every distance of a block
+            gid = Ib + (torch.arange(nb, device=dev) * B).view(nb, 1, 1)
+            key = (Db.to(torch.int64) << 32) | gid
+            key = torch.where((Ib < 0) | (gid >= n), torch.full_like(key, torch.iinfo(torch.int64).max), key)
+            key = key.permute(1, 0, 2).reshape(nq, nb * B)
+            kk = min(k, nb * B)
+            best = torch.topk(key, kk, dim=1, largest=False, sorted=True).values
+            if kk < k:
+                best = torch.cat([best, torch.full((nq, k - kk), torch.iinfo(torch.int64).max, dtype=torch.int64, device=dev)], dim=1)
+            none = best == torch.iinfo(torch.int64).max
+            Ds.append(torch.where(none, torch.full_like(best, 0x7FFFFFFF), best >> 32).to(torch.int32))
+            Is.append(torch.where(none, torch.full_like(best, -1), (best & 0xFFFFFFFF) + id_offset))
+        D, I = torch.stack(Ds), torch.stack(Is)
+        if np.dtype(dist_dtype) == np.dtype(np.float32):
+            D = torch.where(I < 0, torch.full_like(D, 0, dtype=torch.float32) + 3.4028234663852886e38, D.to(torch.float32))
+        if squeeze:
+            D, I = D[0], I[0]
+        if was_numpy:
+            return D.cpu().numpy(), I.cpu().numpy()
         return D, I
 
     def search_compact(self, q, k: int, observed=None, missing=None, w0: int = 0, out=None):
@@ -407,9 +491,52 @@ class WindowedL2Index(_IndexBase):
         flags = L.X_ON_DEVICE if a.on_device else 0
         L.check(self._lib.snv_index_add(self._h, a.ptr, n, L.DT_F32, flags, _current_stream(self.device)), "snv_index_add")
 
+    def _search_large_k(self, q, k, w0, id_offset):
+        """k > 32 by the block path (see WindowedHammingIndex._search_large_k): the window's rows re-added as blocks of 32, one
+        launch with k = 32 returns every distance of every block, torch.topk on (float bits << 32 | id) keys selects."""
+        if torch is None or not torch.cuda.is_available():
+            raise RuntimeError("search with k > 32 needs torch with CUDA")
+        a = _Arg(q)
+        was_numpy = not a.on_device
+        qt = a.arr if a.on_device else torch.from_numpy(np.ascontiguousarray(a.arr)).to(f"cuda:{self.device}")
+        qt = qt.float()
+        squeeze = qt.dim() == 2
+        if squeeze:
+            qt = qt.unsqueeze(0)
+        nw, nq = int(qt.shape[0]), int(qt.shape[1])
+        n, B = self.ntotal, MAX_K
+        nb = max(1, -(-n // B))
+        dev = qt.device
+        Ds, Is = [], []
+        for w in range(nw):
+            rows = torch.from_numpy(self.export_rows(w0 + w)).to(dev)
+            pad = torch.zeros((nb * B - n, self.d), dtype=torch.float32, device=dev)
+            blocks = WindowedL2Index(self.d, nb, self.device, self.precision, center=self.center)
+            blocks.add(torch.cat([rows, pad]).reshape(nb, B, self.d))
+            Db, Ib = blocks.search(qt[w].unsqueeze(0).expand(nb, nq, self.d).contiguous(), B)
+            gid = Ib + (torch.arange(nb, device=dev) * B).view(nb, 1, 1)
+            key = (Db.clamp_min(0).view(torch.int32).to(torch.int64) << 32) | gid       # non-negative float bits order like the floats
+            key = torch.where((Ib < 0) | (gid >= n), torch.full_like(key, torch.iinfo(torch.int64).max), key)
+            key = key.permute(1, 0, 2).reshape(nq, nb * B)
+            kk = min(k, nb * B)
+            best = torch.topk(key, kk, dim=1, largest=False, sorted=True).values
+            if kk < k:
+                best = torch.cat([best, torch.full((nq, k - kk), torch.iinfo(torch.int64).max, dtype=torch.int64, device=dev)], dim=1)
+            none = best == torch.iinfo(torch.int64).max
+            Ds.append(torch.where(none, torch.full((1,), 3.4028234663852886e38, device=dev), (best >> 32).to(torch.int32).view(torch.float32)))
+            Is.append(torch.where(none, torch.full_like(best, -1), (best & 0xFFFFFFFF) + id_offset))
+        D, I = torch.stack(Ds), torch.stack(Is)
+        if squeeze:
+            D, I = D[0], I[0]
+        if was_numpy:
+            return D.cpu().numpy(), I.cpu().numpy()
+        return D, I
+
     def search(self, q, k: int, w0: int = 0, id_offset: int = 0):
         if int(k) < 1:
             raise ValueError("k must be >= 1")
+        if int(k) > MAX_K:
+            return self._search_large_k(q, int(k), int(w0), int(id_offset))
         a = _Arg(q)
         if a.np_dtype != np.dtype(np.float32):
             a = _Arg(a.arr.float() if _is_torch(a.arr) else a.arr.astype(np.float32))

@@ -602,3 +602,39 @@ def test_dense_packed_rows_equal_strided_rows(d):
     D, I = idx2.search(q, k)
     np.testing.assert_array_equal(I, I1)
     np.testing.assert_array_equal(D, D1)
+
+
+@pytest.mark.parametrize("k", [33, 100])
+@pytest.mark.parametrize("where", ["host", "device"])
+def test_k_above_32_block_path(k, where):
+    """faiss accepts any k: above the in-register limit the Python classes take the block path (panel as windows of 32 rows,
+    one k = 32 launch, top-k over the keys) - still bit-exact vs the oracle, ties, masks, padding (k > rows) included"""
+    import torch
+
+    rng = np.random.default_rng(k)
+    W, N, Q, d = 2, 70, 9, 200
+    panel = (rng.random((W, N, d)) < 0.4).astype(np.uint8)
+    panel[:, N // 2:] = panel[:, : N - N // 2]           # duplicates -> ties
+    q = (rng.random((W, Q, d)) < 0.4).astype(np.uint8)
+    obs = (rng.random((W, Q, d)) < 0.7).astype(np.uint8)
+    idx = _idx(d, W)
+    idx.add(panel)
+    conv = (lambda x: x) if where == "host" else (lambda x: torch.from_numpy(x).cuda())
+    for m in (None, obs):
+        D, I = idx.search(conv(q), k, observed=None if m is None else conv(m))
+        D, I = (D.cpu().numpy(), I.cpu().numpy()) if hasattr(D, "cpu") else (D, I)
+        assert D.shape == (W, Q, k) and D.dtype == np.int32 and I.dtype == np.int64
+        for w in range(W):
+            De, Ie = O.hamming_topk(panel[w], q[w], k, None if m is None else m[w])
+            np.testing.assert_array_equal(I[w], Ie)
+            np.testing.assert_array_equal(D[w], De)
+    # through the faiss surface (float 0/1 rows -> the L2 index's block path), single window
+    import rag_snvbert_b200.faiss_compat as faiss
+
+    f = faiss.IndexFlatL2(d)
+    f.add(panel[0].astype(np.float32))
+    Df, If = f.search(q[0].astype(np.float32), k)
+    De, Ie = O.hamming_topk(panel[0], q[0], k)
+    np.testing.assert_array_equal(If, Ie)
+    np.testing.assert_array_equal(Df[Ie >= 0], De[Ie >= 0].astype(np.float32))
+    assert (Df[Ie < 0] > 3e38).all()
