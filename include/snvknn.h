@@ -220,6 +220,32 @@ int snv_exchange_pack(int device, const int32_t* D_i32, const int64_t* I, int nw
 int snv_exchange_merge(int device, const int64_t* keys, int parts, int64_t n, int k_in, int k_out, int32_t* Do_i32,
                        int64_t* Io, void* stream);
 
+/*
+ * The same exchange over NVLink peer memory, fused into ONE kernel launch per batch (no collective library on the data
+ * path).  Every rank creates one exchange object (snv_peer_create: a device buffer of a 4 KiB header + two receive slots
+ * of `slot_bytes`, and its 64-byte CUDA IPC handle); the host side all-gathers the handles with whatever transport it
+ * has (torch.distributed, MPI, a file) and snv_peer_open maps the peers' buffers.  snv_peer_exchange then, on `stream`:
+ * packs this rank's D / I [nw][nq][k] into int64 keys, stores each key straight into the receive slot of the rank that
+ * owns the query, raises this rank's flag on every peer (release), waits for every peer's flag (acquire), and merges the
+ * lists that arrived into Do_i32 / Io [nw * nq / world][k_out] - the result of snv_exchange_pack + all-to-all +
+ * snv_exchange_merge.  Rules: every rank makes the same sequence of calls (batch sizes equal on all ranks); all calls of
+ * one object go to ONE stream (slot reuse is ordered by the previous batch's flags); nw * nq * k * 8 <= slot_bytes;
+ * nq % world == 0; k <= 32; ids < 2^40.  A peer that never arrives traps the kernel after 30 s.
+ * snv_peer_open_local wires objects that live in ONE process on one device by pointer (test hook: their exchanges must
+ * then run on different streams, since each waits for the others' pushes).
+ * Replaces, for the row-sharded search of a multi-GPU job, what the reference does on one GPU with a single faiss index
+ * (src/dataset/rag_train_dataset.py:239-281 search + :283 result use); the NCCL route above stays for GPUs without
+ * peer access.
+ */
+#define SNV_PEER_HANDLE_BYTES 64
+typedef struct snv_peer snv_peer;
+int snv_peer_create(int device, int rank, int world, size_t slot_bytes, snv_peer** out, void* handle_out);
+int snv_peer_open(snv_peer* peer, const void* handles /* [world][SNV_PEER_HANDLE_BYTES], rank order */);
+int snv_peer_open_local(snv_peer* peer, snv_peer* const* peers /* [world] */);
+int snv_peer_exchange(snv_peer* peer, const int32_t* D_i32, const int64_t* I, int nw, int64_t nq, int k, int k_out,
+                      int32_t* Do_i32, int64_t* Io, void* stream);
+int snv_peer_destroy(snv_peer* peer);
+
 /* device-side pack helper: rows in `dtype` (U8 / F32 / PACKED_U8 / I64_TOKENS) ->
  * packed uint32 [rows][snv_packed_stride(d)] (device pointers; all on `stream`).
  * For I64_TOKENS `out_observed` (nullable) receives the observed-site plane (token in {5,6}). */

@@ -52,6 +52,11 @@ SYMBOLS = {
     "snv_topk_merge": (_i, [_i, _vp, _vp, _vp, _i, _i64, _i, _i, _vp, _vp, _vp, _vp]),
     "snv_exchange_pack": (_i, [_i, _vp, _vp, _i, _i64, _i, _i, _vp, _vp]),
     "snv_exchange_merge": (_i, [_i, _vp, _i, _i64, _i, _i, _vp, _vp, _vp]),
+    "snv_peer_create": (_i, [_i, _i, _i, _c.c_size_t, _c.POINTER(_vp), _vp]),
+    "snv_peer_open": (_i, [_vp, _vp]),
+    "snv_peer_open_local": (_i, [_vp, _vp]),
+    "snv_peer_exchange": (_i, [_vp, _vp, _vp, _i, _i64, _i, _i, _vp, _vp, _vp]),
+    "snv_peer_destroy": (_i, [_vp]),
     "snv_pack_rows": (_i, [_i, _vp, _i64, _i64, _i, _i, _vp, _vp, _vp]),
     "snv_intersect_masks": (_i, [_i, _vp, _i64, _vp, _i64, _vp, _i, _i64, _i, _vp, _vp]),
     "snv_launch_count": (_i64, []),

@@ -1185,6 +1185,144 @@ int snv_exchange_merge(int device, const int64_t* keys, int parts, int64_t n, in
     return exchange_merge_launch(keys, parts, n, k_in, k_out, Do_i32, Io, (cudaStream_t)stream);
 }
 
+// ------------------------------------------------------------------------------ NVLink peer exchange
+// One allocation per rank: [0, 4 KiB) flag words (source s at byte 16 s) and the block counter (byte 2048), then two
+// receive slots (even / odd epochs).  Peers map it through CUDA IPC; the tables of peer pointers live on the device.
+struct snv_peer {
+    int device = 0, rank = 0, world = 1;
+    size_t slot_bytes = 0;
+    char* base = nullptr;
+    std::vector<char*> peer_base;     // [world]; [rank] = base
+    std::vector<bool> opened;         // mapped through IPC (to be closed)
+    int64_t** d_recv[2] = {nullptr, nullptr};  // device tables [world]
+    uint64_t** d_flags = nullptr;
+    uint64_t epoch = 0;
+    bool wired = false;
+};
+static constexpr size_t kPeerHeader = 4096, kPeerCounterOff = 2048;
+
+static int peer_wire(snv_peer* pe)
+{
+    std::vector<int64_t*> r0(pe->world), r1(pe->world);
+    std::vector<uint64_t*> fl(pe->world);
+    for (int g = 0; g < pe->world; ++g) {
+        r0[g] = (int64_t*)(pe->peer_base[g] + kPeerHeader);
+        r1[g] = (int64_t*)(pe->peer_base[g] + kPeerHeader + pe->slot_bytes);
+        fl[g] = (uint64_t*)pe->peer_base[g];
+    }
+    const size_t tb = (size_t)pe->world * sizeof(void*);
+    if (!pe->d_flags) {
+        SNV_CUDA_CHECK(cudaMalloc((void**)&pe->d_recv[0], tb));
+        SNV_CUDA_CHECK(cudaMalloc((void**)&pe->d_recv[1], tb));
+        SNV_CUDA_CHECK(cudaMalloc((void**)&pe->d_flags, tb));
+    }
+    SNV_CUDA_CHECK(cudaMemcpy(pe->d_recv[0], r0.data(), tb, cudaMemcpyHostToDevice));
+    SNV_CUDA_CHECK(cudaMemcpy(pe->d_recv[1], r1.data(), tb, cudaMemcpyHostToDevice));
+    SNV_CUDA_CHECK(cudaMemcpy(pe->d_flags, fl.data(), tb, cudaMemcpyHostToDevice));
+    pe->wired = true;
+    return SNV_OK;
+}
+
+int snv_peer_create(int device, int rank, int world, size_t slot_bytes, snv_peer** out, void* handle_out)
+{
+    if (!out || world < 1 || world > 64 || rank < 0 || rank >= world || slot_bytes == 0) { set_error("snv_peer_create: bad arguments"); return SNV_ERR_INVALID; }
+    DeviceGuard g(device);
+    if (!g.ok) { set_error("snv_peer_create: cudaSetDevice failed"); return SNV_ERR_CUDA; }
+    snv_peer* pe = new (std::nothrow) snv_peer();
+    if (!pe) return SNV_ERR_NOMEM;
+    pe->device = device; pe->rank = rank; pe->world = world;
+    pe->slot_bytes = (size_t)round_up((int64_t)slot_bytes, 256);
+    pe->peer_base.assign(world, nullptr);
+    pe->opened.assign(world, false);
+    const size_t total = kPeerHeader + 2 * pe->slot_bytes;
+    cudaError_t e = cudaMalloc((void**)&pe->base, total);
+    if (e != cudaSuccess) { cudaGetLastError(); delete pe; set_error("snv_peer_create: out of device memory"); return SNV_ERR_NOMEM; }
+    e = cudaMemset(pe->base, 0, kPeerHeader);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess && handle_out) {
+        cudaIpcMemHandle_t h;
+        e = cudaIpcGetMemHandle(&h, pe->base);
+        if (e == cudaSuccess) memcpy(handle_out, &h, sizeof(h));
+    }
+    if (e != cudaSuccess) {
+        set_error(std::string("snv_peer_create: ") + cudaGetErrorString(e));
+        cudaGetLastError(); cudaFree(pe->base); delete pe;
+        return SNV_ERR_CUDA;
+    }
+    pe->peer_base[rank] = pe->base;
+    *out = pe;
+    return SNV_OK;
+}
+
+int snv_peer_open(snv_peer* pe, const void* handles)
+{
+    if (!pe || !handles) { set_error("snv_peer_open: null argument"); return SNV_ERR_INVALID; }
+    DeviceGuard g(pe->device);
+    if (!g.ok) { set_error("snv_peer_open: cudaSetDevice failed"); return SNV_ERR_CUDA; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == SNV_PEER_HANDLE_BYTES, "IPC handle size");
+    for (int r = 0; r < pe->world; ++r) {
+        if (r == pe->rank || pe->peer_base[r]) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)handles + (size_t)r * sizeof(h), sizeof(h));
+        void* ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            set_error(std::string("snv_peer_open: cannot map rank ") + std::to_string(r) + "'s exchange buffer (no peer access between the GPUs?): " + cudaGetErrorString(e));
+            return SNV_ERR_CUDA;
+        }
+        pe->peer_base[r] = (char*)ptr;
+        pe->opened[r] = true;
+    }
+    return peer_wire(pe);
+}
+
+int snv_peer_open_local(snv_peer* pe, snv_peer* const* peers)
+{
+    if (!pe || !peers) { set_error("snv_peer_open_local: null argument"); return SNV_ERR_INVALID; }
+    DeviceGuard g(pe->device);
+    if (!g.ok) { set_error("snv_peer_open_local: cudaSetDevice failed"); return SNV_ERR_CUDA; }
+    for (int r = 0; r < pe->world; ++r) {
+        if (!peers[r] || peers[r]->rank != r || peers[r]->world != pe->world || peers[r]->slot_bytes != pe->slot_bytes) {
+            set_error("snv_peer_open_local: peers[r] must be rank r of the same world and slot size");
+            return SNV_ERR_INVALID;
+        }
+        pe->peer_base[r] = peers[r]->base;
+    }
+    return peer_wire(pe);
+}
+
+int snv_peer_exchange(snv_peer* pe, const int32_t* D_i32, const int64_t* I, int nw, int64_t nq, int k, int k_out, int32_t* Do_i32,
+                      int64_t* Io, void* stream)
+{
+    if (!pe || !D_i32 || !I || !Do_i32 || !Io || nw < 0 || nq < 0) { set_error("snv_peer_exchange: bad arguments"); return SNV_ERR_INVALID; }
+    if (!pe->wired) { set_error("snv_peer_exchange: call snv_peer_open first"); return SNV_ERR_INVALID; }
+    if ((size_t)nw * (size_t)nq * (size_t)(k > 0 ? k : 0) * 8 > pe->slot_bytes) { set_error("snv_peer_exchange: batch larger than the exchange slot"); return SNV_ERR_INVALID; }
+    DeviceGuard g(pe->device);
+    if (!g.ok) { set_error("snv_peer_exchange: cudaSetDevice failed"); return SNV_ERR_CUDA; }
+    const uint64_t epoch = ++pe->epoch;
+    const int slot = (int)(epoch & 1u);
+    return peer_exchange_launch(D_i32, I, nw, nq, k, pe->world, pe->rank, pe->d_recv[slot], pe->d_flags,
+                                (const int64_t*)(pe->base + kPeerHeader + (size_t)slot * pe->slot_bytes), (const uint64_t*)pe->base,
+                                (unsigned*)(pe->base + kPeerCounterOff), epoch, k_out, Do_i32, Io, (cudaStream_t)stream);
+}
+
+int snv_peer_destroy(snv_peer* pe)
+{
+    if (!pe) return SNV_OK;
+    DeviceGuard g(pe->device);
+    if (g.ok) {
+        cudaDeviceSynchronize();
+        for (int r = 0; r < pe->world; ++r)
+            if (pe->opened[r] && pe->peer_base[r]) cudaIpcCloseMemHandle(pe->peer_base[r]);
+        cudaFree(pe->d_recv[0]); cudaFree(pe->d_recv[1]); cudaFree(pe->d_flags);
+        cudaFree(pe->base);
+        cudaGetLastError();
+    }
+    delete pe;
+    return SNV_OK;
+}
+
 int snv_intersect_masks(int device, const int64_t* ref_pos, int64_t n_ref, const int64_t* tgt_pos, int64_t n_tgt,
                         const int64_t* window_info, int n_windows, int64_t d, int ploidy, uint32_t* out, void* stream_)
 {

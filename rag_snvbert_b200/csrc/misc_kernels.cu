@@ -19,9 +19,39 @@ __device__ __forceinline__ uint64_t warp_min_u64(uint64_t v)
     return v;
 }
 
-// One WARP per query: reselects the best k from parts*kin candidate keys.  Each lane keeps the
-// best KT of its strided share in sorted registers, then k rounds of (warp-min over the lane
-// heads, owner pops).  Keys are unique (they embed the row id) except the empty sentinel.
+// Warp-wide sorting network on one 64-bit key per lane (ascending over the lanes).  The key merges below are one warp
+// per row: 32 keys load as one coalesced 256-byte line, sort in 15 shuffle stages, and fold into the running best 32
+// with the 6-stage bitonic merge - about 200 instructions per 32 keys instead of a serial register insertion per key
+// plus k rounds of warp-minimum + pop (round 1: 1 ms of the 8.2 ms cfg 5 step at 1 GPU went into that).
+__device__ __forceinline__ uint64_t warp_cmpx_u64(uint64_t v, int s, bool take_min)
+{
+    const uint64_t o = __shfl_xor_sync(0xffffffffu, v, s);
+    const bool lt = o < v;
+    return (lt == take_min) ? o : v;
+}
+
+__device__ __forceinline__ uint64_t warp_sort32_u64(uint64_t v, int lane)
+{
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+        for (int s = size >> 1; s > 0; s >>= 1) v = warp_cmpx_u64(v, s, ((lane & size) == 0) == ((lane & s) == 0));
+    }
+    return v;
+}
+
+// cur, other: ascending over the lanes -> the 32 smallest of their union, ascending
+__device__ __forceinline__ uint64_t warp_merge32_u64(uint64_t cur, uint64_t other, int lane)
+{
+    const uint64_t rev = __shfl_sync(0xffffffffu, other, 31 - lane);
+    uint64_t v = rev < cur ? rev : cur;  // bitonic: holds the 32 smallest
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v = warp_cmpx_u64(v, s, (lane & s) == 0);
+    return v;
+}
+
+// One WARP per query: the best k of parts * kin candidate keys (any order; empty = kSent64), ascending.  Keys are
+// unique (they embed the row id) except the empty sentinel.  KT only names the instantiation (k <= 32 either way).
 template <int KT>
 __global__ void __launch_bounds__(256)
 merge_keys_kernel(const uint64_t* __restrict__ keys, int parts, int kin, int64_t nq_total, int k,
@@ -31,34 +61,23 @@ merge_keys_kernel(const uint64_t* __restrict__ keys, int parts, int kin, int64_t
     const int lane = threadIdx.x & 31;
     const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (q >= nq_total) return;  // warp-uniform
-    uint64_t best[KT];
-#pragma unroll
-    for (int i = 0; i < KT; ++i) best[i] = kSent64;
     const uint64_t* src = keys + q * parts * kin;
     const int total = parts * kin;
-    for (int j = lane; j < total; j += 32) {
-        const uint64_t key = src[j];
-        if (key < best[KT - 1]) topk_insert<KT, uint64_t>(best, key);
+    uint64_t cur = kSent64;
+    for (int j0 = 0; j0 < total; j0 += 32) {
+        const uint64_t v = warp_sort32_u64(j0 + lane < total ? src[j0 + lane] : kSent64, lane);
+        cur = j0 ? warp_merge32_u64(cur, v, lane) : v;
     }
-    for (int i = 0; i < k; ++i) {
-        const uint64_t m = warp_min_u64(best[0]);
-        const unsigned owners = __ballot_sync(0xffffffffu, best[0] == m);
-        if (m != kSent64 && lane == __ffs(owners) - 1) {
-#pragma unroll
-            for (int j = 0; j < KT - 1; ++j) best[j] = best[j + 1];
-            best[KT - 1] = kSent64;
-        }
-        if (lane == 0) {
-            const bool empty = m == kSent64;
-            const uint32_t hi = (uint32_t)(m >> 32);
-            const int64_t o = q * k + i;
-            I[o] = empty ? -1 : (int64_t)(uint32_t)m + id_offset;
-            if (float_dist) {
-                if (D_f32) D_f32[o] = empty ? 3.4028234663852886e38f : __uint_as_float(hi);
-            } else {
-                if (D_i32) D_i32[o] = empty ? 0x7FFFFFFF : (int32_t)hi;
-                if (D_f32) D_f32[o] = empty ? 3.4028234663852886e38f : (float)hi;
-            }
+    if (lane < k) {
+        const bool empty = cur == kSent64;
+        const uint32_t hi = (uint32_t)(cur >> 32);
+        const int64_t o = q * k + lane;
+        I[o] = empty ? -1 : (int64_t)(uint32_t)cur + id_offset;
+        if (float_dist) {
+            if (D_f32) D_f32[o] = empty ? 3.4028234663852886e38f : __uint_as_float(hi);
+        } else {
+            if (D_i32) D_i32[o] = empty ? 0x7FFFFFFF : (int32_t)hi;
+            if (D_f32) D_f32[o] = empty ? 3.4028234663852886e38f : (float)hi;
         }
     }
 }
@@ -622,9 +641,9 @@ exchange_pack_kernel(const int32_t* __restrict__ D, const int64_t* __restrict__ 
     }
 }
 
-// keys [parts][n][kin] (what the all-to-all delivered: one sorted list per source rank and row) -> the k_out best per row,
-// unpacked to (int32 distance, int64 id).  One warp per row: every lane keeps the best of its share, then k_out rounds of
-// warp-minimum + pop.  Keys are unique (they embed the id), INT64_MAX = empty.
+// keys [parts][n][kin] (what the all-to-all delivered: one list per source rank and row) -> the k_out best per row,
+// unpacked to (int32 distance, int64 id).  One warp per row, the same sorting network as merge_keys_kernel: each part's
+// list is one coalesced line.  Keys are unique (they embed the id), INT64_MAX = empty.
 template <int KT>
 __global__ void __launch_bounds__(256)
 exchange_merge_kernel(const int64_t* __restrict__ keys, int parts, int64_t n, int kin, int kout, int32_t* __restrict__ Do,
@@ -634,29 +653,141 @@ exchange_merge_kernel(const int64_t* __restrict__ keys, int parts, int64_t n, in
     const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (row >= n) return;  // warp-uniform
     constexpr uint64_t kEmpty = 0x7FFFFFFFFFFFFFFFull;
-    uint64_t best[KT];
-#pragma unroll
-    for (int i = 0; i < KT; ++i) best[i] = kSent64;
-    const int total = parts * kin;
-    for (int t = lane; t < total; t += 32) {
-        const int part = t / kin, j = t - part * kin;
-        const uint64_t key = (uint64_t)keys[((int64_t)part * n + row) * kin + j];
-        if (key < kEmpty && key < best[KT - 1]) topk_insert<KT, uint64_t>(best, key);
-    }
-    for (int i = 0; i < kout; ++i) {
-        const uint64_t m = warp_min_u64(best[0]);
-        const unsigned owners = __ballot_sync(0xffffffffu, best[0] == m);
-        if (m != kSent64 && lane == __ffs(owners) - 1) {
-#pragma unroll
-            for (int j = 0; j < KT - 1; ++j) best[j] = best[j + 1];
-            best[KT - 1] = kSent64;
-        }
-        if (lane == 0) {
-            const bool empty = m == kSent64;
-            Do[row * kout + i] = empty ? 0x7FFFFFFF : (int32_t)(m >> kXchgIdBits);
-            Io[row * kout + i] = empty ? -1 : (int64_t)(m & ((1ull << kXchgIdBits) - 1));
+    uint64_t cur = kSent64;
+    bool first = true;
+    // short lists (kin <= 16): one chunk takes 32 / kin parts at once
+    const int ppc = kin <= 16 ? 32 / kin : 1;
+    const int lp = kin <= 16 ? lane / kin : 0, lj = kin <= 16 ? lane - lp * kin : lane;
+    for (int part0 = 0; part0 < parts; part0 += ppc) {
+        for (int j0 = 0; j0 < kin; j0 += 32) {
+            const int part = part0 + lp, j = j0 + lj;
+            uint64_t v = (lp < ppc && part < parts && j < kin) ? (uint64_t)keys[((int64_t)part * n + row) * kin + j] : kSent64;
+            v = warp_sort32_u64(v >= kEmpty ? kSent64 : v, lane);
+            cur = first ? v : warp_merge32_u64(cur, v, lane);
+            first = false;
         }
     }
+    if (lane < kout) {
+        const bool empty = cur == kSent64;
+        Do[row * kout + lane] = empty ? 0x7FFFFFFF : (int32_t)(cur >> kXchgIdBits);
+        Io[row * kout + lane] = empty ? -1 : (int64_t)(cur & ((1ull << kXchgIdBits) - 1));
+    }
+}
+
+// ---- the exchange fused with its merge, over NVLink peer memory (snv_peer_*): ONE launch per row-sharded batch.
+// Phase 1 (push): every rank turns its scan result into keys and STORES each one straight into the receive area of the
+// rank that owns the query (peer memory mapped through CUDA IPC; posted 256-byte writes through the NVSwitch), fences,
+// and the last block to finish raises this rank's flag on every peer (release, system scope) to the batch's epoch.
+// Phase 2 (merge): wait until every source's flag has reached the epoch (acquire), then the warp-per-row network above
+// reduces the [parts][n][k] lists that arrived to the k_out best.  No block waits for another block of its own launch, and
+// the push depends on nothing remote, so the launch cannot deadlock however few of its blocks are resident (blocks that
+// are not resident yet only delay their rank's flag).  Measured (tools/coexist_check.py): a 128-thread block does NOT
+// become resident next to a scan CTA - 15 warps x 128 registers round up to the whole register file - so the exchange
+// runs between two scans, on a high-priority stream, and is sized to be short (whole GPU, ~50 us) rather than hidden.
+struct PeerXchgParams {
+    const int32_t* D;
+    const int64_t* I;
+    int nw, k, parts, rank, kout;
+    uint32_t nq, qg;
+    int64_t* const* peer_recv;  // [parts] each rank's receive area of this slot: keys [src][nw][qg][k]
+    uint64_t* const* peer_flags;  // [parts] each rank's flag words (one per source, 16 bytes apart)
+    const int64_t* my_recv;
+    const uint64_t* my_flags;
+    unsigned* counter;
+    uint64_t epoch;
+    int32_t* Do;
+    int64_t* Io;
+};
+
+__global__ void __launch_bounds__(128, 16)
+peer_exchange_kernel(const PeerXchgParams p)
+{
+    const int lane = threadIdx.x & 31;
+    // ---- phase 1: pack + push
+    const uint32_t total = (uint32_t)p.nw * p.nq * (uint32_t)p.k;
+    const uint32_t uk = (uint32_t)p.k;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t row = i / uk, j = i - row * uk;
+        const uint32_t w = row / p.nq, q = row - w * p.nq;
+        const uint32_t g = q / p.qg, ql = q - g * p.qg;
+        const int64_t id = p.I[i];
+        const int64_t key = id < 0 ? 0x7FFFFFFFFFFFFFFFLL : (((int64_t)p.D[i] << kXchgIdBits) | (id & ((1LL << kXchgIdBits) - 1)));
+        p.peer_recv[g][(((size_t)p.rank * p.nw + w) * p.qg + ql) * uk + j] = key;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(p.counter, 1u);
+        if (prev == gridDim.x - 1) {
+            *p.counter = 0u;  // for the next launch (stream-ordered)
+            __threadfence_system();
+            for (int g = 0; g < p.parts; ++g)
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.peer_flags[g] + 2 * p.rank), "l"(p.epoch) : "memory");
+        }
+    }
+    // ---- phase 2: wait for every source, merge
+    if ((int)threadIdx.x < p.parts) {
+        const uint64_t* f = p.my_flags + 2 * threadIdx.x;
+        uint64_t t0 = 0, v;
+        for (uint32_t spin = 0;; ++spin) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+            if (v >= p.epoch) break;
+            if ((spin & 1023u) == 1023u) {
+                uint64_t now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > 30000000000ull) {  // 30 s: a peer never arrived
+                    printf("snv peer exchange: rank %d timed out waiting for rank %d (epoch %llu, flag %llu)\n", p.rank,
+                           (int)threadIdx.x, (unsigned long long)p.epoch, (unsigned long long)v);
+                    __trap();
+                }
+            }
+            __nanosleep(spin < 64 ? 100 : 1000);  // the peers are usually a scan away: do not hammer L2 while waiting
+        }
+    }
+    __syncthreads();
+    constexpr uint64_t kEmpty = 0x7FFFFFFFFFFFFFFFull;
+    const uint32_t n = (uint32_t)p.nw * p.qg;
+    const int kin = p.k;
+    const int ppc = kin <= 16 ? 32 / kin : 1;
+    const int lp = kin <= 16 ? lane / kin : 0, lj = kin <= 16 ? lane - lp * kin : lane;
+    const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n; row += warps) {
+        uint64_t cur = kSent64;
+        for (int part0 = 0; part0 < p.parts; part0 += ppc) {
+            const int part = part0 + lp;
+            uint64_t v = kSent64;
+            if (lp < ppc && part < p.parts && lj < kin) v = (uint64_t)__ldcg(p.my_recv + ((size_t)part * n + row) * kin + lj);
+            v = warp_sort32_u64(v >= kEmpty ? kSent64 : v, lane);
+            cur = part0 ? warp_merge32_u64(cur, v, lane) : v;
+        }
+        if (lane < p.kout) {
+            const bool empty = cur == kSent64;
+            p.Do[(size_t)row * p.kout + lane] = empty ? 0x7FFFFFFF : (int32_t)(cur >> kXchgIdBits);
+            p.Io[(size_t)row * p.kout + lane] = empty ? -1 : (int64_t)(cur & ((1ull << kXchgIdBits) - 1));
+        }
+    }
+}
+
+int peer_exchange_launch(const int32_t* D, const int64_t* I, int nw, int64_t nq, int k, int parts, int rank, int64_t* const* peer_recv,
+                         uint64_t* const* peer_flags, const int64_t* my_recv, const uint64_t* my_flags, unsigned* counter,
+                         uint64_t epoch, int kout, int32_t* Do, int64_t* Io, cudaStream_t stream)
+{
+    if (parts < 1 || parts > 64 || nq % parts != 0) { set_error("peer exchange: the queries of a window must split evenly over <= 64 ranks"); return SNV_ERR_INVALID; }
+    if (k < 1 || k > 32 || kout < 1 || kout > k) { set_error("peer exchange: k must be in [1, 32], k_out <= k"); return SNV_ERR_UNSUPPORTED; }
+    if ((int64_t)nw * nq * k >= (int64_t)1 << 31) { set_error("peer exchange: batch too large (nw * nq * k must be < 2^31)"); return SNV_ERR_UNSUPPORTED; }
+    PeerXchgParams p{};
+    p.D = D; p.I = I; p.nw = nw; p.k = k; p.parts = parts; p.rank = rank; p.kout = kout;
+    p.nq = (uint32_t)nq; p.qg = (uint32_t)(nq / parts);
+    p.peer_recv = peer_recv; p.peer_flags = peer_flags; p.my_recv = my_recv; p.my_flags = my_flags;
+    p.counter = counter; p.epoch = epoch; p.Do = Do; p.Io = Io;
+    // 8 blocks of 128 threads per SM (half the thread slots): the whole grid is resident on an idle GPU, so nobody spins
+    // while a sibling waits for a slot, and the latency-bound push / merge get enough warps in flight
+    const int64_t want = std::max<int64_t>(ceil_div((int64_t)nw * nq * k, 128 * 8), ceil_div((int64_t)nw * (nq / parts), 4 * 2));
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)kNumSMs * 8));
+    peer_exchange_kernel<<<grid, 128, 0, stream>>>(p);
+    SNV_LAUNCH_CHECK();
+    return SNV_OK;
 }
 
 int exchange_pack_launch(const int32_t* D, const int64_t* I, int nw, int64_t nq, int k, int parts, int64_t* keys, cudaStream_t stream)

@@ -96,6 +96,107 @@ def search_window_sharded(search_fn: Callable, n_windows: int, world: int, rank:
     return lo, hi, (search_fn(lo, hi) if hi > lo else None)
 
 
+class PeerExchange:
+    """NVLink exchange of a row-sharded search, fused with its merge into one kernel launch per batch (snv_peer_*, see
+    include/snvknn.h): every rank stores its candidate keys straight into the owning rank's receive slot through CUDA IPC
+    peer memory, raises a flag there, waits for the flags of all sources and merges - no collective library on the data
+    path.  torch.distributed only carries the one-off all-gather of the 64-byte IPC handles (and the agreement that every
+    rank could map every peer).
+
+    `PeerExchange.connect(device, slot_bytes, group)` is collective: every rank of `group` calls it with the same
+    `slot_bytes`.  It returns None (on every rank) when some pair of GPUs has no peer access, so the caller can take the
+    NCCL route instead."""
+
+    def __init__(self, handle, device: int, rank: int, world: int, slot_bytes: int):
+        self._h = handle
+        self.device, self.rank, self.world, self.slot_bytes = int(device), int(rank), int(world), int(slot_bytes)
+
+    @classmethod
+    def _create(cls, device: int, rank: int, world: int, slot_bytes: int):
+        import ctypes
+
+        from . import _lib as L
+
+        h = ctypes.c_void_p()
+        raw = ctypes.create_string_buffer(64)
+        L.check(L.lib().snv_peer_create(int(device), int(rank), int(world), int(slot_bytes), ctypes.byref(h), raw), "snv_peer_create")
+        return cls(h, device, rank, world, slot_bytes), raw.raw
+
+    @classmethod
+    def connect(cls, device: int, slot_bytes: int, group=None) -> Optional["PeerExchange"]:
+        import torch
+        import torch.distributed as dist
+
+        from . import _lib as L
+
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        me, raw = cls._create(device, rank, world, slot_bytes)
+        # the handles travel as a CPU-side object gather (64 bytes per rank, once)
+        handles = [None] * world
+        dist.all_gather_object(handles, raw, group=group)
+        rc = L.lib().snv_peer_open(me._h, b"".join(handles))
+        ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device=f"cuda:{device}")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            me.close()
+            return None
+        return me
+
+    @classmethod
+    def connect_local(cls, device: int, world: int, slot_bytes: int):
+        """`world` exchange objects in THIS process on one device, wired by pointer (single-GPU test hook: run their
+        exchanges on different streams)."""
+        import ctypes
+
+        from . import _lib as L
+
+        peers = [cls._create(device, r, world, slot_bytes)[0] for r in range(world)]
+        arr = (ctypes.c_void_p * world)(*[p._h for p in peers])
+        for p in peers:
+            L.check(L.lib().snv_peer_open_local(p._h, arr), "snv_peer_open_local")
+        return peers
+
+    def exchange(self, D, I, k_out: Optional[int] = None, out=None):
+        """D int32 / I int64 [nw, nq, k] (this rank's candidates, global ids) -> (D, I) [nw, nq / world, k_out]: this
+        rank's queries merged over all ranks.  Runs on the current CUDA stream; all calls of one object must use the
+        same stream."""
+        import torch
+
+        from . import _lib as L
+        from .index import _current_stream
+
+        nw, nq, k = (int(x) for x in D.shape)
+        k_out = int(k_out or k)
+        if D.dtype != torch.int32 or I.dtype != torch.int64 or not D.is_contiguous() or not I.is_contiguous():
+            raise ValueError("PeerExchange.exchange: D must be contiguous int32, I contiguous int64")
+        if nq % self.world:
+            raise ValueError("PeerExchange.exchange: the queries of a window must split evenly over the ranks")
+        if nw * nq * k * 8 > self.slot_bytes:
+            raise ValueError("PeerExchange.exchange: batch larger than the exchange slot")
+        qg = nq // self.world
+        if out is None:
+            Do = torch.empty((nw, qg, k_out), dtype=torch.int32, device=D.device)
+            Io = torch.empty((nw, qg, k_out), dtype=torch.int64, device=D.device)
+        else:
+            Do, Io = out
+        L.check(L.lib().snv_peer_exchange(self._h, D.data_ptr(), I.data_ptr(), nw, nq, k, k_out, Do.data_ptr(), Io.data_ptr(),
+                                          _current_stream(self.device)), "snv_peer_exchange")
+        return Do, Io
+
+    def close(self) -> None:
+        if self._h is not None:
+            from . import _lib as L
+
+            L.lib().snv_peer_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class RowShardedSearch:
     """Row-sharded exact k-NN over a multi-window index, pipelined: the panel rows of every window are split over the
     ranks (this rank holds rows [row_lo, row_lo + ntotal)); the merged result comes back sharded by QUERY - rank r
@@ -115,7 +216,9 @@ class RowShardedSearch:
     _ID_BITS = 40
 
     def __init__(self, index, row_lo: int, world: Optional[int] = None, group=None, merge_fn: Optional[Callable] = None,
-                 search_fn: Optional[Callable] = None, chunks: Optional[int] = None):
+                 search_fn: Optional[Callable] = None, chunks: Optional[int] = None, transport: Optional[str] = None):
+        import os
+
         import torch.distributed as dist
 
         self.index = index
@@ -132,6 +235,15 @@ class RowShardedSearch:
         self._side = None
         self._pending = None
         self._last = ""
+        # exchange transport on CUDA: "peer" = the fused NVLink kernel (PeerExchange), "nccl" = pack + all_to_all_single +
+        # merge; default peer, falling back to nccl when the GPUs have no peer access
+        self.transport = (transport or os.environ.get("SNV_EXCHANGE", "peer")).lower()
+        if self.transport not in ("peer", "nccl"):
+            raise ValueError("transport must be 'peer' or 'nccl'")
+        self._peer = None
+        self._peer_failed = False
+        self._scan_out = search_fn is None   # the default search can write into caller-owned buffers
+        self._rings = {}
 
     def describe(self) -> str:
         return self._last or "not run yet"
@@ -152,6 +264,36 @@ class RowShardedSearch:
         D = torch.where(missing, torch.full_like(key, 0x7FFFFFFF), key >> cls._ID_BITS).to(torch.int32)
         I = torch.where(missing, torch.full_like(key, -1), key & ((1 << cls._ID_BITS) - 1))
         return D, I
+
+    def _scan_buffer(self, device, wc: int, nq: int, k: int):
+        """Two persistent (D, I) scan-result buffers per batch shape, used alternately."""
+        import torch
+
+        shape = (wc, nq, k)
+        ring = self._rings.setdefault(shape, {"bufs": [], "n": 0})
+        i = ring["n"] % 2
+        ring["n"] += 1
+        if len(ring["bufs"]) <= i:
+            ring["bufs"].append({"D": torch.empty(shape, dtype=torch.int32, device=device),
+                                 "I": torch.empty(shape, dtype=torch.int64, device=device), "busy": None})
+        return ring["bufs"][i]
+
+    def _peer_for(self, D, nw: int, nq: int, k: int):
+        """The NVLink exchange object, (re)connected collectively when a batch needs a larger slot.  Every rank sees the
+        same shapes, so every rank takes the same decision."""
+        if self.transport != "peer" or self._peer_failed:
+            return None
+        need = nw * nq * k * 8
+        if self._peer is None or self._peer.slot_bytes < need:
+            import torch
+
+            if self._peer is not None:
+                torch.cuda.synchronize(D.device)
+                self._peer.close()
+            self._peer = PeerExchange.connect(D.device.index, need, self.group)
+            if self._peer is None:
+                self._peer_failed = True
+        return self._peer
 
     def wait(self) -> None:
         """Make the caller's current stream wait for the exchange + merge of the last `search(..., sync=False)`."""
@@ -191,19 +333,36 @@ class RowShardedSearch:
         if on_gpu:
             main = torch.cuda.current_stream(queries.device)
             if self._side is None:
-                self._side = torch.cuda.Stream(queries.device)
+                # high priority: the exchange of batch i goes in front of the scan CTAs of batch i + 1 when both are ready
+                self._side = torch.cuda.Stream(queries.device, priority=-1)
             side = self._side
             side.wait_stream(main)
         for (w0, w1) in bounds:
-            D, I = self.search_fn(queries[w0:w1], k, w0)
             wc = w1 - w0
+            ring = None
+            if on_gpu and self._scan_out:
+                # the scan writes into one of two persistent (D, I) buffers; a buffer is reused only after the exchange
+                # that read it has finished (bounded pipeline depth, no allocator traffic per batch)
+                ring = self._scan_buffer(queries.device, wc, nq, k)
+                if ring["busy"] is not None:
+                    main.wait_event(ring["busy"])
+                D, I = self.index.search(queries[w0:w1], k, w0=w0, id_offset=self.row_lo, out=(ring["D"], ring["I"]))
+            else:
+                D, I = self.search_fn(queries[w0:w1], k, w0)
             if outD is None:
                 outD = torch.empty((nw, q_hi - q_lo, k), dtype=D.dtype, device=D.device)
                 outI = torch.empty((nw, q_hi - q_lo, k), dtype=torch.int64, device=D.device)
+                if on_gpu:
+                    outD.record_stream(side)
+                    outI.record_stream(side)
 
             def exchange_and_merge(D=D, I=I, w0=w0, w1=w1, wc=wc):
+                if on_gpu and even and D.dtype == torch.int32 and self._native and self._peer_for(D, nw, nq, k) is not None:
+                    # NVLink peer path: pack, push, flag, wait and merge in ONE kernel, written into the result slice
+                    self._peer.exchange(D, I, k, out=(outD[w0:w1], outI[w0:w1]))
+                    return
                 if on_gpu and even and D.dtype == torch.int32 and self._native:
-                    # CUDA fast path: one pack kernel, one collective, one merge kernel writing the result slice
+                    # NCCL path: one pack kernel, one collective, one merge kernel writing the result slice
                     from . import _lib as L
                     from .index import _current_stream
 
@@ -243,8 +402,11 @@ class RowShardedSearch:
                 with torch.cuda.stream(side):
                     side.wait_event(ev)
                     exchange_and_merge()
-                D.record_stream(side)
-                I.record_stream(side)
+                    if ring is not None:
+                        ring["busy"] = side.record_event()
+                if ring is None:
+                    D.record_stream(side)
+                    I.record_stream(side)
             else:
                 exchange_and_merge()
         if on_gpu:
@@ -253,8 +415,11 @@ class RowShardedSearch:
                 self._pending = None
             else:
                 self._pending = (side.record_event(), queries.device)
-                outD.record_stream(main)
-                outI.record_stream(main)
-        self._last = (f"{n_chunks} window group(s) per call; per group one all_to_all_single of packed int64 (distance << 40 | id) keys "
-                      f"({nq // G if even else q_hi - q_lo} queries x k from each of {G} ranks) + k-way merge on a side stream, overlapping the next group's scan")
+        if on_gpu and self._peer is not None:
+            self._last = (f"{n_chunks} window group(s) per call; per group ONE fused kernel on a side stream: int64 (distance << 40 | id) keys "
+                          f"stored straight into the owning rank's memory over NVLink (CUDA IPC peer memory), flag, wait, k-way merge "
+                          f"({nq // G} queries x k from each of {G} ranks) - co-resident with, and overlapping, the next scan")
+        else:
+            self._last = (f"{n_chunks} window group(s) per call; per group one all_to_all_single of packed int64 (distance << 40 | id) keys "
+                          f"({nq // G if even else q_hi - q_lo} queries x k from each of {G} ranks) + k-way merge on a side stream, overlapping the next group's scan")
         return q_lo, q_hi, outD, outI

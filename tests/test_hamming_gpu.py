@@ -566,6 +566,70 @@ def test_exchange_pack_and_merge_kernels_match_torch_reference():
         assert torch.equal(Do, De) and torch.equal(Io, Ie)
 
 
+def test_merge_kernels_take_unsorted_lists_and_short_k():
+    """the warp sorting-network merges do not rely on sorted inputs: random key order, k_in 8 / 20 / 32, 1-9 parts"""
+    import torch
+
+    from rag_snvbert_b200 import _lib as L
+    from rag_snvbert_b200.sharding import RowShardedSearch
+
+    g = torch.Generator(device="cuda")
+    g.manual_seed(11)
+    for (G, n, kin, kout) in [(1, 50, 32, 32), (9, 333, 32, 32), (5, 1000, 8, 8), (3, 77, 20, 7), (8, 64, 1, 1), (2, 10, 16, 16)]:
+        D = torch.randint(0, 1031, (G, n, kin), device="cuda", generator=g, dtype=torch.int32)
+        I = torch.randperm(G * n * kin, device="cuda", generator=g).reshape(G, n, kin).to(torch.int64)  # unique ids
+        I = torch.where(torch.rand((G, n, kin), device="cuda", generator=g) < 0.1, -1, I)
+        keys = RowShardedSearch.pack_keys(D, I).contiguous()
+        Do = torch.empty((n, kout), dtype=torch.int32, device="cuda")
+        Io = torch.empty((n, kout), dtype=torch.int64, device="cuda")
+        L.check(L.lib().snv_exchange_merge(0, keys.data_ptr(), G, n, kin, kout, Do.data_ptr(), Io.data_ptr(), 0), "merge")
+        torch.cuda.synchronize()
+        allk = keys.permute(1, 0, 2).reshape(n, G * kin).sort(dim=1).values[:, :kout]
+        De, Ie = RowShardedSearch.unpack_keys(allk)
+        assert torch.equal(Do, De) and torch.equal(Io, Ie), (G, n, kin, kout)
+
+
+@pytest.mark.parametrize("world,nw,nq,k", [(2, 3, 40, 8), (4, 2, 64, 32), (8, 1, 80, 32), (3, 2, 30, 5)])
+def test_peer_exchange_fused_kernel_single_process(world, nw, nq, k):
+    """snv_peer_exchange (pack + NVLink push + flags + merge in one launch) with `world` exchange objects wired by pointer
+    inside this process, one stream each: every rank's output equals the k best of all ranks' candidates for its query
+    slice; three batches in a row exercise both receive slots and the epoch flags."""
+    import torch
+
+    from rag_snvbert_b200.sharding import PeerExchange, RowShardedSearch
+
+    g = torch.Generator(device="cuda")
+    g.manual_seed(world * 100 + k)
+    peers = PeerExchange.connect_local(0, world, nw * nq * k * 8)
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    qg = nq // world
+    try:
+        for batch in range(3):
+            Ds, Is = [], []
+            for r in range(world):
+                D = torch.randint(0, 1031, (nw, nq, k), device="cuda", generator=g, dtype=torch.int32).sort(dim=2).values
+                I = torch.randint(0, 1 << 30, (nw, nq, k), device="cuda", generator=g, dtype=torch.int64) * world + r  # unique over ranks
+                I[:, :, -1] = torch.where(torch.rand((nw, nq), device="cuda", generator=g) < 0.2, -1, I[:, :, -1])
+                D[:, :, -1] = torch.where(I[:, :, -1] < 0, 0x7FFFFFFF, D[:, :, -1])
+                Ds.append(D.contiguous())
+                Is.append(I.contiguous())
+            torch.cuda.synchronize()
+            outs = []
+            for r in range(world):
+                with torch.cuda.stream(streams[r]):
+                    outs.append(peers[r].exchange(Ds[r], Is[r], k))
+            torch.cuda.synchronize()
+            keys = torch.stack([RowShardedSearch.pack_keys(Ds[r], Is[r]) for r in range(world)])  # [src, nw, nq, k]
+            for r in range(world):
+                mine = keys[:, :, r * qg:(r + 1) * qg]                                              # [src, nw, qg, k]
+                best = mine.permute(1, 2, 0, 3).reshape(nw, qg, world * k).sort(dim=2).values[:, :, :k]
+                De, Ie = RowShardedSearch.unpack_keys(best)
+                assert torch.equal(outs[r][0], De) and torch.equal(outs[r][1], Ie), (batch, r)
+    finally:
+        for p in peers:
+            p.close()
+
+
 @pytest.mark.parametrize("d", [1030, 100, 1024, 33])
 def test_dense_packed_rows_equal_strided_rows(d):
     """SNV_DT_PACKED_U32_DENSE: packed rows without the stride padding (the 132-byte wire format) for add, queries and
