@@ -73,6 +73,27 @@
 #ifndef SNV_TC_FOLD_AT
 #define SNV_TC_FOLD_AT 16   // fold inside a tile when some lane holds this many entries (<= SNV_TC_LIST_CAP - 16)
 #endif
+#ifndef SNV_TC_DEFER_FOLD
+#define SNV_TC_DEFER_FOLD 1  // TMEM-A engine: candidates of up to 8 tiles share one fold (each carries its tile's 3-bit tag, added by the index MMA)
+#endif
+#ifndef SNV_TC_TAG_SF
+#define SNV_TC_TAG_SF 0x74777477u  // UE8M0 A scales of the index MMA's two 32-element blocks: 2^-8 (columns), 2^-11 (tile tag)
+#endif
+// Measured on B200 (profiles/r2_tc_fold_variants.txt): k = 32 on a 25,000-row shard 1.279 -> 1.236 ms with 16 warm tiles and
+// windows of 4; every deferred setting LOSES at k <= 8 (cfg 2: 1.487 -> 1.50-1.57 ms; the insert is cheap there and a stale
+// threshold admits more list entries), so the k <= 8 kernels keep one fold per tile.
+#ifndef SNV_TC_FOLD_WARM
+#define SNV_TC_FOLD_WARM 16   // ... after this many tiles of an item folded one by one (the threshold still falls fast there)
+#endif
+#ifndef SNV_TC_FOLD_WINDOW
+#define SNV_TC_FOLD_WINDOW 4  // tiles per common fold: 1, 2, 4 or 8 (the tag has 3 bits)
+#endif
+#ifndef SNV_TC_FOLD_WARM_K8
+#define SNV_TC_FOLD_WARM_K8 0   // the same two knobs for the k <= 8 kernels
+#endif
+#ifndef SNV_TC_FOLD_WINDOW_K8
+#define SNV_TC_FOLD_WINDOW_K8 1
+#endif
 #ifndef SNV_TC_DEFER_PUBLISH
 #define SNV_TC_DEFER_PUBLISH 1  // expanders publish a B slot one k-block late (its stores drain behind the next block's loads)
 #endif
@@ -163,6 +184,12 @@ struct Cfg {
     // every 32 columns.
     static constexpr bool kListEpi = kFp4 && kTwoCta && SNV_TC_LIST_EPI;  // (the single-CTA kernel has no shared memory left for lists)
     static constexpr bool kEpi12 = MODE == MODE_FP4_2CTA_TA && SNV_TC_TA_EPI12;   // (k <= 8 kernels; sizes below cover both)
+    // Deferred folds (TMEM-A engine): the second 32-element block of the index MMA's k-chunk - all zero in the row codes,
+    // column indices need 27 elements - carries  (tile & 7)  at an A scale of 2^-11, so an accumulator reads
+    // a + column / 256 + (tile & 7) / 2048  and list entries of up to 8 consecutive tiles can wait for one common fold:
+    // late in an item a tile leaves candidates in only a few lanes, and a lockstep fold per tile costs a full insertion
+    // round for each of them.
+    static constexpr bool kDeferFold = MODE == MODE_FP4_2CTA_TA && SNV_TC_LIST_EPI && SNV_TC_DEFER_FOLD && !(SNV_TC_TA_EPI12);
     static constexpr int kListCap = kEpi12 ? 24 : SNV_TC_LIST_CAP;
     static constexpr int kFoldAt = kEpi12 ? 8 : SNV_TC_FOLD_AT;
     static constexpr int kPartsMax = kEpi12 ? 3 : 2;
@@ -540,7 +567,7 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             const uint32_t t = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + C::kSfCol;
             uint32_t sfv[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) sfv[i] = (C::kListEpi && i >= 8) ? 0x77777777u : 0x7F7F7F7Fu;
+            for (int i = 0; i < 16; ++i) sfv[i] = (C::kListEpi && i >= 8) ? (C::kDeferFold ? SNV_TC_TAG_SF : 0x77777777u) : 0x7F7F7F7Fu;
             tmem_st_32x32b_x16v(t, sfv);
             tmem_st_32x32b_x16(t + 16u, 0x7F7F7F7Fu);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -861,7 +888,15 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                                         const uint32_t a = dst + (((cb + j) ^ sw2) << 4);
                                         if (wi < ich) sts128(a, expand_panel_word_fp4(wi < p.words ? ww[j] : 0u));
                                         else if (wi == ich) sts128(a, lds128(idx_tab + (uint32_t)r * 32u));
-                                        else if (wi == ich + 1) sts128(a, lds128(idx_tab + (uint32_t)r * 32u + 16u));
+                                        else if (wi == ich + 1) {
+                                            if constexpr (C::kDeferFold) {
+                                                // tile tag t & 7 as E2M1 codes: 0 1 2 3 4 (4 + 1) 6 (6 + 1)
+                                                const uint32_t tagw = (uint32_t)(0x2707260605040200ull >> (8 * (t & 7))) & 0xFFu;
+                                                sts128(a, make_uint4(tagw, 0u, 0u, 0u));
+                                            } else {
+                                                sts128(a, lds128(idx_tab + (uint32_t)r * 32u + 16u));
+                                            }
+                                        }
                                     }
                                 }
                             }
@@ -1077,10 +1112,19 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             [[maybe_unused]] constexpr uint32_t kLStride = (uint32_t)kEpiThreads * 8u;  // bytes between a thread's entries
             [[maybe_unused]] const uint32_t list_base = smem_u32(lists) + (uint32_t)et * 8u;
             [[maybe_unused]] uint32_t lcnt = 0u;
+            // (deferred folds: the argument is the current TILE index of the item, else the tile's first column)
             [[maybe_unused]] auto fold_list = [&](uint32_t tile_col0) {
                 const uint32_t mx = __reduce_max_sync(0xffffffffu, lcnt);
                 if (mx == 0u) return;
                 auto key_of_v = [&](float v) {
+                    if constexpr (C::kDeferFold) {
+                        // 2048 a + 8 c + tag as an integer (|.| < 2^22): the low mantissa bits of v * 2048 + 1.5 * 2^23.  The
+                        // entry's tile is the last one at or before the current tile with that tag.
+                        const int32_t iv = (int32_t)__float_as_uint(fmaf(v, 2048.0f, 12582912.0f)) - 0x4B400000;
+                        const uint32_t tile = tile_col0 - ((tile_col0 - (uint32_t)iv) & 7u);
+                        const uint32_t key = ((uint32_t)((iv >> 11) + qb) << idx_bits) + tile * (uint32_t)BN + ((uint32_t)(iv >> 3) & 255u);
+                        return v < 3.0e38f ? key : kSent32;
+                    }
                     // 256 a + c as an integer (|.| < 2^19): the low mantissa bits of v * 256 + 1.5 * 2^23; +inf (a column
                     // past the panel end) gives a key above every real one
                     const int32_t iv = (int32_t)__float_as_uint(fmaf(v, 256.0f, 12582912.0f)) - 0x4B400000;
@@ -1141,7 +1185,7 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                     cols = cols < 0 ? 0 : (cols > pwidth ? pwidth : cols);
                     const int nch = (cols + G - 1) / G;
                     const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + (uint32_t)pstart;
-                    const uint32_t tile_col0 = (uint32_t)(t * BN);  // columns count from the split's first row
+                    const uint32_t tile_col0 = C::kDeferFold ? (uint32_t)t : (uint32_t)(t * BN);  // columns count from the split's first row
                     thrx[part * BM + row] = thr_mine;
                     thr_other = 3.0e38f;
 #pragma unroll
@@ -1196,7 +1240,18 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                         else mbar_arrive(&tmem_empty[as]);
                     }
 #ifndef TC_DEBUG_NO_FOLD
-                    fold_list(tile_col0);
+                    if constexpr (C::kDeferFold) {
+                        // one by one while the item is young, then once per 8 tiles (before a tag repeats), at the item's end,
+                        // and whenever some lane could not take another 32-column group
+                        constexpr int kWarm = KT <= 8 ? SNV_TC_FOLD_WARM_K8 : SNV_TC_FOLD_WARM;
+                        constexpr int kWin = KT <= 8 ? SNV_TC_FOLD_WINDOW_K8 : SNV_TC_FOLD_WINDOW;
+                        static_assert(kWin == 1 || kWin == 2 || kWin == 4 || kWin == 8, "fold window");
+                        if (t < kWarm || (t & (kWin - 1)) == kWin - 1 || t == it.ntiles - 1 ||
+                            __any_sync(0xffffffffu, lcnt >= (uint32_t)C::kFoldAt))
+                            fold_list(tile_col0);
+                    } else {
+                        fold_list(tile_col0);
+                    }
 #else
                     lcnt = 0u;
 #endif
