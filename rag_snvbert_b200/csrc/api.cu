@@ -1,5 +1,9 @@
 // C ABI of libsnvknn (include/snvknn.h): index objects, staging of host buffers, kernel dispatch.
 #include <algorithm>
+#include <map>
+#include <mutex>
+#include <unordered_map>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -58,6 +62,93 @@ struct DeviceGuard {
     }
 };
 
+// Device blocks of freed indexes / outgrown workspaces are kept (per device, up to SNV_CACHE_MB, default 1024 MiB) and
+// handed to the next allocation of a similar size: the reference builds and drops one faiss index per window
+// (src/dataset/rag_train_dataset.py:107-131, scripts_test/batch_test_faiss_l2.py:104-111), and a raw cudaFree /
+// cudaMalloc pair unmaps and re-maps the pages every time (measured on B200: 2-130 ms spikes per build + search call).
+// dev_free has cudaFree's ordering: it waits for the device before the block can be reused.
+struct DevCache {
+    std::mutex mu;
+    std::multimap<size_t, void*> blocks[64];   // free blocks by capacity
+    std::unordered_map<void*, size_t> cap_of;  // every block handed out or cached
+    size_t cached[64] = {};
+    size_t limit = [] {
+        const char* e = getenv("SNV_CACHE_MB");
+        return (size_t)(e ? std::max(0L, atol(e)) : 1024L) << 20;
+    }();
+};
+DevCache& dev_cache()
+{
+    static DevCache* c = new DevCache();  // never destroyed: the CUDA context may be gone at exit
+    return *c;
+}
+
+static size_t round_block(size_t bytes)
+{
+    const size_t q = bytes <= ((size_t)1 << 20) ? (size_t)4096 : (size_t)1 << 18;
+    return (bytes + q - 1) / q * q;
+}
+
+static void dev_cache_flush(int dev)
+{
+    DevCache& c = dev_cache();
+    for (auto& kv : c.blocks[dev]) { cudaFree(kv.second); c.cap_of.erase(kv.second); }
+    c.blocks[dev].clear();
+    c.cached[dev] = 0;
+}
+
+cudaError_t dev_alloc(void** out, size_t bytes)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    DevCache& c = dev_cache();
+    const size_t want = round_block(bytes ? bytes : 1);
+    std::lock_guard<std::mutex> lk(c.mu);
+    if (dev >= 0 && dev < 64) {
+        auto it = c.blocks[dev].lower_bound(want);
+        if (it != c.blocks[dev].end() && it->first <= want + want / 4) {
+            *out = it->second;
+            c.cached[dev] -= it->first;
+            c.blocks[dev].erase(it);
+            return cudaSuccess;
+        }
+    }
+    cudaError_t e = cudaMalloc(out, want);
+    if (e != cudaSuccess && dev >= 0 && dev < 64 && !c.blocks[dev].empty()) {
+        cudaGetLastError();
+        dev_cache_flush(dev);
+        e = cudaMalloc(out, want);
+    }
+    if (e == cudaSuccess) c.cap_of[*out] = want;
+    return e;
+}
+
+void dev_free(void* p)
+{
+    if (!p) return;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    DevCache& c = dev_cache();
+    std::lock_guard<std::mutex> lk(c.mu);
+    auto it = c.cap_of.find(p);
+    if (it == c.cap_of.end() || dev < 0 || dev >= 64 || it->second > c.limit) {
+        if (it != c.cap_of.end()) c.cap_of.erase(it);
+        cudaFree(p);
+        return;
+    }
+    cudaDeviceSynchronize();  // nothing in flight may still use the block when it is handed out again
+    const size_t cap = it->second;
+    while (c.cached[dev] + cap > c.limit && !c.blocks[dev].empty()) {  // make room: drop the largest cached blocks first
+        auto big = std::prev(c.blocks[dev].end());
+        cudaFree(big->second);
+        c.cap_of.erase(big->second);
+        c.cached[dev] -= big->first;
+        c.blocks[dev].erase(big);
+    }
+    c.blocks[dev].emplace(cap, p);
+    c.cached[dev] += cap;
+}
+
 // grow-only device scratch buffer
 struct Buf {
     void* p = nullptr;
@@ -65,12 +156,13 @@ struct Buf {
     int reserve(size_t bytes)
     {
         if (bytes <= cap) return SNV_OK;
-        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        if (p) { dev_free(p); p = nullptr; cap = 0; }
         size_t want = bytes + bytes / 4;
-        cudaError_t e = cudaMalloc(&p, want);
+        cudaError_t e = dev_alloc(&p, want);
         if (e != cudaSuccess) {
+            cudaGetLastError();
             want = bytes;
-            e = cudaMalloc(&p, want);
+            e = dev_alloc(&p, want);
         }
         if (e != cudaSuccess) {
             p = nullptr;
@@ -82,7 +174,7 @@ struct Buf {
     }
     void release()
     {
-        if (p) cudaFree(p);
+        if (p) dev_free(p);
         p = nullptr;
         cap = 0;
     }
@@ -293,11 +385,11 @@ void snv_index_free(snv_index* idx)
     if (!idx) return;
     DeviceGuard g(idx->device);
     cudaDeviceSynchronize();
-    if (idx->panel) cudaFree(idx->panel);
-    if (idx->rows) cudaFree(idx->rows);
-    if (idx->ops) cudaFree(idx->ops);
-    if (idx->norms) cudaFree(idx->norms);
-    if (idx->mean) cudaFree(idx->mean);
+    if (idx->panel) dev_free(idx->panel);
+    if (idx->rows) dev_free(idx->rows);
+    if (idx->ops) dev_free(idx->ops);
+    if (idx->norms) dev_free(idx->norms);
+    if (idx->mean) dev_free(idx->mean);
     Buf* bufs[] = {&idx->ws_in, &idx->ws_q, &idx->ws_mask, &idx->ws_min, &idx->ws_partial, &idx->ws_di,
                    &idx->ws_df, &idx->ws_i, &idx->ws_qops, &idx->ws_qnorm, &idx->ws_misc};
     for (Buf* b : bufs) b->release();
@@ -321,7 +413,7 @@ int snv_index_reset(snv_index* idx)
 {
     if (!idx) { set_error("snv_index_reset: null index"); return SNV_ERR_INVALID; }
     idx->ntotal = 0;
-    if (idx->mean) { cudaFree(idx->mean); idx->mean = nullptr; }
+    if (idx->mean) { dev_free(idx->mean); idx->mean = nullptr; }
     if (idx->l2_mode & SNV_L2_CENTER_AUTO) idx->l2_mode &= ~SNV_L2_CENTER;  // decided again on the next first add
     return SNV_OK;
 }
@@ -338,9 +430,9 @@ static int grow_arrays(const GrowSpec* specs, int n_specs, int W, int64_t ntotal
 {
     void* fresh[3] = {nullptr, nullptr, nullptr};
     for (int i = 0; i < n_specs; ++i) {
-        cudaError_t e = cudaMalloc(&fresh[i], (size_t)W * new_cap * specs[i].row_bytes);
+        cudaError_t e = dev_alloc(&fresh[i], (size_t)W * new_cap * specs[i].row_bytes);
         if (e != cudaSuccess) {
-            for (int j = 0; j < i; ++j) cudaFree(fresh[j]);
+            for (int j = 0; j < i; ++j) dev_free(fresh[j]);
             set_error(std::string("cudaMalloc(panel): ") + cudaGetErrorString(e));
             return SNV_ERR_NOMEM;
         }
@@ -354,12 +446,12 @@ static int grow_arrays(const GrowSpec* specs, int n_specs, int W, int64_t ntotal
         if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
     }
     if (e != cudaSuccess) {
-        for (int i = 0; i < n_specs; ++i) cudaFree(fresh[i]);
+        for (int i = 0; i < n_specs; ++i) dev_free(fresh[i]);
         set_error(std::string("index growth copy: ") + cudaGetErrorString(e));
         return SNV_ERR_CUDA;
     }
     for (int i = 0; i < n_specs; ++i) {
-        if (*specs[i].arr) cudaFree(*specs[i].arr);
+        if (*specs[i].arr) dev_free(*specs[i].arr);
         *specs[i].arr = fresh[i];
     }
     return SNV_OK;
@@ -450,7 +542,7 @@ int snv_index_add(snv_index* idx, const void* x, int64_t n, int dtype, unsigned 
             const int pchunks = l2_prep_chunks(idx->d);
             if (pchunks > 1) { int rc = idx->ws_qnorm.reserve((size_t)n * pchunks * 4); if (rc) return rc; }
             if (center && !idx->mean) {
-                if (cudaMalloc(&idx->mean, (size_t)W * idx->d * 4) != cudaSuccess) { set_error("cudaMalloc(mean)"); return SNV_ERR_NOMEM; }
+                if (dev_alloc((void**)&idx->mean, (size_t)W * idx->d * 4) != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc(mean)"); return SNV_ERR_NOMEM; }
                 { int rc = idx->ws_partial.reserve(l2_colmean_scratch_bytes(n, idx->d)); if (rc) return rc; }
                 for (int w = 0; w < W; ++w) {
                     int rc = l2_colmean_launch((const float*)xd + (size_t)w * n * idx->d, n, idx->d, idx->mean + (size_t)w * idx->d,

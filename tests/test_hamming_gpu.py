@@ -312,8 +312,18 @@ def test_error_behaviour():
     with pytest.raises(ValueError):
         idx.search(np.zeros((3, 64), np.uint8), 0)
     idx.add(np.zeros((3, 64), np.uint8))
-    with pytest.raises(Exception):
-        idx.search(np.zeros((3, 64), np.uint8), 100)  # k > 32 unsupported (stated limit)
+    # k > 32: the Python classes take the block path (faiss pads with -1 when k > ntotal); caller-owned results are a
+    # stated limit there, and the C-ABI itself refuses k > 32
+    D, I = idx.search(np.zeros((3, 64), np.uint8), 100)
+    assert D.shape == (3, 100) and (np.sort(I[:, :3], axis=1) == np.arange(3)).all() and (I[:, 3:] == -1).all()
+    with pytest.raises(ValueError):
+        idx.search(np.zeros((3, 64), np.uint8), 100, out=(np.empty((3, 100), np.int32), np.empty((3, 100), np.int64)))
+    from rag_snvbert_b200 import _lib as L
+
+    q = np.zeros((3, 64), np.uint8)
+    Dc, Ic = np.empty((3, 40), np.int32), np.empty((3, 40), np.int64)
+    rc = L.lib().snv_index_search(idx._h, 0, 1, q.ctypes.data, 3, L.DT_U8, None, L.MASK_NONE, 40, 0, Dc.ctypes.data, None, Ic.ctypes.data, 0, None)
+    assert rc != 0 and "32" in L.lib().snv_last_error().decode()
 
 
 def test_host_pipeline_many_windows_all_mask_modes():
