@@ -208,13 +208,13 @@ def test_auto_engine_choice_by_shape():
 
 
 def test_randomised_shapes_all_engines_agree():
-    """60 random (windows, rows, queries, sites, k, mask mode, density) combinations, with duplicated rows for ties:
+    """200 random (windows, rows, queries, sites, k, mask mode, density) combinations, with duplicated rows for ties:
     every tensor-core variant returns exactly what the popcount scan returns (tools/fuzz_engines.py runs more)."""
     import subprocess
     import sys
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, CASES="60", SEED="99")
+    env = dict(os.environ, CASES="200", SEED="99")
     env.pop("SNV_HAMMING_ENGINE", None)
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_engines.py")], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

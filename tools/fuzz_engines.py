@@ -17,7 +17,7 @@ TC_ENGINES = tuple(e for e in os.environ.get("ENGINES", "tc,tc4,tc4x2,tc4x2ta").
 # panel sizes around the tile widths (240 / 256 rows; 160 for the TMEM-operand engine)
 N_CHOICES = [1, 7, 100, 239, 240, 241, 479, 481, 1000, 2500, 5008, 12000]
 if "tc4x2ta" in TC_ENGINES:
-    N_CHOICES += [159, 160, 161, 319, 321, 800]
+    N_CHOICES += [159, 160, 161, 319, 321, 800, 2561, 20000]  # 20000 rows: k > 8 items long enough for the 4-tile fold windows
 for case in range(n_cases):
     W = int(rng.choice([1, 1, 2, 3, 5, 9]))
     N = int(rng.choice(N_CHOICES))
