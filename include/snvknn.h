@@ -244,6 +244,14 @@ int snv_peer_open(snv_peer* peer, const void* handles /* [world][SNV_PEER_HANDLE
 int snv_peer_open_local(snv_peer* peer, snv_peer* const* peers /* [world] */);
 int snv_peer_exchange(snv_peer* peer, const int32_t* D_i32, const int64_t* I, int nw, int64_t nq, int k, int k_out,
                       int32_t* Do_i32, int64_t* Io, void* stream);
+/* The two phases separately, for a pipelined caller: snv_peer_push (pack + push + flag; returns the batch's epoch) right
+ * after scan i, snv_peer_merge (wait for every source's flag of that epoch + merge) after scan i + 1 has been queued - by
+ * then the peers' pushes are a whole scan old and no block of the merge waits holding an SM.  Same stream, same call
+ * sequence on every rank; a push may run at most one batch ahead of the merge of the previous one (two slots). */
+int snv_peer_push(snv_peer* peer, const int32_t* D_i32, const int64_t* I, int nw, int64_t nq, int k, uint64_t* epoch_out,
+                  void* stream);
+int snv_peer_merge(snv_peer* peer, uint64_t epoch, int nw, int64_t nq, int k, int k_out, int32_t* Do_i32, int64_t* Io,
+                   void* stream);
 int snv_peer_destroy(snv_peer* peer);
 
 /* device-side pack helper: rows in `dtype` (U8 / F32 / PACKED_U8 / I64_TOKENS) ->

@@ -56,6 +56,8 @@ SYMBOLS = {
     "snv_peer_open": (_i, [_vp, _vp]),
     "snv_peer_open_local": (_i, [_vp, _vp]),
     "snv_peer_exchange": (_i, [_vp, _vp, _vp, _i, _i64, _i, _i, _vp, _vp, _vp]),
+    "snv_peer_push": (_i, [_vp, _vp, _vp, _i, _i64, _i, _c.POINTER(_c.c_uint64), _vp]),
+    "snv_peer_merge": (_i, [_vp, _c.c_uint64, _i, _i64, _i, _i, _vp, _vp, _vp]),
     "snv_peer_destroy": (_i, [_vp]),
     "snv_pack_rows": (_i, [_i, _vp, _i64, _i64, _i, _i, _vp, _vp, _vp]),
     "snv_intersect_masks": (_i, [_i, _vp, _i64, _vp, _i64, _vp, _i, _i64, _i, _vp, _vp]),

@@ -1384,19 +1384,47 @@ int snv_peer_open_local(snv_peer* pe, snv_peer* const* peers)
     return peer_wire(pe);
 }
 
-int snv_peer_exchange(snv_peer* pe, const int32_t* D_i32, const int64_t* I, int nw, int64_t nq, int k, int k_out, int32_t* Do_i32,
-                      int64_t* Io, void* stream)
+static int peer_run(snv_peer* pe, const char* what, int phases, uint64_t epoch, const int32_t* D_i32, const int64_t* I, int nw, int64_t nq,
+                    int k, int k_out, int32_t* Do_i32, int64_t* Io, void* stream)
 {
-    if (!pe || !D_i32 || !I || !Do_i32 || !Io || nw < 0 || nq < 0) { set_error("snv_peer_exchange: bad arguments"); return SNV_ERR_INVALID; }
-    if (!pe->wired) { set_error("snv_peer_exchange: call snv_peer_open first"); return SNV_ERR_INVALID; }
-    if ((size_t)nw * (size_t)nq * (size_t)(k > 0 ? k : 0) * 8 > pe->slot_bytes) { set_error("snv_peer_exchange: batch larger than the exchange slot"); return SNV_ERR_INVALID; }
+    if (!pe || nw < 0 || nq < 0) { set_error(std::string(what) + ": bad arguments"); return SNV_ERR_INVALID; }
+    if ((phases & 1) && (!D_i32 || !I)) { set_error(std::string(what) + ": null candidates"); return SNV_ERR_INVALID; }
+    if ((phases & 2) && (!Do_i32 || !Io)) { set_error(std::string(what) + ": null result buffers"); return SNV_ERR_INVALID; }
+    if (!pe->wired) { set_error(std::string(what) + ": call snv_peer_open first"); return SNV_ERR_INVALID; }
+    if ((size_t)nw * (size_t)nq * (size_t)(k > 0 ? k : 0) * 8 > pe->slot_bytes) { set_error(std::string(what) + ": batch larger than the exchange slot"); return SNV_ERR_INVALID; }
     DeviceGuard g(pe->device);
-    if (!g.ok) { set_error("snv_peer_exchange: cudaSetDevice failed"); return SNV_ERR_CUDA; }
-    const uint64_t epoch = ++pe->epoch;
+    if (!g.ok) { set_error(std::string(what) + ": cudaSetDevice failed"); return SNV_ERR_CUDA; }
     const int slot = (int)(epoch & 1u);
     return peer_exchange_launch(D_i32, I, nw, nq, k, pe->world, pe->rank, pe->d_recv[slot], pe->d_flags,
                                 (const int64_t*)(pe->base + kPeerHeader + (size_t)slot * pe->slot_bytes), (const uint64_t*)pe->base,
-                                (unsigned*)(pe->base + kPeerCounterOff), epoch, k_out, Do_i32, Io, (cudaStream_t)stream);
+                                (unsigned*)(pe->base + kPeerCounterOff), epoch, (phases & 2) ? k_out : 1, Do_i32, Io, phases, (cudaStream_t)stream);
+}
+
+int snv_peer_exchange(snv_peer* pe, const int32_t* D_i32, const int64_t* I, int nw, int64_t nq, int k, int k_out, int32_t* Do_i32,
+                      int64_t* Io, void* stream)
+{
+    if (!pe) { set_error("snv_peer_exchange: null object"); return SNV_ERR_INVALID; }
+    const int rc = peer_run(pe, "snv_peer_exchange", 3, pe->epoch + 1, D_i32, I, nw, nq, k, k_out, Do_i32, Io, stream);
+    if (rc == SNV_OK) ++pe->epoch;
+    return rc;
+}
+
+int snv_peer_push(snv_peer* pe, const int32_t* D_i32, const int64_t* I, int nw, int64_t nq, int k, uint64_t* epoch_out, void* stream)
+{
+    if (!pe || !epoch_out) { set_error("snv_peer_push: null argument"); return SNV_ERR_INVALID; }
+    const int rc = peer_run(pe, "snv_peer_push", 1, pe->epoch + 1, D_i32, I, nw, nq, k, 1, nullptr, nullptr, stream);
+    if (rc == SNV_OK) *epoch_out = ++pe->epoch;
+    return rc;
+}
+
+int snv_peer_merge(snv_peer* pe, uint64_t epoch, int nw, int64_t nq, int k, int k_out, int32_t* Do_i32, int64_t* Io, void* stream)
+{
+    if (!pe) { set_error("snv_peer_merge: null object"); return SNV_ERR_INVALID; }
+    if (epoch == 0 || epoch > pe->epoch || epoch + 1 < pe->epoch) {
+        set_error("snv_peer_merge: epoch must be that of the last or the last-but-one push (its slot has been reused otherwise)");
+        return SNV_ERR_INVALID;
+    }
+    return peer_run(pe, "snv_peer_merge", 2, epoch, nullptr, nullptr, nw, nq, k, k_out, Do_i32, Io, stream);
 }
 
 int snv_peer_destroy(snv_peer* pe)

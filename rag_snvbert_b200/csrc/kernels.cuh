@@ -82,7 +82,7 @@ int exchange_merge_launch(const int64_t* keys, int parts, int64_t n, int kin, in
 // pack + NVLink push + flag + wait + merge in one launch (snv_peer_exchange)
 int peer_exchange_launch(const int32_t* D, const int64_t* I, int nw, int64_t nq, int k, int parts, int rank, int64_t* const* peer_recv,
                          uint64_t* const* peer_flags, const int64_t* my_recv, const uint64_t* my_flags, unsigned* counter,
-                         uint64_t epoch, int kout, int32_t* Do, int64_t* Io, cudaStream_t stream);
+                         uint64_t epoch, int kout, int32_t* Do, int64_t* Io, int phases, cudaStream_t stream);
 
 // ---------------------------------------------------------------- pack
 int pack_launch(const void* x, int64_t rows, int64_t d, int dtype, bool invert, int stride,

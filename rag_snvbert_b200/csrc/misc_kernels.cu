@@ -683,7 +683,10 @@ exchange_merge_kernel(const int64_t* __restrict__ keys, int parts, int64_t n, in
 // the push depends on nothing remote, so the launch cannot deadlock however few of its blocks are resident (blocks that
 // are not resident yet only delay their rank's flag).  Measured (tools/coexist_check.py): a 128-thread block does NOT
 // become resident next to a scan CTA - 15 warps x 128 registers round up to the whole register file - so the exchange
-// runs between two scans, on a high-priority stream, and is sized to be short (whole GPU, ~50 us) rather than hidden.
+// runs between two scans and is sized to be short (whole GPU) rather than hidden.  While its blocks wait for a late peer
+// they hold their SMs, so a PIPELINED caller splits the phases (snv_peer_push right after scan i, snv_peer_merge after
+// scan i + 1: by then every peer's push of batch i is a whole scan old and nobody spins); the fused form is for a caller
+// that needs the result of this batch now.
 struct PeerXchgParams {
     const int32_t* D;
     const int64_t* I;
@@ -697,6 +700,7 @@ struct PeerXchgParams {
     uint64_t epoch;
     int32_t* Do;
     int64_t* Io;
+    int phases;  // bit 0: pack + push + flag, bit 1: wait + merge (3 = the fused exchange)
 };
 
 __global__ void __launch_bounds__(128, 16)
@@ -704,7 +708,7 @@ peer_exchange_kernel(const PeerXchgParams p)
 {
     const int lane = threadIdx.x & 31;
     // ---- phase 1: pack + push
-    const uint32_t total = (uint32_t)p.nw * p.nq * (uint32_t)p.k;
+    const uint32_t total = (p.phases & 1) ? (uint32_t)p.nw * p.nq * (uint32_t)p.k : 0u;
     const uint32_t uk = (uint32_t)p.k;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const uint32_t row = i / uk, j = i - row * uk;
@@ -714,9 +718,9 @@ peer_exchange_kernel(const PeerXchgParams p)
         const int64_t key = id < 0 ? 0x7FFFFFFFFFFFFFFFLL : (((int64_t)p.D[i] << kXchgIdBits) | (id & ((1LL << kXchgIdBits) - 1)));
         p.peer_recv[g][(((size_t)p.rank * p.nw + w) * p.qg + ql) * uk + j] = key;
     }
-    __threadfence_system();
+    if (p.phases & 1) __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if ((p.phases & 1) && threadIdx.x == 0) {
         const unsigned prev = atomicAdd(p.counter, 1u);
         if (prev == gridDim.x - 1) {
             *p.counter = 0u;  // for the next launch (stream-ordered)
@@ -725,6 +729,7 @@ peer_exchange_kernel(const PeerXchgParams p)
                 asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.peer_flags[g] + 2 * p.rank), "l"(p.epoch) : "memory");
         }
     }
+    if (!(p.phases & 2)) return;
     // ---- phase 2: wait for every source, merge
     if ((int)threadIdx.x < p.parts) {
         const uint64_t* f = p.my_flags + 2 * threadIdx.x;
@@ -771,7 +776,7 @@ peer_exchange_kernel(const PeerXchgParams p)
 
 int peer_exchange_launch(const int32_t* D, const int64_t* I, int nw, int64_t nq, int k, int parts, int rank, int64_t* const* peer_recv,
                          uint64_t* const* peer_flags, const int64_t* my_recv, const uint64_t* my_flags, unsigned* counter,
-                         uint64_t epoch, int kout, int32_t* Do, int64_t* Io, cudaStream_t stream)
+                         uint64_t epoch, int kout, int32_t* Do, int64_t* Io, int phases, cudaStream_t stream)
 {
     if (parts < 1 || parts > 64 || nq % parts != 0) { set_error("peer exchange: the queries of a window must split evenly over <= 64 ranks"); return SNV_ERR_INVALID; }
     if (k < 1 || k > 32 || kout < 1 || kout > k) { set_error("peer exchange: k must be in [1, 32], k_out <= k"); return SNV_ERR_UNSUPPORTED; }
@@ -780,10 +785,11 @@ int peer_exchange_launch(const int32_t* D, const int64_t* I, int nw, int64_t nq,
     p.D = D; p.I = I; p.nw = nw; p.k = k; p.parts = parts; p.rank = rank; p.kout = kout;
     p.nq = (uint32_t)nq; p.qg = (uint32_t)(nq / parts);
     p.peer_recv = peer_recv; p.peer_flags = peer_flags; p.my_recv = my_recv; p.my_flags = my_flags;
-    p.counter = counter; p.epoch = epoch; p.Do = Do; p.Io = Io;
+    p.counter = counter; p.epoch = epoch; p.Do = Do; p.Io = Io; p.phases = phases;
     // 8 blocks of 128 threads per SM (half the thread slots): the whole grid is resident on an idle GPU, so nobody spins
     // while a sibling waits for a slot, and the latency-bound push / merge get enough warps in flight
-    const int64_t want = std::max<int64_t>(ceil_div((int64_t)nw * nq * k, 128 * 8), ceil_div((int64_t)nw * (nq / parts), 4 * 2));
+    const int64_t want = std::max<int64_t>((phases & 1) ? ceil_div((int64_t)nw * nq * k, 128 * 8) : 1,
+                                           (phases & 2) ? ceil_div((int64_t)nw * (nq / parts), 4 * 2) : 1);
     const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)kNumSMs * 8));
     peer_exchange_kernel<<<grid, 128, 0, stream>>>(p);
     SNV_LAUNCH_CHECK();

@@ -183,6 +183,34 @@ class PeerExchange:
                                           _current_stream(self.device)), "snv_peer_exchange")
         return Do, Io
 
+    def push(self, D, I) -> int:
+        """Phase 1 alone (pack + push + flag) on the current stream; returns the batch's epoch for `merge`."""
+        import ctypes
+
+        import torch
+
+        from . import _lib as L
+        from .index import _current_stream
+
+        nw, nq, k = (int(x) for x in D.shape)
+        if D.dtype != torch.int32 or I.dtype != torch.int64 or not D.is_contiguous() or not I.is_contiguous():
+            raise ValueError("PeerExchange.push: D must be contiguous int32, I contiguous int64")
+        if nq % self.world:
+            raise ValueError("PeerExchange.push: the queries of a window must split evenly over the ranks")
+        epoch = ctypes.c_uint64(0)
+        L.check(L.lib().snv_peer_push(self._h, D.data_ptr(), I.data_ptr(), nw, nq, k, ctypes.byref(epoch), _current_stream(self.device)),
+                "snv_peer_push")
+        return int(epoch.value)
+
+    def merge(self, epoch: int, nw: int, nq: int, k: int, out, k_out: Optional[int] = None) -> None:
+        """Phase 2 alone (wait for every source's flag of `epoch` + merge into out=(D, I) [nw, nq / world, k_out])."""
+        from . import _lib as L
+        from .index import _current_stream
+
+        Do, Io = out
+        L.check(L.lib().snv_peer_merge(self._h, int(epoch), int(nw), int(nq), int(k), int(k_out or k), Do.data_ptr(), Io.data_ptr(),
+                                       _current_stream(self.device)), "snv_peer_merge")
+
     def close(self) -> None:
         if self._h is not None:
             from . import _lib as L
@@ -244,6 +272,7 @@ class RowShardedSearch:
         self._peer_failed = False
         self._scan_out = search_fn is None   # the default search can write into caller-owned buffers
         self._rings = {}
+        self._merges = []   # NVLink route: (epoch, windows, queries, k, out) of pushed batches whose merge is not queued yet
 
     def describe(self) -> str:
         return self._last or "not run yet"
@@ -265,20 +294,21 @@ class RowShardedSearch:
         I = torch.where(missing, torch.full_like(key, -1), key & ((1 << cls._ID_BITS) - 1))
         return D, I
 
-    def _scan_buffer(self, device, wc: int, nq: int, k: int):
-        """Two persistent (D, I) scan-result buffers per batch shape, used alternately."""
+    def _scan_buffer(self, device, wc: int, nq: int, k: int, ring: int = 2):
+        """`ring` persistent (D, I) scan-result buffers per batch shape, used in turn."""
         import torch
 
         shape = (wc, nq, k)
-        ring = self._rings.setdefault(shape, {"bufs": [], "n": 0})
-        i = ring["n"] % 2
+        nring = ring
+        ring = self._rings.setdefault((shape, nring), {"bufs": [], "n": 0})
+        i = ring["n"] % nring
         ring["n"] += 1
         if len(ring["bufs"]) <= i:
             ring["bufs"].append({"D": torch.empty(shape, dtype=torch.int32, device=device),
                                  "I": torch.empty(shape, dtype=torch.int64, device=device), "busy": None})
         return ring["bufs"][i]
 
-    def _peer_for(self, D, nw: int, nq: int, k: int):
+    def _peer_for(self, device, nw: int, nq: int, k: int):
         """The NVLink exchange object, (re)connected collectively when a batch needs a larger slot.  Every rank sees the
         same shapes, so every rank takes the same decision."""
         if self.transport != "peer" or self._peer_failed:
@@ -288,17 +318,54 @@ class RowShardedSearch:
             import torch
 
             if self._peer is not None:
-                torch.cuda.synchronize(D.device)
+                self._flush_merges()
+                torch.cuda.synchronize(device)
                 self._peer.close()
-            self._peer = PeerExchange.connect(D.device.index, need, self.group)
+            self._peer = PeerExchange.connect(device.index, need, self.group)
             if self._peer is None:
                 self._peer_failed = True
         return self._peer
+
+    def _flush_merges(self) -> None:
+        """Queue the merges of the batches pushed so far (current stream)."""
+        for (epoch, wc, nq, k, out) in self._merges:
+            self._peer.merge(epoch, wc, nq, k, out)
+        self._merges = []
+
+    def _search_peer(self, queries, k: int, sync: bool, bounds, q_lo: int, q_hi: int):
+        """NVLink route, everything on the caller's stream.  sync=True: scan, then the fused exchange (one kernel).
+        sync=False: scan i, merge of batch i - 1, push of batch i - the merge of a batch is queued behind the NEXT scan, when
+        every peer's push is a whole scan old, so none of its blocks waits for a late peer while holding an SM; `wait()`
+        queues the last merge."""
+        import torch
+
+        nw, nq = int(queries.shape[0]), int(queries.shape[1])
+        G = self.world
+        dev = queries.device
+        outD = torch.empty((nw, q_hi - q_lo, k), dtype=torch.int32, device=dev)
+        outI = torch.empty((nw, q_hi - q_lo, k), dtype=torch.int64, device=dev)
+        for (w0, w1) in bounds:
+            wc = w1 - w0
+            buf = self._scan_buffer(dev, wc, nq, k, ring=1)   # stream order alone protects it: the push reads it before the next scan
+            D, I = self.index.search(queries[w0:w1], k, w0=w0, id_offset=self.row_lo, out=(buf["D"], buf["I"]))
+            self._flush_merges()
+            if sync and w1 == nw:
+                self._peer.exchange(D, I, k, out=(outD[w0:w1], outI[w0:w1]))
+            else:
+                self._merges.append((self._peer.push(D, I), wc, nq, k, (outD[w0:w1], outI[w0:w1])))
+        self._pending = None
+        self._last = (f"{len(bounds)} window group(s) per call; NVLink peer memory (CUDA IPC), no collective library on the data path: "
+                      f"int64 (distance << 40 | id) keys stored straight into the owning rank's receive slot + flag "
+                      f"({nq // G} queries x k to each of {G} ranks), then wait + k-way merge - "
+                      + ("one fused kernel" if sync else "push after scan i, merge queued behind scan i + 1 (no block waits for a late peer)"))
+        return q_lo, q_hi, outD, outI
 
     def wait(self) -> None:
         """Make the caller's current stream wait for the exchange + merge of the last `search(..., sync=False)`."""
         import torch
 
+        if self._merges:
+            self._flush_merges()
         if self._pending is not None:
             torch.cuda.current_stream(self._pending[1]).wait_event(self._pending[0])
             self._pending = None
@@ -330,6 +397,9 @@ class RowShardedSearch:
         on_gpu = queries.is_cuda
         outD = outI = None
         main = side = None
+        if (on_gpu and even and self._native and self._scan_out and int(k) <= 32
+                and self._peer_for(queries.device, nw, nq, int(k)) is not None):
+            return self._search_peer(queries, int(k), sync, bounds, q_lo, q_hi)
         if on_gpu:
             main = torch.cuda.current_stream(queries.device)
             if self._side is None:
@@ -357,10 +427,6 @@ class RowShardedSearch:
                     outI.record_stream(side)
 
             def exchange_and_merge(D=D, I=I, w0=w0, w1=w1, wc=wc):
-                if on_gpu and even and D.dtype == torch.int32 and self._native and self._peer_for(D, nw, nq, k) is not None:
-                    # NVLink peer path: pack, push, flag, wait and merge in ONE kernel, written into the result slice
-                    self._peer.exchange(D, I, k, out=(outD[w0:w1], outI[w0:w1]))
-                    return
                 if on_gpu and even and D.dtype == torch.int32 and self._native:
                     # NCCL path: one pack kernel, one collective, one merge kernel writing the result slice
                     from . import _lib as L
@@ -415,11 +481,6 @@ class RowShardedSearch:
                 self._pending = None
             else:
                 self._pending = (side.record_event(), queries.device)
-        if on_gpu and self._peer is not None:
-            self._last = (f"{n_chunks} window group(s) per call; per group ONE fused kernel on a side stream: int64 (distance << 40 | id) keys "
-                          f"stored straight into the owning rank's memory over NVLink (CUDA IPC peer memory), flag, wait, k-way merge "
-                          f"({nq // G} queries x k from each of {G} ranks) - co-resident with, and overlapping, the next scan")
-        else:
-            self._last = (f"{n_chunks} window group(s) per call; per group one all_to_all_single of packed int64 (distance << 40 | id) keys "
-                          f"({nq // G if even else q_hi - q_lo} queries x k from each of {G} ranks) + k-way merge on a side stream, overlapping the next group's scan")
+        self._last = (f"{n_chunks} window group(s) per call; per group one all_to_all_single of packed int64 (distance << 40 | id) keys "
+                      f"({nq // G if even else q_hi - q_lo} queries x k from each of {G} ranks) + k-way merge on a side stream, overlapping the next group's scan")
         return q_lo, q_hi, outD, outI

@@ -41,7 +41,7 @@ t0 = torch.cuda.Event(enable_timing=True); t0.record()
 side_ev = []
 for i in range(steps):
     s.search(q, k, sync=False)
-    e = torch.cuda.Event(enable_timing=True); e.record(s._side); side_ev.append(e)
+    e = torch.cuda.Event(enable_timing=True); e.record(s._side) if s._side is not None else e.record(); side_ev.append(e)
 s.wait(); t1 = torch.cuda.Event(enable_timing=True); t1.record(); torch.cuda.synchronize()
 rows = [{"scan_start": round(t0.elapsed_time(a), 3), "scan_end": round(t0.elapsed_time(b), 3), "exchange_end": round(t0.elapsed_time(e), 3)}
         for (a, b), e in zip(ev, side_ev)]
