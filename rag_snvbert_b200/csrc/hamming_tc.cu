@@ -73,6 +73,15 @@
 #ifndef SNV_TC_FOLD_AT
 #define SNV_TC_FOLD_AT 16   // fold inside a tile when some lane holds this many entries (<= SNV_TC_LIST_CAP - 16)
 #endif
+// Quad scan (four columns per test: FMNMX3 + FMNMX + FSETP, 16-byte list entries): 40 % fewer scan instructions, but measured
+// SLOWER on B200 (profiles/r2_tc_quad_scan_variants.txt: cfg 2 1.518 -> 1.762 ms per 296 windows, k = 32 shard 1.244 -> 1.514 ms):
+// every entry drags three more values through the fold's threshold checks.  Kept behind the flags, off.
+#ifndef SNV_TC_QUAD_SCAN
+#define SNV_TC_QUAD_SCAN 0
+#endif
+#ifndef SNV_TC_QUAD_SCAN_K32
+#define SNV_TC_QUAD_SCAN_K32 0
+#endif
 #ifndef SNV_TC_DEFER_FOLD
 #define SNV_TC_DEFER_FOLD 1  // TMEM-A engine: candidates of up to 8 tiles share one fold (each carries its tile's 3-bit tag, added by the index MMA)
 #endif
@@ -1109,8 +1118,12 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             // entries.  a < thr  <=>  a + c / 256 < thr  for integer a, thr and c < 256; the threshold only ever
             // decreases, so a stale one admits extra candidates but never loses one, and the fold re-checks every
             // member of a pair against the current k-th best key.
-            [[maybe_unused]] constexpr uint32_t kLStride = (uint32_t)kEpiThreads * 8u;  // bytes between a thread's entries
-            [[maybe_unused]] const uint32_t list_base = smem_u32(lists) + (uint32_t)et * 8u;
+            // quad scan: 16-byte entries (four adjacent columns), half as many of them in the same shared memory
+            constexpr bool kQuad = TA && C::kListEpi && !C::kEpi12 && (KT <= 8 ? SNV_TC_QUAD_SCAN : SNV_TC_QUAD_SCAN_K32);
+            constexpr uint32_t kEntry = kQuad ? 16u : 8u;
+            constexpr uint32_t kFoldMark = kQuad ? (uint32_t)C::kFoldAt / 2u : (uint32_t)C::kFoldAt;
+            [[maybe_unused]] constexpr uint32_t kLStride = (uint32_t)kEpiThreads * kEntry;  // bytes between a thread's entries
+            [[maybe_unused]] const uint32_t list_base = smem_u32(lists) + (uint32_t)et * kEntry;
             [[maybe_unused]] uint32_t lcnt = 0u;
             // (deferred folds: the argument is the current TILE index of the item, else the tile's first column)
             [[maybe_unused]] auto fold_list = [&](uint32_t tile_col0) {
@@ -1136,6 +1149,30 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                 // sentinel, leaves the list unchanged: straight-line code); the larger one is a candidate only if it is
                 // below the threshold the scan used as well, which is rare, so its insert sits behind a branch the warp
                 // seldom takes.  Values order like their keys: v = a + c / 256.
+                if constexpr (kQuad) {
+                    // one entry (four values) per round: the smallest is what qualified the quad and goes in unguarded
+                    // (k <= 8) or behind the usual test; each of the others is a candidate only if it is below the scan's
+                    // threshold as well (and is not the smallest again), which is rare
+#pragma unroll 1
+                    for (uint32_t i = 0; i < mx; ++i) {
+                        float v0 = 3.0e38f, v1 = 3.0e38f, v2 = 3.0e38f, v3 = 3.0e38f;
+                        if (i < lcnt) asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v0), "=f"(v1), "=f"(v2), "=f"(v3) : "r"(list_base + i * kLStride));
+                        float lo;
+                        asm("min.f32 %0, %1, %2, %3;" : "=f"(lo) : "f"(v0), "f"(v1), "f"(v2));
+                        lo = fminf(lo, v3);
+                        const uint32_t klo = key_of_v(lo);
+                        if constexpr (KT <= 8) topk_insert<KT, uint32_t>(best, klo);
+                        else if (klo < best[KT - 1]) topk_insert<KT, uint32_t>(best, klo);
+                        const float vv[4] = {v0, v1, v2, v3};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            if (vv[e] < thr && vv[e] > lo) {
+                                const uint32_t kh = key_of_v(vv[e]);
+                                if (kh < best[KT - 1]) topk_insert<KT, uint32_t>(best, kh);
+                            }
+                        }
+                    }
+                } else {
 #pragma unroll 1
                 for (uint32_t i = 0; i < mx; i += 2) {
                     float v[4] = {3.0e38f, 3.0e38f, 3.0e38f, 3.0e38f};
@@ -1152,6 +1189,7 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                             if (khi < best[KT - 1]) topk_insert<KT, uint32_t>(best, khi);
                         }
                     }
+                }
                 }
                 lcnt = 0u;
                 refresh_thr();
@@ -1201,6 +1239,19 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 #ifdef TC_DEBUG_NO_EPI
                         return;
 #endif
+                        if constexpr (kQuad) {
+                            static_for<G / 4>([&](auto jc) {
+                                constexpr int j = 4 * decltype(jc)::value;
+                                const float a0 = __uint_as_float(acc[j]), a1 = __uint_as_float(acc[j + 1]);
+                                const float a2 = __uint_as_float(acc[j + 2]), a3 = __uint_as_float(acc[j + 3]);
+                                float m;
+                                asm("min.f32 %0, %1, %2, %3;" : "=f"(m) : "f"(a0), "f"(a1), "f"(a2));
+                                if (fminf(m, a3) < thr) {
+                                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(list_base + lcnt * kLStride), "f"(a0), "f"(a1), "f"(a2), "f"(a3) : "memory");
+                                    lcnt += 1u;
+                                }
+                            });
+                        } else {
                         static_for<G / 2>([&](auto jc) {
                             constexpr int j = 2 * decltype(jc)::value;
                             const float a0 = __uint_as_float(acc[j]), a1 = __uint_as_float(acc[j + 1]);
@@ -1209,8 +1260,9 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                                 lcnt += 1u;
                             }
                         });
+                        }
                         // keep every list behind the fold mark, so that the next group always fits
-                        if (u + 1 < nch && __any_sync(0xffffffffu, lcnt >= (uint32_t)C::kFoldAt)) fold_list(tile_col0);
+                        if (u + 1 < nch && __any_sync(0xffffffffu, lcnt >= kFoldMark)) fold_list(tile_col0);
                     };
                     if (nch > 0) tmem_ld_cols<G>(tbase, accA);
                     if (nch > 0) {
@@ -1247,7 +1299,7 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                         constexpr int kWin = KT <= 8 ? SNV_TC_FOLD_WINDOW_K8 : SNV_TC_FOLD_WINDOW;
                         static_assert(kWin == 1 || kWin == 2 || kWin == 4 || kWin == 8, "fold window");
                         if (t < kWarm || (t & (kWin - 1)) == kWin - 1 || t == it.ntiles - 1 ||
-                            __any_sync(0xffffffffu, lcnt >= (uint32_t)C::kFoldAt))
+                            __any_sync(0xffffffffu, lcnt >= kFoldMark))
                             fold_list(tile_col0);
                     } else {
                         fold_list(tile_col0);
