@@ -762,7 +762,8 @@ static int search_hamming(snv_index* idx, int w0, int nw, const void* q, int64_t
         for (int i = 0; i < snv_index::kPipeStreams; ++i) SNV_CUDA_CHECK(cudaStreamWaitEvent(idx->pipe_stream[i], idx->pipe_start, 0));
     }
 
-    for (int c = 0; c < nchunks; ++c) {
+    // one chunk; an error return leaves the loop, and the internal streams are joined with the caller's stream either way
+    auto run_chunk = [&](int c) -> int {
         const int wb = bounds[c];
         const int wc = bounds[c + 1] - wb;
         const int64_t r0 = (int64_t)wb * nq, rows = (int64_t)wc * nq;
@@ -841,12 +842,22 @@ static int search_hamming(snv_index* idx, int w0, int nw, const void* q, int64_t
             if (D_f32) SNV_CUDA_CHECK(cudaMemcpyAsync(D_f32 + o0, p.D_f32, cnt * 4, cudaMemcpyDeviceToHost, cs));
             SNV_CUDA_CHECK(cudaMemcpyAsync(I + o0, p.I, cnt * 8, cudaMemcpyDeviceToHost, cs));
         }
-    }
+        return SNV_OK;
+    };
+    rc = SNV_OK;
+    for (int c = 0; c < nchunks && rc == SNV_OK; ++c) rc = run_chunk(c);
     if (piped) {
         for (int i = 0; i < snv_index::kPipeStreams; ++i) {
-            SNV_CUDA_CHECK(cudaEventRecord(idx->pipe_done[i], idx->pipe_stream[i]));
-            SNV_CUDA_CHECK(cudaStreamWaitEvent(stream, idx->pipe_done[i], 0));
+            const cudaError_t e1 = cudaEventRecord(idx->pipe_done[i], idx->pipe_stream[i]);
+            const cudaError_t e2 = e1 == cudaSuccess ? cudaStreamWaitEvent(stream, idx->pipe_done[i], 0) : e1;
+            if (e2 != cudaSuccess && rc == SNV_OK) { set_error(std::string("search: joining the pipeline streams: ") + cudaGetErrorString(e2)); rc = SNV_ERR_CUDA; }
         }
+    }
+    if (rc != SNV_OK) {
+        // chunks already queued still use the shared workspaces and the caller's buffers: let them finish before returning
+        cudaStreamSynchronize(stream);
+        cudaGetLastError();
+        return rc;
     }
     if (!out_dev || !q_dev) SNV_CUDA_CHECK(cudaStreamSynchronize(stream));
     return SNV_OK;
