@@ -230,7 +230,7 @@ int snv_exchange_merge(int device, const int64_t* keys, int parts, int64_t n, in
  * lists that arrived into Do_i32 / Io [nw * nq / world][k_out] - the result of snv_exchange_pack + all-to-all +
  * snv_exchange_merge.  Rules: every rank makes the same sequence of calls (batch sizes equal on all ranks); all calls of
  * one object go to ONE stream (slot reuse is ordered by the previous batch's flags); nw * nq * k * 8 <= slot_bytes;
- * nq % world == 0; k <= 32; ids < 2^40.  A peer that never arrives traps the kernel after 30 s.
+ * nq % world == 0; k <= 32; ids < 2^40.  A peer that never arrives traps the kernel after SNV_PEER_TIMEOUT_S seconds (default 60) instead of hanging it.
  * snv_peer_open_local wires objects that live in ONE process on one device by pointer (test hook: their exchanges must
  * then run on different streams, since each waits for the others' pushes).
  * Replaces, for the row-sharded search of a multi-GPU job, what the reference does on one GPU with a single faiss index

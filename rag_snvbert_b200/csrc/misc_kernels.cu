@@ -701,6 +701,7 @@ struct PeerXchgParams {
     int32_t* Do;
     int64_t* Io;
     int phases;  // bit 0: pack + push + flag, bit 1: wait + merge (3 = the fused exchange)
+    uint64_t timeout_ns;  // a source that has not raised its flag after this long traps the kernel
 };
 
 __global__ void __launch_bounds__(128, 16)
@@ -741,7 +742,7 @@ peer_exchange_kernel(const PeerXchgParams p)
                 uint64_t now;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
                 if (t0 == 0) t0 = now;
-                else if (now - t0 > 30000000000ull) {  // 30 s: a peer never arrived
+                else if (now - t0 > p.timeout_ns) {  // a peer never arrived
                     printf("snv peer exchange: rank %d timed out waiting for rank %d (epoch %llu, flag %llu)\n", p.rank,
                            (int)threadIdx.x, (unsigned long long)p.epoch, (unsigned long long)v);
                     __trap();
@@ -786,6 +787,11 @@ int peer_exchange_launch(const int32_t* D, const int64_t* I, int nw, int64_t nq,
     p.nq = (uint32_t)nq; p.qg = (uint32_t)(nq / parts);
     p.peer_recv = peer_recv; p.peer_flags = peer_flags; p.my_recv = my_recv; p.my_flags = my_flags;
     p.counter = counter; p.epoch = epoch; p.Do = Do; p.Io = Io; p.phases = phases;
+    {
+        // SNV_PEER_TIMEOUT_S: how long the merge waits for a rank that is behind (default 60 s) before it traps instead of hanging
+        static const uint64_t timeout_s = [] { const char* e = getenv("SNV_PEER_TIMEOUT_S"); const long v = e ? atol(e) : 60; return (uint64_t)(v > 0 ? v : 60); }();
+        p.timeout_ns = timeout_s * 1000000000ull;
+    }
     // 8 blocks of 128 threads per SM (half the thread slots): the whole grid is resident on an idle GPU, so nobody spins
     // while a sibling waits for a slot, and the latency-bound push / merge get enough warps in flight
     const int64_t want = std::max<int64_t>((phases & 1) ? ceil_div((int64_t)nw * nq * k, 128 * 8) : 1,
