@@ -633,6 +633,7 @@ static int hamming_chunk_bounds(const HammingSearchParams& p, bool host_io, std:
             int64_t cw = std::max<int64_t>(unit, nw / target / unit * unit);
             if (cw * per_w < 2 * units) cw = ceil_div(2 * units, per_w);
             chunk_w = (int)std::min<int64_t>(cw, nw);
+            if (const char* e = getenv("SNV_PIPE_CHUNK_W")) chunk_w = (int)std::min<int64_t>(std::max(1, atoi(e)), nw);  // tuning override
         } else {
             // popcount engine: a chunk keeps enough CTAs (>= 16 per SM) that the scan needs no row split
             chunk_w = (int)std::max<int64_t>(ceil_div(nw, 16), ceil_div((int64_t)kNumSMs * 16, qtiles));
