@@ -30,24 +30,29 @@
 // tile; slots are released and accumulators published with multicast tcgen05.commit, the peer's TMA completes on the
 // leader's barrier, the peer's expanders / epilogue arrive on the leader's barriers through mapa.
 //
-// Query operand in tensor memory (MODE_FP4_2CTA_TA, opt-in bring-up: SNV_HAMMING_ENGINE=tc4x2ta, <= 1280 sites): the
-// shared-memory port is what bounds the pair kernel (MMA operand reads + expander stores + TMA writes), and 38 % of
-// that traffic is the query tile, re-fetched and re-read for every panel tile.  Here the epilogue warps write an
-// item's query rows to TMEM once (tcgen05.st, thread = query row = lane, 8 codes per column) and the MMAs take A from
-// there (tcgen05.mma [d], [a], b-desc): no A ring, no A traffic.  TMEM = 2 x 160 accumulator columns + 160 operand
-// columns + 32 scale columns, so tiles are 160 panel rows wide.
+// Query operand in tensor memory (MODE_FP4_2CTA_TA, engine 5: the DEFAULT for windows of up to 1216 sites; forced with
+// SNV_HAMMING_ENGINE=tc4x2ta): the shared-memory port is what bounds the plain pair kernel (MMA operand reads + expander
+// stores + TMA writes), and 38 % of that traffic is the query tile, re-fetched and re-read for every panel tile.  Here the
+// epilogue warps build an item's query operand in TMEM once, straight from the PACKED query rows (global loads, in-register
+// expansion, tcgen05.st; thread = query row = lane, 8 codes per column) and the MMAs take A from there (tcgen05.mma [d],
+// [a], b-desc): no A ring, no A traffic, no expanded query operands in HBM, no side kernel.  TMEM = 2 x 160 accumulator
+// columns + 160 operand columns + 32 scale columns, so tiles are 160 panel rows wide; the producers work per TILE (one
+// raw TMA box of whole packed rows, one B slot of 5 k-block sub-tiles, one barrier wait and 18 MMAs per tile).
 //
 // CTA (480 threads, one per SM, persistent over (window, query tile [pair], row split) items):
-//   warp 0       TMA producer of the query operand tile A [128 x 128 B] (SWIZZLE_128B)
+//   warp 0       TMA producer of the query operand tile A [128 x 128 B] (SWIZZLE_128B; idle in the TMEM-A mode)
 //   warp 1       TMEM allocator + MMA issuer (one elected lane): tcgen05.mma M128 / M256 into one of two accumulator stages
-//   warp 2       TMA producer of the raw packed panel k-blocks [rows x 16 / 32 B]
-//   warps 3-6    expanders: packed bits -> operand tile B (one 128-byte row per panel row and k-block)
-//   warps 7-14   epilogue: thread = query (TMEM lane), two warps per lane quarter on the two column halves of a
-//                tile; per column one compare of the raw accumulator with the threshold, a predicated store into
-//                the column's slot in shared memory and a predicated bit in a 32-column mask; after each chunk
-//                the lanes pop their mask bits in lockstep and insert 32-bit keys (distance << idx_bits | row) into
-//                a sorted register top-k; the halves exchange thresholds, are merged in shared memory and the
-//                final (D, I) rows are written by the kernel itself.
+//   warp 2       TMA producer of the raw packed panel rows
+//   warps 3-6    expanders: packed bits -> operand tile B (one 128-byte row per panel row and k-block) + the rows'
+//                column-index code block (and, TMEM-A mode, the tile tag block)
+//   warps 7-14   epilogue: thread = query (TMEM lane), two warps per lane quarter on the two column parts of a tile.
+//                fp4 CTA-pair engines (candidate-list epilogue): one extra MMA per tile adds column / 256 (+ tile tag /
+//                2048) to every accumulator, so a candidate is self-describing: the scan takes the columns in pairs
+//                (minimum, compare, predicated 8-byte append to the thread's list in shared memory) and the lists are
+//                folded into a sorted register top-k of 32-bit keys (distance << idx_bits | row) once per tile part
+//                (k > 8: once per 4 tiles after the first 16).  Other engines: per column a compare, a predicated store
+//                into the column's slot and a bit in a 32-column mask, popped in lockstep after each chunk.  The parts
+//                exchange thresholds, are merged in shared memory and the final (D, I) rows are written by the kernel.
 #include <cuda.h>
 
 #include <algorithm>
