@@ -8,10 +8,12 @@ src/dataset/embedding_rag_infer_dataset.py:218), so both modes 
     searches it with NO data-path collective; results live in disjoint slices.
   * row-sharded panel (BASELINE cfg 5): rank g holds panel rows [g*N/G, (g+1)*N/G) of every
     window, searches its rows with GLOBAL ids (id_offset), then ONE exchange of the per-rank
-    (D, I) [Q, k] (NCCL over NVLink on the GPU box, gloo in the CPU tests) - an all-gather (every rank
-    gets the full result) or an all-to-all (the result stays sharded by query: 1/G of the traffic and of
-    the merge work) - and an on-device k-way merge on the (distance, id) order.  Result == unsharded
-    search by construction.
+    candidates and an on-device k-way merge on the (distance, id) order; result == unsharded search by
+    construction.  On the GPU box the exchange is `PeerExchange` - candidate keys stored straight into the
+    owning rank's memory over NVLink (CUDA IPC peer memory) and merged by the same kernel, no collective
+    library on the data path - with an NCCL route (`all_to_all_single`) for GPUs without peer access; the
+    stateless helpers below use an all-gather (every rank gets the full result) or an all-to-all (the result
+    stays sharded by query: 1/G of the traffic and of the merge work), NCCL on GPUs and gloo in the CPU tests.
 
 `search_fn` / `merge_fn` are injected so the plumbing (offsets, gather order, shapes) is testable
 on CPU with world_size 2 over gloo; on the GPU they are the CUDA index's search and
@@ -232,10 +234,12 @@ class RowShardedSearch:
     wants and moves 1/G of the bytes an all-gather would.
 
     Per call the windows are cut into `chunks` groups.  For each group: local scan with global ids on the caller's
-    stream; then, on a side stream, ONE all_to_all_single of the packed candidates (one int64 key = distance << 40 | id
-    per neighbour instead of separate int32 / int64 arrays: 8 instead of 12 bytes on the wire, one collective
-    instead of two) and the on-device k-way merge - overlapping the next group's scan.  The result equals the
-    unsharded search by construction of the (distance, id) total order.
+    stream, then the exchange of the packed candidates (one int64 key = distance << 40 | id per neighbour instead of
+    separate int32 / int64 arrays: 8 instead of 12 bytes on the wire) and the on-device k-way merge.
+    transport="peer" (default): `PeerExchange` on the caller's stream - one fused kernel for sync=True, push / merge
+    split around the next scan for sync=False (see `_search_peer`).  transport="nccl" (or no peer access): ONE
+    all_to_all_single + merge on a side stream, overlapping the next group's scan.  The result equals the unsharded
+    search by construction of the (distance, id) total order.
 
     `search_fn(queries [nw_c, nq, ..], k, w0) -> (D, I) [nw_c, nq, k]` (ids global) and `merge_fn(D [G, n, k], I [G, n, k], k)`
     are injectable so that the plumbing runs on CPU tensors over gloo in the tests; by default they are the CUDA
