@@ -38,6 +38,26 @@ def test_no_cpu_fallback_without_device():
             IndexHamming(1030)
 
 
+def test_peer_exchange_argument_checks_and_no_device():
+    """snv_peer_*: bad arguments are refused before any device work; without a CUDA device creation fails loudly
+    (no host-memory stand-in for the exchange buffer)"""
+    import ctypes
+
+    from rag_snvbert_b200 import _lib
+
+    L = _lib.lib()
+    h = ctypes.c_void_p()
+    raw = ctypes.create_string_buffer(64)
+    assert L.snv_peer_create(0, 2, 2, 1024, ctypes.byref(h), raw) == 1        # rank outside the world
+    assert L.snv_peer_create(0, 0, 0, 1024, ctypes.byref(h), raw) == 1        # empty world
+    assert L.snv_peer_create(0, 0, 2, 0, ctypes.byref(h), raw) == 1           # no slot
+    assert L.snv_peer_open(None, raw) == 1 and L.snv_peer_exchange(None, None, None, 1, 2, 8, 8, None, None, None) == 1
+    assert L.snv_peer_destroy(None) == 0
+    if _lib.device_count() == 0:
+        assert L.snv_peer_create(0, 0, 2, 1024, ctypes.byref(h), raw) != 0
+        assert not h.value
+
+
 def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, "rag_snvbert_b200")
     for dirpath, _, files in os.walk(pkg):
