@@ -1670,9 +1670,10 @@ size_t hamming_tc_plan(const HammingSearchParams& p, HammingTcPlan& plan)
     {
         double best_cost = -1.0;
         const int64_t max_split = std::max<int64_t>(min_split, std::min<int64_t>(32, plan.n_tiles / 2));
-        // tiles of time per candidate insertion round, and per partial key merged afterwards (fitted on B200:
-        // cfg 5 at 1-8 GPUs, profiles/r1_bench_cfg5_*)
-        double ins = plan.kt == 8 ? 0.04 : 0.3;
+        // tiles of time per candidate insertion round, and per partial key merged afterwards (fitted on B200: cfg 5 at
+        // 1-8 GPUs, profiles/r1_bench_cfg5_*; k = 32 re-fitted for the round-2 epilogue - with 0.3 the 200,000-row panel
+        // was cut into two row splits, 7.16 ms per 8 windows; unsplit items + tail split: 6.51 ms)
+        double ins = plan.kt == 8 ? 0.04 : 0.6;
         const double merge_per_key = 3.5e-5;
         if (const char* e = getenv("SNV_TC_INS")) ins = atof(e) > 0 ? atof(e) : ins;  // tuning override
         for (int64_t s = min_split; s <= max_split; ++s) {
@@ -1705,7 +1706,7 @@ size_t hamming_tc_plan(const HammingSearchParams& p, HammingTcPlan& plan)
         if (s2 >= 2) {
             const int64_t per = ceil_div(plan.n_tiles, s2);
             s2 = ceil_div(plan.n_tiles, per);
-            const double ins = plan.kt == 8 ? 0.04 : 0.3;
+            const double ins = plan.kt == 8 ? 0.04 : 0.6;
             auto item_cost = [&](double tiles) { return tiles + 0.25 + ins * plan.kt * (1.0 + std::log(std::max(1.0, tiles * BN / plan.kt))); };
             const double now = (double)(R + 1) * item_cost((double)plan.n_tiles);
             const double then = (double)R * item_cost((double)plan.n_tiles) + item_cost((double)per) +
