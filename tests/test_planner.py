@@ -128,6 +128,8 @@ def test_cfg_shapes_pick_expected_plans(L, force_engine):
     # cfg 5 step on one GPU (k = 32)
     plan, items = L.debug_hamming_plan(8, 10000, 200000, 1030, 32)
     assert plan["engine"] == 5 and plan["kt"] == 32
+    # unsplit items + tail split (measured 6.5 ms against 7.2 ms for two row splits, round 2)
+    assert plan["nsplit"] == 1 and plan["tail_items"] == 24 and plan["tail_split"] == 3
     # its 8-GPU row shard: 8 windows x 40 tile pairs = 320 items = 4 rounds + 24 -> the 24 trailing items are cut in 3
     plan, items = L.debug_hamming_plan(8, 10000, 25000, 1030, 32)
     assert plan["engine"] == 5 and plan["kt"] == 32 and plan["nsplit"] == 1
